@@ -1,0 +1,124 @@
+"""Pin the numpy oracle to vectors produced by the unmodified reference module
+(tests/golden/make_golden.py).  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pointnet_oracle as orc
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "case_*.npz")))
+
+
+def _digest(g):
+    flat = np.asarray(g, np.float64).reshape(-1)
+    idx = np.linspace(0, flat.size - 1, num=min(flat.size, 64)).astype(np.int64)
+    return np.concatenate([[flat.sum(), np.abs(flat).sum()], flat[idx]])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_oracle_matches_reference(path):
+    gold = np.load(path)
+    C, seed = int(gold["C"]), int(gold["seed"])
+    sd = orc.synth_state(C, seed)
+    x, labels, cw = gold["x"], gold["labels"], gold["class_w"]
+
+    # eval logits + argmax (pcs.py:450-452)
+    le = orc.forward_eval(sd, x)
+    np.testing.assert_allclose(le, gold["eval_logits"], rtol=0, atol=2e-5)
+    agree = (orc.argmax_labels(le) == gold["eval_argmax"]).mean()
+    assert agree >= 0.999
+
+    # train forward, loss, every gradient, BN buffer update (pcs.py:241-254)
+    lt, cache, newbuf = orc.forward_train(sd, x)
+    np.testing.assert_allclose(lt, gold["train_logits"], rtol=0, atol=5e-5)
+    loss, dlogits = orc.weighted_ce(lt, labels, cw)
+    assert abs(loss - float(gold["loss"])) < 1e-5
+    grads = orc.backward(cache, dlogits)
+    for key in gold.files:
+        if key.startswith("gd/"):
+            name = key[3:]
+            ref = gold[key]
+            got = _digest(grads[name])
+            if name.endswith(".bias") and name.split(".")[0] in orc.CONV_NAMES[:-1]:
+                # a conv bias followed by train-mode BN has a mathematically zero gradient;
+                # the reference holds fp32 round-off there (|g| ~ 1e-8 per entry)
+                assert ref[1] / grads[name].size < 1e-6 and got[1] / grads[name].size < 1e-6, name
+                continue
+            scale = max(ref[1] / max(grads[name].size, 1), 1e-7)   # mean |g|
+            np.testing.assert_allclose(got[2:], ref[2:], rtol=0, atol=2e-2 * scale + 1e-6, err_msg=name)
+            assert abs(got[1] - ref[1]) <= 2e-3 * ref[1] + 1e-6 * grads[name].size, name
+        elif key.startswith("g/"):
+            name = key[2:]
+            ref = gold[key]
+            if name.endswith(".bias") and name.split(".")[0] in orc.CONV_NAMES[:-1]:
+                continue
+            tol = 1e-3 * np.abs(ref).max() + 1e-6
+            np.testing.assert_allclose(grads[name], ref, rtol=0, atol=tol, err_msg=name)
+        elif key.startswith("buf/"):
+            name = key[4:]
+            if name.endswith("num_batches_tracked"):
+                assert int(newbuf[name]) == int(gold[key])
+            else:
+                np.testing.assert_allclose(newbuf[name], gold[key], rtol=1e-4, atol=1e-6, err_msg=name)
+
+
+def test_ragged_padding_contract(golden_dir):
+    """Padded rows are real zero inputs with label -1 (pcs.py:53-61)."""
+    gold = np.load(os.path.join(golden_dir, "case_ragged_c3.npz"))
+    x, labels = gold["x"], gold["labels"]
+    assert x.shape == (3, 128, 4) and labels.shape == (3, 128)
+    assert (labels[0, 70:] == -1).all() and (x[0, 70:] == 0).all()
+    assert (labels[1, 33:] == -1).all() and (labels[2] >= 0).all()
+
+
+def test_collate_matches_fixture(golden_dir):
+    rng = np.random.default_rng(0)
+    pts = [rng.random((n, 4), dtype=np.float32) for n in (5, 9, 2)]
+    lab = [rng.integers(0, 3, (n,)) for n in (5, 9, 2)]
+    p, l, m = orc.collate(pts, lab)
+    assert p.shape == (3, 9, 4) and l.dtype == np.int64 and m.dtype == bool
+    assert (l[0, 5:] == -1).all() and m[2].sum() == 2 and (p[2, 2:] == 0).all()
+
+
+def test_ce_ignore_index_and_weights():
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal((2, 7, 4))
+    y = rng.integers(0, 4, (2, 7))
+    y[0, 3:] = -1
+    w = np.array([1.0, 2.0, 0.5, 1.5])
+    loss, dz = orc.weighted_ce(z, y, w)
+    # finite-difference check of one coordinate
+    e = 1e-6
+    z2 = z.copy(); z2[1, 2, 1] += e
+    l2, _ = orc.weighted_ce(z2, y, w)
+    assert abs((l2 - loss) / e - dz[1, 2, 1]) < 1e-5
+    assert (dz[0, 3:] == 0).all()
+
+
+def test_backward_finite_difference():
+    """Oracle gradients vs central differences on a tiny problem (fp64)."""
+    C = 3
+    sd = orc.synth_state(C, 3)
+    rng = np.random.default_rng(2)
+    x = rng.random((2, 6, 4))
+    y = rng.integers(0, C, (2, 6)); y[1, 4:] = -1
+    w = np.array([1.0, 0.7, 1.3])
+
+    def loss_of(sd_):
+        lt, cache, _ = orc.forward_train(sd_, x)
+        l, dz = orc.weighted_ce(lt, y, w)
+        return l, cache, dz
+
+    l0, cache, dz = loss_of(sd)
+    grads = orc.backward(cache, dz)
+    for name, idx in (("conv3.weight", (5, 7, 0)), ("bn_global.weight", (100,)), ("seg_conv1.weight", (9, 500, 0)),
+                      ("seg_conv4.bias", (1,)), ("conv1.weight", (3, 2, 0)), ("bn2.bias", (10,))):
+        sdp = {k: np.array(v, dtype=np.float64) for k, v in sd.items()}
+        sdm = {k: np.array(v, dtype=np.float64) for k, v in sd.items()}
+        e = 1e-5
+        sdp[name][idx] += e
+        sdm[name][idx] -= e
+        fd = (loss_of(sdp)[0] - loss_of(sdm)[0]) / (2 * e)
+        assert abs(fd - grads[name][idx]) < 1e-6 + 1e-4 * abs(fd), (name, fd, grads[name][idx])
