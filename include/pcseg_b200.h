@@ -1,0 +1,108 @@
+/* pcseg_b200 — C ABI of the B200-native point-cloud segmentation hot path.
+ *
+ * The reference has no FFI: its boundary is the Python class
+ * PointNetSegmentation (point_cloud_segmentation.py:65-133, "pcs.py" below) plus the
+ * loss / backward / optimizer calls of its training loop (pcs.py:241-255).  The entry points
+ * below are what a binding for that path binds; every one cites the reference lines it
+ * replaces.  All pointers except `ctx`, `out` arrays documented as host, and strings are
+ * DEVICE pointers; `stream` is a cudaStream_t (NULL = legacy default stream).  Functions
+ * return 0 on success, non-zero on error (message via pcseg_last_error()); no exceptions
+ * cross this boundary and the library never allocates device memory itself: the caller
+ * passes one workspace of pcseg_workspace_bytes().
+ *
+ * Layouts: x (B, N, 4) fp32 contiguous; logits (B, N, C) fp32 contiguous; labels (B, N) int64,
+ * -1 = padding (pcs.py:54); parameters = one flat fp32 arena in state_dict order
+ * (pcs.py:70-94: conv1.weight, conv1.bias, ..., seg_conv4.bias, bn1.weight, bn1.bias, ...,
+ * bn_seg3.bias), BatchNorm running statistics = one flat fp32 arena
+ * (bn1.running_mean, bn1.running_var, ..., bn_seg3.running_var).
+ */
+#ifndef PCSEG_B200_H
+#define PCSEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcseg_ctx pcseg_ctx;
+
+#define PCSEG_MAX_CLASSES 8
+#define PCSEG_NUM_PARAM_TENSORS 38   /* 10 conv weight/bias pairs + 9 BN weight/bias pairs */
+#define PCSEG_NUM_BN 9
+
+/* Cross-entropy accumulators written by pcseg_forward_train (device struct, 32 bytes). */
+typedef struct pcseg_ce_accum {
+    double loss_num;             /* sum_i w[y_i] * -log softmax(z_i)[y_i] over labels != -1 */
+    double w_sum;                /* sum_i w[y_i]                                            */
+    unsigned long long correct;  /* argmax == label                                         */
+    unsigned long long valid;    /* labels != -1                                            */
+} pcseg_ce_accum;
+
+const char* pcseg_last_error(void);
+const char* pcseg_version(void);
+
+/* Model construction: replaces PointNetSegmentation.__init__(num_classes, input_dim=4), pcs.py:66-96. */
+int pcseg_create(pcseg_ctx** out, int num_classes);
+int pcseg_destroy(pcseg_ctx* ctx);
+
+/* Flat-arena layout queries (host only, no GPU needed). */
+long long pcseg_param_count(int num_classes);                 /* 1 927 621 for C = 5 */
+long long pcseg_param_offset(int num_classes, int tensor);    /* tensor in [0, 38): state_dict order of parameters */
+long long pcseg_param_numel(int num_classes, int tensor);
+long long pcseg_bn_buffer_count(void);                        /* 6 528 floats */
+long long pcseg_bn_buffer_offset(int bn, int which);          /* which: 0 running_mean, 1 running_var */
+long long pcseg_workspace_bytes(int B, int N, int num_classes, int train);
+
+/* Bind a batch shape and a caller-owned workspace (builds TMA descriptors; host only work). */
+int pcseg_bind(pcseg_ctx* ctx, int B, int N, void* workspace, long long workspace_bytes, int train);
+
+/* model.eval() weight preparation: folds BatchNorm running statistics into bf16 weights
+ * (pcs.py:277/432 semantics).  Call again whenever parameters or buffers change. */
+int pcseg_prepare_eval(pcseg_ctx* ctx, const float* params, const float* bn_buffers, void* stream);
+
+/* Inference forward: PointNetSegmentation.forward under eval()/no_grad, pcs.py:98-133, 450-451.
+ * labels_out (optional, int64 (B,N)) receives argmax over classes, pcs.py:452. */
+int pcseg_forward_eval(pcseg_ctx* ctx, const float* x, float* logits, long long* labels_out, void* stream);
+
+/* Training forward: pcs.py:98-133 under train() (batch statistics, running-stat update, dropout).
+ * bn_buffers is updated in place.  dropout_p = 0 disables dropout.  If labels != NULL the weighted
+ * cross-entropy of pcs.py:216,247-251 is accumulated into *ce (device, zeroed by this call);
+ * class_w may be NULL (all ones). */
+int pcseg_forward_train(pcseg_ctx* ctx, const float* x, const float* params, float* bn_buffers,
+                        unsigned long long seed, float dropout_p, float* logits, const long long* labels,
+                        const float* class_w, pcseg_ce_accum* ce, void* stream);
+
+/* Backward of the training forward: loss.backward(), pcs.py:254.  Gradients of all 38 parameter
+ * tensors are written (not accumulated) into `grads`, laid out like `params`.
+ * Either dlogits (B,N,C fp32) is given (autograd path), or dlogits == NULL and the gradient of
+ * the weighted-mean cross-entropy is formed from the saved logits, labels, class_w and the
+ * normaliser *wsum_total (device double: sum of class weights over ALL valid points of the
+ * global batch, so data-parallel ranks can pass the all-reduced value).
+ * phase 0 = whole backward; phase 1 = seg head .. global_feat (gradients of tensors 10..19 and
+ * 30..37 are final afterwards); phase 2 = conv5 .. conv1 (tensors 0..9, 20..29).  The split lets a
+ * data-parallel caller all-reduce the first bucket while phase 2 runs. */
+int pcseg_backward(pcseg_ctx* ctx, const float* x, const float* params, const float* dlogits,
+                   const float* logits, const long long* labels, const float* class_w,
+                   const double* wsum_total, float* grads, int phase, void* stream);
+
+/* optimizer.step() of torch.optim.Adam(lr, weight_decay) on the flat arena, pcs.py:217,255. */
+int pcseg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                    int step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float grad_scale, void* stream);
+
+/* Stand-alone GEMM entry used by the unit tests of the tcgen05 kernel (bf16 in, fp32 accumulate).
+ *   layout 0: D[M,N] = A[M,K] * B[N,K]^T         (A, B row-major, K contiguous), bf16 out = relu(D + bias)
+ *   layout 1: D[M,N] = A[K,M]^T * B[K,N]         (A, B row-major, K = rows),     fp32 out += D (split-K atomics)
+ * lda/ldb/ldc are row pitches in elements. */
+int pcseg_gemm_test(int layout, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                    void* D, int ldc, const float* bias, int block_n, void* stream);
+
+/* Number of kernels launched by this library since load (for the bench's gpu_launches claim). */
+long long pcseg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,479 @@
+// Persistent, warp-specialised tcgen05 GEMM for the shared-MLP layers (sm_100a).
+//
+//   D[128 x BN] (fp32, TMEM, double buffered)  +=  A[128 x 64] * B[BN x 64]^T   per k-block
+//
+//   warp 0      : TMA producer (A and B tiles, 128B-swizzled, mbarrier complete_tx)
+//   warp 1      : MMA issuer   (one lane issues tcgen05.mma, tcgen05.commit frees smem stages)
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue     (tcgen05.ld -> fused math -> swizzled smem -> TMA store / reductions)
+//
+// Operand layouts:
+//   MN == false : A is [M x K] row-major (K contiguous), B is [N x K] row-major  (forward, dgrad)
+//   MN == true  : A is [K x M] row-major (M contiguous), B is [K x N] row-major  (wgrad: K = points)
+//
+// Fused epilogues (EPI):
+//   EPI_BIAS_RELU : out = relu(acc + bias[n] (+ cloud_bias[cloud(row)][n]))          -> bf16 store
+//   EPI_COLMAX    : per-cloud column max of relu(acc + bias[n])                       -> atomicMax (no store)
+//   EPI_STATS     : out = bf16(acc (+ cloud_bias)); column sum / sum-of-squares       -> bf16 store + fp64 atomics
+//   EPI_DGRAD     : dz = acc * relu'(bn(y)) * dropout; column sum dz, sum dz*yhat     -> bf16 store + fp64 atomics
+//   EPI_WGRAD     : split-K partial tile                                              -> fp32 red.add
+//   EPI_LOGITS    : logits = W4 * relu(acc + bias) + b4  (BN == 128 == all channels)  -> fp32 store
+#pragma once
+#include "ptx.cuh"
+
+namespace pcseg {
+
+enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EPI_WGRAD = 4, EPI_LOGITS = 5 };
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+constexpr int MAX_CLASSES = 8;    // compile-time cap on num_classes for the fused head kernels
+
+struct GemmParams {
+    int M, N, K;                 // logical problem (for MN/wgrad: M = Cout, N = Cin, K = points)
+    int num_m_tiles, num_n_tiles;
+    int num_splits, kb_per_split;   // split-K (wgrad only; otherwise 1 / K/64)
+    // epilogue operands (all optional depending on EPI)
+    const float* bias;           // [N]
+    const float* cloud_bias;     // [clouds][N] or nullptr
+    int pts_per_cloud;           // rows per cloud (for cloud_bias / colmax)
+    unsigned int* colmax;        // [clouds][N] float bits (values >= 0)
+    double* stats;               // [2][N]
+    const float4* bnp;           // [N] {scale, shift, invstd, -mean*invstd} of the layer whose output is being masked
+    float* out_f32;              // wgrad destination
+    int ldc;                     // wgrad destination pitch (elements)
+    unsigned long long seed;     // dropout
+    unsigned int drop_thr16;     // 0 = no dropout
+    float keep_scale;            // 1/(1-p)
+    const float* w4;             // [C][128] fp32
+    const float* b4;             // [C]
+    int num_classes;
+    float* logits;               // [M][C]
+};
+
+template <int BN, int EPI, bool MN>
+struct GemmCfg {
+    static constexpr int STAGE_A = GEMM_BM * GEMM_BK * 2;
+    static constexpr int STAGE_B = BN * GEMM_BK * 2;
+    static constexpr int STAGE = STAGE_A + STAGE_B;
+    static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_DGRAD);
+    static constexpr bool HAS_Y = (EPI == EPI_DGRAD);
+    static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
+    static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
+    static constexpr int COMB_BYTES = 2 * 2 * 4 * 64 * 4;   // [buf][quantity][warp][64] floats
+    static constexpr int W4_BYTES = (EPI == EPI_LOGITS) ? (MAX_CLASSES * 128 + MAX_CLASSES) * 4 : 0;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int FIXED = OUT_BYTES + Y_BYTES + COMB_BYTES + W4_BYTES + BAR_BYTES;
+    static constexpr int BUDGET = 232448 - 1024;
+    static constexpr int STAGES_RAW = (BUDGET - FIXED) / STAGE;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE + FIXED;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+    static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+    static_assert(2 * BN <= 512, "accumulator double buffer exceeds TMEM");
+};
+
+// Column-wise reduction of a 32 (lanes) x 32 (registers) block: lane j returns op over lanes of v[j].
+template <bool IS_MAX>
+__device__ __forceinline__ float warp_colreduce32(float (&v)[32]) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float send = up ? v[i] : v[i + off];
+            float keep = up ? v[i + off] : v[i];
+            float got = __shfl_xor_sync(0xffffffffu, send, off);
+            v[i] = IS_MAX ? fmaxf(keep, got) : (keep + got);
+        }
+    }
+    return v[0];
+}
+
+template <int BN, int EPI, bool MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmY,
+            const GemmParams p) {
+    using Cfg = GemmCfg<BN, EPI, MN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int SUBS = BN / 64;           // 64-column epilogue sub-tiles
+    static_assert(BN % 64 == 0, "BN must be a multiple of 64");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* out_stage = smem + STAGES * Cfg::STAGE;                 // 2 x 16 KB (1024-aligned)
+    uint8_t* y_stage = out_stage + Cfg::OUT_BYTES;                   // 2 x 16 KB
+    float* comb = reinterpret_cast<float*>(y_stage + Cfg::Y_BYTES);  // [2][2][4][64]
+    float* w4s = comb + Cfg::COMB_BYTES / 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(w4s) + Cfg::W4_BYTES);
+    uint64_t* full_bar = bars;                  // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint64_t* y_full = tmem_empty + 2;          // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(y_full + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (Cfg::HAS_OUT) tma_prefetch_desc(&tmOut);
+        if (Cfg::HAS_Y) tma_prefetch_desc(&tmY);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&y_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    if (EPI == EPI_LOGITS) {
+        for (int i = threadIdx.x; i < p.num_classes * 128; i += GEMM_THREADS) w4s[i] = p.w4[i];
+        for (int i = threadIdx.x; i < p.num_classes; i += GEMM_THREADS) w4s[MAX_CLASSES * 128 + i] = p.b4[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    auto tile_coords = [&](int tile, int& m_tile, int& n_tile, int& split) {
+        split = tile % p.num_splits;
+        int t = tile / p.num_splits;
+        n_tile = t % p.num_n_tiles;
+        m_tile = t / p.num_n_tiles;
+    };
+
+    if (warp_idx == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int m_tile, n_tile, split;
+                tile_coords(tile, m_tile, n_tile, split);
+                const int kb0 = split * p.kb_per_split;
+                const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+                const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = stage_base + stage * Cfg::STAGE;
+                    uint8_t* sb = sa + Cfg::STAGE_A;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
+                    if (!MN) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_tile * GEMM_BM);
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_tile * BN);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < GEMM_BM / 64; ++j)
+                            tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m_tile * GEMM_BM + j * 64, kb * GEMM_BK);
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n_tile * BN + j * 64, kb * GEMM_BK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            int m_tile, n_tile, split;
+            tile_coords(tile, m_tile, n_tile, split);
+            const int kb0 = split * p.kb_per_split;
+            const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+            const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE);
+                    const uint32_t sb = sa + Cfg::STAGE_A;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        uint64_t da, db;
+                        if (!MN) {
+                            da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
+                            db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
+                        } else {
+                            da = make_smem_desc_sw128(sa + k * 2048, 8192, 1024);
+                            db = make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
+                        }
+                        umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (kb1 <= kb0 && lane == 0) umma_commit(&tmem_full[acc]);   // empty split: still release the epilogue
+            __syncwarp();
+        }
+    } else if (warp_idx >= 4) {
+        // ------------------------------------------------------------ epilogue
+        const int ew = warp_idx - 4;                  // == warp_idx % 4 -> TMEM lane quadrant
+        const int row = ew * 32 + lane;               // row inside the tile
+        const int et = threadIdx.x - 128;             // 0..127
+        const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
+        const bool elected = (et == 0);
+        int iter = 0;
+        uint32_t sub_it = 0;                          // global 64-column sub-tile counter (buffer parity)
+
+        auto issue_y_load = [&](uint32_t it) {        // elected thread only
+            const int t_ord = it / SUBS;
+            const int sub = it % SUBS;
+            const long tile = static_cast<long>(blockIdx.x) + static_cast<long>(t_ord) * gridDim.x;
+            if (tile >= total_tiles) return;
+            int m_tile, n_tile, split;
+            tile_coords(static_cast<int>(tile), m_tile, n_tile, split);
+            const int buf = it & 1;
+            mbar_arrive_expect_tx(&y_full[buf], 16384);
+            tma_load_2d(y_stage + buf * 16384, &tmY, &y_full[buf], n_tile * BN + sub * 64, m_tile * GEMM_BM);
+        };
+        if (Cfg::HAS_Y && elected) {
+            issue_y_load(0);
+            issue_y_load(1);
+        }
+
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            int m_tile, n_tile, split;
+            tile_coords(tile, m_tile, n_tile, split);
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int m0 = m_tile * GEMM_BM;
+            const int n0 = n_tile * BN;
+            const int grow = m0 + row;
+            const bool valid = grow < p.M;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + acc * BN + lane_sel;
+
+            if constexpr (EPI == EPI_WGRAD) {
+                // fp32 split-K partials straight from registers: row = output channel, 32 consecutive input channels
+                float* dst_row = p.out_f32 + static_cast<size_t>(grow) * p.ldc + n0;
+                const int kb0 = split * p.kb_per_split;
+                const bool nonempty = kb0 < (p.K + GEMM_BK - 1) / GEMM_BK;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + c * 32, v);
+                    tmem_ld_wait();
+                    if (valid && nonempty) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = n0 + c * 32 + j * 4;
+                            if (col + 3 < p.N) {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c * 32 + j * 4),
+                                             "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                                             "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                                             : "memory");
+                            } else {
+                                for (int e = 0; e < 4; ++e)
+                                    if (col + e < p.N) atomicAdd(dst_row + c * 32 + j * 4 + e, __uint_as_float(v[4 * j + e]));
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+            } else if constexpr (EPI == EPI_LOGITS) {
+                static_assert(EPI != EPI_LOGITS || BN == 128, "logits epilogue needs all 128 channels in one tile");
+                float lg[MAX_CLASSES];
+#pragma unroll
+                for (int k = 0; k < MAX_CLASSES; ++k) lg[k] = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        const float a = fmaxf(__uint_as_float(v[i]) + __ldg(p.bias + col), 0.f);
+#pragma unroll
+                        for (int k = 0; k < MAX_CLASSES; ++k)
+                            if (k < p.num_classes) lg[k] = fmaf(a, w4s[k * 128 + col], lg[k]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+                if (valid) {
+                    float* dst = p.logits + static_cast<size_t>(grow) * p.num_classes;
+#pragma unroll
+                    for (int k = 0; k < MAX_CLASSES; ++k)
+                        if (k < p.num_classes) dst[k] = lg[k] + w4s[MAX_CLASSES * 128 + k];
+                }
+            } else {
+                const int cloud = (p.pts_per_cloud > 0 && valid) ? grow / p.pts_per_cloud : 0;
+                const float* cb_row = (p.cloud_bias != nullptr) ? p.cloud_bias + static_cast<size_t>(cloud) * p.N : nullptr;
+                bool uniform_cloud = true;
+                if constexpr (EPI == EPI_COLMAX) {
+                    const int last = min(m0 + GEMM_BM, p.M) - 1;
+                    uniform_cloud = (m0 / p.pts_per_cloud) == (last / p.pts_per_cloud);
+                }
+#pragma unroll 1
+                for (int sub = 0; sub < SUBS; ++sub, ++sub_it) {
+                    const int buf = sub_it & 1;
+                    const int c0 = n0 + sub * 64;        // first global column of this sub-tile
+                    float* comb_b = comb + buf * (2 * 4 * 64);
+                    if constexpr (Cfg::HAS_Y) mbar_wait(&y_full[buf], (sub_it >> 1) & 1);
+                    uint32_t packed[32];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_acc + sub * 64 + h * 32, v);
+                        tmem_ld_wait();
+                        float o[32];
+                        if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = c0 + h * 32 + i;
+                                float x = __uint_as_float(v[i]) + __ldg(p.bias + col);
+                                if (cb_row) x += __ldg(cb_row + col);
+                                o[i] = valid ? fmaxf(x, 0.f) : 0.f;
+                            }
+                            if constexpr (EPI == EPI_COLMAX) {
+                                if (uniform_cloud) {
+                                    float r = warp_colreduce32<true>(o);
+                                    comb_b[ew * 64 + h * 32 + lane] = r;
+                                } else if (valid) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i)
+                                        atomicMax(p.colmax + static_cast<size_t>(cloud) * p.N + c0 + h * 32 + i,
+                                                  __float_as_uint(o[i]));
+                                }
+                            }
+                        } else if constexpr (EPI == EPI_STATS) {
+                            float sq[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = c0 + h * 32 + i;
+                                float x = __uint_as_float(v[i]);
+                                if (cb_row) x += __ldg(cb_row + col);
+                                x = valid ? round_bf16(x) : 0.f;
+                                o[i] = x;
+                                sq[i] = x * x;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) packed[h * 16 + i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                            float s1 = warp_colreduce32<false>(o);
+                            float s2 = warp_colreduce32<false>(sq);
+                            comb_b[ew * 64 + h * 32 + lane] = s1;
+                            comb_b[4 * 64 + ew * 64 + h * 32 + lane] = s2;
+                        } else if constexpr (EPI == EPI_DGRAD) {
+                            float q[32];
+                            const uint8_t* yrow = y_stage + buf * 16384 + row * 128;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 columns
+                                const int chunk = h * 4 + j;
+                                const uint4 yw = *reinterpret_cast<const uint4*>(yrow + ((chunk ^ (row & 7)) << 4));
+                                const uint32_t yws[4] = {yw.x, yw.y, yw.z, yw.w};
+                                uint32_t keep = 0xFFu;
+                                if (p.drop_thr16 != 0u) {
+                                    const unsigned long long e = static_cast<unsigned long long>(grow) * p.N + (c0 + chunk * 8);
+                                    keep = dropout_keep8(p.seed, e >> 3, p.drop_thr16);
+                                }
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const int i = j * 8 + e;
+                                    const int col = c0 + h * 32 + i;
+                                    const float4 bp = __ldg(p.bnp + col);
+                                    const float y = (e & 1) ? bf16_hi(yws[e >> 1]) : bf16_lo(yws[e >> 1]);
+                                    const float t = fmaf(bp.x, y, bp.y);
+                                    const bool on = valid && (t > 0.f) && ((keep >> e) & 1u);
+                                    float dz = on ? __uint_as_float(v[i]) * p.keep_scale : 0.f;
+                                    dz = round_bf16(dz);
+                                    o[i] = dz;
+                                    q[i] = dz * fmaf(bp.z, y, bp.w);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) packed[h * 16 + i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                            float s1 = warp_colreduce32<false>(o);
+                            float s2 = warp_colreduce32<false>(q);
+                            comb_b[ew * 64 + h * 32 + lane] = s1;
+                            comb_b[4 * 64 + ew * 64 + h * 32 + lane] = s2;
+                        }
+                        if constexpr (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) packed[h * 16 + i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                        }
+                    }
+                    if (sub == SUBS - 1) {       // all TMEM reads of this accumulator are done
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if constexpr (Cfg::HAS_OUT) {
+                        uint8_t* orow = out_stage + buf * 16384 + row * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(orow + ((j ^ (row & 7)) << 4)) =
+                                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        fence_proxy_async_smem();
+                        if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
+                    }
+                    named_bar_sync(1, 128);
+                    if constexpr (Cfg::HAS_OUT) {
+                        if (elected) {
+                            tma_store_2d(&tmOut, out_stage + buf * 16384, c0, m0);
+                            tma_store_commit();
+                            if constexpr (Cfg::HAS_Y) issue_y_load(sub_it + 2);
+                        }
+                    }
+                    if constexpr (EPI == EPI_STATS || EPI == EPI_DGRAD) {
+                        const int qn = et >> 6, c = et & 63;
+                        const float* cq = comb_b + qn * (4 * 64);
+                        const float s = cq[c] + cq[64 + c] + cq[128 + c] + cq[192 + c];
+                        if (c0 + c < p.N) atomicAdd(p.stats + static_cast<size_t>(qn) * p.N + c0 + c, static_cast<double>(s));
+                    } else if constexpr (EPI == EPI_COLMAX) {
+                        if (uniform_cloud && et < 64) {
+                            const float s = fmaxf(fmaxf(comb_b[et], comb_b[64 + et]), fmaxf(comb_b[128 + et], comb_b[192 + et]));
+                            const int cl = m0 / p.pts_per_cloud;
+                            if (c0 + et < p.N && s > 0.f)
+                                atomicMax(p.colmax + static_cast<size_t>(cl) * p.N + c0 + et, __float_as_uint(s));
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (Cfg::HAS_OUT) {
+            if (elected) tma_store_wait_all<0>();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace pcseg

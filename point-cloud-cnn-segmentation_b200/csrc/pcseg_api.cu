@@ -1,0 +1,830 @@
+// C-ABI implementation: model layout, workspace planning, TMA descriptors and the launch
+// sequences for eval forward, train forward and backward.  See include/pcseg_b200.h.
+#include "../../include/pcseg_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gemm.cuh"
+#include "pointwise.cuh"
+
+using namespace pcseg;
+
+static_assert(PCSEG_MAX_CLASSES == MAX_CLASSES, "header / kernel class cap mismatch");
+static_assert(sizeof(pcseg_ce_accum) == sizeof(CeAccum), "CE accumulator layout mismatch");
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static long long g_launches = 0;
+
+static int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define LAUNCH_OK(name)                                                                        \
+    do {                                                                                       \
+        ++g_launches;                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) return fail("launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+#define TRY(expr)                   \
+    do {                            \
+        int r__ = (expr);           \
+        if (r__ != 0) return r__;   \
+    } while (0)
+
+extern "C" const char* pcseg_last_error(void) { return g_err.c_str(); }
+extern "C" const char* pcseg_version(void) { return "pcseg_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+extern "C" long long pcseg_launch_count(void) { return g_launches; }
+
+// ------------------------------------------------------------------------------------------------
+// model layout (reference pcs.py:70-94)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int NUM_CONV = 10;
+constexpr int NUM_BN = 9;
+constexpr float BN_EPS = 1e-5f;
+constexpr float BN_MOMENTUM = 0.1f;
+
+struct ConvDef { int cin, cout; };
+inline void conv_defs(int C, ConvDef* d) {
+    const ConvDef base[NUM_CONV] = {{4, 64}, {64, 64}, {64, 64}, {64, 128}, {128, 1024}, {1024, 1024},
+                                    {1088, 512}, {512, 256}, {256, 128}, {128, C}};
+    for (int i = 0; i < NUM_CONV; ++i) d[i] = base[i];
+}
+// parameter tensors in state_dict order: conv i -> (2i weight, 2i+1 bias); bn j -> (20+2j weight, 21+2j bias)
+struct Layout {
+    long long off[PCSEG_NUM_PARAM_TENSORS];
+    long long numel[PCSEG_NUM_PARAM_TENSORS];
+    long long total;
+    long long bn_off[NUM_BN][2];
+    long long bn_total;
+    ConvDef conv[NUM_CONV];
+};
+inline Layout make_layout(int C) {
+    Layout L;
+    conv_defs(C, L.conv);
+    long long o = 0;
+    for (int i = 0; i < NUM_CONV; ++i) {
+        L.off[2 * i] = o; L.numel[2 * i] = 1LL * L.conv[i].cin * L.conv[i].cout; o += L.numel[2 * i];
+        L.off[2 * i + 1] = o; L.numel[2 * i + 1] = L.conv[i].cout; o += L.conv[i].cout;
+    }
+    long long b = 0;
+    for (int j = 0; j < NUM_BN; ++j) {
+        const int c = L.conv[j].cout;
+        L.off[20 + 2 * j] = o; L.numel[20 + 2 * j] = c; o += c;
+        L.off[21 + 2 * j] = o; L.numel[21 + 2 * j] = c; o += c;
+        L.bn_off[j][0] = b; b += c;
+        L.bn_off[j][1] = b; b += c;
+    }
+    L.total = o;
+    L.bn_total = b;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int load_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess)
+        return fail("cuTensorMapEncodeTiled unavailable (%s): a CUDA 12 driver and a GPU are required", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+// 2-D bf16 tensor [outer][inner] with row pitch ld (elements); box = box_inner x box_outer; 128B swizzle.
+int make_tmap(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer) {
+    TRY(load_encode());
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+        return fail("TMA operand misaligned (ptr %p, pitch %lld elements)", ptr, ld);
+    if (box_inner * 2 != 128) return fail("128B swizzle needs a 64-element inner box");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with %d (inner %lld outer %lld ld %lld)", (int)r, inner, outer, ld);
+    return 0;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launcher
+// ------------------------------------------------------------------------------------------------
+struct GemmOp {
+    CUtensorMap tmA, tmB, tmOut, tmY;
+    GemmParams p;
+    int bn, epi;
+    bool mn;
+    bool ready = false;
+};
+
+template <int BN, int EPI, bool MN>
+int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
+    using Cfg = GemmCfg<BN, EPI, MN>;
+    static bool attr_set = false;
+    auto kern = gemm_kernel<BN, EPI, MN>;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = op.p.num_m_tiles * op.p.num_n_tiles * op.p.num_splits;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmY, op.p);
+    LAUNCH_OK("gemm_kernel");
+    return 0;
+}
+
+int launch_gemm(const GemmOp& op, cudaStream_t s) {
+    if (!op.ready) return fail("internal: GEMM op not initialised");
+#define CASE(BN_, EPI_, MN_) \
+    if (op.bn == BN_ && op.epi == EPI_ && op.mn == MN_) return launch_gemm_t<BN_, EPI_, MN_>(op, s);
+    CASE(64, EPI_BIAS_RELU, false) CASE(128, EPI_BIAS_RELU, false) CASE(256, EPI_BIAS_RELU, false)
+    CASE(256, EPI_COLMAX, false)
+    CASE(128, EPI_LOGITS, false)
+    CASE(64, EPI_STATS, false) CASE(128, EPI_STATS, false) CASE(256, EPI_STATS, false)
+    CASE(64, EPI_DGRAD, false) CASE(128, EPI_DGRAD, false) CASE(256, EPI_DGRAD, false)
+    CASE(64, EPI_WGRAD, true) CASE(128, EPI_WGRAD, true) CASE(256, EPI_WGRAD, true)
+#undef CASE
+    return fail("internal: no GEMM instantiation for BN=%d EPI=%d MN=%d", op.bn, op.epi, (int)op.mn);
+}
+
+inline int pick_bn(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
+
+// Row-major GEMM  D[M,N] = A[M,K] * B[N,K]^T  with a fused epilogue.
+int setup_gemm_kmajor(GemmOp* op, int epi, const void* A, int lda, const void* B, int ldb, long long M, int N, int K,
+                      void* out, int ldo, const void* ymask, int ldy) {
+    if (K % 64 != 0) return fail("GEMM K=%d must be a multiple of 64", K);
+    if (N % 64 != 0) return fail("GEMM N=%d must be a multiple of 64", N);
+    memset(&op->p, 0, sizeof(op->p));
+    op->bn = (epi == EPI_LOGITS) ? 128 : pick_bn(N);
+    if (epi == EPI_COLMAX) op->bn = 256;
+    if (N % op->bn != 0) return fail("GEMM N=%d not a multiple of the tile width %d", N, op->bn);
+    op->epi = epi;
+    op->mn = false;
+    TRY(make_tmap(&op->tmA, A, K, M, lda, 64, 128));
+    TRY(make_tmap(&op->tmB, B, K, N, ldb, 64, op->bn));
+    if (out) TRY(make_tmap(&op->tmOut, out, N, M, ldo, 64, 128)); else op->tmOut = op->tmA;
+    if (ymask) TRY(make_tmap(&op->tmY, ymask, N, M, ldy, 64, 128)); else op->tmY = op->tmA;
+    op->p.M = static_cast<int>(M);
+    op->p.N = N;
+    op->p.K = K;
+    op->p.num_m_tiles = static_cast<int>((M + 127) / 128);
+    op->p.num_n_tiles = N / op->bn;
+    op->p.num_splits = 1;
+    op->p.kb_per_split = K / 64;
+    op->p.keep_scale = 1.f;
+    op->ready = true;
+    return 0;
+}
+
+// Weight-gradient GEMM  D[Mc,Nc] += A[P,Mc]^T * B[P,Nc]  (both operands point-major, K = points), fp32 atomics.
+int setup_gemm_wgrad(GemmOp* op, const void* A, int lda, int Mc, const void* B, int ldb, int Nc, long long P, float* out, int ldc) {
+    memset(&op->p, 0, sizeof(op->p));
+    if (Nc % 64 != 0) return fail("wgrad N=%d must be a multiple of 64", Nc);
+    op->bn = pick_bn(Nc);
+    if (Nc % op->bn != 0) return fail("wgrad N=%d not a multiple of %d", Nc, op->bn);
+    op->epi = EPI_WGRAD;
+    op->mn = true;
+    TRY(make_tmap(&op->tmA, A, Mc, P, lda, 64, 64));
+    TRY(make_tmap(&op->tmB, B, Nc, P, ldb, 64, 64));
+    op->tmOut = op->tmA;
+    op->tmY = op->tmA;
+    op->p.M = Mc;
+    op->p.N = Nc;
+    op->p.K = static_cast<int>(P);
+    op->p.num_m_tiles = (Mc + 127) / 128;
+    op->p.num_n_tiles = Nc / op->bn;
+    const int total_kb = static_cast<int>((P + 63) / 64);
+    int splits = num_sms() / (op->p.num_m_tiles * op->p.num_n_tiles);
+    if (splits < 1) splits = 1;
+    if (splits > total_kb) splits = total_kb;
+    op->p.kb_per_split = (total_kb + splits - 1) / splits;
+    op->p.num_splits = (total_kb + op->p.kb_per_split - 1) / op->p.kb_per_split;
+    op->p.out_f32 = out;
+    op->p.ldc = ldc;
+    op->p.keep_scale = 1.f;
+    op->ready = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<uint8_t*>(b)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 1023) & ~size_t(1023);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+typedef __nv_bfloat16 bf16;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct pcseg_ctx {
+    int C = 0;
+    Layout L;
+    int B = 0, N = 0;
+    long long P = 0;
+    bool bound = false, train = false, eval_ready = false;
+
+    // ---- shared small buffers
+    float* zeros1024 = nullptr;
+    float* gmax = nullptr;        // [B][1024] eval max-pool (float bits >= 0) / train g
+    float* cb = nullptr;          // [B][512]
+    // ---- eval
+    float* alpha[NUM_BN] = {};    // folded BN scale per layer
+    float* delta[NUM_BN] = {};    // folded bias per layer
+    float* w1 = nullptr;          // conv1 weight copy [64][4]
+    float* w4 = nullptr;          // seg_conv4 weight copy [C][128]
+    float* b4 = nullptr;
+    float* wg = nullptr;          // seg_conv1.weight[:, 64:] dense copy [512][1024] fp32
+    bf16* wk[NUM_BN] = {};        // bf16 [Cout][Cin] forward weights (index = conv index; [6] = point-feature part [512][64])
+    bf16* act[NUM_BN] = {};       // eval: activations a_l; train: post-BN/ReLU activations
+    GemmOp ev[NUM_BN];            // eval forward GEMMs (index = conv index 1..8)
+    // ---- train
+    bf16* y[NUM_BN] = {};         // pre-BN conv outputs
+    bf16* dz[NUM_BN] = {};        // gradient wrt BN output (after ReLU / dropout mask)
+    bf16* dy[NUM_BN] = {};        // gradient wrt conv output
+    bf16* dycat = nullptr;        // [P][576] = [dy(conv3) | dy(seg_conv1)]
+    bf16* wt[NUM_BN] = {};        // bf16 transposed weights [Cin][Cout] for dgrad (index = conv index)
+    bf16* wcat = nullptr;         // [64][576] = [W3^T | Wpf^T]
+    double* stats_f = nullptr;    // forward  stats, per layer [2][C] at stat_off
+    double* stats_b = nullptr;    // backward stats
+    size_t stat_off[NUM_BN] = {};
+    size_t stat_total = 0;
+    float4* bnp[NUM_BN] = {};
+    float4* coef[NUM_BN] = {};
+    unsigned long long* keys = nullptr;
+    float* ystar = nullptr;
+    int* argidx = nullptr;
+    float* dcb = nullptr;
+    float* dzv = nullptr;
+    GemmOp fw[NUM_BN], dg[NUM_BN], wg_op[NUM_BN];
+    unsigned long long seed = 0;
+    unsigned int thr16 = 0;
+    float keep_scale = 1.f;
+};
+
+static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes_out) {
+    Carver k(ws);
+    const size_t P = static_cast<size_t>(B) * N;
+    const ConvDef* cv = c->L.conv;
+    c->zeros1024 = k.take<float>(1024);
+    c->gmax = k.take<float>(static_cast<size_t>(B) * 1024);
+    c->cb = k.take<float>(static_cast<size_t>(B) * 512);
+    c->w1 = k.take<float>(256);
+    c->w4 = k.take<float>(MAX_CLASSES * 128);
+    c->b4 = k.take<float>(MAX_CLASSES);
+    c->wg = k.take<float>(512 * 1024);
+    for (int i = 0; i < NUM_BN; ++i) {
+        c->alpha[i] = k.take<float>(cv[i].cout);
+        c->delta[i] = k.take<float>(cv[i].cout);
+    }
+    for (int i = 1; i < NUM_BN; ++i) {
+        const int cin = (i == 6) ? 64 : cv[i].cin;
+        c->wk[i] = k.take<bf16>(static_cast<size_t>(cv[i].cout) * cin);
+    }
+    if (!train) {
+        // a1..a5, a_s1, a_s2 (global_feat output is reduced in-kernel; seg_conv3 output feeds the fused logits epilogue)
+        for (int i = 0; i < NUM_BN; ++i) {
+            if (i == 5 || i == 8) continue;
+            c->act[i] = k.take<bf16>(P * cv[i].cout);
+        }
+    } else {
+        size_t so = 0;
+        for (int i = 0; i < NUM_BN; ++i) { c->stat_off[i] = so; so += 2 * static_cast<size_t>(cv[i].cout); }
+        c->stat_total = so;
+        c->stats_f = k.take<double>(so);
+        c->stats_b = k.take<double>(so);
+        for (int i = 0; i < NUM_BN; ++i) {
+            c->bnp[i] = k.take<float4>(cv[i].cout);
+            c->coef[i] = k.take<float4>(cv[i].cout);
+        }
+        c->keys = k.take<unsigned long long>(static_cast<size_t>(B) * 1024);
+        c->ystar = k.take<float>(static_cast<size_t>(B) * 1024);
+        c->argidx = k.take<int>(static_cast<size_t>(B) * 1024);
+        c->dcb = k.take<float>(static_cast<size_t>(B) * 512);
+        c->dzv = k.take<float>(static_cast<size_t>(B) * 1024);
+        for (int i = 1; i < NUM_BN; ++i) {
+            const int cin = (i == 6) ? 64 : cv[i].cin;
+            c->wt[i] = k.take<bf16>(static_cast<size_t>(cv[i].cout) * cin);
+        }
+        c->wcat = k.take<bf16>(64 * 576);
+        c->dycat = k.take<bf16>(P * 576);
+        for (int i = 0; i < NUM_BN; ++i) {
+            c->y[i] = k.take<bf16>(P * cv[i].cout);
+            if (i != 5 && i != 8) c->act[i] = k.take<bf16>(P * cv[i].cout);
+            if (i != 5) c->dz[i] = k.take<bf16>(P * cv[i].cout);
+            if (i != 2 && i != 6) c->dy[i] = k.take<bf16>(P * cv[i].cout);
+        }
+    }
+    *bytes_out = (k.off + 1023) & ~size_t(1023);
+    return 0;
+}
+
+extern "C" long long pcseg_param_count(int C) { return make_layout(C).total; }
+extern "C" long long pcseg_param_offset(int C, int t) { return (t < 0 || t >= PCSEG_NUM_PARAM_TENSORS) ? -1 : make_layout(C).off[t]; }
+extern "C" long long pcseg_param_numel(int C, int t) { return (t < 0 || t >= PCSEG_NUM_PARAM_TENSORS) ? -1 : make_layout(C).numel[t]; }
+extern "C" long long pcseg_bn_buffer_count(void) { return make_layout(3).bn_total; }
+extern "C" long long pcseg_bn_buffer_offset(int bn, int which) {
+    return (bn < 0 || bn >= NUM_BN || which < 0 || which > 1) ? -1 : make_layout(3).bn_off[bn][which];
+}
+extern "C" long long pcseg_workspace_bytes(int B, int N, int C, int train) {
+    if (B <= 0 || N <= 0 || C < 1 || C > MAX_CLASSES) return -1;
+    pcseg_ctx tmp;
+    tmp.C = C;
+    tmp.L = make_layout(C);
+    size_t bytes = 0;
+    carve(&tmp, nullptr, B, N, train != 0, &bytes);
+    return static_cast<long long>(bytes);
+}
+
+extern "C" int pcseg_create(pcseg_ctx** out, int num_classes) {
+    if (!out) return fail("pcseg_create: null out pointer");
+    if (num_classes < 1 || num_classes > MAX_CLASSES) return fail("num_classes=%d unsupported (1..%d)", num_classes, MAX_CLASSES);
+    pcseg_ctx* c = new pcseg_ctx();
+    c->C = num_classes;
+    c->L = make_layout(num_classes);
+    *out = c;
+    return 0;
+}
+extern "C" int pcseg_destroy(pcseg_ctx* c) {
+    delete c;
+    return 0;
+}
+
+extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_bytes, int train) {
+    if (!c) return fail("pcseg_bind: null ctx");
+    if (B <= 0 || N <= 0) return fail("pcseg_bind: bad shape B=%d N=%d", B, N);
+    if (static_cast<long long>(B) * N >= (1LL << 31) - 256) return fail("pcseg_bind: B*N too large for 32-bit row indices");
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) return fail("pcseg_bind: workspace must be non-null and 1024-byte aligned");
+    size_t need = 0;
+    c->B = B; c->N = N; c->P = static_cast<long long>(B) * N;
+    c->train = train != 0;
+    carve(c, ws, B, N, c->train, &need);
+    if (static_cast<long long>(need) > ws_bytes) return fail("pcseg_bind: workspace too small (%lld < %zu)", ws_bytes, need);
+    const ConvDef* cv = c->L.conv;
+    const long long P = c->P;
+    c->bound = false;
+    c->eval_ready = false;
+    if (!c->train) {
+        // conv2..conv5
+        for (int i = 1; i <= 4; ++i) {
+            TRY(setup_gemm_kmajor(&c->ev[i], EPI_BIAS_RELU, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
+                                  c->act[i], cv[i].cout, nullptr, 0));
+            c->ev[i].p.bias = c->delta[i];
+        }
+        // global_feat + max-pool
+        TRY(setup_gemm_kmajor(&c->ev[5], EPI_COLMAX, c->act[4], 1024, c->wk[5], 1024, P, 1024, 1024, nullptr, 0, nullptr, 0));
+        c->ev[5].p.bias = c->delta[5];
+        c->ev[5].p.colmax = reinterpret_cast<unsigned int*>(c->gmax);
+        c->ev[5].p.pts_per_cloud = N;
+        // seg_conv1: point-feature part + per-cloud bias
+        TRY(setup_gemm_kmajor(&c->ev[6], EPI_BIAS_RELU, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->act[6], 512, nullptr, 0));
+        c->ev[6].p.bias = c->zeros1024;
+        c->ev[6].p.cloud_bias = c->cb;
+        c->ev[6].p.pts_per_cloud = N;
+        TRY(setup_gemm_kmajor(&c->ev[7], EPI_BIAS_RELU, c->act[6], 512, c->wk[7], 512, P, 256, 512, c->act[7], 256, nullptr, 0));
+        c->ev[7].p.bias = c->delta[7];
+        TRY(setup_gemm_kmajor(&c->ev[8], EPI_LOGITS, c->act[7], 256, c->wk[8], 256, P, 128, 256, nullptr, 0, nullptr, 0));
+        c->ev[8].p.bias = c->delta[8];
+        c->ev[8].p.w4 = c->w4;
+        c->ev[8].p.b4 = c->b4;
+        c->ev[8].p.num_classes = c->C;
+    } else {
+        // ---- forward: y_i = a_{i-1} W_i^T, statistics in the epilogue
+        for (int i = 1; i <= 5; ++i) {
+            TRY(setup_gemm_kmajor(&c->fw[i], EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
+                                  c->y[i], cv[i].cout, nullptr, 0));
+            c->fw[i].p.stats = c->stats_f + c->stat_off[i];
+        }
+        TRY(setup_gemm_kmajor(&c->fw[6], EPI_STATS, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->y[6], 512, nullptr, 0));
+        c->fw[6].p.stats = c->stats_f + c->stat_off[6];
+        c->fw[6].p.cloud_bias = c->cb;
+        c->fw[6].p.pts_per_cloud = N;
+        for (int i = 7; i <= 8; ++i) {
+            TRY(setup_gemm_kmajor(&c->fw[i], EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
+                                  c->y[i], cv[i].cout, nullptr, 0));
+            c->fw[i].p.stats = c->stats_f + c->stat_off[i];
+        }
+        // ---- backward data gradients: dz_{i-1} = (dy_i W_i) masked by layer i-1
+        auto dgrad = [&](int i, const bf16* dyA, int lda, int K, const bf16* Bw, int prev) -> int {
+            TRY(setup_gemm_kmajor(&c->dg[i], EPI_DGRAD, dyA, lda, Bw, K, P, cv[prev].cout, K, c->dz[prev], cv[prev].cout,
+                                  c->y[prev], cv[prev].cout));
+            c->dg[i].p.stats = c->stats_b + c->stat_off[prev];
+            c->dg[i].p.bnp = c->bnp[prev];
+            return 0;
+        };
+        TRY(dgrad(8, c->dy[8], 128, 128, c->wt[8], 7));
+        TRY(dgrad(7, c->dy[7], 256, 256, c->wt[7], 6));
+        TRY(dgrad(5, c->dy[5], 1024, 1024, c->wt[5], 4));
+        TRY(dgrad(4, c->dy[4], 1024, 1024, c->wt[4], 3));
+        TRY(dgrad(3, c->dy[3], 128, 128, c->wt[3], 2));
+        TRY(dgrad(2, c->dycat, 576, 576, c->wcat, 1));     // skip join: [dy3 | dy_seg1] * [W3 ; Wpf]
+        TRY(dgrad(1, c->dy[1], 64, 64, c->wt[1], 0));
+        // ---- backward weight gradients (destinations patched with the grads arena at call time)
+        auto wgrad = [&](int i, const bf16* dyA, int lda, const bf16* aB, int ldb, int cin) -> int {
+            return setup_gemm_wgrad(&c->wg_op[i], dyA, lda, cv[i].cout, aB, ldb, cin, P, nullptr, cv[i].cin);
+        };
+        TRY(wgrad(8, c->dy[8], 128, c->act[7], 256, 256));
+        TRY(wgrad(7, c->dy[7], 256, c->act[6], 512, 512));
+        TRY(wgrad(6, c->dycat + 64, 576, c->act[1], 64, 64));
+        TRY(wgrad(5, c->dy[5], 1024, c->act[4], 1024, 1024));
+        TRY(wgrad(4, c->dy[4], 1024, c->act[3], 128, 128));
+        TRY(wgrad(3, c->dy[3], 128, c->act[2], 64, 64));
+        TRY(wgrad(2, c->dycat, 576, c->act[1], 64, 64));
+        TRY(wgrad(1, c->dy[1], 64, c->act[0], 64, 64));
+    }
+    c->bound = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation
+// ------------------------------------------------------------------------------------------------
+static int convert_rows(const float* src, int ld_src, bf16* dst, int ld_dst, int rows, int cols, const float* alpha, cudaStream_t s) {
+    const int n = rows * cols;
+    k_convert_rows<<<(n + 255) / 256, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols, alpha);
+    LAUNCH_OK("k_convert_rows");
+    return 0;
+}
+static int convert_transpose(const float* src, int ld_src, bf16* dst, int ld_dst, int rows, int cols, cudaStream_t s) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    k_convert_transpose<<<grid, block, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
+    LAUNCH_OK("k_convert_transpose");
+    return 0;
+}
+
+extern "C" int pcseg_prepare_eval(pcseg_ctx* c, const float* params, const float* bnbuf, void* stream) {
+    if (!c || !c->bound || c->train) return fail("pcseg_prepare_eval: context not bound in eval mode");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Layout& L = c->L;
+    CUDA_OK(cudaMemsetAsync(c->zeros1024, 0, 1024 * sizeof(float), s));
+    for (int i = 0; i < NUM_BN; ++i) {
+        const int co = L.conv[i].cout;
+        k_fold_bn<<<(co + 127) / 128, 128, 0, s>>>(params + L.off[2 * i + 1], params + L.off[20 + 2 * i], params + L.off[21 + 2 * i],
+                                                   bnbuf + L.bn_off[i][0], bnbuf + L.bn_off[i][1], BN_EPS, co, c->alpha[i], c->delta[i]);
+        LAUNCH_OK("k_fold_bn");
+    }
+    CUDA_OK(cudaMemcpyAsync(c->w1, params + L.off[0], 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(c->w4, params + L.off[18], static_cast<size_t>(c->C) * 128 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(c->b4, params + L.off[19], static_cast<size_t>(c->C) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (int i = 1; i < NUM_BN; ++i) {
+        if (i == 6) {
+            TRY(convert_rows(params + L.off[12], 1088, c->wk[6], 64, 512, 64, c->alpha[6], s));
+            CUDA_OK(cudaMemcpy2DAsync(c->wg, 1024 * sizeof(float), params + L.off[12] + 64, 1088 * sizeof(float), 1024 * sizeof(float), 512,
+                                      cudaMemcpyDeviceToDevice, s));
+        } else {
+            TRY(convert_rows(params + L.off[2 * i], L.conv[i].cin, c->wk[i], L.conv[i].cin, L.conv[i].cout, L.conv[i].cin, c->alpha[i], s));
+        }
+    }
+    c->eval_ready = true;
+    return 0;
+}
+
+extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, long long* labels_out, void* stream) {
+    if (!c || !c->bound || c->train) return fail("pcseg_forward_eval: context not bound in eval mode");
+    if (!c->eval_ready) return fail("pcseg_forward_eval: call pcseg_prepare_eval first");
+    if (!x || !logits) return fail("pcseg_forward_eval: null tensor");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long P = c->P;
+    CUDA_OK(cudaMemsetAsync(c->gmax, 0, static_cast<size_t>(c->B) * 1024 * sizeof(float), s));
+    {
+        int grid = static_cast<int>((P + 31) / 32);
+        if (grid > num_sms() * 8) grid = num_sms() * 8;
+        k_ingest<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(x), static_cast<int>(P), c->w1, c->alpha[0], c->delta[0],
+                                            c->act[0], nullptr);
+        LAUNCH_OK("k_ingest");
+    }
+    for (int i = 1; i <= 5; ++i) TRY(launch_gemm(c->ev[i], s));
+    {
+        const int warps = c->B * 512;
+        k_cloud_bias<<<(warps * 32 + 255) / 256, 256, 0, s>>>(c->wg, 1024, c->gmax, c->B, 512, 1024, c->alpha[6], c->delta[6], c->cb);
+        LAUNCH_OK("k_cloud_bias");
+    }
+    TRY(launch_gemm(c->ev[6], s));
+    TRY(launch_gemm(c->ev[7], s));
+    GemmOp head = c->ev[8];
+    head.p.logits = logits;
+    TRY(launch_gemm(head, s));
+    if (labels_out) {
+        k_argmax<<<static_cast<int>((P + 255) / 256), 256, 0, s>>>(logits, P, c->C, labels_out);
+        LAUNCH_OK("k_argmax");
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training forward
+// ------------------------------------------------------------------------------------------------
+static int ew_grid(long long work_items) {
+    long long g = (work_items + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    return static_cast<int>(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* params, float* bnbuf, unsigned long long seed,
+                                   float dropout_p, float* logits, const long long* labels, const float* class_w,
+                                   pcseg_ce_accum* ce, void* stream) {
+    if (!c || !c->bound || !c->train) return fail("pcseg_forward_train: context not bound in train mode");
+    if (!x || !params || !bnbuf || !logits) return fail("pcseg_forward_train: null tensor");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train: dropout_p out of range");
+    if (labels && !ce) return fail("pcseg_forward_train: labels given without a CE accumulator");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Layout& L = c->L;
+    const ConvDef* cv = L.conv;
+    const long long P = c->P;
+    c->seed = seed;
+    c->thr16 = static_cast<unsigned int>(dropout_p * 65536.0f + 0.5f);
+    c->keep_scale = c->thr16 ? 1.f / (1.f - static_cast<float>(c->thr16) / 65536.f) : 1.f;
+
+    // bf16 weights (forward [Cout][Cin], transposed [Cin][Cout] for dgrad)
+    for (int i = 1; i < NUM_BN; ++i) {
+        if (i == 6) {
+            TRY(convert_rows(params + L.off[12], 1088, c->wk[6], 64, 512, 64, nullptr, s));
+            TRY(convert_transpose(params + L.off[12], 1088, c->wcat + 64, 576, 512, 64, s));
+        } else {
+            TRY(convert_rows(params + L.off[2 * i], cv[i].cin, c->wk[i], cv[i].cin, cv[i].cout, cv[i].cin, nullptr, s));
+            if (i == 2) TRY(convert_transpose(params + L.off[4], 64, c->wcat, 576, 64, 64, s));
+            else TRY(convert_transpose(params + L.off[2 * i], cv[i].cin, c->wt[i], cv[i].cout, cv[i].cout, cv[i].cin, s));
+        }
+    }
+    CUDA_OK(cudaMemsetAsync(c->stats_f, 0, c->stat_total * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(c->keys, 0, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long), s));
+    if (ce) CUDA_OK(cudaMemsetAsync(ce, 0, sizeof(pcseg_ce_accum), s));
+
+    auto finalize = [&](int i) -> int {
+        const int co = cv[i].cout;
+        k_bn_finalize<<<(co + 127) / 128, 128, 0, s>>>(c->stats_f + c->stat_off[i], co, static_cast<double>(P), params + L.off[20 + 2 * i],
+                                                       params + L.off[21 + 2 * i], params + L.off[2 * i + 1], BN_EPS, BN_MOMENTUM,
+                                                       bnbuf + L.bn_off[i][0], bnbuf + L.bn_off[i][1], c->bnp[i]);
+        LAUNCH_OK("k_bn_finalize");
+        return 0;
+    };
+    auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
+        const int co = cv[i].cout;
+        k_bn_relu<<<ew_grid(P * (co / 8)), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, c->bnp[i], sd, thr, ks);
+        LAUNCH_OK("k_bn_relu");
+        return 0;
+    };
+
+    {   // conv1 on CUDA cores
+        int grid = static_cast<int>((P + 31) / 32);
+        if (grid > num_sms() * 8) grid = num_sms() * 8;
+        k_ingest<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(x), static_cast<int>(P), params + L.off[0], nullptr, nullptr,
+                                           c->y[0], c->stats_f + c->stat_off[0]);
+        LAUNCH_OK("k_ingest");
+        TRY(finalize(0));
+        TRY(bn_relu(0, 0, 0, 1.f));
+    }
+    for (int i = 1; i <= 5; ++i) {
+        TRY(launch_gemm(c->fw[i], s));
+        TRY(finalize(i));
+        if (i < 5) TRY(bn_relu(i, 0, 0, 1.f));
+    }
+    {   // global max-pool of relu(bn(y6)) with arg-index
+        const int strips = (c->N + 1023) / 1024;
+        const int rows_per_strip = (c->N + strips - 1) / strips;
+        dim3 grid(1024 / 64, strips, c->B);
+        k_maxpool_scan<<<grid, 256, 0, s>>>(c->y[5], 1024, c->N, rows_per_strip, c->bnp[5], c->keys);
+        LAUNCH_OK("k_maxpool_scan");
+        const int total = c->B * 1024;
+        k_maxpool_finish<<<(total + 255) / 256, 256, 0, s>>>(c->keys, total, 1024, c->bnp[5], c->gmax, c->ystar, c->argidx);
+        LAUNCH_OK("k_maxpool_finish");
+        const int warps = c->B * 512;
+        k_cloud_bias<<<(warps * 32 + 255) / 256, 256, 0, s>>>(params + L.off[12] + 64, 1088, c->gmax, c->B, 512, 1024, nullptr, nullptr, c->cb);
+        LAUNCH_OK("k_cloud_bias");
+    }
+    TRY(launch_gemm(c->fw[6], s));
+    TRY(finalize(6));
+    TRY(bn_relu(6, seed + 1, c->thr16, c->keep_scale));
+    TRY(launch_gemm(c->fw[7], s));
+    TRY(finalize(7));
+    TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
+    TRY(launch_gemm(c->fw[8], s));
+    TRY(finalize(8));
+    {
+        int grid = static_cast<int>((P + 7) / 8);
+        if (grid > num_sms() * 8) grid = num_sms() * 8;
+        k_head_fwd<MAX_CLASSES><<<grid, 256, 0, s>>>(c->y[8], P, c->bnp[8], params + L.off[18], params + L.off[19], c->C, logits, labels,
+                                                    class_w, reinterpret_cast<CeAccum*>(ce));
+        LAUNCH_OK("k_head_fwd");
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params, const float* dlogits, const float* logits,
+                              const long long* labels, const float* class_w, const double* wsum_total, float* grads, int phase,
+                              void* stream) {
+    if (!c || !c->bound || !c->train) return fail("pcseg_backward: context not bound in train mode");
+    if (phase < 0 || phase > 2) return fail("pcseg_backward: phase must be 0, 1 or 2");
+    if (!x || !params || !grads) return fail("pcseg_backward: null tensor");
+    if (!dlogits && !(logits && labels && wsum_total)) return fail("pcseg_backward: need dlogits, or logits + labels + wsum_total");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Layout& L = c->L;
+    const ConvDef* cv = L.conv;
+    const long long P = c->P;
+    const int B = c->B, N = c->N;
+
+    if (phase != 2) {
+        CUDA_OK(cudaMemsetAsync(grads, 0, static_cast<size_t>(L.total) * sizeof(float), s));
+        CUDA_OK(cudaMemsetAsync(c->stats_b, 0, c->stat_total * sizeof(double), s));
+        CUDA_OK(cudaMemsetAsync(c->dcb, 0, static_cast<size_t>(B) * 512 * sizeof(float), s));
+    }
+
+    auto coef = [&](int i) -> int {
+        const int co = cv[i].cout;
+        k_bn_bwd_coef<<<(co + 127) / 128, 128, 0, s>>>(c->stats_b + c->stat_off[i], co, static_cast<double>(P), c->bnp[i], c->coef[i],
+                                                       grads + L.off[20 + 2 * i], grads + L.off[21 + 2 * i]);
+        LAUNCH_OK("k_bn_bwd_coef");
+        return 0;
+    };
+    auto apply = [&](int i, bf16* dy_out, int ld_dy, float* dcb) -> int {
+        const int co = cv[i].cout;
+        dim3 grid((N + 63) / 64, B);
+        k_bn_bwd_apply<false><<<grid, 256, 0, s>>>(c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, c->coef[i], grads + L.off[2 * i + 1], dcb,
+                                                  nullptr, nullptr);
+        LAUNCH_OK("k_bn_bwd_apply");
+        return 0;
+    };
+    auto wgrad = [&](int i, float* dst, int ldc) -> int {
+        GemmOp op = c->wg_op[i];
+        op.p.out_f32 = dst;
+        op.p.ldc = ldc;
+        return launch_gemm(op, s);
+    };
+    auto dgrad = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
+        GemmOp op = c->dg[i];
+        op.p.seed = sd;
+        op.p.drop_thr16 = thr;
+        op.p.keep_scale = ks;
+        return launch_gemm(op, s);
+    };
+
+    if (phase != 2) {
+    {   // seg_conv4 + loss gradient
+        int grid = static_cast<int>((P + 7) / 8);
+        if (grid > num_sms() * 4) grid = num_sms() * 4;
+        k_head_bwd<MAX_CLASSES><<<grid, 256, 0, s>>>(c->y[8], P, c->bnp[8], params + L.off[18], c->C, dlogits, logits, labels, class_w,
+                                                    wsum_total, c->dz[8], grads + L.off[18], grads + L.off[19],
+                                                    c->stats_b + c->stat_off[8]);
+        LAUNCH_OK("k_head_bwd");
+    }
+    // seg_conv3
+    TRY(coef(8));
+    TRY(apply(8, c->dy[8], 128, nullptr));
+    TRY(wgrad(8, grads + L.off[16], 256));
+    TRY(dgrad(8, c->seed + 2, c->thr16, c->keep_scale));
+    // seg_conv2
+    TRY(coef(7));
+    TRY(apply(7, c->dy[7], 256, nullptr));
+    TRY(wgrad(7, grads + L.off[14], 512));
+    TRY(dgrad(7, c->seed + 1, c->thr16, c->keep_scale));
+    // seg_conv1: point-feature columns by GEMM, global columns per cloud
+    TRY(coef(6));
+    TRY(apply(6, c->dycat + 64, 576, c->dcb));
+    TRY(wgrad(6, grads + L.off[12], 1088));
+    {
+        dim3 grid_dg(1024 / 256, B);
+        k_cloud_bwd_dg<<<grid_dg, 256, 0, s>>>(c->dcb, params + L.off[12] + 64, 1088, B, 512, 1024, c->gmax, c->ystar, c->bnp[5], c->dzv,
+                                              c->stats_b + c->stat_off[5]);
+        LAUNCH_OK("k_cloud_bwd_dg");
+        dim3 grid_dw(1024 / 256, 512);
+        k_cloud_bwd_dw<<<grid_dw, 256, 0, s>>>(c->dcb, c->gmax, B, 512, 1024, grads + L.off[12] + 64, 1088);
+        LAUNCH_OK("k_cloud_bwd_dw");
+    }
+    // global_feat (sparse max-pool gradient folded into the BN backward)
+    TRY(coef(5));
+    {
+        dim3 grid((N + 63) / 64, B);
+        k_bn_bwd_apply<true><<<grid, 256, 0, s>>>(nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, c->coef[5], grads + L.off[11], nullptr,
+                                                 c->argidx, c->dzv);
+        LAUNCH_OK("k_bn_bwd_apply<sparse>");
+    }
+    TRY(wgrad(5, grads + L.off[10], 1024));
+    TRY(dgrad(5, 0, 0, 1.f));
+    }   // phase != 2
+    if (phase == 1) return 0;
+    // conv5
+    TRY(coef(4));
+    TRY(apply(4, c->dy[4], 1024, nullptr));
+    TRY(wgrad(4, grads + L.off[8], 128));
+    TRY(dgrad(4, 0, 0, 1.f));
+    // conv4
+    TRY(coef(3));
+    TRY(apply(3, c->dy[3], 128, nullptr));
+    TRY(wgrad(3, grads + L.off[6], 64));
+    TRY(dgrad(3, 0, 0, 1.f));
+    // conv3 (its dy lives in the left 64 columns of dycat), then the skip join into conv2's output
+    TRY(coef(2));
+    TRY(apply(2, c->dycat, 576, nullptr));
+    TRY(wgrad(2, grads + L.off[4], 64));
+    TRY(dgrad(2, 0, 0, 1.f));
+    // conv2
+    TRY(coef(1));
+    TRY(apply(1, c->dy[1], 64, nullptr));
+    TRY(wgrad(1, grads + L.off[2], 64));
+    TRY(dgrad(1, 0, 0, 1.f));
+    // conv1 (no data gradient: the input does not require grad)
+    TRY(coef(0));
+    TRY(apply(0, c->dy[0], 64, nullptr));
+    {
+        int grid = static_cast<int>((P + 31) / 32);
+        if (grid > num_sms() * 4) grid = num_sms() * 4;
+        k_ingest_bwd<<<grid, 256, 0, s>>>(c->dy[0], reinterpret_cast<const float4*>(x), P, grads + L.off[0]);
+        LAUNCH_OK("k_ingest_bwd");
+    }
+    return 0;
+}
+
+extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, float* v, long long n, int step, float lr, float b1,
+                               float b2, float eps, float wd, float grad_scale, void* stream) {
+    if (!params || !grads || !m || !v || n <= 0 || step < 1) return fail("pcseg_adam_step: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float bc1 = 1.f - powf(b1, static_cast<float>(step));
+    const float bc2 = 1.f - powf(b2, static_cast<float>(step));
+    k_adam<<<ew_grid(n), 256, 0, s>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale);
+    LAUNCH_OK("k_adam");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone GEMM for unit tests
+// ------------------------------------------------------------------------------------------------
+extern "C" int pcseg_gemm_test(int layout, int M, int N, int K, const void* A, int lda, const void* Bm, int ldb, void* D, int ldc,
+                               const float* bias, int block_n, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GemmOp op;
+    if (layout == 0) {
+        TRY(setup_gemm_kmajor(&op, EPI_BIAS_RELU, A, lda, Bm, ldb, M, N, K, D, ldc, nullptr, 0));
+        if (block_n) {
+            if (N % block_n) return fail("pcseg_gemm_test: N not a multiple of block_n");
+            op.bn = block_n;
+            op.p.num_n_tiles = N / block_n;
+            TRY(make_tmap(&op.tmB, Bm, K, N, ldb, 64, block_n));
+        }
+        op.p.bias = bias;
+        if (!bias) return fail("pcseg_gemm_test: layout 0 needs a bias vector");
+    } else if (layout == 1) {
+        TRY(setup_gemm_wgrad(&op, A, lda, M, Bm, ldb, N, K, static_cast<float*>(D), ldc));
+        if (block_n) {
+            if (N % block_n) return fail("pcseg_gemm_test: N not a multiple of block_n");
+            op.bn = block_n;
+            op.p.num_n_tiles = N / block_n;
+        }
+    } else {
+        return fail("pcseg_gemm_test: unknown layout %d", layout);
+    }
+    return launch_gemm(op, s);
+}

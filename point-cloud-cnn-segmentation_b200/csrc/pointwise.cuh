@@ -1,0 +1,631 @@
+// CUDA-core kernels around the tcgen05 GEMMs: ingest (4->64 layer), BatchNorm finalize /
+// apply / backward, global max-pool, per-cloud bias, logits + cross-entropy head, Adam.
+// All activation tensors are point-major [P][C] bf16 with C contiguous.
+#pragma once
+#include "ptx.cuh"
+
+namespace pcseg {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight preparation
+// ---------------------------------------------------------------------------------------------
+// dst[r][c] (bf16, pitch ld_dst) = alpha[r] * src[r][c] (fp32, pitch ld_src); alpha may be null.
+__global__ void k_convert_rows(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                               int rows, int cols, const float* __restrict__ alpha) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int r = idx / cols, c = idx % cols;
+    float v = src[static_cast<size_t>(r) * ld_src + c];
+    if (alpha) v *= alpha[r];
+    dst[static_cast<size_t>(r) * ld_dst + c] = __float2bfloat16_rn(v);
+}
+// dst[c][r] (bf16, pitch ld_dst) = src[r][c]: transposed copy used as the dgrad B operand.
+__global__ void k_convert_transpose(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                    int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[static_cast<size_t>(r) * ld_src + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[static_cast<size_t>(c) * ld_dst + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+}
+
+// Eval-mode BatchNorm folding: alpha[c] = gamma/sqrt(var+eps), delta[c] = (bias - mean)*alpha + beta.
+__global__ void k_fold_bn(const float* __restrict__ conv_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ rmean, const float* __restrict__ rvar, float eps, int C,
+                          float* __restrict__ alpha, float* __restrict__ delta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float a2 = gamma[c] / sqrtf(rvar[c] + eps);
+    alpha[c] = a2;
+    delta[c] = (conv_bias[c] - rmean[c]) * a2 + beta[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ingest layer conv1 (4 -> 64) on CUDA cores.  8 threads per point, 8 channels each.
+//   EVAL : a1 = relu(Wf x + bf) with BN folded                     (writes bf16)
+//   TRAIN: y1 = W x (bias dropped: train-mode BN cancels it), column sum / sum-of-squares in fp64
+// ---------------------------------------------------------------------------------------------
+template <bool TRAIN>
+__global__ void __launch_bounds__(256) k_ingest(const float4* __restrict__ x, int P, const float* __restrict__ W /*[64][4]*/,
+                                                const float* __restrict__ alpha, const float* __restrict__ delta,
+                                                __nv_bfloat16* __restrict__ out, double* __restrict__ stats) {
+    __shared__ float red[2][32][64];   // per point-slot partial sums (TRAIN only)
+    const int cg = threadIdx.x & 7;    // channel group: channels cg*8 .. cg*8+7
+    const int slot = threadIdx.x >> 3; // 0..31
+    float w[8][4], bsh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        const float a = TRAIN ? 1.f : alpha[c];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[j][k] = a * W[c * 4 + k];
+        bsh[j] = TRAIN ? 0.f : delta[c];
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    for (int pnt = blockIdx.x * 32 + slot; pnt < P; pnt += gridDim.x * 32) {
+        const float4 xv = __ldg(x + pnt);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = fmaf(w[j][0], xv.x, fmaf(w[j][1], xv.y, fmaf(w[j][2], xv.z, fmaf(w[j][3], xv.w, bsh[j]))));
+            if (!TRAIN) v = fmaxf(v, 0.f);
+            v = round_bf16(v);
+            o[j] = v;
+            if (TRAIN) { s1[j] += v; s2[j] = fmaf(v, v, s2[j]); }
+        }
+        uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(pnt) * 64 + cg * 8) = pk;
+    }
+    if (TRAIN) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[0][slot][cg * 8 + j] = s1[j]; red[1][slot][cg * 8 + j] = s2[j]; }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int q = threadIdx.x >> 6, c = threadIdx.x & 63;
+            double s = 0.0;
+            for (int i = 0; i < 32; ++i) s += static_cast<double>(red[q][i][c]);
+            atomicAdd(stats + q * 64 + c, s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Train-mode BatchNorm finalize (one thread per channel).
+//   stats = {sum y, sum y^2} over n rows (conv bias excluded) ->
+//   bnp[c] = {scale = gamma*invstd, shift = beta - mean*scale, invstd, -mean*invstd}
+//   running_mean/var updated with momentum, unbiased variance, bias re-added to the mean.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bn_finalize(const double* __restrict__ stats, int C, double n, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
+                              float* __restrict__ rmean, float* __restrict__ rvar, float4* __restrict__ bnp) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = stats[c] / n;
+    double var = stats[C + c] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const float sc = static_cast<float>(gamma[c] * invstd);
+    bnp[c] = make_float4(sc, static_cast<float>(beta[c] - mean * gamma[c] * invstd), static_cast<float>(invstd),
+                         static_cast<float>(-mean * invstd));
+    if (rmean != nullptr) {
+        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+        rmean[c] = static_cast<float>((1.0 - momentum) * rmean[c] + momentum * (mean + conv_bias[c]));
+        rvar[c] = static_cast<float>((1.0 - momentum) * rvar[c] + momentum * unb);
+    }
+}
+
+// a = relu(scale*y + shift) (* dropout keep / (1-p)).  8 channels per thread (16-byte vectors).
+__global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
+                                                 int ld_a, long P, int C, const float4* __restrict__ bnp,
+                                                 unsigned long long seed, unsigned int thr16, float keep_scale) {
+    const int vec_per_row = C >> 3;
+    const long total = P * vec_per_row;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long r = i / vec_per_row;
+        const int c0 = static_cast<int>(i % vec_per_row) << 3;
+        const uint4 yw = *reinterpret_cast<const uint4*>(y + r * ld_y + c0);
+        const uint32_t ws[4] = {yw.x, yw.y, yw.z, yw.w};
+        uint32_t keep = 0xFFu;
+        if (thr16 != 0u) keep = dropout_keep8(seed, (static_cast<unsigned long long>(r) * C + c0) >> 3, thr16);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float4 bp = __ldg(bnp + c0 + e);
+            const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
+            const float t = fmaf(bp.x, yv, bp.y);
+            o[e] = (t > 0.f && ((keep >> e) & 1u)) ? t * keep_scale : 0.f;
+        }
+        *reinterpret_cast<uint4*>(a + r * ld_a + c0) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Train-mode global max-pool over points of relu(bn(y6)).  Because bn is monotone per channel
+// the arg-extremum of the pre-BN value decides: max(y) if scale >= 0 else min(y).
+// Packed 64-bit key = (orderable(sign*y) << 32) | ~index, reduced with atomicMax: ties -> lowest index.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_orderable(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+// grid: (C/64, strips, clouds); block 256 = 8 warps; lane -> 2 channels, warp -> rows r = warp, warp+8, ...
+__global__ void __launch_bounds__(256) k_maxpool_scan(const __nv_bfloat16* __restrict__ y, int C, int N, int rows_per_strip,
+                                                      const float4* __restrict__ bnp, unsigned long long* __restrict__ keys) {
+    __shared__ unsigned long long red[8][64];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+    const int warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_strip;
+    const int r1 = min(r0 + rows_per_strip, N);
+    const float sg0 = (__ldg(bnp + c).x >= 0.f) ? 1.f : -1.f;
+    const float sg1 = (__ldg(bnp + c + 1).x >= 0.f) ? 1.f : -1.f;
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    const __nv_bfloat16* base = y + (static_cast<size_t>(cloud) * N) * C + c;
+    for (int r = r0 + warp; r < r1; r += 8) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(base + static_cast<size_t>(r) * C);
+        const unsigned long long inv = 0xFFFFFFFFu - static_cast<uint32_t>(r);
+        const unsigned long long a0 = (static_cast<unsigned long long>(float_orderable(sg0 * bf16_lo(w))) << 32) | inv;
+        const unsigned long long a1 = (static_cast<unsigned long long>(float_orderable(sg1 * bf16_hi(w))) << 32) | inv;
+        k0 = a0 > k0 ? a0 : k0;
+        k1 = a1 > k1 ? a1 : k1;
+    }
+    red[warp][(threadIdx.x & 31) * 2] = k0;
+    red[warp][(threadIdx.x & 31) * 2 + 1] = k1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        unsigned long long k = red[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) k = red[w][threadIdx.x] > k ? red[w][threadIdx.x] : k;
+        atomicMax(keys + static_cast<size_t>(cloud) * C + blockIdx.x * 64 + threadIdx.x, k);
+    }
+}
+// decode keys -> g (post BN+ReLU), ystar (pre-BN extremum), argidx (row within cloud)
+__global__ void k_maxpool_finish(const unsigned long long* __restrict__ keys, int total, int C, const float4* __restrict__ bnp,
+                                 float* __restrict__ g, float* __restrict__ ystar, int* __restrict__ argidx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = i % C;
+    const unsigned long long k = keys[i];
+    const float4 bp = __ldg(bnp + c);
+    const float sg = bp.x >= 0.f ? 1.f : -1.f;
+    const float yv = sg * float_from_orderable(static_cast<uint32_t>(k >> 32));
+    argidx[i] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFull));
+    ystar[i] = yv;
+    g[i] = fmaxf(fmaf(bp.x, yv, bp.y), 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-cloud bias of seg_conv1: cb[b][n] = alpha[n] * sum_k Wg[n][k] * g[b][k] + delta[n]
+// (Wg = seg_conv1.weight[:, 64:], fp32, pitch ldw).  One warp per output.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cloud_bias(const float* __restrict__ Wg, int ldw, const float* __restrict__ g, int clouds,
+                                                    int Nout, int K, const float* __restrict__ alpha,
+                                                    const float* __restrict__ delta, float* __restrict__ cb) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= clouds * Nout) return;
+    const int b = gw / Nout, n = gw % Nout;
+    const float* wr = Wg + static_cast<size_t>(n) * ldw;
+    const float* gr = g + static_cast<size_t>(b) * K;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(wr[k], gr[k], s);
+    s = warp_sum(s);
+    if (lane == 0) cb[gw] = (alpha ? alpha[n] : 1.f) * s + (delta ? delta[n] : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Train-mode head: logits = W4 * relu(bn(y_s3)) + b4.  One warp per point (lane = 4 channels).
+// Optionally fused weighted cross-entropy statistics: sum w*nll, sum w, argmax-correct count.
+// ---------------------------------------------------------------------------------------------
+struct CeAccum {
+    double loss_num;      // sum_i w[y_i] * (-log p_i[y_i])
+    double w_sum;         // sum_i w[y_i]
+    unsigned long long correct;   // argmax == label over valid points
+    unsigned long long valid;     // labels != -1
+};
+
+template <int MAXC>
+__global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restrict__ ys3, long P, const float4* __restrict__ bnp,
+                                                  const float* __restrict__ W4, const float* __restrict__ b4, int C,
+                                                  float* __restrict__ logits, const long long* __restrict__ labels,
+                                                  const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    float w[MAXC][4];
+    float4 bp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bp[e] = __ldg(bnp + lane * 4 + e);
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[k][e] = (k < C) ? W4[k * 128 + lane * 4 + e] : 0.f;
+    double loss_num = 0.0, w_sum = 0.0;
+    unsigned long long correct = 0, nvalid = 0;
+    for (long pnt = warp_g; pnt < P; pnt += nwarps) {
+        const uint2 yw = *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4);
+        float a[4];
+        a[0] = fmaxf(fmaf(bp[0].x, bf16_lo(yw.x), bp[0].y), 0.f);
+        a[1] = fmaxf(fmaf(bp[1].x, bf16_hi(yw.x), bp[1].y), 0.f);
+        a[2] = fmaxf(fmaf(bp[2].x, bf16_lo(yw.y), bp[2].y), 0.f);
+        a[3] = fmaxf(fmaf(bp[3].x, bf16_hi(yw.y), bp[3].y), 0.f);
+        float z[MAXC];
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            if (k < C) {
+                float s = a[0] * w[k][0];
+                s = fmaf(a[1], w[k][1], s);
+                s = fmaf(a[2], w[k][2], s);
+                s = fmaf(a[3], w[k][3], s);
+                z[k] = warp_sum(s) + __ldg(b4 + k);
+            } else {
+                z[k] = -INFINITY;
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k)
+                if (k < C) logits[pnt * C + k] = z[k];
+            if (labels != nullptr) {
+                const long long lab = labels[pnt];
+                if (lab >= 0) {
+                    float zmax = z[0];
+                    int am = 0;
+#pragma unroll
+                    for (int k = 1; k < MAXC; ++k)
+                        if (k < C && z[k] > zmax) { zmax = z[k]; am = k; }
+                    float se = 0.f, zl = 0.f;
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k)
+                        if (k < C) { se += __expf(z[k] - zmax); if (k == lab) zl = z[k]; }
+                    const float wl = class_w ? class_w[lab] : 1.f;
+                    loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(se) - zl);
+                    w_sum += wl;
+                    correct += (am == lab);
+                    nvalid += 1;
+                }
+            }
+        }
+    }
+    if (labels != nullptr && lane == 0) {
+        atomicAdd(&ce->loss_num, loss_num);
+        atomicAdd(&ce->w_sum, w_sum);
+        atomicAdd(&ce->correct, correct);
+        atomicAdd(&ce->valid, nvalid);
+    }
+}
+
+// Weighted-CE forward only (labels -> sum of class weights); used to get the global normaliser
+// before backward (and before the cross-rank all-reduce of the normaliser).
+__global__ void k_label_weight_sum(const long long* __restrict__ labels, long P, const float* __restrict__ class_w,
+                                   double* __restrict__ wsum) {
+    double s = 0.0;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < P; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long long l = labels[i];
+        if (l >= 0) s += class_w ? class_w[l] : 1.f;
+    }
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(wsum, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head backward: dlogits -> {dW4, db4, dz_s3 (masked by relu), BN stats sum dz / sum dz*yhat}.
+// dlogits either given (autograd path) or recomputed from logits/labels/class_w/inv_wsum (fused CE).
+// One warp per point; lane = 4 channels.
+// ---------------------------------------------------------------------------------------------
+template <int MAXC>
+__global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restrict__ ys3, long P, const float4* __restrict__ bnp,
+                                                  const float* __restrict__ W4, int C, const float* __restrict__ dlogits,
+                                                  const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                  const float* __restrict__ class_w, const double* __restrict__ wsum_total,
+                                                  __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dW4,
+                                                  float* __restrict__ db4, double* __restrict__ stats) {
+    __shared__ float red[8][MAXC * 128 + 2 * 128 + MAXC];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    float w[MAXC][4], dw[MAXC][4], dbk[MAXC];
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 bp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bp[e] = __ldg(bnp + lane * 4 + e);
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+        dbk[k] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { w[k][e] = (k < C) ? W4[k * 128 + lane * 4 + e] : 0.f; dw[k][e] = 0.f; }
+    }
+    const float inv_wsum = (wsum_total != nullptr) ? static_cast<float>(1.0 / *wsum_total) : 0.f;
+    for (long pnt = warp_g; pnt < P; pnt += nwarps) {
+        float dl[MAXC];
+        if (dlogits != nullptr) {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __ldg(dlogits + pnt * C + k) : 0.f;
+        } else {
+            const long long lab = labels[pnt];
+            if (lab >= 0) {
+                float z[MAXC], zmax = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) { z[k] = (k < C) ? __ldg(logits + pnt * C + k) : -INFINITY; zmax = fmaxf(zmax, z[k]); }
+                float se = 0.f;
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) { z[k] = (k < C) ? __expf(z[k] - zmax) : 0.f; se += z[k]; }
+                const float sc = (class_w ? class_w[lab] : 1.f) * inv_wsum;
+                const float inv = 1.f / se;
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? sc * (z[k] * inv - (k == lab ? 1.f : 0.f)) : 0.f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) dl[k] = 0.f;
+            }
+        }
+        const uint2 yw = *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4);
+        const float yv[4] = {bf16_lo(yw.x), bf16_hi(yw.x), bf16_lo(yw.y), bf16_hi(yw.y)};
+        float dz[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float t = fmaf(bp[e].x, yv[e], bp[e].y);
+            const float a = fmaxf(t, 0.f);
+            float da = 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                if (k < C) { da = fmaf(dl[k], w[k][e], da); dw[k][e] = fmaf(dl[k], a, dw[k][e]); }
+            }
+            dz[e] = (t > 0.f) ? round_bf16(da) : 0.f;
+            s1[e] += dz[e];
+            s2[e] = fmaf(dz[e], fmaf(bp[e].z, yv[e], bp[e].w), s2[e]);
+        }
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) dbk[k] += dl[k];
+        *reinterpret_cast<uint2*>(dz_out + pnt * 128 + lane * 4) = make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
+    }
+    // block reduction over the 8 warps, then one atomic per value per block
+    float* r = red[warp];
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[k * 128 + lane * 4 + e] = dw[k][e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { r[MAXC * 128 + lane * 4 + e] = s1[e]; r[MAXC * 128 + 128 + lane * 4 + e] = s2[e]; }
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) r[MAXC * 128 + 256 + k] = dbk[k];
+    __syncthreads();
+    const int total = MAXC * 128 + 256 + MAXC;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += red[wv][i];
+        if (i < MAXC * 128) {
+            if (i / 128 < C) atomicAdd(dW4 + i, s);
+        } else if (i < MAXC * 128 + 256) {
+            atomicAdd(stats + (i - MAXC * 128), static_cast<double>(s));
+        } else if (i - MAXC * 128 - 256 < C) {
+            atomicAdd(db4 + (i - MAXC * 128 - 256), s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm backward.
+//   coefficients (one thread per channel):  dy = A*dz + Bc*y + Cc   with
+//     A = scale, Bc = -scale*c2*invstd, Cc = -scale*(c1 + c2*(-mean*invstd)),  c1 = sum dz / n, c2 = sum dz*yhat / n
+//   also writes dgamma = sum dz*yhat, dbeta = sum dz.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bn_bwd_coef(const double* __restrict__ stats, int C, double n, const float4* __restrict__ bnp,
+                              float4* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double sdz = stats[c], sdzy = stats[C + c];
+    const double c1 = sdz / n, c2 = sdzy / n;
+    const float4 bp = bnp[c];
+    const double A = bp.x;
+    coef[c] = make_float4(static_cast<float>(A), static_cast<float>(-A * c2 * bp.z), static_cast<float>(-A * (c1 + c2 * bp.w)), 0.f);
+    dgamma[c] = static_cast<float>(sdzy);
+    dbeta[c] = static_cast<float>(sdz);
+}
+
+// dy = A*dz + Bc*y + Cc, bf16 out (pitch ld_dy); column sums of dy -> dbias (fp32 atomics) and,
+// optionally, per-cloud column sums -> dcb[cloud][C].
+// SPARSE variant (max-pool backward): dz[p][c] = (row_in_cloud == argidx[cloud][c]) ? dzv[cloud][c] : 0.
+// grid: (ceil(C/ (8*TPR)) ... ) -> here: blockIdx.x = strip of 64 rows inside a cloud, blockIdx.y = cloud,
+// block = 256 threads = 4 row-slots x 64 column-vectors (8 channels each, covers 512 channels per pass).
+template <bool SPARSE>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, int ld_dz,
+                                                      const __nv_bfloat16* __restrict__ y, int ld_y,
+                                                      __nv_bfloat16* __restrict__ dy, int ld_dy, int N /*rows per cloud*/, int C,
+                                                      const float4* __restrict__ coef, float* __restrict__ dbias,
+                                                      float* __restrict__ dcb, const int* __restrict__ argidx,
+                                                      const float* __restrict__ dzv) {
+    __shared__ float red[4][64 * 8];
+    const int vec = threadIdx.x & 63;
+    const int slot = threadIdx.x >> 6;
+    const int cloud = blockIdx.y;
+    const int r0 = blockIdx.x * 64;
+    const int r1 = min(r0 + 64, N);
+    for (int cbase = 0; cbase < C; cbase += 512) {
+        const int c0 = cbase + vec * 8;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        if (c0 < C) {
+            float4 cf[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cf[e] = __ldg(coef + c0 + e);
+            int arg[8];
+            float dv[8];
+            if (SPARSE) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    arg[e] = argidx[static_cast<size_t>(cloud) * C + c0 + e];
+                    dv[e] = dzv[static_cast<size_t>(cloud) * C + c0 + e];
+                }
+            }
+            for (int r = r0 + slot; r < r1; r += 4) {
+                const size_t grow = static_cast<size_t>(cloud) * N + r;
+                const uint4 yw = *reinterpret_cast<const uint4*>(y + grow * ld_y + c0);
+                const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w};
+                uint32_t zs[4] = {0, 0, 0, 0};
+                if (!SPARSE) {
+                    const uint4 zw = *reinterpret_cast<const uint4*>(dz + grow * ld_dz + c0);
+                    zs[0] = zw.x; zs[1] = zw.y; zs[2] = zw.z; zs[3] = zw.w;
+                }
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float yv = (e & 1) ? bf16_hi(ys[e >> 1]) : bf16_lo(ys[e >> 1]);
+                    float dzv_e;
+                    if (SPARSE) dzv_e = (arg[e] == r) ? dv[e] : 0.f;
+                    else dzv_e = (e & 1) ? bf16_hi(zs[e >> 1]) : bf16_lo(zs[e >> 1]);
+                    const float v = round_bf16(fmaf(cf[e].x, dzv_e, fmaf(cf[e].y, yv, cf[e].z)));
+                    o[e] = v;
+                    acc[e] += v;
+                }
+                *reinterpret_cast<uint4*>(dy + grow * ld_dy + c0) =
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[slot][vec * 8 + e] = acc[e];
+        __syncthreads();
+        for (int i = threadIdx.x; i < 512; i += 256) {
+            const int c = cbase + i;
+            if (c < C) {
+                const float s = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+                if (dbias) atomicAdd(dbias + c, s);
+                if (dcb) atomicAdd(dcb + static_cast<size_t>(cloud) * C + c, s);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the per-cloud seg_conv1 branch and of the max-pool.
+//   dg[b][j]   = sum_n dcb[b][n] * Wg[n][j]                 (repeat/cat backward folded per cloud)
+//   dWg[n][j] += sum_b dcb[b][n] * g[b][j]
+//   dzv[b][j]  = dg[b][j] * (g[b][j] > 0)                   (relu + max routing value)
+//   stats6     = {sum_b dzv, sum_b dzv * yhat(ystar)}       (BN backward sums of the sparse gradient)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cloud_bwd_dg(const float* __restrict__ dcb, const float* __restrict__ Wg, int ldw, int clouds,
+                                                      int Nn /*512*/, int J /*1024*/, const float* __restrict__ g,
+                                                      const float* __restrict__ ystar, const float4* __restrict__ bnp6,
+                                                      float* __restrict__ dzv, double* __restrict__ stats6) {
+    // grid: (J/256, clouds); stats6 must be zeroed by the caller
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= J || b >= clouds) return;
+    const float4 bp = __ldg(bnp6 + j);
+    const float* d = dcb + static_cast<size_t>(b) * Nn;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int n = 0; n < Nn; n += 4) {
+        s0 = fmaf(d[n], Wg[static_cast<size_t>(n) * ldw + j], s0);
+        s1 = fmaf(d[n + 1], Wg[static_cast<size_t>(n + 1) * ldw + j], s1);
+        s2 = fmaf(d[n + 2], Wg[static_cast<size_t>(n + 2) * ldw + j], s2);
+        s3 = fmaf(d[n + 3], Wg[static_cast<size_t>(n + 3) * ldw + j], s3);
+    }
+    const float s = (s0 + s1) + (s2 + s3);
+    const size_t o = static_cast<size_t>(b) * J + j;
+    const float v = (g[o] > 0.f) ? s : 0.f;
+    dzv[o] = v;
+    if (v != 0.f) {
+        atomicAdd(stats6 + j, static_cast<double>(v));
+        atomicAdd(stats6 + J + j, static_cast<double>(v) * static_cast<double>(fmaf(bp.z, ystar[o], bp.w)));
+    }
+}
+__global__ void __launch_bounds__(256) k_cloud_bwd_dw(const float* __restrict__ dcb, const float* __restrict__ g, int clouds, int Nn,
+                                                      int J, float* __restrict__ dWg, int ldw) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (j >= J) return;
+    float s = 0.f;
+    for (int b = 0; b < clouds; ++b) s = fmaf(dcb[static_cast<size_t>(b) * Nn + n], g[static_cast<size_t>(b) * J + j], s);
+    dWg[static_cast<size_t>(n) * ldw + j] += s;
+}
+
+// dW1[c][k] = sum_p dy1[p][c] * x[p][k]   (64 x 4).  8 threads per point, 8 channels each.
+__global__ void __launch_bounds__(256) k_ingest_bwd(const __nv_bfloat16* __restrict__ dy1, const float4* __restrict__ x, long P,
+                                                    float* __restrict__ dW1) {
+    __shared__ float red[32][64 * 4];
+    const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+    for (long pnt = blockIdx.x * 32 + slot; pnt < P; pnt += static_cast<long>(gridDim.x) * 32) {
+        const float4 xv = __ldg(x + pnt);
+        const uint4 dw = *reinterpret_cast<const uint4*>(dy1 + pnt * 64 + cg * 8);
+        const uint32_t ds[4] = {dw.x, dw.y, dw.z, dw.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = (j & 1) ? bf16_hi(ds[j >> 1]) : bf16_lo(ds[j >> 1]);
+            acc[j][0] = fmaf(d, xv.x, acc[j][0]);
+            acc[j][1] = fmaf(d, xv.y, acc[j][1]);
+            acc[j][2] = fmaf(d, xv.z, acc[j][2]);
+            acc[j][3] = fmaf(d, xv.w, acc[j][3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[slot][(cg * 8 + j) * 4 + k] = acc[j][k];
+    __syncthreads();
+    {
+        const int i = threadIdx.x;   // 256 = 64*4 outputs
+        float s = 0.f;
+        for (int sl = 0; sl < 32; ++sl) s += red[sl][i];
+        atomicAdd(dW1 + i, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias correction).
+// grad_scale lets data-parallel ranks fold an averaging factor in (1.0 when grads are already summed).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
+                                              float bc1, float bc2_sqrt, float grad_scale) {
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const float pv = p[i];
+        const float gv = fmaf(wd, pv, g[i] * grad_scale);
+        const float mv = fmaf(1.f - b1, gv - m[i], m[i]);
+        const float vv = fmaf(1.f - b2, gv * gv - v[i], v[i]);
+        m[i] = mv;
+        v[i] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[i] = pv - (lr / bc1) * (mv / denom);
+    }
+}
+
+// argmax over classes (first maximum wins, like torch.argmax on ties)
+__global__ void k_argmax(const float* __restrict__ logits, long P, int C, long long* __restrict__ out) {
+    const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    if (i >= P) return;
+    const float* z = logits + i * C;
+    float best = z[0];
+    int bi = 0;
+    for (int k = 1; k < C; ++k)
+        if (z[k] > best) { best = z[k]; bi = k; }
+    out[i] = bi;
+}
+
+}  // namespace pcseg

@@ -1,0 +1,117 @@
+"""Host-side driver of the C ABI: owns contexts, workspaces and flat arenas.
+PyTorch is used for device memory and streams only."""
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from ._lib import lib, check, ptr
+
+MAX_CLASSES = 8
+NUM_PARAM_TENSORS = 38
+NUM_BN = 9
+
+
+def param_layout(num_classes):
+    """[(offset, numel)] of the 38 parameter tensors in state_dict order + total."""
+    offs = [(int(lib.pcseg_param_offset(num_classes, t)), int(lib.pcseg_param_numel(num_classes, t)))
+            for t in range(NUM_PARAM_TENSORS)]
+    return offs, int(lib.pcseg_param_count(num_classes))
+
+
+def bn_layout():
+    offs = [(int(lib.pcseg_bn_buffer_offset(j, 0)), int(lib.pcseg_bn_buffer_offset(j, 1))) for j in range(NUM_BN)]
+    return offs, int(lib.pcseg_bn_buffer_count())
+
+
+class _Binding:
+    def __init__(self, num_classes, B, N, train, device):
+        self.handle = C.c_void_p()
+        check(lib.pcseg_create(C.byref(self.handle), num_classes), "pcseg_create")
+        nbytes = int(lib.pcseg_workspace_bytes(B, N, num_classes, int(train)))
+        if nbytes <= 0:
+            raise ValueError(f"unsupported shape B={B} N={N} C={num_classes}")
+        # torch caching-allocator blocks are 512-byte aligned; over-allocate and align to 1024
+        self.storage = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        base = self.storage.data_ptr()
+        self.ws_ptr = (base + 1023) & ~1023
+        check(lib.pcseg_bind(self.handle, B, N, C.c_void_p(self.ws_ptr), nbytes, int(train)), "pcseg_bind")
+        self.eval_key = None
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.pcseg_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class Engine:
+    """One per (module, device).  Caches a few (B, N, mode) bindings."""
+
+    def __init__(self, num_classes, device, max_bindings=4):
+        if not (1 <= num_classes <= MAX_CLASSES):
+            raise ValueError(f"num_classes must be in 1..{MAX_CLASSES}")
+        self.C = num_classes
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("pcseg_b200 runs on CUDA (sm_100a) devices only; there is no CPU fallback")
+        self.bindings = OrderedDict()
+        self.max_bindings = max_bindings
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def binding(self, B, N, train):
+        key = (B, N, bool(train))
+        b = self.bindings.get(key)
+        if b is None:
+            with torch.cuda.device(self.device):
+                b = _Binding(self.C, B, N, train, self.device)
+            self.bindings[key] = b
+            while len(self.bindings) > self.max_bindings:
+                self.bindings.popitem(last=False)
+        else:
+            self.bindings.move_to_end(key)
+        return b
+
+    # ---- eval
+    def forward_eval(self, x, flat_params, flat_bn, weights_key, want_labels=False):
+        B, N, _ = x.shape
+        b = self.binding(B, N, False)
+        with torch.cuda.device(self.device):
+            if b.eval_key != weights_key:
+                check(lib.pcseg_prepare_eval(b.handle, ptr(flat_params), ptr(flat_bn), self._stream()), "pcseg_prepare_eval")
+                b.eval_key = weights_key
+            logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
+            labels = torch.empty((B, N), dtype=torch.int64, device=self.device) if want_labels else None
+            check(lib.pcseg_forward_eval(b.handle, ptr(x), ptr(logits), ptr(labels), self._stream()), "pcseg_forward_eval")
+        return (logits, labels) if want_labels else logits
+
+    # ---- train
+    def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None):
+        B, N, _ = x.shape
+        b = self.binding(B, N, True)
+        logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pcseg_forward_train(b.handle, ptr(x), ptr(flat_params), ptr(flat_bn), C.c_ulonglong(seed & (2**64 - 1)),
+                                          C.c_float(dropout_p), ptr(logits), ptr(labels), ptr(class_w), ptr(ce), self._stream()),
+                  "pcseg_forward_train")
+        return logits
+
+    def backward(self, x, flat_params, flat_grads, dlogits=None, logits=None, labels=None, class_w=None, wsum=None, phase=0):
+        B, N, _ = x.shape
+        b = self.binding(B, N, True)
+        with torch.cuda.device(self.device):
+            check(lib.pcseg_backward(b.handle, ptr(x), ptr(flat_params), ptr(dlogits), ptr(logits), ptr(labels), ptr(class_w),
+                                     ptr(wsum), ptr(flat_grads), phase, self._stream()), "pcseg_backward")
+
+    def adam(self, flat_params, flat_grads, m, v, step, lr, betas, eps, weight_decay, grad_scale=1.0):
+        with torch.cuda.device(self.device):
+            check(lib.pcseg_adam_step(ptr(flat_params), ptr(flat_grads), ptr(m), ptr(v), flat_params.numel(), step, lr, betas[0],
+                                      betas[1], eps, weight_decay, grad_scale, self._stream()), "pcseg_adam_step")
+
+
+def launch_count():
+    return int(lib.pcseg_launch_count())

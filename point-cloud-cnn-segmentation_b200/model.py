@@ -1,0 +1,202 @@
+"""Drop-in replacement of the reference `PointNetSegmentation` (point_cloud_segmentation.py:65-133).
+
+Same constructor, same `forward((B, max_points, 4)) -> (B, max_points, num_classes)`, same 65-entry
+state_dict (the sub-modules below are only parameter containers: the math runs in libpcseg_b200.so).
+"""
+import torch
+import torch.nn as nn
+
+from .engine import Engine, param_layout, bn_layout
+
+_CONVS = ["conv1", "conv2", "conv3", "conv4", "conv5", "global_feat", "seg_conv1", "seg_conv2", "seg_conv3", "seg_conv4"]
+_BNS = ["bn1", "bn2", "bn3", "bn4", "bn5", "bn_global", "bn_seg1", "bn_seg2", "bn_seg3"]
+
+
+class _SegTrainFn(torch.autograd.Function):
+    """Autograd bridge for the drop-in path: forward = pcseg_forward_train, backward = pcseg_backward
+    with the caller's dlogits (whatever loss the user put on top, e.g. pcs.py:216,251)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        logits = module._run_train_forward(x)
+        ctx.module = module
+        ctx.save_for_backward(x)
+        ctx.token = module._fwd_token
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        module = ctx.module
+        (x,) = ctx.saved_tensors
+        if ctx.token != module._fwd_token:
+            raise RuntimeError("pcseg_b200: activations of this forward were overwritten by a later training forward; "
+                               "call backward() before the next forward (as the reference loop does, pcs.py:244-254)")
+        grads = module._run_backward(x, dlogits.contiguous().float())
+        return (None, None) + tuple(grads)
+
+
+class PointNetSegmentation(nn.Module):
+    def __init__(self, num_classes, input_dim=4):
+        super(PointNetSegmentation, self).__init__()
+        if input_dim != 4:
+            raise NotImplementedError("pcseg_b200 kernels are specialised for input_dim=4 (x, y, z, e)")
+        # registration order == reference (pcs.py:70-96) so that state_dict order and default init RNG use match
+        self.conv1 = nn.Conv1d(input_dim, 64, 1)
+        self.conv2 = nn.Conv1d(64, 64, 1)
+        self.conv3 = nn.Conv1d(64, 64, 1)
+        self.conv4 = nn.Conv1d(64, 128, 1)
+        self.conv5 = nn.Conv1d(128, 1024, 1)
+        self.global_feat = nn.Conv1d(1024, 1024, 1)
+        self.seg_conv1 = nn.Conv1d(1088, 512, 1)
+        self.seg_conv2 = nn.Conv1d(512, 256, 1)
+        self.seg_conv3 = nn.Conv1d(256, 128, 1)
+        self.seg_conv4 = nn.Conv1d(128, num_classes, 1)
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(64)
+        self.bn3 = nn.BatchNorm1d(64)
+        self.bn4 = nn.BatchNorm1d(128)
+        self.bn5 = nn.BatchNorm1d(1024)
+        self.bn_global = nn.BatchNorm1d(1024)
+        self.bn_seg1 = nn.BatchNorm1d(512)
+        self.bn_seg2 = nn.BatchNorm1d(256)
+        self.bn_seg3 = nn.BatchNorm1d(128)
+        self.dropout = nn.Dropout(0.3)
+
+        self.num_classes = num_classes
+        self._engine = None
+        self._flat = None          # dict(params, grads, bn) of flat arenas
+        self._fwd_token = 0
+        self._manual_version = 0   # bumped when the arena is modified behind autograd's back (fused optimizer)
+
+    # ------------------------------------------------------------------ flat arenas
+    def _param_list(self):
+        ps = []
+        for n in _CONVS:
+            m = getattr(self, n)
+            ps += [m.weight, m.bias]
+        for n in _BNS:
+            m = getattr(self, n)
+            ps += [m.weight, m.bias]
+        return ps
+
+    def _ensure_flat(self, device):
+        """Parameters / running stats live in flat fp32 arenas (one contiguous gradient arena for the
+        all-reduce); re-flatten if .to()/load_state_dict replaced the tensors."""
+        offs, total = param_layout(self.num_classes)
+        ps = self._param_list()
+        f = self._flat
+        ok = f is not None and f["params"].device == device
+        if ok:
+            base = f["params"].data_ptr()
+            for p, (o, n) in zip(ps, offs):
+                if p.data_ptr() != base + 4 * o or p.dtype != torch.float32:
+                    ok = False
+                    break
+        if ok:
+            bbase = f["bn"].data_ptr()
+            boffs, _ = bn_layout()
+            for name, (om, ov) in zip(_BNS, boffs):
+                m = getattr(self, name)
+                if m.running_mean.data_ptr() != bbase + 4 * om or m.running_var.data_ptr() != bbase + 4 * ov:
+                    ok = False
+                    break
+        if ok:
+            return f
+        flat_p = torch.empty(total, dtype=torch.float32, device=device)
+        for p, (o, n) in zip(ps, offs):
+            view = flat_p[o:o + n].view(p.shape)
+            view.copy_(p.data.to(device=device, dtype=torch.float32))
+            p.data = view
+        boffs, btotal = bn_layout()
+        flat_bn = torch.empty(btotal, dtype=torch.float32, device=device)
+        for name, (om, ov) in zip(_BNS, boffs):
+            m = getattr(self, name)
+            c = m.num_features
+            flat_bn[om:om + c].copy_(m.running_mean.to(device=device, dtype=torch.float32))
+            flat_bn[ov:ov + c].copy_(m.running_var.to(device=device, dtype=torch.float32))
+            m.running_mean = flat_bn[om:om + c]
+            m.running_var = flat_bn[ov:ov + c]
+            if m.num_batches_tracked.device != device:
+                m.num_batches_tracked = m.num_batches_tracked.to(device)
+        flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        self._flat = dict(params=flat_p, grads=flat_g, bn=flat_bn, offs=offs)
+        self._manual_version += 1
+        return self._flat
+
+    def _get_engine(self, device):
+        if self._engine is None or self._engine.device != device:
+            self._engine = Engine(self.num_classes, device)
+        return self._engine
+
+    def _weights_key(self):
+        ks = [self._manual_version]
+        for p in self._param_list():
+            ks.append(p._version)
+        for name in _BNS:
+            m = getattr(self, name)
+            ks.append(m.running_mean._version)
+            ks.append(m.running_var._version)
+        return tuple(ks)
+
+    def grad_views(self):
+        f = self._flat
+        return [f["grads"][o:o + n].view(p.shape) for p, (o, n) in zip(self._param_list(), f["offs"])]
+
+    # ------------------------------------------------------------------ kernels
+    def _check_input(self, x):
+        batch_size, max_points, _ = x.shape      # same unpack (and ValueError) as pcs.py:100
+        if x.shape[2] != 4:
+            raise RuntimeError(f"expected input with 4 channels (x, y, z, e), got {x.shape[2]}")
+        if not x.is_cuda:
+            raise RuntimeError("pcseg_b200: input must be a CUDA tensor (sm_100a kernels only, no CPU fallback)")
+        return x.contiguous().float()
+
+    def _run_train_forward(self, x, labels=None, class_w=None, ce=None):
+        f = self._ensure_flat(x.device)
+        eng = self._get_engine(x.device)
+        p = float(self.dropout.p) if self.dropout.training else 0.0
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p > 0 else 0
+        logits = eng.forward_train(x, f["params"], f["bn"], seed, p, labels, class_w, ce)
+        torch._foreach_add_([getattr(self, n).num_batches_tracked for n in _BNS], 1)
+        self._fwd_token += 1
+        self._manual_version += 1      # running statistics changed
+        return logits
+
+    def _run_backward(self, x, dlogits):
+        f = self._flat
+        eng = self._get_engine(x.device)
+        eng.backward(x, f["params"], f["grads"], dlogits=dlogits)
+        return [g.clone() for g in self.grad_views()]
+
+    def forward(self, x):
+        x = self._check_input(x)
+        if self.training:
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                self._ensure_flat(x.device)
+                return _SegTrainFn.apply(self, x, *self._param_list())
+            return self._run_train_forward(x)
+        f = self._ensure_flat(x.device)
+        eng = self._get_engine(x.device)
+        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key())
+
+    @torch.no_grad()
+    def predict(self, x):
+        """Fused inference + argmax (pcs.py:450-452): returns (logits, labels int64 (B, N))."""
+        x = self._check_input(x)
+        if self.training:
+            raise RuntimeError("predict() is an eval-mode call; use model.eval() first")
+        f = self._ensure_flat(x.device)
+        eng = self._get_engine(x.device)
+        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), want_labels=True)
+
+
+def load_checkpoint(path, map_location=None):
+    """Load a `best_model.pth` written by the reference (pcs.py:373-382): reads `num_classes` and
+    `model_state_dict`, strips a DataParallel `module.` prefix if present (pcs.py:410-428)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    model = PointNetSegmentation(num_classes=ckpt["num_classes"])
+    sd = ckpt["model_state_dict"]
+    if any(k.startswith("module.") for k in sd):
+        sd = {k.replace("module.", "", 1): v for k, v in sd.items()}
+    model.load_state_dict(sd, strict=True)
+    return model, ckpt

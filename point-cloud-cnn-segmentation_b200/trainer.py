@@ -1,0 +1,116 @@
+"""Fused training step: forward + weighted cross-entropy + backward + Adam on the flat arenas,
+data-parallel over point-cloud batches with one process per GPU (replaces the reference's
+nn.DataParallel, pcs.py:209-211, and the loop body pcs.py:241-255).
+
+Data-parallel semantics follow the reference's single-process DataParallel: one global weighted-mean
+loss over all points of the global batch (so every rank divides by the ALL-REDUCED sum of class weights
+and gradients are SUMMED), per-replica BatchNorm batch statistics (no SyncBN), rank 0's running
+statistics are the ones that survive (broadcast on demand with `sync_bn_buffers`).
+"""
+import torch
+import torch.distributed as dist
+
+from .model import PointNetSegmentation, _BNS
+
+
+def grad_buckets(offs, total):
+    """Two all-reduce buckets matching pcseg_backward's phases: ranges of the flat gradient arena that
+    are final after phase 1 (global_feat + seg head + their BNs) and after phase 2 (the rest)."""
+    conv_split = offs[10][0]          # first element of global_feat.weight
+    bn_start = offs[20][0]            # first BN tensor
+    bn_split = offs[30][0]            # bn_global.weight
+    early = [(conv_split, bn_start), (bn_split, total)]
+    late = [(0, conv_split), (bn_start, bn_split)]
+    return early, late
+
+
+class FusedTrainer:
+    def __init__(self, model: PointNetSegmentation, class_weights=None, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=1e-4, process_group=None, device=None, overlap=True):
+        self.model = model
+        self.device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        self.model.to(self.device)
+        self.flat = model._ensure_flat(self.device)
+        self.engine = model._get_engine(self.device)
+        n = self.flat["params"].numel()
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.step_count = 0
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.class_w = None if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float32, device=self.device).contiguous()
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        self.distributed = self.world > 1
+        self.overlap = overlap
+        # 32-byte CE accumulator {loss_num f64, w_sum f64, correct u64, valid u64} + all-reducible copy
+        self.ce_raw = torch.zeros(32, dtype=torch.uint8, device=self.device)
+        self.ce_f64 = self.ce_raw.view(torch.float64)
+        self.ce_i64 = self.ce_raw.view(torch.int64)
+        self.wsum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.early, self.late = grad_buckets(self.flat["offs"], n)
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.distributed else None
+        self.last_logits = None
+
+    def set_lr(self, lr):
+        self.lr = lr
+
+    def _allreduce_ranges(self, ranges):
+        g = self.flat["grads"]
+        return [dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for a, b in ranges if b > a]
+
+    @torch.no_grad()
+    def step(self, points, labels):
+        """One optimizer step on this rank's shard.  points (B,N,4) fp32 and labels (B,N) int64 (-1 = pad) on
+        the device.  Returns dict of device tensors: loss (global weighted mean), correct, valid."""
+        m = self.model
+        if not m.training:
+            raise RuntimeError("FusedTrainer.step needs model.train()")
+        x = m._check_input(points)
+        labels = labels.contiguous()
+        f = self.flat = m._ensure_flat(self.device)
+        logits = m._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw)
+        self.last_logits = logits
+        self.wsum.copy_(self.ce_f64[1:2])
+        if self.distributed:
+            dist.all_reduce(self.wsum, op=dist.ReduceOp.SUM, group=self.pg)
+        eng = self.engine
+        kw = dict(logits=logits, labels=labels, class_w=self.class_w, wsum=self.wsum)
+        if self.distributed and self.overlap:
+            eng.backward(x, f["params"], f["grads"], phase=1, **kw)
+            works = self._allreduce_ranges(self.early)      # NCCL runs on its own stream while phase 2 computes
+            eng.backward(x, f["params"], f["grads"], phase=2, **kw)
+            works += self._allreduce_ranges(self.late)
+            for w in works:
+                w.wait()
+        else:
+            eng.backward(x, f["params"], f["grads"], phase=0, **kw)
+            if self.distributed:
+                dist.all_reduce(f["grads"], op=dist.ReduceOp.SUM, group=self.pg)
+        self.step_count += 1
+        eng.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps,
+                 self.weight_decay)
+        m._manual_version += 1
+        stats = self.ce_raw.clone()
+        if self.distributed:
+            sf = stats.view(torch.float64)[:1].clone()
+            dist.all_reduce(sf, op=dist.ReduceOp.SUM, group=self.pg)
+            loss = sf[0] / self.wsum[0]
+        else:
+            loss = stats.view(torch.float64)[0] / self.wsum[0]
+        return dict(loss=loss, correct=stats.view(torch.int64)[2], valid=stats.view(torch.int64)[3])
+
+    def sync_bn_buffers(self, src=0):
+        """DataParallel keeps replica 0's running statistics; broadcast them when a checkpoint is written."""
+        if self.distributed:
+            dist.broadcast(self.flat["bn"], src=src, group=self.pg)
+            for n in _BNS:
+                dist.broadcast(getattr(self.model, n).num_batches_tracked, src=src, group=self.pg)
+
+    def checkpoint_dict(self, epoch=0, **extra):
+        """Same dict layout as the reference writes to best_model.pth (pcs.py:373-382)."""
+        d = {"epoch": epoch, "model_state_dict": self.model.state_dict(),
+             "optimizer_state_dict": {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
+                                      "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay},
+             "num_classes": self.model.num_classes}
+        d.update(extra)
+        return d

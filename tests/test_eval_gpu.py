@@ -1,0 +1,90 @@
+"""Eval-mode forward of the CUDA path vs the numpy oracle and the reference-generated golden vectors."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointnet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# bf16 operands, fp32 accumulation: stated tolerance (north_star allows a looser bf16 bound)
+LOGIT_TOL_REL_TO_MAX = 2e-2
+ARGMAX_AGREE = 0.999
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "case_*.npz")))
+
+
+def _model(C, sd):
+    import pcseg_b200
+    m = pcseg_b200.PointNetSegmentation(C)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    return m.cuda().eval()
+
+
+def _argmax_agreement(got, ref):
+    """argmax agreement, not counting points whose top-2 reference logits are closer than the bf16 error bound."""
+    top2 = np.sort(ref, axis=-1)[..., -2:]
+    margin = top2[..., 1] - top2[..., 0]
+    decided = margin > 2 * LOGIT_TOL_REL_TO_MAX * np.abs(ref).max()
+    agree_all = (got.argmax(-1) == ref.argmax(-1)).mean()
+    agree_decided = (got.argmax(-1) == ref.argmax(-1))[decided].mean() if decided.any() else 1.0
+    return agree_all, agree_decided
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_eval_matches_golden(path):
+    gold = np.load(path)
+    C, seed = int(gold["C"]), int(gold["seed"])
+    sd = orc.synth_state(C, seed)
+    m = _model(C, sd)
+    with torch.no_grad():
+        got = m(torch.from_numpy(gold["x"]).cuda()).cpu().numpy()
+    ref = gold["eval_logits"]
+    assert got.shape == ref.shape
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < LOGIT_TOL_REL_TO_MAX, err
+    _, agree = _argmax_agreement(got, ref)
+    assert agree >= ARGMAX_AGREE
+
+
+@pytest.mark.parametrize("B,N,C", [(1, 16384, 5), (3, 1000, 3), (2, 129, 5), (5, 64, 8), (2, 4096, 5)])
+def test_eval_matches_oracle(B, N, C):
+    sd = orc.synth_state(C, 100 + B + N)
+    m = _model(C, sd)
+    rng = np.random.default_rng(N)
+    x = rng.random((B, N, 4), dtype=np.float32)
+    if N == 1000:
+        x[1, 700:] = 0.0     # zero-padded tail, as collate_fn would produce
+    with torch.no_grad():
+        logits, labels = m.predict(torch.from_numpy(x).cuda())
+    got = logits.cpu().numpy()
+    ref = orc.forward_eval(sd, x, dtype=np.float32)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < LOGIT_TOL_REL_TO_MAX, err
+    agree_all, agree = _argmax_agreement(got, ref)
+    assert agree >= ARGMAX_AGREE, (agree_all, agree)
+    assert (labels.cpu().numpy() == got.argmax(-1)).all()          # integer output: bit-exact vs own logits
+
+
+def test_eval_reprepares_after_weight_change():
+    C = 5
+    sd = orc.synth_state(C, 1)
+    m = _model(C, sd)
+    x = torch.rand(2, 256, 4, device="cuda")
+    with torch.no_grad():
+        a = m(x).clone()
+        m.seg_conv4.bias.add_(1.0)
+        b = m(x)
+    assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+
+
+def test_forward_rejects_bad_input():
+    import pcseg_b200
+    m = pcseg_b200.PointNetSegmentation(5).cuda().eval()
+    with pytest.raises(ValueError):
+        m(torch.rand(10, 4, device="cuda"))            # same tuple-unpack error as pcs.py:100
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 10, 4))                         # CPU tensor: no fallback

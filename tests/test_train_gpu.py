@@ -1,0 +1,172 @@
+"""Training forward / loss / backward / running statistics of the CUDA path vs the oracle (dropout p=0)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointnet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "case_*.npz")))
+LOGIT_TOL = 3e-2       # relative to max |logit| (bf16 activations through 10 layers with batch statistics)
+GRAD_TOL = 6e-2        # relative to max |grad| of the tensor
+GRAD_COS = 0.995       # cosine similarity of each gradient tensor
+
+
+def _model(C, sd):
+    import pcseg_b200
+    m = pcseg_b200.PointNetSegmentation(C)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    m = m.cuda().train()
+    m.dropout.p = 0.0
+    return m
+
+
+def _check_grads(named_grads, ref_grads, min_cos=GRAD_COS):
+    bad = []
+    for name, g in named_grads:
+        r = np.asarray(ref_grads[name], np.float64).reshape(g.shape)
+        g = g.astype(np.float64)
+        if name.endswith(".bias") and name.split(".")[0] in orc.CONV_NAMES[:-1]:
+            # mathematically zero (bias before train-mode BN); only require it to be tiny
+            other = np.abs(np.asarray(ref_grads[name.replace(".bias", ".weight")])).max()
+            if np.abs(g).max() > 5e-2 * other + 1e-6:
+                bad.append((name, "nonzero bias grad", np.abs(g).max()))
+            continue
+        scale = np.abs(r).max()
+        if scale < 1e-7:
+            if np.abs(g).max() > 1e-5:
+                bad.append((name, "expected ~0", np.abs(g).max()))
+            continue
+        err = np.abs(g - r).max() / scale
+        cos = float((g * r).sum() / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+        if err > GRAD_TOL or cos < min_cos:
+            bad.append((name, err, cos))
+    assert not bad, bad
+
+
+def _run_case(C, sd, x, labels, cw):
+    m = _model(C, sd)
+    xt = torch.from_numpy(x).cuda()
+    lt = torch.from_numpy(labels).cuda()
+    crit = torch.nn.CrossEntropyLoss(ignore_index=-1, weight=torch.from_numpy(cw).cuda())
+    logits = m(xt)
+    loss = crit(logits.contiguous().view(-1, C), lt.view(-1))      # exactly the reference call sequence, pcs.py:244-254
+    loss.backward()
+    return m, logits.detach().cpu().numpy(), float(loss.item())
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_train_step_matches_oracle_on_golden_inputs(path):
+    gold = np.load(path)
+    C, seed = int(gold["C"]), int(gold["seed"])
+    sd = orc.synth_state(C, seed)
+    x, labels, cw = gold["x"], gold["labels"], gold["class_w"]
+    m, logits, loss = _run_case(C, sd, x, labels, cw)
+
+    ref_logits, cache, newbuf = orc.forward_train(sd, x)
+    np.testing.assert_allclose(ref_logits, gold["train_logits"], atol=5e-5)     # oracle itself is pinned
+    err = np.abs(logits - ref_logits).max() / np.abs(ref_logits).max()
+    assert err < LOGIT_TOL, err
+    ref_loss, dlog = orc.weighted_ce(ref_logits, labels, cw)
+    assert abs(loss - ref_loss) < 1e-2 * abs(ref_loss)
+    assert abs(loss - float(gold["loss"])) < 1e-2 * abs(ref_loss)
+
+    grads = orc.backward(cache, dlog)
+    # B == 1 makes every gradient through the global branch mathematically zero -> skip cosine there
+    named = [(n, p.grad.detach().cpu().numpy()) for n, p in m.named_parameters()]
+    _check_grads(named, grads, min_cos=GRAD_COS if x.shape[0] > 1 else -1.0)
+
+    for name, buf in m.named_buffers():
+        if name.endswith("num_batches_tracked"):
+            assert int(buf.item()) == int(gold["buf/" + name])
+        else:
+            np.testing.assert_allclose(buf.cpu().numpy(), newbuf[name], rtol=2e-2, atol=2e-3, err_msg=name)
+
+
+@pytest.mark.parametrize("B,N,C", [(4, 512, 5), (2, 1000, 3), (8, 2048, 5)])
+def test_train_step_matches_oracle(B, N, C):
+    sd = orc.synth_state(C, 7 * B + N)
+    rng = np.random.default_rng(B * N)
+    x = rng.random((B, N, 4), dtype=np.float32)
+    labels = rng.integers(0, C, (B, N)).astype(np.int64)
+    if N == 1000:
+        x[0, 600:] = 0.0
+        labels[0, 600:] = -1
+    cw = (0.5 + rng.random(C)).astype(np.float32)
+    m, logits, loss = _run_case(C, sd, x, labels, cw)
+    ref_logits, cache, newbuf = orc.forward_train(sd, x)
+    err = np.abs(logits - ref_logits).max() / np.abs(ref_logits).max()
+    assert err < LOGIT_TOL, err
+    ref_loss, dlog = orc.weighted_ce(ref_logits, labels, cw)
+    assert abs(loss - ref_loss) < 1e-2 * abs(ref_loss)
+    grads = orc.backward(cache, dlog)
+    _check_grads([(n, p.grad.detach().cpu().numpy()) for n, p in m.named_parameters()], grads)
+
+
+def test_fused_trainer_matches_autograd_path():
+    """FusedTrainer (fused CE + backward + Adam) vs the autograd path + torch.optim.Adam on the same step."""
+    import pcseg_b200
+    C, B, N = 5, 4, 768
+    sd = orc.synth_state(C, 42)
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.random((B, N, 4), dtype=np.float32)).cuda()
+    labels = torch.from_numpy(rng.integers(-1, C, (B, N)).astype(np.int64)).cuda()
+    cw = torch.tensor([0.5, 1.0, 2.0, 0.75, 0.75], device="cuda")
+
+    m1 = _model(C, sd)
+    opt = torch.optim.Adam(m1.parameters(), lr=1e-3, weight_decay=1e-4)
+    crit = torch.nn.CrossEntropyLoss(ignore_index=-1, weight=cw)
+    opt.zero_grad()
+    out = m1(x)
+    loss1 = crit(out.contiguous().view(-1, C), labels.view(-1))
+    loss1.backward()
+    g1 = torch.cat([p.grad.reshape(-1) for p in m1._param_list()])
+    opt.step()
+
+    m2 = _model(C, sd)
+    tr = pcseg_b200.FusedTrainer(m2, class_weights=cw, lr=1e-3, weight_decay=1e-4)
+    res = tr.step(x, labels)
+    assert abs(float(res["loss"].item()) - float(loss1.item())) < 1e-4 * abs(float(loss1.item())) + 1e-5
+    g2 = tr.flat["grads"]
+    assert torch.allclose(g1, g2, rtol=1e-3, atol=1e-6 + 1e-3 * g1.abs().max().item())
+    p1 = torch.cat([p.detach().reshape(-1) for p in m1._param_list()])
+    p2 = tr.flat["params"]
+    # Adam normalises the step to ~lr, so compare parameters with an lr-sized tolerance
+    assert (p1 - p2).abs().max().item() < 2.5e-3
+    valid = int((labels >= 0).sum().item())
+    assert int(res["valid"].item()) == valid
+    pred = out.argmax(-1)
+    assert int(res["correct"].item()) == int(((pred == labels) & (labels >= 0)).sum().item())
+
+
+def test_dropout_statistics_and_determinism():
+    """p=0.3: kept fraction ~0.7 on the seg-head activations is not observable from outside, so check the
+    observable contract instead: training output differs from p=0, is finite, and backward runs."""
+    C, B, N = 5, 2, 1024
+    sd = orc.synth_state(C, 9)
+    m = _model(C, sd)
+    x = torch.rand(B, N, 4, device="cuda")
+    with torch.no_grad():
+        base = m(x).clone()
+    m.dropout.p = 0.3
+    torch.manual_seed(0)
+    out = m(x)
+    assert torch.isfinite(out).all()
+    assert (out.detach() - base).abs().max().item() > 1e-4
+    out.sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_backward_twice_is_rejected():
+    C = 3
+    m = _model(C, orc.synth_state(C, 2))
+    x = torch.rand(2, 128, 4, device="cuda")
+    a = m(x)
+    b = m(x)
+    b.sum().backward()
+    with pytest.raises(RuntimeError):
+        a.sum().backward()
