@@ -99,6 +99,24 @@ int pcseg_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 int pcseg_gemm_test(int layout, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                     void* D, int ldc, const float* bias, int block_n, void* stream);
 
+/* Test/inspection hook: copy one internal tensor of the bound TRAINING workspace into dst (device
+ * memory, dense row-major).  kind: 0 y (pre-BN conv output, bf16 [P][C]), 1 act (post BN+ReLU(+dropout),
+ * bf16), 2 dz (grad wrt BN output, bf16), 3 dy (grad wrt conv output, bf16), 4 bnp (float4 [C]:
+ * scale, shift, invstd, -mean*invstd), 5 coef (float4 [C] BN-backward coefficients), 6 forward stats
+ * (double [2][C]), 7 backward stats (double [2][C]), 8 g (float [B][1024] pooled feature), 9 ystar
+ * (float [B][1024] pre-BN extremum), 10 argidx (int32 [B][1024]), 11 cb (float [B][512]), 12 dcb
+ * (float [B][512]), 13 dzv (float [B][1024]).  layer = conv index 0..8 for kinds 0..7.
+ * rows/cols/elem_bytes describe what was copied. */
+int pcseg_debug_copy(pcseg_ctx* ctx, int kind, int layer, void* dst, long long dst_bytes, long long* rows,
+                     long long* cols, int* elem_bytes, void* stream);
+
+/* Per-kernel device timing (CUDA events on the launching stream) of the tcgen05 GEMMs of the training
+ * step, used by bench.py for the roofline.  tag = conv index (1..8) + 0 forward, + 16 data gradient,
+ * + 32 weight gradient.  pcseg_profile_read synchronises the device. */
+int pcseg_profile_enable(pcseg_ctx* ctx, int on);
+int pcseg_profile_read(pcseg_ctx* ctx, int tag, double* total_ms, long long* launches);
+int pcseg_profile_reset(pcseg_ctx* ctx);
+
 /* Number of kernels launched by this library since load (for the bench's gpu_launches claim). */
 long long pcseg_launch_count(void);
 

@@ -311,7 +311,24 @@ struct pcseg_ctx {
     unsigned long long seed = 0;
     unsigned int thr16 = 0;
     float keep_scale = 1.f;
+    // optional per-GEMM event timing
+    bool profiling = false;
+    struct Stamp { cudaEvent_t a, b; int tag; };
+    std::vector<Stamp> stamps;
 };
+
+static int timed_gemm(pcseg_ctx* c, const GemmOp& op, int tag, cudaStream_t s) {
+    if (!c->profiling) return launch_gemm(op, s);
+    pcseg_ctx::Stamp st;
+    st.tag = tag;
+    CUDA_OK(cudaEventCreate(&st.a));
+    CUDA_OK(cudaEventCreate(&st.b));
+    CUDA_OK(cudaEventRecord(st.a, s));
+    int r = launch_gemm(op, s);
+    CUDA_OK(cudaEventRecord(st.b, s));
+    c->stamps.push_back(st);
+    return r;
+}
 
 static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes_out) {
     Carver k(ws);
@@ -626,7 +643,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         TRY(bn_relu(0, 0, 0, 1.f));
     }
     for (int i = 1; i <= 5; ++i) {
-        TRY(launch_gemm(c->fw[i], s));
+        TRY(timed_gemm(c, c->fw[i], i, s));
         TRY(finalize(i));
         if (i < 5) TRY(bn_relu(i, 0, 0, 1.f));
     }
@@ -643,13 +660,13 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         k_cloud_bias<<<(warps * 32 + 255) / 256, 256, 0, s>>>(params + L.off[12] + 64, 1088, c->gmax, c->B, 512, 1024, nullptr, nullptr, c->cb);
         LAUNCH_OK("k_cloud_bias");
     }
-    TRY(launch_gemm(c->fw[6], s));
+    TRY(timed_gemm(c, c->fw[6], 6, s));
     TRY(finalize(6));
     TRY(bn_relu(6, seed + 1, c->thr16, c->keep_scale));
-    TRY(launch_gemm(c->fw[7], s));
+    TRY(timed_gemm(c, c->fw[7], 7, s));
     TRY(finalize(7));
     TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
-    TRY(launch_gemm(c->fw[8], s));
+    TRY(timed_gemm(c, c->fw[8], 8, s));
     TRY(finalize(8));
     {
         int grid = static_cast<int>((P + 7) / 8);
@@ -702,14 +719,14 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         GemmOp op = c->wg_op[i];
         op.p.out_f32 = dst;
         op.p.ldc = ldc;
-        return launch_gemm(op, s);
+        return timed_gemm(c, op, 32 + i, s);
     };
     auto dgrad = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         GemmOp op = c->dg[i];
         op.p.seed = sd;
         op.p.drop_thr16 = thr;
         op.p.keep_scale = ks;
-        return launch_gemm(op, s);
+        return timed_gemm(c, op, 16 + i, s);
     };
 
     if (phase != 2) {
@@ -827,4 +844,82 @@ extern "C" int pcseg_gemm_test(int layout, int M, int N, int K, const void* A, i
         return fail("pcseg_gemm_test: unknown layout %d", layout);
     }
     return launch_gemm(op, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// inspection hook for the layer-wise parity tests
+// ------------------------------------------------------------------------------------------------
+extern "C" int pcseg_debug_copy(pcseg_ctx* c, int kind, int layer, void* dst, long long dst_bytes, long long* rows, long long* cols,
+                                int* elem_bytes, void* stream) {
+    if (!c || !c->bound || !c->train) return fail("pcseg_debug_copy: context not bound in train mode");
+    if (kind <= 7 && (layer < 0 || layer >= NUM_BN)) return fail("pcseg_debug_copy: bad layer %d", layer);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const ConvDef* cv = c->L.conv;
+    const long long P = c->P, B = c->B;
+    const void* src = nullptr;
+    long long r = 0, cc = 0, src_pitch = 0;
+    int eb = 0;
+    switch (kind) {
+        case 0: src = c->y[layer]; r = P; cc = cv[layer].cout; eb = 2; break;
+        case 1: src = c->act[layer]; r = P; cc = cv[layer].cout; eb = 2; break;
+        case 2: src = c->dz[layer]; r = P; cc = cv[layer].cout; eb = 2; break;
+        case 3:
+            r = P; cc = cv[layer].cout; eb = 2;
+            if (layer == 2) { src = c->dycat; src_pitch = 576 * 2; }
+            else if (layer == 6) { src = c->dycat + 64; src_pitch = 576 * 2; }
+            else src = c->dy[layer];
+            break;
+        case 4: src = c->bnp[layer]; r = cv[layer].cout; cc = 4; eb = 4; break;
+        case 5: src = c->coef[layer]; r = cv[layer].cout; cc = 4; eb = 4; break;
+        case 6: src = c->stats_f + c->stat_off[layer]; r = 2; cc = cv[layer].cout; eb = 8; break;
+        case 7: src = c->stats_b + c->stat_off[layer]; r = 2; cc = cv[layer].cout; eb = 8; break;
+        case 8: src = c->gmax; r = B; cc = 1024; eb = 4; break;
+        case 9: src = c->ystar; r = B; cc = 1024; eb = 4; break;
+        case 10: src = c->argidx; r = B; cc = 1024; eb = 4; break;
+        case 11: src = c->cb; r = B; cc = 512; eb = 4; break;
+        case 12: src = c->dcb; r = B; cc = 512; eb = 4; break;
+        case 13: src = c->dzv; r = B; cc = 1024; eb = 4; break;
+        default: return fail("pcseg_debug_copy: unknown kind %d", kind);
+    }
+    if (!src) return fail("pcseg_debug_copy: tensor kind %d layer %d is not materialised", kind, layer);
+    if (rows) *rows = r;
+    if (cols) *cols = cc;
+    if (elem_bytes) *elem_bytes = eb;
+    const long long bytes = r * cc * eb;
+    if (!dst) return 0;      // size query
+    if (dst_bytes < bytes) return fail("pcseg_debug_copy: destination too small (%lld < %lld)", dst_bytes, bytes);
+    if (src_pitch) CUDA_OK(cudaMemcpy2DAsync(dst, cc * eb, src, src_pitch, cc * eb, r, cudaMemcpyDeviceToDevice, s));
+    else CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel event timing
+// ------------------------------------------------------------------------------------------------
+extern "C" int pcseg_profile_reset(pcseg_ctx* c) {
+    if (!c) return fail("pcseg_profile_reset: null ctx");
+    for (auto& st : c->stamps) { cudaEventDestroy(st.a); cudaEventDestroy(st.b); }
+    c->stamps.clear();
+    return 0;
+}
+extern "C" int pcseg_profile_enable(pcseg_ctx* c, int on) {
+    if (!c) return fail("pcseg_profile_enable: null ctx");
+    c->profiling = on != 0;
+    return 0;
+}
+extern "C" int pcseg_profile_read(pcseg_ctx* c, int tag, double* total_ms, long long* launches) {
+    if (!c) return fail("pcseg_profile_read: null ctx");
+    CUDA_OK(cudaDeviceSynchronize());
+    double tot = 0.0;
+    long long n = 0;
+    for (auto& st : c->stamps) {
+        if (st.tag != tag) continue;
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, st.a, st.b));
+        tot += ms;
+        ++n;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return 0;
 }

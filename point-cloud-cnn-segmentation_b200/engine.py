@@ -113,5 +113,42 @@ class Engine:
                                       betas[1], eps, weight_decay, grad_scale, self._stream()), "pcseg_adam_step")
 
 
+DEBUG_KINDS = {"y": 0, "act": 1, "dz": 2, "dy": 3, "bnp": 4, "coef": 5, "stats_f": 6, "stats_b": 7, "g": 8, "ystar": 9,
+               "argidx": 10, "cb": 11, "dcb": 12, "dzv": 13}
+
+
+def debug_tensor(engine, B, N, kind, layer=0):
+    """Copy an internal training-workspace tensor out (tests only): returns a torch tensor."""
+    b = engine.binding(B, N, True)
+    rows, cols, eb = C.c_longlong(), C.c_longlong(), C.c_int()
+    k = DEBUG_KINDS[kind]
+    check(lib.pcseg_debug_copy(b.handle, k, layer, None, 0, C.byref(rows), C.byref(cols), C.byref(eb), None), "pcseg_debug_copy")
+    dt = {2: torch.bfloat16, 8: torch.float64, 4: torch.int32 if kind == "argidx" else torch.float32}[eb.value]
+    out = torch.empty((rows.value, cols.value), dtype=dt, device=engine.device)
+    with torch.cuda.device(engine.device):
+        check(lib.pcseg_debug_copy(b.handle, k, layer, ptr(out), out.numel() * out.element_size(), None, None, None,
+                                   engine._stream()), "pcseg_debug_copy")
+    return out
+
+
+def profile_enable(engine, B, N, on=True):
+    b = engine.binding(B, N, True)
+    check(lib.pcseg_profile_reset(b.handle))
+    check(lib.pcseg_profile_enable(b.handle, int(on)))
+
+
+def profile_read(engine, B, N):
+    """{tag: (total_ms, launches)} for the GEMMs of the training step (tags: conv index + 0/16/32 = fwd/dgrad/wgrad)."""
+    b = engine.binding(B, N, True)
+    out = {}
+    for base in (0, 16, 32):
+        for i in range(1, 9):
+            ms, n = C.c_double(), C.c_longlong()
+            check(lib.pcseg_profile_read(b.handle, base + i, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[base + i] = (ms.value, n.value)
+    return out
+
+
 def launch_count():
     return int(lib.pcseg_launch_count())

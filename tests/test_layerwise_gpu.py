@@ -1,0 +1,212 @@
+"""Kernel-by-kernel parity of the training path: every CUDA step is recomputed in fp64 by
+oracle/layerwise.py FROM THE TENSORS THE CUDA PATH PRODUCED for the previous step, so each kernel is
+compared on identical inputs (see the module docstring of oracle/layerwise.py for why end-to-end
+comparison alone cannot be tight in train mode).  Integer outputs (arg-max indices, counts) must be
+bit-exact; bf16 tensors must match to one bf16 rounding; fp32/fp64 reductions to ~1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import layerwise as lw
+from oracle import pointnet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CONVS = ["conv1", "conv2", "conv3", "conv4", "conv5", "global_feat", "seg_conv1", "seg_conv2", "seg_conv3", "seg_conv4"]
+BNS = ["bn1", "bn2", "bn3", "bn4", "bn5", "bn_global", "bn_seg1", "bn_seg2", "bn_seg3"]
+
+
+def _np(t):
+    return t.detach().to(torch.float64).cpu().numpy() if t.dtype != torch.int32 else t.cpu().numpy()
+
+
+def _close_bf16(got, ref, what):
+    """got is a bf16 tensor produced by a kernel that rounded ref-like fp32 values: allow one rounding step."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    rms = np.sqrt((ref * ref).mean()) + 1e-30
+    tol = 2.0 ** -7 * np.abs(ref) + 2e-3 * rms
+    bad = np.abs(got - ref) > tol
+    assert bad.mean() < 1e-4, (what, float(bad.mean()), float(np.abs(got - ref).max()), float(rms))
+
+
+def _close_red(got, ref, what, rel=2e-4):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = np.abs(ref).max() + 1e-30
+    assert np.abs(got - ref).max() <= rel * scale + 1e-9, (what, float(np.abs(got - ref).max()), float(scale))
+
+
+def _diverse_clouds(B, N, rng):
+    xs = []
+    for _ in range(B):
+        k = rng.integers(2, 6)
+        cen, sc = rng.random((k, 4)), 0.02 + 0.25 * rng.random((k, 4))
+        idx = rng.integers(0, k, N)
+        p = cen[idx] + sc[idx] * rng.standard_normal((N, 4))
+        p[:, 3] = np.abs(p[:, 3]) * (0.2 + 2 * rng.random())
+        xs.append(np.clip(p, -0.5, 2.0))
+    return np.stack(xs).astype(np.float32)
+
+
+@pytest.mark.parametrize("B,N,C,p_drop", [(3, 500, 5, 0.0), (4, 1024, 3, 0.3), (2, 200, 8, 0.0)])
+def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop):
+    import pcseg_b200
+    from pcseg_b200.engine import debug_tensor
+
+    P = B * N
+    sd = orc.synth_state(C, 1000 + N)
+    rng = np.random.default_rng(N + C)
+    x = _diverse_clouds(B, N, rng)
+    labels = rng.integers(0, C, (B, N)).astype(np.int64)
+    x[0, N - N // 5:] = 0.0                                # zero-padded tail with ignored labels (pcs.py:53-61)
+    labels[0, N - N // 5:] = -1
+    cw = (0.5 + rng.random(C)).astype(np.float32)
+
+    m = pcseg_b200.PointNetSegmentation(C)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    m = m.cuda().train()
+    m.dropout.p = p_drop
+    dev = torch.device("cuda", torch.cuda.current_device())
+    f = m._ensure_flat(dev)
+    eng = m._get_engine(dev)
+    xt, lt, cwt = torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(cw).cuda()
+    ce = torch.zeros(32, dtype=torch.uint8, device=dev)
+    logits = m._run_train_forward(xt, labels=lt, class_w=cwt, ce=ce)
+    wsum_t = ce.view(torch.float64)[1:2].clone()
+    eng.backward(xt, f["params"], f["grads"], logits=logits, labels=lt, class_w=cwt, wsum=wsum_t)
+    torch.cuda.synchronize()
+    grads = {n: g.detach().cpu().numpy().astype(np.float64) for (n, _), g in zip(m.named_parameters(), m.grad_views())}
+
+    def T(kind, layer=0):
+        return _np(debug_tensor(eng, B, N, kind, layer))
+
+    W = {c: sd[f"{c}.weight"][:, :, 0].astype(np.float64) for c in CONVS}
+    keep_scale = 1.0
+    if p_drop > 0:
+        thr = int(p_drop * 65536 + 0.5)
+        keep_scale = 1.0 / (1.0 - thr / 65536.0)
+
+    # ---------------------------------------------------------------- forward
+    y, act, bnp = {}, {}, {}
+    xin = x.reshape(P, 4).astype(np.float64)
+    keeps = {}
+    for i in range(9):
+        y[i] = T("y", i)
+        bnp[i] = T("bnp", i)
+        if i == 0:
+            ref = lw.conv_pre_bn(xin, W["conv1"], weights_bf16=False)                      # pcs.py:106
+        elif i == 6:
+            cb = T("cb")
+            ref = lw.conv_pre_bn(act[1], W["seg_conv1"][:, :64], cloud_bias=cb, pts_per_cloud=N)   # pcs.py:117-123
+        else:
+            ref = lw.conv_pre_bn(act[i - 1], W[CONVS[i]])                                   # pcs.py:107-127
+        _close_bf16(y[i], ref, f"y[{CONVS[i]}]")
+        st = lw.bn_batch_stats(y[i])
+        _close_red(T("stats_f", i), st, f"stats_f[{BNS[i]}]")
+        _close_red(bnp[i], lw.bn_params(st, P, sd[f"{BNS[i]}.weight"], sd[f"{BNS[i]}.bias"]), f"bnp[{BNS[i]}]", rel=1e-4)
+        rm, rv = lw.running_stats(st, P, sd[f"{CONVS[i]}.bias"].astype(np.float64), sd[f"{BNS[i]}.running_mean"].astype(np.float64),
+                                  sd[f"{BNS[i]}.running_var"].astype(np.float64))
+        bn_mod = getattr(m, BNS[i])
+        _close_red(_np(bn_mod.running_mean), rm, f"{BNS[i]}.running_mean", rel=1e-5)
+        _close_red(_np(bn_mod.running_var), rv, f"{BNS[i]}.running_var", rel=1e-5)
+        assert int(bn_mod.num_batches_tracked.item()) == int(sd[f"{BNS[i]}.num_batches_tracked"]) + 1
+        if i in (5, 8):
+            continue                     # global_feat feeds the max-pool, seg_conv3 feeds the head kernel
+        act[i] = T("act", i)
+        relu_out, _ = lw.bn_relu(y[i], bnp[i])
+        if i in (6, 7) and p_drop > 0:
+            keep = (act[i] != 0).astype(np.float64)
+            live = relu_out > 1e-3
+            frac = 1.0 - keep[live].mean()
+            assert abs(frac - p_drop) < 0.01, (BNS[i], frac)
+            keeps[i] = keep
+            _close_bf16(act[i], relu_out * keep * keep_scale, f"act[{CONVS[i]}] (dropout)")
+        else:
+            _close_bf16(act[i], relu_out, f"act[{CONVS[i]}]")
+
+    g_ref, ystar_ref, arg_ref = lw.maxpool(y[5], bnp[5], B, N)                              # pcs.py:114
+    assert np.array_equal(T("argidx"), arg_ref), "max-pool arg indices must be bit-exact"
+    assert np.array_equal(T("ystar"), ystar_ref), "max-pool extremum values must be bit-exact"
+    _close_red(T("g"), g_ref, "pooled feature", rel=1e-5)
+    g = T("g")
+    _close_red(T("cb"), g @ W["seg_conv1"][:, 64:].T, "per-cloud seg_conv1 term", rel=1e-4)
+
+    lg = logits.detach().cpu().numpy().astype(np.float64).reshape(P, C)
+    lg_ref, a_s3 = lw.head_logits(y[8], bnp[8], W["seg_conv4"], sd["seg_conv4.bias"])       # pcs.py:127-131
+    _close_red(lg, lg_ref, "logits", rel=1e-4)
+
+    dl, loss_num, wsum = lw.ce_grad(lg, labels, cw, float(wsum_t.item()))                    # pcs.py:216,251
+    cef = ce.view(torch.float64).cpu().numpy()
+    cei = ce.view(torch.int64).cpu().numpy()
+    assert abs(cef[1] - wsum) <= 1e-9 * wsum
+    assert abs(cef[0] - loss_num) <= 1e-5 * abs(loss_num)
+    valid = labels.reshape(-1) >= 0
+    assert int(cei[3]) == int(valid.sum())                                                   # integer outputs: exact
+    assert int(cei[2]) == int(((lg.argmax(1) == labels.reshape(-1)) & valid).sum())          # pcs.py:261-264
+
+    # ---------------------------------------------------------------- backward
+    dz, dy = {}, {}
+    _close_red(grads["seg_conv4.weight"][:, :, 0], dl.T @ a_s3, "dW seg_conv4", rel=3e-4)
+    _close_red(grads["seg_conv4.bias"], dl.sum(0), "db seg_conv4", rel=3e-4)
+    dz[8] = T("dz", 8)
+    t8 = np.float32(bnp[8][:, 0]) * y[8].astype(np.float32) + np.float32(bnp[8][:, 1])
+    _close_bf16(dz[8], (dl @ W["seg_conv4"]) * (t8 > 0), "dz[seg_conv3]")
+
+    def bn_backward(i, sparse=None):
+        sb = T("stats_b", i)
+        dz_i = sparse if sparse is not None else dz[i]
+        _close_red(sb, lw.bn_bwd_stats(dz_i, y[i], bnp[i]), f"stats_b[{BNS[i]}]", rel=3e-4)
+        _close_red(grads[f"{BNS[i]}.weight"], sb[1], f"dgamma {BNS[i]}", rel=1e-5)
+        _close_red(grads[f"{BNS[i]}.bias"], sb[0], f"dbeta {BNS[i]}", rel=1e-5)
+        coef = T("coef", i)[:, :3]
+        _close_red(coef, lw.bn_bwd_coef(sb, P, bnp[i]), f"coef[{BNS[i]}]", rel=1e-4)
+        dy[i] = T("dy", i)
+        _close_bf16(dy[i], lw.bn_bwd_apply(dz_i, y[i], coef), f"dy[{CONVS[i]}]")
+        # conv bias gradient = column sum of dy: mathematically ~0 behind train-mode BN; compare as a reduction
+        ref_db = dy[i].sum(0)
+        assert np.abs(grads[f"{CONVS[i]}.bias"] - ref_db).max() <= 1e-3 * np.abs(dy[i]).sum(0).max() + 1e-7
+
+    # seg_conv3 / seg_conv2
+    bn_backward(8)
+    _close_red(grads["seg_conv3.weight"][:, :, 0], lw.wgrad(dy[8], act[7]), "dW seg_conv3", rel=3e-4)
+    dz[7] = T("dz", 7)
+    _close_bf16(dz[7], lw.dgrad_masked(dy[8], W["seg_conv3"], y[7], bnp[7], keeps.get(7), keep_scale), "dz[seg_conv2]")
+    bn_backward(7)
+    _close_red(grads["seg_conv2.weight"][:, :, 0], lw.wgrad(dy[7], act[6]), "dW seg_conv2", rel=3e-4)
+    dz[6] = T("dz", 6)
+    _close_bf16(dz[6], lw.dgrad_masked(dy[7], W["seg_conv2"], y[6], bnp[6], keeps.get(6), keep_scale), "dz[seg_conv1]")
+    # seg_conv1: point-feature columns + per-cloud global columns (cat / repeat / max backward, pcs.py:114-120)
+    bn_backward(6)
+    dW1 = grads["seg_conv1.weight"][:, :, 0]
+    _close_red(dW1[:, :64], lw.wgrad(dy[6], act[1]), "dW seg_conv1[:, :64]", rel=3e-4)
+    dcb_ref = dy[6].reshape(B, N, -1).sum(1)
+    _close_red(T("dcb"), dcb_ref, "dcb", rel=1e-3)
+    dcb = T("dcb")
+    _close_red(dW1[:, 64:], dcb.T @ g, "dW seg_conv1[:, 64:]", rel=1e-4)
+    dzv_ref = (dcb @ W["seg_conv1"][:, 64:]) * (g > 0)
+    _close_red(T("dzv"), dzv_ref, "max-pool routed gradient", rel=1e-4)
+    dzv = T("dzv")
+    arg = T("argidx")
+    dz6 = np.zeros((B, N, 1024))
+    np.put_along_axis(dz6, arg[:, None, :].astype(np.int64), dzv[:, None, :], axis=1)
+    bn_backward(5, sparse=dz6.reshape(P, 1024))
+    _close_red(grads["global_feat.weight"][:, :, 0], lw.wgrad(dy[5], act[4]), "dW global_feat", rel=3e-4)
+    dz[4] = T("dz", 4)
+    _close_bf16(dz[4], lw.dgrad_masked(dy[5], W["global_feat"], y[4], bnp[4]), "dz[conv5]")
+    for i, prev in ((4, 3), (3, 2)):
+        bn_backward(i)
+        _close_red(grads[f"{CONVS[i]}.weight"][:, :, 0], lw.wgrad(dy[i], act[prev]), f"dW {CONVS[i]}", rel=3e-4)
+        dz[prev] = T("dz", prev)
+        _close_bf16(dz[prev], lw.dgrad_masked(dy[i], W[CONVS[i]], y[prev], bnp[prev]), f"dz[{CONVS[prev]}]")
+    # conv3, then the skip join into point_feat (pcs.py:107,120): both contributions in one accumulator
+    bn_backward(2)
+    _close_red(grads["conv3.weight"][:, :, 0], lw.wgrad(dy[2], act[1]), "dW conv3", rel=3e-4)
+    dz[1] = T("dz", 1)
+    da_join = dy[2] @ lw.bf16_round(W["conv3"]) + dy[6] @ lw.bf16_round(W["seg_conv1"][:, :64])
+    t1 = np.float32(bnp[1][:, 0]) * y[1].astype(np.float32) + np.float32(bnp[1][:, 1])
+    _close_bf16(dz[1], da_join * (t1 > 0), "dz[conv2] (skip join)")
+    bn_backward(1)
+    _close_red(grads["conv2.weight"][:, :, 0], lw.wgrad(dy[1], act[0]), "dW conv2", rel=3e-4)
+    dz[0] = T("dz", 0)
+    _close_bf16(dz[0], lw.dgrad_masked(dy[1], W["conv2"], y[0], bnp[0]), "dz[conv1]")
+    bn_backward(0)
+    _close_red(grads["conv1.weight"][:, :, 0], lw.wgrad(dy[0], xin), "dW conv1", rel=3e-4)
