@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the point-cloud segmentation hot path (BASELINE.json metric: segmentation points/sec,
+fwd+bwd training step).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg3_train|cfg2_eval|cfg3_eval]
+
+One "step" = one full training step (forward with batch statistics and dropout p=0.3, weighted
+cross-entropy, backward of all 38 parameter tensors, NCCL gradient all-reduce when N > 1, Adam) on one
+batch of synthetic clouds.  N = 1 workload: BASELINE.json configs[1] = batch 8 x 16 384 points, C = 5.
+N > 1: every rank runs that batch on its own clouds (weak scaling, data parallel).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (clouds per rank, points per cloud, mode)
+    "cfg2": (8, 16384, "train"),
+    "cfg3_train": (16, 131072, "train"),
+    "cfg2_eval": (8, 16384, "eval"),
+    "cfg3_eval": (16, 131072, "eval"),
+}
+NUM_CLASSES = 5
+DROPOUT_P = 0.3
+# algorithmic FLOPs per point: fwd 2*(1 392 896 + 128 C); fwd+bwd = 3x fwd - 512
+FWD_FLOP_PER_PT = 2 * (1392896 + 128 * NUM_CLASSES)
+TRAIN_FLOP_PER_PT = 3 * FWD_FLOP_PER_PT - 512
+GFEAT_FLOP_PER_PT = 2 * 1024 * 1024          # one global_feat GEMM (forward, dgrad or wgrad), per point
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(B, N, C, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.random((B, N, 4), dtype=np.float32)               # xyz,e ~ U[0,1)
+    labels = rng.integers(0, C, (B, N)).astype(np.int64)
+    return x, labels
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the numpy oracle (port of the reference algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(mode, C):
+    import torch
+    from oracle.torch_port import TorchCpuPort
+    port = TorchCpuPort(C, seed=1234, threads=os.cpu_count())
+    cw = torch.ones(C)
+
+    def train_step(x, labels):
+        return port.train_step(torch.from_numpy(x), torch.from_numpy(labels), cw, DROPOUT_P)
+
+    def eval_step(x, labels):
+        return port.eval_step(torch.from_numpy(x))
+
+    return train_step if mode == "train" else eval_step
+
+
+def time_cpu(mode, B, N, C, steps, warmup, budget_s):
+    """Times the oracle port on a bounded sample of the workload (whole clouds of the same size when they fit
+    the budget, otherwise shorter clouds); returns points/s and a description of the sample."""
+    step = cpu_step_fn(mode, C)
+    xs, ls = synth_batch(1, 2048, C, 99)
+    t0 = time.perf_counter()
+    step(xs, ls)
+    step(xs, ls)
+    per_pt = (time.perf_counter() - t0) / 2 / 2048
+    total_steps = steps + warmup
+    pts_budget = max(2048, int(budget_s / max(per_pt, 1e-9) / max(total_steps, 1)))
+    if pts_budget >= N:
+        b, n = max(1, min(B, pts_budget // N)), N
+    else:
+        b, n = 1, max(2048, (pts_budget // 1024) * 1024)
+    x, lab = synth_batch(b, n, C, 5)
+    for _ in range(warmup):
+        step(x, lab)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(x, lab)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return b * n / dt, dt * 1e3, f"{b} cloud(s) x {n} points per step ({steps} timed steps, torch-CPU fp32 port of the reference step, all host threads, {mode})"
+
+
+def run_reference(args, B, N, mode):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    warmup = max(0, min(args.warmup, 3))
+    value, ms, sample = time_cpu(mode, B, N, NUM_CLASSES, steps, warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": metric_name(mode), "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_desc(args.workload, B, N, mode), "num_classes": NUM_CLASSES},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def metric_name(mode):
+    return "segmentation points/sec (fwd+bwd train step)" if mode == "train" else "segmentation points/sec (fwd inference)"
+
+
+def workload_desc(name, B, N, mode):
+    return f"{name}: {mode} step, batch {B} x {N} points per GPU, C={NUM_CLASSES}, dropout {DROPOUT_P if mode == 'train' else 0}"
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU leg
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, B, N, mode):
+    import torch
+    import torch.distributed as dist
+
+    import pcseg_b200
+    from pcseg_b200.engine import profile_enable, profile_read
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    C = NUM_CLASSES
+    torch.manual_seed(1234)                        # same random-init weights on every rank
+    model = pcseg_b200.PointNetSegmentation(C).to(dev)
+    x_np, lab_np = synth_batch(B, N, C, 100 + rank)
+    x_host = torch.from_numpy(x_np).pin_memory()
+    lab_host = torch.from_numpy(lab_np).pin_memory()
+    x_dev = x_host.to(dev)
+    lab_dev = lab_host.to(dev)
+    cw = torch.ones(C, device=dev)
+
+    if mode == "train":
+        model.train()
+        trainer = pcseg_b200.FusedTrainer(model, class_weights=cw, lr=1e-3, weight_decay=1e-4, device=dev)
+
+        def step_resident():
+            return trainer.step(x_dev, lab_dev)["loss"]
+
+        def step_e2e():
+            xd = x_host.to(dev, non_blocking=True)
+            ld = lab_host.to(dev, non_blocking=True)
+            return float(trainer.step(xd, ld)["loss"].item())          # D2H read of the loss every step (pcs.py:258)
+        h2d = x_host.numel() * 4 + lab_host.numel() * 8
+        d2h = 8
+        flop_per_pt = TRAIN_FLOP_PER_PT
+    else:
+        model.eval()
+
+        def step_resident():
+            with torch.no_grad():
+                return model(x_dev)
+
+        out_host = torch.empty((B, N), dtype=torch.int64).pin_memory()
+
+        def step_e2e():
+            xd = x_host.to(dev, non_blocking=True)
+            with torch.no_grad():
+                _, labels = model.predict(xd)
+            out_host.copy_(labels, non_blocking=True)                   # per-point predicted labels back to the host (pcs.py:452-454)
+            torch.cuda.synchronize()
+            return out_host
+        h2d = x_host.numel() * 4
+        d2h = B * N * 8
+        flop_per_pt = FWD_FLOP_PER_PT
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+    for _ in range(warmup):
+        step_resident()
+    barrier()
+
+    eng = model._get_engine(dev)
+    if mode == "train":
+        profile_enable(eng, B, N, True)
+    sampler = ClockSampler(local_rank)
+    launches0 = pcseg_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = pcseg_b200.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    prof = profile_read(eng, B, N) if mode == "train" else {}
+    if mode == "train":
+        profile_enable(eng, B, N, False)
+
+    # end-to-end: pinned host inputs copied every step, result read back every step
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pts_per_step = B * N * world
+    ms_per_step = ms_total / steps
+    value = pts_per_step / (ms_per_step * 1e-3)
+    e2e_value = pts_per_step / (e2e_ms_total / steps * 1e-3)
+    peaks = measured_peaks()
+
+    roof = None
+    kernels = {}
+    if prof:
+        names = {5: "global_feat fwd GEMM (1024x1024, stats epilogue)", 21: "global_feat dgrad GEMM (mask+stats epilogue)",
+                 37: "global_feat wgrad GEMM (MN-major, split-K)"}
+        for tag, (ms, n) in prof.items():
+            kernels[str(tag)] = {"ms_per_launch": ms / n, "launches": n}
+        tag = max((5, 21, 37), key=lambda tg: prof.get(tg, (0, 1))[0])
+        ms, n = prof[tag]
+        achieved = GFEAT_FLOP_PER_PT * B * N / (ms / n * 1e-3) / 1e12
+        share = sum(prof.get(tg, (0, 1))[0] for tg in (5, 21, 37)) / ms_total
+        roof = {"bound": "tensor", "kernel": names[tag], "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                "ms_per_launch": ms / n, "global_feat_gemms_share_of_step": share}
+    step_tflops = flop_per_pt * B * N / (ms_per_step * 1e-3) / 1e12        # per GPU
+
+    cores = os.cpu_count() or 1
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        cpu_value, _, cpu_sample = time_cpu(mode, B, N, C, steps=2, warmup=1, budget_s=8.0)
+        cpu = {"value": cpu_value, "unit": "points/s", "cores": cores, "kind": "port", "sample": cpu_sample}
+    else:
+        cpu = None
+
+    line = {
+        "metric": metric_name(mode), "value": value, "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_desc(args.workload, B, N, mode), "num_classes": C, "l2_policy": "working set (GBs of activations) >> 126 MB L2, no flush needed",
+                   "optimizer": "Adam lr 1e-3 wd 1e-4 (inside the timed step)" if mode == "train" else None,
+                   "parallelism": f"dp{world}" if world > 1 else "single"},
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_total / steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
+        "gemm_kernels": kernels,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    B, N, mode = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, B, N, mode)
+    else:
+        run_ours(args, B, N, mode)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,7 +5,7 @@
 //   warp 0      : TMA producer (A and B tiles, 128B-swizzled, mbarrier complete_tx)
 //   warp 1      : MMA issuer   (one lane issues tcgen05.mma, tcgen05.commit frees smem stages)
 //   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue     (tcgen05.ld -> fused math -> swizzled smem -> TMA store / reductions)
+//   warps 4..11 : epilogue     (tcgen05.ld -> fused math -> swizzled smem -> TMA store / reductions)
 //
 // Operand layouts:
 //   MN == false : A is [M x K] row-major (K contiguous), B is [N x K] row-major  (forward, dgrad)
@@ -27,7 +27,9 @@ enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EP
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 128 + EPI_THREADS;
 constexpr int MAX_CLASSES = 8;    // compile-time cap on num_classes for the fused head kernels
 
 struct GemmParams {
@@ -136,7 +138,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&tmem_empty[i], EPI_THREADS);
             mbar_init(&y_full[i], 1);
         }
         fence_barrier_init();
@@ -237,10 +239,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
         }
     } else if (warp_idx >= 4) {
-        // ------------------------------------------------------------ epilogue
-        const int ew = warp_idx - 4;                  // == warp_idx % 4 -> TMEM lane quadrant
+        // ------------------------------------------------------------ epilogue (8 warps)
+        // warp w reads TMEM lanes 32*(w%4)..+31 (hardware restriction); the two warps of a lane quadrant split
+        // every 64-column sub-tile into its left / right 32 columns.
+        const int ew = warp_idx & 3;                  // TMEM lane quadrant == row group
+        const int half = (warp_idx - 4) >> 2;         // 0: columns 0..31 of each sub-tile, 1: columns 32..63
         const int row = ew * 32 + lane;               // row inside the tile
-        const int et = threadIdx.x - 128;             // 0..127
+        const int et = threadIdx.x - 128;             // 0..255
         const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
         const bool elected = (et == 0);
         int iter = 0;
@@ -281,7 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int kb0 = split * p.kb_per_split;
                 const bool nonempty = kb0 < (p.K + GEMM_BK - 1) / GEMM_BK;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = half; c < BN / 32; c += 2) {
                     uint32_t v[32];
                     tmem_ld_32x32(t_acc + c * 32, v);
                     tmem_ld_wait();
@@ -309,7 +314,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int k = 0; k < MAX_CLASSES; ++k) lg[k] = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = half; c < BN / 32; c += 2) {
                     uint32_t v[32];
                     tmem_ld_32x32(t_acc + c * 32, v);
                     tmem_ld_wait();
@@ -324,11 +329,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 tc_fence_before();
                 mbar_arrive(&tmem_empty[acc]);
-                if (valid) {
+                // combine the two column halves through shared memory: comb[row][class]
+                named_bar_sync(1, EPI_THREADS);       // previous tile's readers are done with comb
+                if (half == 1) {
+#pragma unroll
+                    for (int k = 0; k < MAX_CLASSES; ++k) comb[row * MAX_CLASSES + k] = lg[k];
+                }
+                named_bar_sync(1, EPI_THREADS);
+                if (half == 0 && valid) {
                     float* dst = p.logits + static_cast<size_t>(grow) * p.num_classes;
 #pragma unroll
                     for (int k = 0; k < MAX_CLASSES; ++k)
-                        if (k < p.num_classes) dst[k] = lg[k] + w4s[MAX_CLASSES * 128 + k];
+                        if (k < p.num_classes) dst[k] = lg[k] + comb[row * MAX_CLASSES + k] + w4s[MAX_CLASSES * 128 + k];
                 }
             } else {
                 const int cloud = (p.pts_per_cloud > 0 && valid) ? grow / p.pts_per_cloud : 0;
@@ -341,123 +353,118 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
                 for (int sub = 0; sub < SUBS; ++sub, ++sub_it) {
                     const int buf = sub_it & 1;
-                    const int c0 = n0 + sub * 64;        // first global column of this sub-tile
+                    const int c0 = n0 + sub * 64 + half * 32;     // first global column handled by this thread
                     float* comb_b = comb + buf * (2 * 4 * 64);
                     if constexpr (Cfg::HAS_Y) mbar_wait(&y_full[buf], (sub_it >> 1) & 1);
-                    uint32_t packed[32];
+                    uint32_t packed[16];
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + sub * 64 + half * 32, v);
+                    tmem_ld_wait();
+                    if (sub == SUBS - 1) {       // all TMEM reads of this accumulator (by this thread) are done
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                    float o[32];
+                    if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_acc + sub * 64 + h * 32, v);
-                        tmem_ld_wait();
-                        float o[32];
-                        if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int col = c0 + h * 32 + i;
-                                float x = __uint_as_float(v[i]) + __ldg(p.bias + col);
-                                if (cb_row) x += __ldg(cb_row + col);
-                                o[i] = valid ? fmaxf(x, 0.f) : 0.f;
-                            }
-                            if constexpr (EPI == EPI_COLMAX) {
-                                if (uniform_cloud) {
-                                    float r = warp_colreduce32<true>(o);
-                                    comb_b[ew * 64 + h * 32 + lane] = r;
-                                } else if (valid) {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i)
-                                        atomicMax(p.colmax + static_cast<size_t>(cloud) * p.N + c0 + h * 32 + i,
-                                                  __float_as_uint(o[i]));
-                                }
-                            }
-                        } else if constexpr (EPI == EPI_STATS) {
-                            float sq[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int col = c0 + h * 32 + i;
-                                float x = __uint_as_float(v[i]);
-                                if (cb_row) x += __ldg(cb_row + col);
-                                x = valid ? round_bf16(x) : 0.f;
-                                o[i] = x;
-                                sq[i] = x * x;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) packed[h * 16 + i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
-                            float s1 = warp_colreduce32<false>(o);
-                            float s2 = warp_colreduce32<false>(sq);
-                            comb_b[ew * 64 + h * 32 + lane] = s1;
-                            comb_b[4 * 64 + ew * 64 + h * 32 + lane] = s2;
-                        } else if constexpr (EPI == EPI_DGRAD) {
-                            float q[32];
-                            const uint8_t* yrow = y_stage + buf * 16384 + row * 128;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 columns
-                                const int chunk = h * 4 + j;
-                                const uint4 yw = *reinterpret_cast<const uint4*>(yrow + ((chunk ^ (row & 7)) << 4));
-                                const uint32_t yws[4] = {yw.x, yw.y, yw.z, yw.w};
-                                uint32_t keep = 0xFFu;
-                                if (p.drop_thr16 != 0u) {
-                                    const unsigned long long e = static_cast<unsigned long long>(grow) * p.N + (c0 + chunk * 8);
-                                    keep = dropout_keep8(p.seed, e >> 3, p.drop_thr16);
-                                }
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const int i = j * 8 + e;
-                                    const int col = c0 + h * 32 + i;
-                                    const float4 bp = __ldg(p.bnp + col);
-                                    const float y = (e & 1) ? bf16_hi(yws[e >> 1]) : bf16_lo(yws[e >> 1]);
-                                    const float t = fmaf(bp.x, y, bp.y);
-                                    const bool on = valid && (t > 0.f) && ((keep >> e) & 1u);
-                                    float dz = on ? __uint_as_float(v[i]) * p.keep_scale : 0.f;
-                                    dz = round_bf16(dz);
-                                    o[i] = dz;
-                                    q[i] = dz * fmaf(bp.z, y, bp.w);
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) packed[h * 16 + i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
-                            float s1 = warp_colreduce32<false>(o);
-                            float s2 = warp_colreduce32<false>(q);
-                            comb_b[ew * 64 + h * 32 + lane] = s1;
-                            comb_b[4 * 64 + ew * 64 + h * 32 + lane] = s2;
+                        for (int i = 0; i < 32; ++i) {
+                            float x = __uint_as_float(v[i]) + __ldg(p.bias + c0 + i);
+                            if (cb_row) x += __ldg(cb_row + c0 + i);
+                            o[i] = valid ? fmaxf(x, 0.f) : 0.f;
                         }
                         if constexpr (EPI == EPI_BIAS_RELU) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) packed[h * 16 + i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                            for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                        } else {
+                            if (uniform_cloud) {
+                                float r = warp_colreduce32<true>(o);
+                                comb_b[ew * 64 + half * 32 + lane] = r;
+                            } else if (valid) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    atomicMax(p.colmax + static_cast<size_t>(cloud) * p.N + c0 + i, __float_as_uint(o[i]));
+                            }
                         }
-                    }
-                    if (sub == SUBS - 1) {       // all TMEM reads of this accumulator are done
-                        tc_fence_before();
-                        mbar_arrive(&tmem_empty[acc]);
+                    } else if constexpr (EPI == EPI_STATS) {
+                        float sq[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x = __uint_as_float(v[i]);
+                            if (cb_row) x += __ldg(cb_row + c0 + i);
+                            x = valid ? round_bf16(x) : 0.f;
+                            o[i] = x;
+                            sq[i] = x * x;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                        float s1 = warp_colreduce32<false>(o);
+                        float s2 = warp_colreduce32<false>(sq);
+                        comb_b[ew * 64 + half * 32 + lane] = s1;
+                        comb_b[4 * 64 + ew * 64 + half * 32 + lane] = s2;
+                    } else if constexpr (EPI == EPI_DGRAD) {
+                        float q[32];
+                        const uint8_t* yrow = y_stage + buf * 16384 + row * 128;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 columns
+                            const int chunk = half * 4 + j;
+                            const uint4 yw = *reinterpret_cast<const uint4*>(yrow + ((chunk ^ (row & 7)) << 4));
+                            const uint32_t yws[4] = {yw.x, yw.y, yw.z, yw.w};
+                            uint32_t keep = 0xFFu;
+                            if (p.drop_thr16 != 0u) {
+                                const unsigned long long e = static_cast<unsigned long long>(grow) * p.N + (c0 + j * 8);
+                                keep = dropout_keep8(p.seed, e >> 3, p.drop_thr16);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int i = j * 8 + e;
+                                const float4 bp = __ldg(p.bnp + c0 + i);
+                                const float y = (e & 1) ? bf16_hi(yws[e >> 1]) : bf16_lo(yws[e >> 1]);
+                                const float t = fmaf(bp.x, y, bp.y);
+                                const bool on = valid && (t > 0.f) && ((keep >> e) & 1u);
+                                float dz = on ? __uint_as_float(v[i]) * p.keep_scale : 0.f;
+                                dz = round_bf16(dz);
+                                o[i] = dz;
+                                q[i] = dz * fmaf(bp.z, y, bp.w);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                        float s1 = warp_colreduce32<false>(o);
+                        float s2 = warp_colreduce32<false>(q);
+                        comb_b[ew * 64 + half * 32 + lane] = s1;
+                        comb_b[4 * 64 + ew * 64 + half * 32 + lane] = s2;
                     }
                     if constexpr (Cfg::HAS_OUT) {
                         uint8_t* orow = out_stage + buf * 16384 + row * 128;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<uint4*>(orow + ((j ^ (row & 7)) << 4)) =
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(orow + (((half * 4 + j) ^ (row & 7)) << 4)) =
                                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                         fence_proxy_async_smem();
                         if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
                     }
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, EPI_THREADS);
                     if constexpr (Cfg::HAS_OUT) {
                         if (elected) {
-                            tma_store_2d(&tmOut, out_stage + buf * 16384, c0, m0);
+                            tma_store_2d(&tmOut, out_stage + buf * 16384, n0 + sub * 64, m0);
                             tma_store_commit();
                             if constexpr (Cfg::HAS_Y) issue_y_load(sub_it + 2);
                         }
                     }
                     if constexpr (EPI == EPI_STATS || EPI == EPI_DGRAD) {
-                        const int qn = et >> 6, c = et & 63;
-                        const float* cq = comb_b + qn * (4 * 64);
-                        const float s = cq[c] + cq[64 + c] + cq[128 + c] + cq[192 + c];
-                        if (c0 + c < p.N) atomicAdd(p.stats + static_cast<size_t>(qn) * p.N + c0 + c, static_cast<double>(s));
+                        if (et < 128) {
+                            const int qn = et >> 6, c = et & 63;
+                            const float* cq = comb_b + qn * (4 * 64);
+                            const float s = cq[c] + cq[64 + c] + cq[128 + c] + cq[192 + c];
+                            const int col = n0 + sub * 64 + c;
+                            if (col < p.N) atomicAdd(p.stats + static_cast<size_t>(qn) * p.N + col, static_cast<double>(s));
+                        }
                     } else if constexpr (EPI == EPI_COLMAX) {
                         if (uniform_cloud && et < 64) {
                             const float s = fmaxf(fmaxf(comb_b[et], comb_b[64 + et]), fmaxf(comb_b[128 + et], comb_b[192 + et]));
                             const int cl = m0 / p.pts_per_cloud;
-                            if (c0 + et < p.N && s > 0.f)
-                                atomicMax(p.colmax + static_cast<size_t>(cl) * p.N + c0 + et, __float_as_uint(s));
+                            const int col = n0 + sub * 64 + et;
+                            if (col < p.N && s > 0.f) atomicMax(p.colmax + static_cast<size_t>(cl) * p.N + col, __float_as_uint(s));
                         }
                     }
                 }

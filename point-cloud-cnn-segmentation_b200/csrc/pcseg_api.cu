@@ -582,6 +582,15 @@ extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, l
 // ------------------------------------------------------------------------------------------------
 // training forward
 // ------------------------------------------------------------------------------------------------
+// grid for the row-strip elementwise kernels: enough blocks to fill the GPU, each with >= 4 passes of rows
+static int strip_grid(long long rows, int C) {
+    const int rpp = 256 / (C / 8);
+    long long g = rows / (4LL * rpp * 4);
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
 static int ew_grid(long long work_items) {
     long long g = (work_items + 255) / 256;
     const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -628,7 +637,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     };
     auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         const int co = cv[i].cout;
-        k_bn_relu<<<ew_grid(P * (co / 8)), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, c->bnp[i], sd, thr, ks);
+        k_bn_relu<<<strip_grid(P, co), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, c->bnp[i], sd, thr, ks);
         LAUNCH_OK("k_bn_relu");
         return 0;
     };
@@ -681,6 +690,14 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+// rows per strip of k_bn_bwd_apply: ~8 passes per block, but keep at least ~4 blocks per SM in flight
+static int apply_rows_per_strip(int N, int B, int C) {
+    const int rpp = 256 / (C / 8);
+    int rps = rpp * 2 * 8;
+    while (rps > rpp * 2 && static_cast<long long>((N + rps - 1) / rps) * B < 4LL * num_sms()) rps /= 2;
+    return rps;
+}
+
 extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params, const float* dlogits, const float* logits,
                               const long long* labels, const float* class_w, const double* wsum_total, float* grads, int phase,
                               void* stream) {
@@ -709,9 +726,10 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     };
     auto apply = [&](int i, bf16* dy_out, int ld_dy, float* dcb) -> int {
         const int co = cv[i].cout;
-        dim3 grid((N + 63) / 64, B);
-        k_bn_bwd_apply<false><<<grid, 256, 0, s>>>(c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, c->coef[i], grads + L.off[2 * i + 1], dcb,
-                                                  nullptr, nullptr);
+        const int rps = apply_rows_per_strip(N, B, co);
+        dim3 grid((N + rps - 1) / rps, B);
+        k_bn_bwd_apply<false><<<grid, 256, 0, s>>>(c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, c->coef[i],
+                                                  grads + L.off[2 * i + 1], dcb, nullptr, nullptr);
         LAUNCH_OK("k_bn_bwd_apply");
         return 0;
     };
@@ -764,9 +782,10 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     // global_feat (sparse max-pool gradient folded into the BN backward)
     TRY(coef(5));
     {
-        dim3 grid((N + 63) / 64, B);
-        k_bn_bwd_apply<true><<<grid, 256, 0, s>>>(nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, c->coef[5], grads + L.off[11], nullptr,
-                                                 c->argidx, c->dzv);
+        const int rps = apply_rows_per_strip(N, B, 1024);
+        dim3 grid((N + rps - 1) / rps, B);
+        k_bn_bwd_apply<true><<<grid, 256, 0, s>>>(nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, c->coef[5], grads + L.off[11],
+                                                 nullptr, c->argidx, c->dzv);
         LAUNCH_OK("k_bn_bwd_apply<sparse>");
     }
     TRY(wgrad(5, grads + L.off[10], 1024));

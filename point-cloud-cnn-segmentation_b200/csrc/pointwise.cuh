@@ -128,29 +128,49 @@ __global__ void k_bn_finalize(const double* __restrict__ stats, int C, double n,
     }
 }
 
-// a = relu(scale*y + shift) (* dropout keep / (1-p)).  8 channels per thread (16-byte vectors).
+// a = relu(scale*y + shift) (* dropout keep / (1-p)).  Each thread owns 8 fixed channels (scale/shift live in
+// registers) and walks down the rows of its block's strip; 4 independent 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
                                                  int ld_a, long P, int C, const float4* __restrict__ bnp,
                                                  unsigned long long seed, unsigned int thr16, float keep_scale) {
-    const int vec_per_row = C >> 3;
-    const long total = P * vec_per_row;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const long r = i / vec_per_row;
-        const int c0 = static_cast<int>(i % vec_per_row) << 3;
-        const uint4 yw = *reinterpret_cast<const uint4*>(y + r * ld_y + c0);
-        const uint32_t ws[4] = {yw.x, yw.y, yw.z, yw.w};
-        uint32_t keep = 0xFFu;
-        if (thr16 != 0u) keep = dropout_keep8(seed, (static_cast<unsigned long long>(r) * C + c0) >> 3, thr16);
-        float o[8];
+    const int tpr = C >> 3;                       // threads per row (C <= 2048)
+    const int rpp = 256 / tpr;                    // rows per pass
+    const int c0 = (threadIdx.x % tpr) << 3;
+    const int rslot = threadIdx.x / tpr;
+    float sc[8], sh[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float4 bp = __ldg(bnp + c0 + e);
-            const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
-            const float t = fmaf(bp.x, yv, bp.y);
-            o[e] = (t > 0.f && ((keep >> e) & 1u)) ? t * keep_scale : 0.f;
+    for (int e = 0; e < 8; ++e) {
+        const float4 bp = __ldg(bnp + c0 + e);
+        sc[e] = bp.x;
+        sh[e] = bp.y;
+    }
+    const long rows_per_block = (P + gridDim.x - 1) / gridDim.x;
+    const long r_begin = blockIdx.x * rows_per_block;
+    const long r_end = min(P, r_begin + rows_per_block);
+    for (long r = r_begin + rslot; r < r_end; r += 4L * rpp) {
+        uint4 yw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long rr = r + static_cast<long>(u) * rpp;
+            if (rr < r_end) yw[u] = *reinterpret_cast<const uint4*>(y + rr * ld_y + c0);
         }
-        *reinterpret_cast<uint4*>(a + r * ld_a + c0) =
-            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long rr = r + static_cast<long>(u) * rpp;
+            if (rr >= r_end) break;
+            const uint32_t ws[4] = {yw[u].x, yw[u].y, yw[u].z, yw[u].w};
+            uint32_t keep = 0xFFu;
+            if (thr16 != 0u) keep = dropout_keep8(seed, (static_cast<unsigned long long>(rr) * C + c0) >> 3, thr16);
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
+                const float t = fmaf(sc[e], yv, sh[e]);
+                o[e] = (t > 0.f && ((keep >> e) & 1u)) ? t * keep_scale : 0.f;
+            }
+            *reinterpret_cast<uint4*>(a + rr * ld_a + c0) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
     }
 }
 
@@ -446,75 +466,77 @@ __global__ void k_bn_bwd_coef(const double* __restrict__ stats, int C, double n,
 // dy = A*dz + Bc*y + Cc, bf16 out (pitch ld_dy); column sums of dy -> dbias (fp32 atomics) and,
 // optionally, per-cloud column sums -> dcb[cloud][C].
 // SPARSE variant (max-pool backward): dz[p][c] = (row_in_cloud == argidx[cloud][c]) ? dzv[cloud][c] : 0.
-// grid: (ceil(C/ (8*TPR)) ... ) -> here: blockIdx.x = strip of 64 rows inside a cloud, blockIdx.y = cloud,
-// block = 256 threads = 4 row-slots x 64 column-vectors (8 channels each, covers 512 channels per pass).
+// grid: (strips per cloud, clouds); every thread owns 8 fixed channels (coefficients in registers) and walks
+// down the rows of its strip, two rows in flight.
 template <bool SPARSE>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, int ld_dz,
                                                       const __nv_bfloat16* __restrict__ y, int ld_y,
                                                       __nv_bfloat16* __restrict__ dy, int ld_dy, int N /*rows per cloud*/, int C,
-                                                      const float4* __restrict__ coef, float* __restrict__ dbias,
-                                                      float* __restrict__ dcb, const int* __restrict__ argidx,
-                                                      const float* __restrict__ dzv) {
-    __shared__ float red[4][64 * 8];
-    const int vec = threadIdx.x & 63;
-    const int slot = threadIdx.x >> 6;
+                                                      int rows_per_strip, const float4* __restrict__ coef,
+                                                      float* __restrict__ dbias, float* __restrict__ dcb,
+                                                      const int* __restrict__ argidx, const float* __restrict__ dzv) {
+    __shared__ float red[256 * 8];
+    const int tpr = C >> 3;
+    const int rpp = 256 / tpr;
+    const int c0 = (threadIdx.x % tpr) << 3;
+    const int rslot = threadIdx.x / tpr;
     const int cloud = blockIdx.y;
-    const int r0 = blockIdx.x * 64;
-    const int r1 = min(r0 + 64, N);
-    for (int cbase = 0; cbase < C; cbase += 512) {
-        const int c0 = cbase + vec * 8;
-        float acc[8];
+    const int r0 = blockIdx.x * rows_per_strip;
+    const int r1 = min(r0 + rows_per_strip, N);
+    float cA[8], cB[8], cC[8], acc[8];
+    int arg[8];
+    float dv[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        if (c0 < C) {
-            float4 cf[8];
+    for (int e = 0; e < 8; ++e) {
+        const float4 cf = __ldg(coef + c0 + e);
+        cA[e] = cf.x; cB[e] = cf.y; cC[e] = cf.z;
+        acc[e] = 0.f;
+        if (SPARSE) {
+            arg[e] = argidx[static_cast<size_t>(cloud) * C + c0 + e];
+            dv[e] = dzv[static_cast<size_t>(cloud) * C + c0 + e];
+        }
+    }
+    const size_t base = static_cast<size_t>(cloud) * N;
+    for (int r = r0 + rslot; r < r1; r += 2 * rpp) {
+        uint4 yw[2], zw[2];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) cf[e] = __ldg(coef + c0 + e);
-            int arg[8];
-            float dv[8];
-            if (SPARSE) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    arg[e] = argidx[static_cast<size_t>(cloud) * C + c0 + e];
-                    dv[e] = dzv[static_cast<size_t>(cloud) * C + c0 + e];
-                }
-            }
-            for (int r = r0 + slot; r < r1; r += 4) {
-                const size_t grow = static_cast<size_t>(cloud) * N + r;
-                const uint4 yw = *reinterpret_cast<const uint4*>(y + grow * ld_y + c0);
-                const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w};
-                uint32_t zs[4] = {0, 0, 0, 0};
-                if (!SPARSE) {
-                    const uint4 zw = *reinterpret_cast<const uint4*>(dz + grow * ld_dz + c0);
-                    zs[0] = zw.x; zs[1] = zw.y; zs[2] = zw.z; zs[3] = zw.w;
-                }
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float yv = (e & 1) ? bf16_hi(ys[e >> 1]) : bf16_lo(ys[e >> 1]);
-                    float dzv_e;
-                    if (SPARSE) dzv_e = (arg[e] == r) ? dv[e] : 0.f;
-                    else dzv_e = (e & 1) ? bf16_hi(zs[e >> 1]) : bf16_lo(zs[e >> 1]);
-                    const float v = round_bf16(fmaf(cf[e].x, dzv_e, fmaf(cf[e].y, yv, cf[e].z)));
-                    o[e] = v;
-                    acc[e] += v;
-                }
-                *reinterpret_cast<uint4*>(dy + grow * ld_dy + c0) =
-                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        for (int u = 0; u < 2; ++u) {
+            const int rr = r + u * rpp;
+            if (rr < r1) {
+                yw[u] = *reinterpret_cast<const uint4*>(y + (base + rr) * ld_y + c0);
+                if (!SPARSE) zw[u] = *reinterpret_cast<const uint4*>(dz + (base + rr) * ld_dz + c0);
             }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) red[slot][vec * 8 + e] = acc[e];
-        __syncthreads();
-        for (int i = threadIdx.x; i < 512; i += 256) {
-            const int c = cbase + i;
-            if (c < C) {
-                const float s = red[0][i] + red[1][i] + red[2][i] + red[3][i];
-                if (dbias) atomicAdd(dbias + c, s);
-                if (dcb) atomicAdd(dcb + static_cast<size_t>(cloud) * C + c, s);
+        for (int u = 0; u < 2; ++u) {
+            const int rr = r + u * rpp;
+            if (rr >= r1) break;
+            const uint32_t ys[4] = {yw[u].x, yw[u].y, yw[u].z, yw[u].w};
+            const uint32_t zs[4] = {zw[u].x, zw[u].y, zw[u].z, zw[u].w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float yv = (e & 1) ? bf16_hi(ys[e >> 1]) : bf16_lo(ys[e >> 1]);
+                float dze;
+                if (SPARSE) dze = (arg[e] == rr) ? dv[e] : 0.f;
+                else dze = (e & 1) ? bf16_hi(zs[e >> 1]) : bf16_lo(zs[e >> 1]);
+                const float v = round_bf16(fmaf(cA[e], dze, fmaf(cB[e], yv, cC[e])));
+                o[e] = v;
+                acc[e] += v;
             }
+            *reinterpret_cast<uint4*>(dy + (base + rr) * ld_dy + c0) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
-        __syncthreads();
+    }
+    // red[slot][C] : combine the row slots, then one atomic per column per block
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[rslot * C + c0 + e] = acc[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float sum = 0.f;
+        for (int sl = 0; sl < rpp; ++sl) sum += red[sl * C + c];
+        if (dbias) atomicAdd(dbias + c, sum);
+        if (dcb) atomicAdd(dcb + static_cast<size_t>(cloud) * C + c, sum);
     }
 }
 

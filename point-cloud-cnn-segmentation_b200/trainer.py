@@ -13,15 +13,7 @@ import torch.distributed as dist
 from .model import PointNetSegmentation, _BNS
 
 
-def grad_buckets(offs, total):
-    """Two all-reduce buckets matching pcseg_backward's phases: ranges of the flat gradient arena that
-    are final after phase 1 (global_feat + seg head + their BNs) and after phase 2 (the rest)."""
-    conv_split = offs[10][0]          # first element of global_feat.weight
-    bn_start = offs[20][0]            # first BN tensor
-    bn_split = offs[30][0]            # bn_global.weight
-    early = [(conv_split, bn_start), (bn_split, total)]
-    late = [(0, conv_split), (bn_start, bn_split)]
-    return early, late
+from .trainer_protocol import GradSync, grad_buckets  # noqa: E402
 
 
 class FusedTrainer:
@@ -39,7 +31,8 @@ class FusedTrainer:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.class_w = None if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float32, device=self.device).contiguous()
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        self.sync = GradSync(self.flat["grads"], process_group)
+        self.world = self.sync.world
         self.distributed = self.world > 1
         self.overlap = overlap
         # 32-byte CE accumulator {loss_num f64, w_sum f64, correct u64, valid u64} + all-reducible copy
@@ -54,10 +47,6 @@ class FusedTrainer:
     def set_lr(self, lr):
         self.lr = lr
 
-    def _allreduce_ranges(self, ranges):
-        g = self.flat["grads"]
-        return [dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True) for a, b in ranges if b > a]
-
     @torch.no_grad()
     def step(self, points, labels):
         """One optimizer step on this rank's shard.  points (B,N,4) fp32 and labels (B,N) int64 (-1 = pad) on
@@ -71,21 +60,20 @@ class FusedTrainer:
         logits = m._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw)
         self.last_logits = logits
         self.wsum.copy_(self.ce_f64[1:2])
-        if self.distributed:
-            dist.all_reduce(self.wsum, op=dist.ReduceOp.SUM, group=self.pg)
+        self.sync.g = f["grads"]
+        self.sync.reduce_normaliser(self.wsum)
         eng = self.engine
         kw = dict(logits=logits, labels=labels, class_w=self.class_w, wsum=self.wsum)
         if self.distributed and self.overlap:
             eng.backward(x, f["params"], f["grads"], phase=1, **kw)
-            works = self._allreduce_ranges(self.early)      # NCCL runs on its own stream while phase 2 computes
+            self.sync.launch(self.early)                    # NCCL runs on its own stream while phase 2 computes
             eng.backward(x, f["params"], f["grads"], phase=2, **kw)
-            works += self._allreduce_ranges(self.late)
-            for w in works:
-                w.wait()
+            self.sync.launch(self.late)
+            self.sync.wait()
         else:
             eng.backward(x, f["params"], f["grads"], phase=0, **kw)
-            if self.distributed:
-                dist.all_reduce(f["grads"], op=dist.ReduceOp.SUM, group=self.pg)
+            self.sync.launch([(0, f["grads"].numel())])
+            self.sync.wait()
         self.step_count += 1
         eng.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps,
                  self.weight_decay)

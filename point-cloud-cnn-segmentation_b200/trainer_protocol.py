@@ -1,0 +1,54 @@
+"""Backend-agnostic collective protocol of the data-parallel training step (no CUDA dependency, so the
+CPU test-suite can exercise it with gloo)."""
+import torch.distributed as dist
+
+
+def grad_buckets(offs, total):
+    """Two all-reduce buckets matching pcseg_backward's phases: ranges of the flat gradient arena that
+    are final after phase 1 (global_feat + seg head + their BNs) and after phase 2 (the rest)."""
+    conv_split = offs[10][0]          # first element of global_feat.weight
+    bn_start = offs[20][0]            # first BN tensor
+    bn_split = offs[30][0]            # bn_global.weight
+    early = [(conv_split, bn_start), (bn_split, total)]
+    late = [(0, conv_split), (bn_start, bn_split)]
+    return early, late
+
+
+class GradSync:
+    """Collective protocol of the data-parallel step (backend-agnostic: NCCL on GPUs, gloo in the CPU tests).
+
+    * `reduce_normaliser`: SUM all-reduce of the scalar sum of class weights, BEFORE backward, so that every
+      rank scales its dlogits by 1 / (global sum) -- the reference computes ONE weighted-mean loss over the
+      gathered logits of all replicas (pcs.py:244-251 under nn.DataParallel).
+    * `launch(ranges)` / `wait()`: asynchronous SUM all-reduce of slices of the flat gradient arena (summing
+      equals DataParallel's reduce-add of replica gradients); launched per bucket so that the first bucket's
+      transfer overlaps the rest of backward.
+    """
+
+    def __init__(self, flat_grads, process_group=None):
+        self.g = flat_grads
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.works = []
+
+    @property
+    def active(self):
+        return self.world > 1
+
+    def reduce_normaliser(self, t):
+        if self.active:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+        return t
+
+    def launch(self, ranges):
+        if self.active:
+            for a, b in ranges:
+                if b > a:
+                    self.works.append(dist.all_reduce(self.g[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+

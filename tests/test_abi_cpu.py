@@ -1,0 +1,109 @@
+"""CPU-only checks of the C-ABI boundary: the shared library loads without a GPU, exports every symbol
+include/pcseg_b200.h declares, and its host-side layout queries match the reference's state_dict."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pcseg_b200.h")
+LIB = os.path.join(ROOT, "point-cloud-cnn-segmentation_b200", "lib", "libpcseg_b200.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    return ctypes.CDLL(LIB)
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcseg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 18
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header():
+    import pcseg_b200
+    from pcseg_b200._lib import EXPORTS
+    assert sorted(EXPORTS) == declared_symbols()
+
+
+def test_layout_matches_reference_state_dict(lib):
+    from oracle import pointnet_oracle as orc
+    lib.pcseg_param_count.restype = ctypes.c_longlong
+    lib.pcseg_param_offset.restype = ctypes.c_longlong
+    lib.pcseg_param_numel.restype = ctypes.c_longlong
+    lib.pcseg_bn_buffer_count.restype = ctypes.c_longlong
+    for C in (3, 5):
+        spec = [(n, s) for n, s, dt in orc.state_dict_spec(C) if dt == np.float32 and "running" not in n]
+        assert len(spec) == 38
+        off = 0
+        for t, (name, shape) in enumerate(spec):
+            assert lib.pcseg_param_offset(C, t) == off, name
+            assert lib.pcseg_param_numel(C, t) == int(np.prod(shape)), name
+            off += int(np.prod(shape))
+        assert lib.pcseg_param_count(C) == off
+    assert lib.pcseg_param_count(5) == 1927621
+    assert lib.pcseg_bn_buffer_count() == 6528
+
+
+def test_error_paths_without_gpu(lib):
+    lib.pcseg_last_error.restype = ctypes.c_char_p
+    lib.pcseg_workspace_bytes.restype = ctypes.c_longlong
+    h = ctypes.c_void_p()
+    assert lib.pcseg_create(ctypes.byref(h), 99) != 0
+    assert b"num_classes" in lib.pcseg_last_error()
+    assert lib.pcseg_create(ctypes.byref(h), 5) == 0
+    assert lib.pcseg_forward_eval(h, None, None, None, None) != 0     # not bound
+    assert lib.pcseg_workspace_bytes(8, 16384, 5, 1) > lib.pcseg_workspace_bytes(8, 16384, 5, 0) > 0
+    assert lib.pcseg_workspace_bytes(0, 16, 5, 1) == -1
+    lib.pcseg_destroy(h)
+
+
+def test_module_is_a_state_dict_drop_in():
+    """Same 65 state_dict entries / shapes / dtypes / order as the reference module (pcs.py:70-94), identical default
+    initialisation under the same torch seed, and strict loading of a reference-layout checkpoint (pcs.py:373-382,
+    401-430) with and without the DataParallel `module.` prefix."""
+    import io
+    import torch
+    import pcseg_b200
+    from oracle import pointnet_oracle as orc
+    C = 5
+    m = pcseg_b200.PointNetSegmentation(C)
+    sd = m.state_dict()
+    spec = orc.state_dict_spec(C)
+    assert list(sd.keys()) == [n for n, _, _ in spec]
+    for n, shape, dt in spec:
+        assert tuple(sd[n].shape) == tuple(shape), n
+        assert sd[n].dtype == (torch.int64 if dt == np.int64 else torch.float32), n
+    # default init parity with torch.nn (what the reference constructor does)
+    torch.manual_seed(3)
+    a = pcseg_b200.PointNetSegmentation(C)
+    torch.manual_seed(3)
+    ref_conv = torch.nn.Conv1d(4, 64, 1)
+    assert torch.equal(a.conv1.weight, ref_conv.weight) and torch.equal(a.conv1.bias, ref_conv.bias)
+    # checkpoint round trip in the reference's dict layout
+    synth = {k: torch.from_numpy(np.asarray(v)) for k, v in orc.synth_state(C, 1).items()}
+    for prefix in ("", "module."):
+        ckpt = {"epoch": 3, "model_state_dict": {prefix + k: v for k, v in synth.items()}, "optimizer_state_dict": {},
+                "train_loss": 1.0, "val_loss": 1.1, "f1_class2": 0.5, "f1_per_class": [0.1] * C, "num_classes": C}
+        buf = io.BytesIO()
+        torch.save(ckpt, buf)
+        buf.seek(0)
+        model, loaded = pcseg_b200.load_checkpoint(buf)
+        assert loaded["num_classes"] == C
+        for k, v in synth.items():
+            assert torch.equal(model.state_dict()[k], v), k
+    with pytest.raises(NotImplementedError):
+        pcseg_b200.PointNetSegmentation(C, input_dim=3)

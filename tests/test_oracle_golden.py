@@ -122,3 +122,26 @@ def test_backward_finite_difference():
         sdm[name][idx] -= e
         fd = (loss_of(sdp)[0] - loss_of(sdm)[0]) / (2 * e)
         assert abs(fd - grads[name][idx]) < 1e-6 + 1e-4 * abs(fd), (name, fd, grads[name][idx])
+
+
+@pytest.mark.parametrize("path", CASES[:1], ids=["torch_port"])
+def test_torch_cpu_port_matches_reference(path):
+    """The timed CPU baseline port (oracle/torch_port.py) reproduces the reference's logits, loss and gradients."""
+    import torch
+    from oracle.torch_port import TorchCpuPort
+    gold = np.load(path)
+    C, seed = int(gold["C"]), int(gold["seed"])
+    port = TorchCpuPort(C, state=orc.synth_state(C, seed))
+    x = torch.from_numpy(gold["x"])
+    np.testing.assert_allclose(port.forward(x, False).detach().numpy(), gold["eval_logits"], atol=2e-5)
+    logits = port.forward(x, True, dropout_p=0.0)
+    np.testing.assert_allclose(logits.detach().numpy(), gold["train_logits"], atol=5e-5)
+    loss = torch.nn.functional.cross_entropy(logits.view(-1, C), torch.from_numpy(gold["labels"]).view(-1),
+                                             weight=torch.from_numpy(gold["class_w"]), ignore_index=-1)
+    assert abs(loss.item() - float(gold["loss"])) < 1e-5
+    loss.backward()
+    for name in ("seg_conv4.weight", "bn_seg1.weight", "conv1.weight"):
+        g = port.p[name].grad.numpy()
+        ref = gold["g/" + name] if ("g/" + name) in gold.files else None
+        if ref is not None:
+            np.testing.assert_allclose(g, ref, atol=1e-3 * np.abs(ref).max() + 1e-6)

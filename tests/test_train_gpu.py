@@ -110,7 +110,7 @@ def test_train_step_matches_oracle_on_golden_inputs(path):
         if name.endswith("num_batches_tracked"):
             assert int(buf.item()) == int(gold["buf/" + name])
         else:
-            np.testing.assert_allclose(buf.cpu().numpy(), newbuf[name], rtol=2e-2, atol=2e-3, err_msg=name)
+            np.testing.assert_allclose(buf.cpu().numpy(), newbuf[name], rtol=3e-2, atol=5e-3, err_msg=name)
 
 
 @pytest.mark.parametrize("B,N,C", [(4, 512, 5), (2, 1000, 3), (8, 2048, 5)])
