@@ -15,6 +15,7 @@
 //   EPI_BIAS_RELU : out = relu(acc + bias[n] (+ cloud_bias[cloud(row)][n]))          -> bf16 store
 //   EPI_COLMAX    : per-cloud column max of relu(acc + bias[n])                       -> atomicMax (no store)
 //   EPI_STATS     : out = bf16(acc (+ cloud_bias)); column sum / sum-of-squares       -> bf16 store + fp64 atomics
+//   EPI_STATS_POOL: EPI_STATS + per-cloud arg-extremum of every column (train-mode max-pool, keys via atomicMax)
 //   EPI_DGRAD     : dz = acc * relu'(bn(y)) * dropout; column sum dz, sum dz*yhat     -> bf16 store + fp64 atomics
 //   EPI_WGRAD     : split-K partial tile                                              -> fp32 red.add
 //   EPI_LOGITS    : logits = W4 * relu(acc + bias) + b4  (BN == 128 == all channels)  -> fp32 store
@@ -23,7 +24,7 @@
 
 namespace pcseg {
 
-enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EPI_WGRAD = 4, EPI_LOGITS = 5 };
+enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EPI_WGRAD = 4, EPI_LOGITS = 5, EPI_STATS_POOL = 6 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -52,6 +53,8 @@ struct GemmParams {
     const float* b4;             // [C]
     int num_classes;
     float* logits;               // [M][C]
+    const float* gamma;          // [N] BN weight: its sign picks max / min for the fused train-mode max-pool
+    unsigned long long* pool_keys;   // [clouds][N] packed (orderable value << 32 | ~row) arg-extremum keys
 };
 
 template <int BN, int EPI, bool MN>
@@ -59,7 +62,7 @@ struct GemmCfg {
     static constexpr int STAGE_A = GEMM_BM * GEMM_BK * 2;
     static constexpr int STAGE_B = BN * GEMM_BK * 2;
     static constexpr int STAGE = STAGE_A + STAGE_B;
-    static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_DGRAD);
+    static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD);
     static constexpr bool HAS_Y = (EPI == EPI_DGRAD);
     static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
     static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
@@ -266,6 +269,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             issue_y_load(0);
             issue_y_load(1);
         }
+        constexpr bool COLACC = (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD);
+        if constexpr (COLACC) {
+            // per-CTA column accumulators [2][BN]: valid because every tile of this CTA has the same n_tile
+            // (the host launches a grid that is a multiple of num_n_tiles)
+            for (int i = et; i < 2 * BN; i += EPI_THREADS) comb[i] = 0.f;
+            named_bar_sync(1, EPI_THREADS);
+        }
 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             int m_tile, n_tile, split;
@@ -346,10 +356,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int cloud = (p.pts_per_cloud > 0 && valid) ? grow / p.pts_per_cloud : 0;
                 const float* cb_row = (p.cloud_bias != nullptr) ? p.cloud_bias + static_cast<size_t>(cloud) * p.N : nullptr;
                 bool uniform_cloud = true;
-                if constexpr (EPI == EPI_COLMAX) {
+                if constexpr (EPI == EPI_COLMAX || EPI == EPI_STATS_POOL) {
                     const int last = min(m0 + GEMM_BM, p.M) - 1;
                     uniform_cloud = (m0 / p.pts_per_cloud) == (last / p.pts_per_cloud);
                 }
+                const bool pool_uniform = uniform_cloud;
 #pragma unroll 1
                 for (int sub = 0; sub < SUBS; ++sub, ++sub_it) {
                     const int buf = sub_it & 1;
@@ -385,54 +396,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     atomicMax(p.colmax + static_cast<size_t>(cloud) * p.N + c0 + i, __float_as_uint(o[i]));
                             }
                         }
-                    } else if constexpr (EPI == EPI_STATS) {
-                        float sq[32];
+                    } else if constexpr (EPI == EPI_STATS || EPI == EPI_STATS_POOL) {
+                        // pass 1 (row-mapped): accumulator (+ per-cloud term) -> bf16 -> staging tile
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             float x = __uint_as_float(v[i]);
                             if (cb_row) x += __ldg(cb_row + c0 + i);
-                            x = valid ? round_bf16(x) : 0.f;
-                            o[i] = x;
-                            sq[i] = x * x;
+                            o[i] = valid ? x : 0.f;
                         }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
-                        float s1 = warp_colreduce32<false>(o);
-                        float s2 = warp_colreduce32<false>(sq);
-                        comb_b[ew * 64 + half * 32 + lane] = s1;
-                        comb_b[4 * 64 + ew * 64 + half * 32 + lane] = s2;
                     } else if constexpr (EPI == EPI_DGRAD) {
-                        float q[32];
-                        const uint8_t* yrow = y_stage + buf * 16384 + row * 128;
+                        // pass 1 (row-mapped): dA * 1/(1-p) -> bf16 -> staging tile (masking happens column-mapped in pass 2)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 columns
-                            const int chunk = half * 4 + j;
-                            const uint4 yw = *reinterpret_cast<const uint4*>(yrow + ((chunk ^ (row & 7)) << 4));
-                            const uint32_t yws[4] = {yw.x, yw.y, yw.z, yw.w};
-                            uint32_t keep = 0xFFu;
-                            if (p.drop_thr16 != 0u) {
-                                const unsigned long long e = static_cast<unsigned long long>(grow) * p.N + (c0 + j * 8);
-                                keep = dropout_keep8(p.seed, e >> 3, p.drop_thr16);
-                            }
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const int i = j * 8 + e;
-                                const float4 bp = __ldg(p.bnp + c0 + i);
-                                const float y = (e & 1) ? bf16_hi(yws[e >> 1]) : bf16_lo(yws[e >> 1]);
-                                const float t = fmaf(bp.x, y, bp.y);
-                                const bool on = valid && (t > 0.f) && ((keep >> e) & 1u);
-                                float dz = on ? __uint_as_float(v[i]) * p.keep_scale : 0.f;
-                                dz = round_bf16(dz);
-                                o[i] = dz;
-                                q[i] = dz * fmaf(bp.z, y, bp.w);
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
-                        float s1 = warp_colreduce32<false>(o);
-                        float s2 = warp_colreduce32<false>(q);
-                        comb_b[ew * 64 + half * 32 + lane] = s1;
-                        comb_b[4 * 64 + ew * 64 + half * 32 + lane] = s2;
+                        for (int i = 0; i < 16; ++i)
+                            packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.keep_scale, __uint_as_float(v[2 * i + 1]) * p.keep_scale);
                     }
                     if constexpr (Cfg::HAS_OUT) {
                         uint8_t* orow = out_stage + buf * 16384 + row * 128;
@@ -444,6 +422,158 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
                     }
                     named_bar_sync(1, EPI_THREADS);
+                    if constexpr (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD) {
+                        // pass 2 (column-mapped): warp pw owns the 16-byte chunk pw (8 columns) of all 128 rows,
+                        // lane l handles rows l, l+32, l+64, l+96; per-column parameters live in registers.
+                        const int pw = warp_idx - 4;
+                        const int colbase = n0 + sub * 64 + pw * 8;
+                        uint8_t* tile_s = out_stage + buf * 16384;
+                        float s1[8], s2[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+                        if constexpr (EPI == EPI_DGRAD) {
+                            float sc[8], sh[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float4 bp = __ldg(p.bnp + colbase + e);
+                                sc[e] = bp.x;
+                                sh[e] = bp.y;
+                            }
+                            const uint8_t* ytile = y_stage + buf * 16384;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = lane + 32 * i;
+                                const int off = r * 128 + ((pw ^ (r & 7)) << 4);
+                                const uint4 dw = *reinterpret_cast<const uint4*>(tile_s + off);
+                                const uint4 yw = *reinterpret_cast<const uint4*>(ytile + off);
+                                const uint32_t ds[4] = {dw.x, dw.y, dw.z, dw.w};
+                                const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w};
+                                uint32_t keep = 0xFFu;
+                                if (p.drop_thr16 != 0u) {
+                                    const unsigned long long e0 = static_cast<unsigned long long>(m0 + r) * p.N + colbase;
+                                    keep = dropout_keep8(p.seed, e0 >> 3, p.drop_thr16);
+                                }
+                                float dz[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float yv = (e & 1) ? bf16_hi(ys[e >> 1]) : bf16_lo(ys[e >> 1]);
+                                    const float da = (e & 1) ? bf16_hi(ds[e >> 1]) : bf16_lo(ds[e >> 1]);
+                                    const bool on = (fmaf(sc[e], yv, sh[e]) > 0.f) && ((keep >> e) & 1u);
+                                    dz[e] = on ? da : 0.f;
+                                    s1[e] += dz[e];
+                                    s2[e] = fmaf(dz[e], yv, s2[e]);
+                                }
+                                *reinterpret_cast<uint4*>(tile_s + off) = make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]),
+                                                                                      pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
+                            }
+                        } else {
+                            float bestv[8], sg[8];
+                            int besti[8];
+                            const int row0_in_cloud = (EPI == EPI_STATS_POOL) ? (m0 % p.pts_per_cloud) : 0;   // uniform tiles only
+                            if constexpr (EPI == EPI_STATS_POOL) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    bestv[e] = -INFINITY;
+                                    besti[e] = 0;
+                                    sg[e] = (__ldg(p.gamma + colbase + e) >= 0.f) ? 1.f : -1.f;
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = lane + 32 * i;
+                                const uint4 xw = *reinterpret_cast<const uint4*>(tile_s + r * 128 + ((pw ^ (r & 7)) << 4));
+                                const uint32_t xs[4] = {xw.x, xw.y, xw.z, xw.w};
+                                const bool row_ok = (m0 + r) < p.M;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float x = (e & 1) ? bf16_hi(xs[e >> 1]) : bf16_lo(xs[e >> 1]);
+                                    s1[e] += x;
+                                    s2[e] = fmaf(x, x, s2[e]);
+                                    if constexpr (EPI == EPI_STATS_POOL) {
+                                        const float sx = sg[e] * x;
+                                        if (pool_uniform) {
+                                            // rows are visited in increasing order: strict '>' keeps the first maximum
+                                            const bool better = row_ok && (sx > bestv[e]);
+                                            bestv[e] = better ? sx : bestv[e];
+                                            besti[e] = better ? r : besti[e];
+                                        } else if (row_ok) {
+                                            const int gr = m0 + r;
+                                            const uint32_t bb = __float_as_uint(sx);
+                                            const uint32_t ord = (bb & 0x80000000u) ? ~bb : (bb | 0x80000000u);
+                                            const unsigned long long key = (static_cast<unsigned long long>(ord) << 32) |
+                                                                           (0xFFFFFFFFu - static_cast<uint32_t>(gr % p.pts_per_cloud));
+                                            atomicMax(p.pool_keys + static_cast<size_t>(gr / p.pts_per_cloud) * p.N + colbase + e, key);
+                                        }
+                                    }
+                                }
+                            }
+                            if constexpr (EPI == EPI_STATS_POOL) {
+                                if (pool_uniform) {
+                                    unsigned long long best[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        const uint32_t bb = __float_as_uint(bestv[e]);
+                                        const uint32_t ord = (bb & 0x80000000u) ? ~bb : (bb | 0x80000000u);
+                                        best[e] = (bestv[e] == -INFINITY) ? 0ull
+                                                  : ((static_cast<unsigned long long>(ord) << 32) |
+                                                     (0xFFFFFFFFu - static_cast<uint32_t>(row0_in_cloud + besti[e])));
+                                    }
+                                    // 8 keys x 32 lanes -> lanes with (lane & 3) == 0 hold the warp-wide max of one column
+#pragma unroll
+                                    for (int offk = 16, cnt = 4; offk >= 4; offk >>= 1, cnt >>= 1) {
+                                        const bool up = (lane & offk) != 0;
+#pragma unroll
+                                        for (int e = 0; e < cnt; ++e) {
+                                            const unsigned long long send = up ? best[e] : best[e + cnt];
+                                            const unsigned long long keepk = up ? best[e + cnt] : best[e];
+                                            const unsigned long long got = __shfl_xor_sync(0xffffffffu, send, offk);
+                                            best[e] = keepk > got ? keepk : got;
+                                        }
+                                    }
+#pragma unroll
+                                    for (int offk = 2; offk >= 1; offk >>= 1) {
+                                        const unsigned long long got = __shfl_xor_sync(0xffffffffu, best[0], offk);
+                                        best[0] = best[0] > got ? best[0] : got;
+                                    }
+                                    if ((lane & 3) == 0 && best[0] != 0ull) {
+                                        const int colk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                                        atomicMax(p.pool_keys + static_cast<size_t>(m0 / p.pts_per_cloud) * p.N + colbase + colk, best[0]);
+                                    }
+                                }
+                            }
+                        }
+                        // warp reduction of the 16 partial sums: lane (q<<4 | c2<<3 | c1<<2 | c0<<1 | x) ends with quantity q, column c
+                        {
+                            const bool up16 = (lane & 16) != 0;
+                            float t[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float send = up16 ? s1[e] : s2[e];
+                                const float keepv = up16 ? s2[e] : s1[e];
+                                t[e] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
+#pragma unroll
+                            for (int offk = 8, cnt = 4; offk >= 2; offk >>= 1, cnt >>= 1) {
+                                const bool up = (lane & offk) != 0;
+#pragma unroll
+                                for (int e = 0; e < cnt; ++e) {
+                                    const float send = up ? t[e] : t[e + cnt];
+                                    const float keepv = up ? t[e + cnt] : t[e];
+                                    t[e] = keepv + __shfl_xor_sync(0xffffffffu, send, offk);
+                                }
+                            }
+                            t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+                            if ((lane & 1) == 0) {
+                                const int qn = lane >> 4;
+                                const int colk = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                                comb[qn * BN + sub * 64 + pw * 8 + colk] += t[0];      // unique owner: no race
+                            }
+                        }
+                        if constexpr (EPI == EPI_DGRAD) {
+                            fence_proxy_async_smem();
+                            named_bar_sync(2, EPI_THREADS);     // staging tile was modified in place
+                        }
+                    }
                     if constexpr (Cfg::HAS_OUT) {
                         if (elected) {
                             tma_store_2d(&tmOut, out_stage + buf * 16384, n0 + sub * 64, m0);
@@ -451,14 +581,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if constexpr (Cfg::HAS_Y) issue_y_load(sub_it + 2);
                         }
                     }
-                    if constexpr (EPI == EPI_STATS || EPI == EPI_DGRAD) {
-                        if (et < 128) {
-                            const int qn = et >> 6, c = et & 63;
-                            const float* cq = comb_b + qn * (4 * 64);
-                            const float s = cq[c] + cq[64 + c] + cq[128 + c] + cq[192 + c];
-                            const int col = n0 + sub * 64 + c;
-                            if (col < p.N) atomicAdd(p.stats + static_cast<size_t>(qn) * p.N + col, static_cast<double>(s));
-                        }
+                    if constexpr (false) {
                     } else if constexpr (EPI == EPI_COLMAX) {
                         if (uniform_cloud && et < 64) {
                             const float s = fmaxf(fmaxf(comb_b[et], comb_b[64 + et]), fmaxf(comb_b[128 + et], comb_b[192 + et]));
@@ -466,6 +589,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const int col = n0 + sub * 64 + et;
                             if (col < p.N && s > 0.f) atomicMax(p.colmax + static_cast<size_t>(cl) * p.N + col, __float_as_uint(s));
                         }
+                    }
+                }
+            }
+        }
+        if constexpr (COLACC) {
+            named_bar_sync(1, EPI_THREADS);
+            const int n0_fixed = (blockIdx.x % p.num_n_tiles) * BN;
+            if (blockIdx.x < total_tiles) {
+                for (int c = et; c < BN; c += EPI_THREADS) {
+                    const int col = n0_fixed + c;
+                    if (col >= p.N) continue;
+                    const float a0 = comb[c], a1 = comb[BN + c];
+                    if constexpr (EPI == EPI_DGRAD) {
+                        const float4 bp = __ldg(p.bnp + col);      // sum dz*yhat = invstd * sum(dz*y) + (-mean*invstd) * sum dz
+                        atomicAdd(p.stats + col, static_cast<double>(a0));
+                        atomicAdd(p.stats + p.N + col, static_cast<double>(bp.z) * a1 + static_cast<double>(bp.w) * a0);
+                    } else {
+                        atomicAdd(p.stats + col, static_cast<double>(a0));
+                        atomicAdd(p.stats + p.N + col, static_cast<double>(a1));
                     }
                 }
             }

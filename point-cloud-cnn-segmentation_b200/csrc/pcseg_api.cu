@@ -166,7 +166,8 @@ int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
         attr_set = true;
     }
     const int tiles = op.p.num_m_tiles * op.p.num_n_tiles * op.p.num_splits;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    if (!MN) grid = (grid / op.p.num_n_tiles) * op.p.num_n_tiles;   // every CTA keeps one n_tile (per-CTA column accumulators)
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmY, op.p);
     LAUNCH_OK("gemm_kernel");
     return 0;
@@ -180,6 +181,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t s) {
     CASE(256, EPI_COLMAX, false)
     CASE(128, EPI_LOGITS, false)
     CASE(64, EPI_STATS, false) CASE(128, EPI_STATS, false) CASE(256, EPI_STATS, false)
+    CASE(256, EPI_STATS_POOL, false)
     CASE(64, EPI_DGRAD, false) CASE(128, EPI_DGRAD, false) CASE(256, EPI_DGRAD, false)
     CASE(64, EPI_WGRAD, true) CASE(128, EPI_WGRAD, true) CASE(256, EPI_WGRAD, true)
 #undef CASE
@@ -195,7 +197,7 @@ int setup_gemm_kmajor(GemmOp* op, int epi, const void* A, int lda, const void* B
     if (N % 64 != 0) return fail("GEMM N=%d must be a multiple of 64", N);
     memset(&op->p, 0, sizeof(op->p));
     op->bn = (epi == EPI_LOGITS) ? 128 : pick_bn(N);
-    if (epi == EPI_COLMAX) op->bn = 256;
+    if (epi == EPI_COLMAX || epi == EPI_STATS_POOL) op->bn = 256;
     if (N % op->bn != 0) return fail("GEMM N=%d not a multiple of the tile width %d", N, op->bn);
     op->epi = epi;
     op->mn = false;
@@ -459,10 +461,12 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
     } else {
         // ---- forward: y_i = a_{i-1} W_i^T, statistics in the epilogue
         for (int i = 1; i <= 5; ++i) {
-            TRY(setup_gemm_kmajor(&c->fw[i], EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
-                                  c->y[i], cv[i].cout, nullptr, 0));
+            TRY(setup_gemm_kmajor(&c->fw[i], i == 5 ? EPI_STATS_POOL : EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P,
+                                  cv[i].cout, cv[i].cin, c->y[i], cv[i].cout, nullptr, 0));
             c->fw[i].p.stats = c->stats_f + c->stat_off[i];
         }
+        c->fw[5].p.pool_keys = c->keys;          // train-mode max-pool fused into global_feat's epilogue
+        c->fw[5].p.pts_per_cloud = N;
         TRY(setup_gemm_kmajor(&c->fw[6], EPI_STATS, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->y[6], 512, nullptr, 0));
         c->fw[6].p.stats = c->stats_f + c->stat_off[6];
         c->fw[6].p.cloud_bias = c->cb;
@@ -612,16 +616,26 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     c->thr16 = static_cast<unsigned int>(dropout_p * 65536.0f + 0.5f);
     c->keep_scale = c->thr16 ? 1.f / (1.f - static_cast<float>(c->thr16) / 65536.f) : 1.f;
 
-    // bf16 weights (forward [Cout][Cin], transposed [Cin][Cout] for dgrad)
-    for (int i = 1; i < NUM_BN; ++i) {
-        if (i == 6) {
-            TRY(convert_rows(params + L.off[12], 1088, c->wk[6], 64, 512, 64, nullptr, s));
-            TRY(convert_transpose(params + L.off[12], 1088, c->wcat + 64, 576, 512, 64, s));
-        } else {
-            TRY(convert_rows(params + L.off[2 * i], cv[i].cin, c->wk[i], cv[i].cin, cv[i].cout, cv[i].cin, nullptr, s));
-            if (i == 2) TRY(convert_transpose(params + L.off[4], 64, c->wcat, 576, 64, 64, s));
-            else TRY(convert_transpose(params + L.off[2 * i], cv[i].cin, c->wt[i], cv[i].cout, cv[i].cout, cv[i].cin, s));
+    // bf16 weights (forward [Cout][Cin], transposed [Cin][Cout] for dgrad): one launch for all 16 conversions
+    {
+        ConvertJobs jobs;
+        int nj = 0;
+        auto add = [&](const float* src, int ld_src, bf16* dst, int ld_dst, int rows, int cols, int tr) {
+            jobs.job[nj++] = ConvertJob{src, dst, ld_src, ld_dst, rows, cols, tr};
+        };
+        for (int i = 1; i < NUM_BN; ++i) {
+            if (i == 6) {
+                add(params + L.off[12], 1088, c->wk[6], 64, 512, 64, 0);
+                add(params + L.off[12], 1088, c->wcat + 64, 576, 512, 64, 1);
+            } else {
+                add(params + L.off[2 * i], cv[i].cin, c->wk[i], cv[i].cin, cv[i].cout, cv[i].cin, 0);
+                if (i == 2) add(params + L.off[4], 64, c->wcat, 576, 64, 64, 1);
+                else add(params + L.off[2 * i], cv[i].cin, c->wt[i], cv[i].cout, cv[i].cout, cv[i].cin, 1);
+            }
         }
+        jobs.count = nj;
+        k_convert_multi<<<dim3(64, nj), 256, 0, s>>>(jobs);
+        LAUNCH_OK("k_convert_multi");
     }
     CUDA_OK(cudaMemsetAsync(c->stats_f, 0, c->stat_total * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(c->keys, 0, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long), s));
@@ -652,16 +666,17 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         TRY(bn_relu(0, 0, 0, 1.f));
     }
     for (int i = 1; i <= 5; ++i) {
-        TRY(timed_gemm(c, c->fw[i], i, s));
+        if (i == 5) {
+            GemmOp op = c->fw[5];
+            op.p.gamma = params + L.off[20 + 2 * 5];
+            TRY(timed_gemm(c, op, 5, s));
+        } else {
+            TRY(timed_gemm(c, c->fw[i], i, s));
+        }
         TRY(finalize(i));
         if (i < 5) TRY(bn_relu(i, 0, 0, 1.f));
     }
     {   // global max-pool of relu(bn(y6)) with arg-index
-        const int strips = (c->N + 1023) / 1024;
-        const int rows_per_strip = (c->N + strips - 1) / strips;
-        dim3 grid(1024 / 64, strips, c->B);
-        k_maxpool_scan<<<grid, 256, 0, s>>>(c->y[5], 1024, c->N, rows_per_strip, c->bnp[5], c->keys);
-        LAUNCH_OK("k_maxpool_scan");
         const int total = c->B * 1024;
         k_maxpool_finish<<<(total + 255) / 256, 256, 0, s>>>(c->keys, total, 1024, c->bnp[5], c->gmax, c->ystar, c->argidx);
         LAUNCH_OK("k_maxpool_finish");
@@ -750,7 +765,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     if (phase != 2) {
     {   // seg_conv4 + loss gradient
         int grid = static_cast<int>((P + 7) / 8);
-        if (grid > num_sms() * 4) grid = num_sms() * 4;
+        if (grid > num_sms() * 2) grid = num_sms() * 2;
         k_head_bwd<MAX_CLASSES><<<grid, 256, 0, s>>>(c->y[8], P, c->bnp[8], params + L.off[18], c->C, dlogits, logits, labels, class_w,
                                                     wsum_total, c->dz[8], grads + L.off[18], grads + L.off[19],
                                                     c->stats_b + c->stat_off[8]);
@@ -771,7 +786,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     TRY(apply(6, c->dycat + 64, 576, c->dcb));
     TRY(wgrad(6, grads + L.off[12], 1088));
     {
-        dim3 grid_dg(1024 / 256, B);
+        dim3 grid_dg(1024 / 32, B);
         k_cloud_bwd_dg<<<grid_dg, 256, 0, s>>>(c->dcb, params + L.off[12] + 64, 1088, B, 512, 1024, c->gmax, c->ystar, c->bnp[5], c->dzv,
                                               c->stats_b + c->stat_off[5]);
         LAUNCH_OK("k_cloud_bwd_dg");

@@ -41,6 +41,28 @@ __global__ void k_convert_transpose(const float* __restrict__ src, int ld_src, _
     }
 }
 
+// All fp32 -> bf16 weight conversions of one training step in a single launch (blockIdx.y = job).
+struct ConvertJob {
+    const float* src;
+    __nv_bfloat16* dst;
+    int ld_src, ld_dst, rows, cols, transpose;
+};
+constexpr int MAX_CONVERT_JOBS = 16;
+struct ConvertJobs {
+    ConvertJob job[MAX_CONVERT_JOBS];
+    int count;
+};
+__global__ void __launch_bounds__(256) k_convert_multi(const ConvertJobs jobs) {
+    const ConvertJob j = jobs.job[blockIdx.y];
+    const int n = j.rows * j.cols;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int r = idx / j.cols, c = idx % j.cols;
+        const float v = j.src[static_cast<size_t>(r) * j.ld_src + c];
+        if (j.transpose) j.dst[static_cast<size_t>(c) * j.ld_dst + r] = __float2bfloat16_rn(v);
+        else j.dst[static_cast<size_t>(r) * j.ld_dst + c] = __float2bfloat16_rn(v);
+    }
+}
+
 // Eval-mode BatchNorm folding: alpha[c] = gamma/sqrt(var+eps), delta[c] = (bias - mean)*alpha + beta.
 __global__ void k_fold_bn(const float* __restrict__ conv_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ rmean, const float* __restrict__ rvar, float eps, int C,
@@ -266,9 +288,12 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
                                                   const float* __restrict__ W4, const float* __restrict__ b4, int C,
                                                   float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
+    __shared__ double red_d[8][2];
+    __shared__ unsigned long long red_u[8][2];
     const int lane = threadIdx.x & 31;
-    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = threadIdx.x >> 5;
+    const long warp_g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
     float w[MAXC][4];
     float4 bp[4];
 #pragma unroll
@@ -277,16 +302,31 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
     for (int k = 0; k < MAXC; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) w[k][e] = (k < C) ? W4[k * 128 + lane * 4 + e] : 0.f;
+    float bias_k = (lane < C) ? __ldg(b4 + lane) : 0.f;
+    float cw_l = (class_w != nullptr && lane < C) ? __ldg(class_w + lane) : 1.f;
     double loss_num = 0.0, w_sum = 0.0;
     unsigned long long correct = 0, nvalid = 0;
+    uint2 yw_next = make_uint2(0, 0);
+    long long lab_next = -1;
+    if (warp_g < P) {
+        yw_next = *reinterpret_cast<const uint2*>(ys3 + warp_g * 128 + lane * 4);
+        if (labels != nullptr && lane == 0) lab_next = labels[warp_g];
+    }
     for (long pnt = warp_g; pnt < P; pnt += nwarps) {
-        const uint2 yw = *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4);
+        const uint2 yw = yw_next;
+        const long long lab = lab_next;
+        const long nxt = pnt + nwarps;
+        if (nxt < P) {                                   // prefetch the next point before the dependent math
+            yw_next = *reinterpret_cast<const uint2*>(ys3 + nxt * 128 + lane * 4);
+            if (labels != nullptr && lane == 0) lab_next = labels[nxt];
+        }
         float a[4];
         a[0] = fmaxf(fmaf(bp[0].x, bf16_lo(yw.x), bp[0].y), 0.f);
         a[1] = fmaxf(fmaf(bp[1].x, bf16_hi(yw.x), bp[1].y), 0.f);
         a[2] = fmaxf(fmaf(bp[2].x, bf16_lo(yw.y), bp[2].y), 0.f);
         a[3] = fmaxf(fmaf(bp[3].x, bf16_hi(yw.y), bp[3].y), 0.f);
-        float z[MAXC];
+        // lane k ends up holding logit k (k < C): reduce each class over the warp, keep it on lane k
+        float zmine = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
             if (k < C) {
@@ -294,41 +334,47 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
                 s = fmaf(a[1], w[k][1], s);
                 s = fmaf(a[2], w[k][2], s);
                 s = fmaf(a[3], w[k][3], s);
-                z[k] = warp_sum(s) + __ldg(b4 + k);
-            } else {
-                z[k] = -INFINITY;
+                s = warp_sum(s);
+                if (lane == k) zmine = s;
             }
         }
-        if (lane == 0) {
+        zmine += bias_k;
+        if (lane < C) logits[pnt * C + lane] = zmine;
+        if (labels != nullptr) {
+            const long long labv = __shfl_sync(0xffffffffu, lab, 0);
+            if (labv >= 0) {                             // warp-uniform
+                float zm = (lane < C) ? zmine : -INFINITY;
+                float zmax = zm;
 #pragma unroll
-            for (int k = 0; k < MAXC; ++k)
-                if (k < C) logits[pnt * C + k] = z[k];
-            if (labels != nullptr) {
-                const long long lab = labels[pnt];
-                if (lab >= 0) {
-                    float zmax = z[0];
-                    int am = 0;
+                for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));   // C <= 8 lanes
+                const unsigned am_mask = __ballot_sync(0xffffffffu, lane < C && zm == zmax);
+                const int am = __ffs(am_mask) - 1;       // first maximum, like torch.argmax
+                float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
 #pragma unroll
-                    for (int k = 1; k < MAXC; ++k)
-                        if (k < C && z[k] > zmax) { zmax = z[k]; am = k; }
-                    float se = 0.f, zl = 0.f;
-#pragma unroll
-                    for (int k = 0; k < MAXC; ++k)
-                        if (k < C) { se += __expf(z[k] - zmax); if (k == lab) zl = z[k]; }
-                    const float wl = class_w ? class_w[lab] : 1.f;
-                    loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(se) - zl);
+                for (int o = 4; o >= 1; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                const float zl = __shfl_sync(0xffffffffu, zmine, static_cast<int>(labv));
+                const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(labv));
+                if (lane == 0) {
+                    loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(ex) - zl);
                     w_sum += wl;
-                    correct += (am == lab);
+                    correct += (am == labv);
                     nvalid += 1;
                 }
             }
         }
     }
-    if (labels != nullptr && lane == 0) {
-        atomicAdd(&ce->loss_num, loss_num);
-        atomicAdd(&ce->w_sum, w_sum);
-        atomicAdd(&ce->correct, correct);
-        atomicAdd(&ce->valid, nvalid);
+    if (labels != nullptr) {
+        if (lane == 0) { red_d[warp][0] = loss_num; red_d[warp][1] = w_sum; red_u[warp][0] = correct; red_u[warp][1] = nvalid; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a0 = 0.0, a1 = 0.0;
+            unsigned long long u0 = 0, u1 = 0;
+            for (int i = 0; i < 8; ++i) { a0 += red_d[i][0]; a1 += red_d[i][1]; u0 += red_u[i][0]; u1 += red_u[i][1]; }
+            atomicAdd(&ce->loss_num, a0);
+            atomicAdd(&ce->w_sum, a1);
+            atomicAdd(&ce->correct, u0);
+            atomicAdd(&ce->valid, u1);
+        }
     }
 }
 
@@ -360,44 +406,64 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
     __shared__ float red[8][MAXC * 128 + 2 * 128 + MAXC];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    float w[MAXC][4], dw[MAXC][4], dbk[MAXC];
+    const long warp_g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+    float w[MAXC][4], dw[MAXC][4];
+    float dbk = 0.f;                                   // lane k accumulates db4[k]
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     float4 bp[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) bp[e] = __ldg(bnp + lane * 4 + e);
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-        dbk[k] = 0.f;
+    for (int k = 0; k < MAXC; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) { w[k][e] = (k < C) ? W4[k * 128 + lane * 4 + e] : 0.f; dw[k][e] = 0.f; }
-    }
+    const bool fused = (dlogits == nullptr);
     const float inv_wsum = (wsum_total != nullptr) ? static_cast<float>(1.0 / *wsum_total) : 0.f;
+    const float cw_l = (class_w != nullptr && lane < C) ? __ldg(class_w + lane) : 1.f;
+    const float* zsrc = fused ? logits : dlogits;
+
+    uint2 yw_next = make_uint2(0, 0);
+    float z_next = 0.f;
+    long long lab_next = -1;
+    if (warp_g < P) {
+        yw_next = *reinterpret_cast<const uint2*>(ys3 + warp_g * 128 + lane * 4);
+        if (lane < C) z_next = zsrc[warp_g * C + lane];
+        if (fused && lane == 0) lab_next = labels[warp_g];
+    }
     for (long pnt = warp_g; pnt < P; pnt += nwarps) {
-        float dl[MAXC];
-        if (dlogits != nullptr) {
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __ldg(dlogits + pnt * C + k) : 0.f;
-        } else {
-            const long long lab = labels[pnt];
+        const uint2 yw = yw_next;
+        const float zin = z_next;
+        const long long lab0 = lab_next;
+        const long nxt = pnt + nwarps;
+        if (nxt < P) {
+            yw_next = *reinterpret_cast<const uint2*>(ys3 + nxt * 128 + lane * 4);
+            if (lane < C) z_next = zsrc[nxt * C + lane];
+            if (fused && lane == 0) lab_next = labels[nxt];
+        }
+        float dl_mine = zin;                              // lane k holds dlogit k
+        if (fused) {
+            const long long lab = __shfl_sync(0xffffffffu, lab0, 0);
             if (lab >= 0) {
-                float z[MAXC], zmax = -INFINITY;
+                const float zm = (lane < C) ? zin : -INFINITY;
+                float zmax = zm;
 #pragma unroll
-                for (int k = 0; k < MAXC; ++k) { z[k] = (k < C) ? __ldg(logits + pnt * C + k) : -INFINITY; zmax = fmaxf(zmax, z[k]); }
-                float se = 0.f;
+                for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                const float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
+                float se = ex;
 #pragma unroll
-                for (int k = 0; k < MAXC; ++k) { z[k] = (k < C) ? __expf(z[k] - zmax) : 0.f; se += z[k]; }
-                const float sc = (class_w ? class_w[lab] : 1.f) * inv_wsum;
-                const float inv = 1.f / se;
-#pragma unroll
-                for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? sc * (z[k] * inv - (k == lab ? 1.f : 0.f)) : 0.f;
+                for (int o = 4; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+                const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(lab));
+                dl_mine = wl * inv_wsum * (ex / se - (lane == lab ? 1.f : 0.f));
             } else {
-#pragma unroll
-                for (int k = 0; k < MAXC; ++k) dl[k] = 0.f;
+                dl_mine = 0.f;
             }
         }
-        const uint2 yw = *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4);
+        if (lane >= C) dl_mine = 0.f;
+        dbk += dl_mine;
+        float dl[MAXC];
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __shfl_sync(0xffffffffu, dl_mine, k) : 0.f;
         const float yv[4] = {bf16_lo(yw.x), bf16_hi(yw.x), bf16_lo(yw.y), bf16_hi(yw.y)};
         float dz[4];
 #pragma unroll
@@ -413,8 +479,6 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
             s1[e] += dz[e];
             s2[e] = fmaf(dz[e], fmaf(bp[e].z, yv[e], bp[e].w), s2[e]);
         }
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) dbk[k] += dl[k];
         *reinterpret_cast<uint2*>(dz_out + pnt * 128 + lane * 4) = make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
     }
     // block reduction over the 8 warps, then one atomic per value per block
@@ -425,9 +489,7 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
         for (int e = 0; e < 4; ++e) r[k * 128 + lane * 4 + e] = dw[k][e];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { r[MAXC * 128 + lane * 4 + e] = s1[e]; r[MAXC * 128 + 128 + lane * 4 + e] = s2[e]; }
-    if (lane == 0)
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) r[MAXC * 128 + 256 + k] = dbk[k];
+    if (lane < MAXC) r[MAXC * 128 + 256 + lane] = dbk;
     __syncthreads();
     const int total = MAXC * 128 + 256 + MAXC;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -551,26 +613,35 @@ __global__ void __launch_bounds__(256) k_cloud_bwd_dg(const float* __restrict__ 
                                                       int Nn /*512*/, int J /*1024*/, const float* __restrict__ g,
                                                       const float* __restrict__ ystar, const float4* __restrict__ bnp6,
                                                       float* __restrict__ dzv, double* __restrict__ stats6) {
-    // grid: (J/256, clouds); stats6 must be zeroed by the caller
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    // grid: (J/32, clouds); block 256 = 8 warps; lane -> output j, warp -> 1/8 of the Nn-long reduction.
+    // stats6 must be zeroed by the caller.
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
     const int b = blockIdx.y;
-    if (j >= J || b >= clouds) return;
-    const float4 bp = __ldg(bnp6 + j);
     const float* d = dcb + static_cast<size_t>(b) * Nn;
+    const int n0 = warp * (Nn / 8), n1 = n0 + Nn / 8;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int n = 0; n < Nn; n += 4) {
+    for (int n = n0; n < n1; n += 4) {
         s0 = fmaf(d[n], Wg[static_cast<size_t>(n) * ldw + j], s0);
         s1 = fmaf(d[n + 1], Wg[static_cast<size_t>(n + 1) * ldw + j], s1);
         s2 = fmaf(d[n + 2], Wg[static_cast<size_t>(n + 2) * ldw + j], s2);
         s3 = fmaf(d[n + 3], Wg[static_cast<size_t>(n + 3) * ldw + j], s3);
     }
-    const float s = (s0 + s1) + (s2 + s3);
-    const size_t o = static_cast<size_t>(b) * J + j;
-    const float v = (g[o] > 0.f) ? s : 0.f;
-    dzv[o] = v;
-    if (v != 0.f) {
-        atomicAdd(stats6 + j, static_cast<double>(v));
-        atomicAdd(stats6 + J + j, static_cast<double>(v) * static_cast<double>(fmaf(bp.z, ystar[o], bp.w)));
+    part[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += part[wv][lane];
+        const float4 bp = __ldg(bnp6 + j);
+        const size_t o = static_cast<size_t>(b) * J + j;
+        const float v = (g[o] > 0.f) ? s : 0.f;
+        dzv[o] = v;
+        if (v != 0.f) {
+            atomicAdd(stats6 + j, static_cast<double>(v));
+            atomicAdd(stats6 + J + j, static_cast<double>(v) * static_cast<double>(fmaf(bp.z, ystar[o], bp.w)));
+        }
     }
 }
 __global__ void __launch_bounds__(256) k_cloud_bwd_dw(const float* __restrict__ dcb, const float* __restrict__ g, int clouds, int Nn,
