@@ -28,7 +28,7 @@ enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EP
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;     // 16 was measured slightly slower (epilogues are issue-bound, not latency-bound)
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 128 + EPI_THREADS;
 constexpr int MAX_CLASSES = 8;    // compile-time cap on num_classes for the fused head kernels
@@ -66,7 +66,8 @@ struct GemmCfg {
     static constexpr bool HAS_Y = (EPI == EPI_DGRAD);
     static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
     static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
-    static constexpr int COMB_BYTES = 2 * 2 * 4 * 64 * 4;   // [buf][quantity][warp][64] floats
+    static constexpr int COMB_BYTES = (EPI == EPI_LOGITS) ? (EPI_WARPS / 4 - 1) * 128 * MAX_CLASSES * 4 + 1024
+                                                             : 4096;   // column accumulators / colmax exchange / logits partials
     static constexpr int W4_BYTES = (EPI == EPI_LOGITS) ? (MAX_CLASSES * 128 + MAX_CLASSES) * 4 : 0;
     static constexpr int BAR_BYTES = 256;
     static constexpr int FIXED = OUT_BYTES + Y_BYTES + COMB_BYTES + W4_BYTES + BAR_BYTES;
@@ -80,19 +81,29 @@ struct GemmCfg {
     static_assert(2 * BN <= 512, "accumulator double buffer exceeds TMEM");
 };
 
-// Column-wise reduction of a 32 (lanes) x 32 (registers) block: lane j returns op over lanes of v[j].
-template <bool IS_MAX>
-__device__ __forceinline__ float warp_colreduce32(float (&v)[32]) {
+// Column-wise reduction of a 32 (lanes) x CW (registers) block.  CW == 32: lane j returns op over lanes of v[j];
+// CW == 16: lane j returns column j >> 1.
+template <int CW, bool IS_MAX>
+__device__ __forceinline__ float warp_colreduce(float (&v)[CW]) {
     const uint32_t lane = lane_id();
+    int cnt = CW / 2;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
+        if (cnt >= 1) {
+            const bool up = (lane & off) != 0;
 #pragma unroll
-        for (int i = 0; i < off; ++i) {
-            float send = up ? v[i] : v[i + off];
-            float keep = up ? v[i + off] : v[i];
-            float got = __shfl_xor_sync(0xffffffffu, send, off);
-            v[i] = IS_MAX ? fmaxf(keep, got) : (keep + got);
+            for (int i = 0; i < CW / 2; ++i) {
+                if (i < cnt) {
+                    float send = up ? v[i] : v[i + cnt];
+                    float keep = up ? v[i + cnt] : v[i];
+                    float got = __shfl_xor_sync(0xffffffffu, send, off);
+                    v[i] = IS_MAX ? fmaxf(keep, got) : (keep + got);
+                }
+            }
+            cnt >>= 1;
+        } else {
+            float got = __shfl_xor_sync(0xffffffffu, v[0], off);
+            v[0] = IS_MAX ? fmaxf(v[0], got) : (v[0] + got);
         }
     }
     return v[0];
@@ -242,13 +253,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
         }
     } else if (warp_idx >= 4) {
-        // ------------------------------------------------------------ epilogue (8 warps)
-        // warp w reads TMEM lanes 32*(w%4)..+31 (hardware restriction); the two warps of a lane quadrant split
-        // every 64-column sub-tile into its left / right 32 columns.
+        // ------------------------------------------------------------ epilogue (EPI_WARPS warps)
+        // Pass 1 is row-mapped: warp w may only read TMEM lanes 32*(w%4)..+31, so the NQ warps that share a lane
+        // quadrant split every 64-column sub-tile into NQ column groups of CW columns.
+        // Pass 2 (STATS / DGRAD) is column-mapped over the bf16 staging tile and is free of that restriction.
+        constexpr int NQ = EPI_WARPS / 4;             // column groups per sub-tile in pass 1
+        constexpr int CW = 64 / NQ;                   // columns per thread in pass 1 (32 or 16)
+        constexpr int NH = EPI_WARPS / 8;             // row groups in pass 2
+        constexpr int RPT = 4 / NH;                   // rows per thread in pass 2
         const int ew = warp_idx & 3;                  // TMEM lane quadrant == row group
-        const int half = (warp_idx - 4) >> 2;         // 0: columns 0..31 of each sub-tile, 1: columns 32..63
+        const int cq = (warp_idx - 4) >> 2;           // column group of this warp
         const int row = ew * 32 + lane;               // row inside the tile
-        const int et = threadIdx.x - 128;             // 0..255
+        const int et = threadIdx.x - 128;             // 0..EPI_THREADS-1
         const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
         const bool elected = (et == 0);
         int iter = 0;
@@ -271,9 +287,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         constexpr bool COLACC = (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD);
         if constexpr (COLACC) {
-            // per-CTA column accumulators [2][BN]: valid because every tile of this CTA has the same n_tile
+            // per-CTA column accumulators [NH][2][BN]: valid because every tile of this CTA has the same n_tile
             // (the host launches a grid that is a multiple of num_n_tiles)
-            for (int i = et; i < 2 * BN; i += EPI_THREADS) comb[i] = 0.f;
+            for (int i = et; i < NH * 2 * BN; i += EPI_THREADS) comb[i] = 0.f;
             named_bar_sync(1, EPI_THREADS);
         }
 
@@ -291,27 +307,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t t_acc = tmem_base + acc * BN + lane_sel;
 
             if constexpr (EPI == EPI_WGRAD) {
-                // fp32 split-K partials straight from registers: row = output channel, 32 consecutive input channels
+                // fp32 split-K partials straight from registers: row = output channel, CW consecutive input channels
                 float* dst_row = p.out_f32 + static_cast<size_t>(grow) * p.ldc + n0;
                 const int kb0 = split * p.kb_per_split;
                 const bool nonempty = kb0 < (p.K + GEMM_BK - 1) / GEMM_BK;
 #pragma unroll 1
-                for (int c = half; c < BN / 32; c += 2) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_acc + c * 32, v);
+                for (int c = cq; c < BN / CW; c += NQ) {
+                    uint32_t v[CW];
+                    tmem_ld_cols<CW>(t_acc + c * CW, v);
                     tmem_ld_wait();
                     if (valid && nonempty) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int col = n0 + c * 32 + j * 4;
+                        for (int j = 0; j < CW / 4; ++j) {
+                            const int col = n0 + c * CW + j * 4;
                             if (col + 3 < p.N) {
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c * 32 + j * 4),
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c * CW + j * 4),
                                              "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
                                              "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
                                              : "memory");
                             } else {
                                 for (int e = 0; e < 4; ++e)
-                                    if (col + e < p.N) atomicAdd(dst_row + c * 32 + j * 4 + e, __uint_as_float(v[4 * j + e]));
+                                    if (col + e < p.N) atomicAdd(dst_row + c * CW + j * 4 + e, __uint_as_float(v[4 * j + e]));
                             }
                         }
                     }
@@ -324,13 +340,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int k = 0; k < MAX_CLASSES; ++k) lg[k] = 0.f;
 #pragma unroll 1
-                for (int c = half; c < BN / 32; c += 2) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_acc + c * 32, v);
+                for (int c = cq; c < BN / CW; c += NQ) {
+                    uint32_t v[CW];
+                    tmem_ld_cols<CW>(t_acc + c * CW, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = c * 32 + i;
+                    for (int i = 0; i < CW; ++i) {
+                        const int col = c * CW + i;
                         const float a = fmaxf(__uint_as_float(v[i]) + __ldg(p.bias + col), 0.f);
 #pragma unroll
                         for (int k = 0; k < MAX_CLASSES; ++k)
@@ -339,18 +355,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 tc_fence_before();
                 mbar_arrive(&tmem_empty[acc]);
-                // combine the two column halves through shared memory: comb[row][class]
+                // combine the NQ column groups through shared memory: comb[cq-1][row][class]
                 named_bar_sync(1, EPI_THREADS);       // previous tile's readers are done with comb
-                if (half == 1) {
+                if (cq > 0) {
 #pragma unroll
-                    for (int k = 0; k < MAX_CLASSES; ++k) comb[row * MAX_CLASSES + k] = lg[k];
+                    for (int k = 0; k < MAX_CLASSES; ++k) comb[((cq - 1) * 128 + row) * MAX_CLASSES + k] = lg[k];
                 }
                 named_bar_sync(1, EPI_THREADS);
-                if (half == 0 && valid) {
+                if (cq == 0 && valid) {
                     float* dst = p.logits + static_cast<size_t>(grow) * p.num_classes;
 #pragma unroll
-                    for (int k = 0; k < MAX_CLASSES; ++k)
-                        if (k < p.num_classes) dst[k] = lg[k] + comb[row * MAX_CLASSES + k] + w4s[MAX_CLASSES * 128 + k];
+                    for (int k = 0; k < MAX_CLASSES; ++k) {
+                        if (k < p.num_classes) {
+                            float z = lg[k] + w4s[MAX_CLASSES * 128 + k];
+#pragma unroll
+                            for (int q = 1; q < NQ; ++q) z += comb[((q - 1) * 128 + row) * MAX_CLASSES + k];
+                            dst[k] = z;
+                        }
+                    }
                 }
             } else {
                 const int cloud = (p.pts_per_cloud > 0 && valid) ? grow / p.pts_per_cloud : 0;
@@ -364,69 +386,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
                 for (int sub = 0; sub < SUBS; ++sub, ++sub_it) {
                     const int buf = sub_it & 1;
-                    const int c0 = n0 + sub * 64 + half * 32;     // first global column handled by this thread
-                    float* comb_b = comb + buf * (2 * 4 * 64);
+                    const int c0 = n0 + sub * 64 + cq * CW;       // first global column handled by this thread in pass 1
+                    float* comb_b = comb + buf * (4 * 64);        // COLMAX only: [buf][row group][64]
                     if constexpr (Cfg::HAS_Y) mbar_wait(&y_full[buf], (sub_it >> 1) & 1);
-                    uint32_t packed[16];
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_acc + sub * 64 + half * 32, v);
+                    uint32_t packed[CW / 2];
+                    uint32_t v[CW];
+                    tmem_ld_cols<CW>(t_acc + sub * 64 + cq * CW, v);
                     tmem_ld_wait();
                     if (sub == SUBS - 1) {       // all TMEM reads of this accumulator (by this thread) are done
                         tc_fence_before();
                         mbar_arrive(&tmem_empty[acc]);
                     }
-                    float o[32];
                     if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX) {
+                        float o[CW];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
+                        for (int i = 0; i < CW; ++i) {
                             float x = __uint_as_float(v[i]) + __ldg(p.bias + c0 + i);
                             if (cb_row) x += __ldg(cb_row + c0 + i);
                             o[i] = valid ? fmaxf(x, 0.f) : 0.f;
                         }
                         if constexpr (EPI == EPI_BIAS_RELU) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                            for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
                         } else {
                             if (uniform_cloud) {
-                                float r = warp_colreduce32<true>(o);
-                                comb_b[ew * 64 + half * 32 + lane] = r;
+                                const float r = warp_colreduce<CW, true>(o);
+                                if (CW == 32 || (lane & 1) == 0) comb_b[ew * 64 + cq * CW + (CW == 32 ? lane : (lane >> 1))] = r;
                             } else if (valid) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i)
+                                for (int i = 0; i < CW; ++i)
                                     atomicMax(p.colmax + static_cast<size_t>(cloud) * p.N + c0 + i, __float_as_uint(o[i]));
                             }
                         }
                     } else if constexpr (EPI == EPI_STATS || EPI == EPI_STATS_POOL) {
                         // pass 1 (row-mapped): accumulator (+ per-cloud term) -> bf16 -> staging tile
+                        float o[CW];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
+                        for (int i = 0; i < CW; ++i) {
                             float x = __uint_as_float(v[i]);
                             if (cb_row) x += __ldg(cb_row + c0 + i);
                             o[i] = valid ? x : 0.f;
                         }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                        for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
                     } else if constexpr (EPI == EPI_DGRAD) {
                         // pass 1 (row-mapped): dA * 1/(1-p) -> bf16 -> staging tile (masking happens column-mapped in pass 2)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
+                        for (int i = 0; i < CW / 2; ++i)
                             packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.keep_scale, __uint_as_float(v[2 * i + 1]) * p.keep_scale);
                     }
                     if constexpr (Cfg::HAS_OUT) {
                         uint8_t* orow = out_stage + buf * 16384 + row * 128;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(orow + (((half * 4 + j) ^ (row & 7)) << 4)) =
+                        for (int j = 0; j < CW / 8; ++j)
+                            *reinterpret_cast<uint4*>(orow + (((cq * (CW / 8) + j) ^ (row & 7)) << 4)) =
                                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                         fence_proxy_async_smem();
                         if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
                     }
                     named_bar_sync(1, EPI_THREADS);
-                    if constexpr (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD) {
-                        // pass 2 (column-mapped): warp pw owns the 16-byte chunk pw (8 columns) of all 128 rows,
-                        // lane l handles rows l, l+32, l+64, l+96; per-column parameters live in registers.
+                    if constexpr (COLACC) {
+                        // pass 2 (column-mapped): warp pw owns 16-byte chunk (pw & 7) = 8 columns of row group (pw >> 3);
+                        // lane l handles rows rg*(128/NH) + l + 32 i; per-column parameters live in registers.
                         const int pw = warp_idx - 4;
-                        const int colbase = n0 + sub * 64 + pw * 8;
+                        const int chunk = pw & 7;
+                        const int rg = pw >> 3;
+                        const int colbase = n0 + sub * 64 + chunk * 8;
+                        const int rbase = rg * (128 / NH) + lane;
                         uint8_t* tile_s = out_stage + buf * 16384;
                         float s1[8], s2[8];
 #pragma unroll
@@ -441,9 +467,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             }
                             const uint8_t* ytile = y_stage + buf * 16384;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int r = lane + 32 * i;
-                                const int off = r * 128 + ((pw ^ (r & 7)) << 4);
+                            for (int i = 0; i < RPT; ++i) {
+                                const int r = rbase + 32 * i;
+                                const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
                                 const uint4 dw = *reinterpret_cast<const uint4*>(tile_s + off);
                                 const uint4 yw = *reinterpret_cast<const uint4*>(ytile + off);
                                 const uint32_t ds[4] = {dw.x, dw.y, dw.z, dw.w};
@@ -479,9 +505,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 }
                             }
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int r = lane + 32 * i;
-                                const uint4 xw = *reinterpret_cast<const uint4*>(tile_s + r * 128 + ((pw ^ (r & 7)) << 4));
+                            for (int i = 0; i < RPT; ++i) {
+                                const int r = rbase + 32 * i;
+                                const uint4 xw = *reinterpret_cast<const uint4*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4));
                                 const uint32_t xs[4] = {xw.x, xw.y, xw.z, xw.w};
                                 const bool row_ok = (m0 + r) < p.M;
 #pragma unroll
@@ -566,7 +592,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if ((lane & 1) == 0) {
                                 const int qn = lane >> 4;
                                 const int colk = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                                comb[qn * BN + sub * 64 + pw * 8 + colk] += t[0];      // unique owner: no race
+                                comb[(rg * 2 + qn) * BN + sub * 64 + chunk * 8 + colk] += t[0];      // unique owner: no race
                             }
                         }
                         if constexpr (EPI == EPI_DGRAD) {
@@ -581,8 +607,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if constexpr (Cfg::HAS_Y) issue_y_load(sub_it + 2);
                         }
                     }
-                    if constexpr (false) {
-                    } else if constexpr (EPI == EPI_COLMAX) {
+                    if constexpr (EPI == EPI_COLMAX) {
                         if (uniform_cloud && et < 64) {
                             const float s = fmaxf(fmaxf(comb_b[et], comb_b[64 + et]), fmaxf(comb_b[128 + et], comb_b[192 + et]));
                             const int cl = m0 / p.pts_per_cloud;
@@ -600,7 +625,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int c = et; c < BN; c += EPI_THREADS) {
                     const int col = n0_fixed + c;
                     if (col >= p.N) continue;
-                    const float a0 = comb[c], a1 = comb[BN + c];
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) { a0 += comb[(h * 2) * BN + c]; a1 += comb[(h * 2 + 1) * BN + c]; }
                     if constexpr (EPI == EPI_DGRAD) {
                         const float4 bp = __ldg(p.bnp + col);      // sum dz*yhat = invstd * sum(dz*y) + (-mean*invstd) * sum dz
                         atomicAdd(p.stats + col, static_cast<double>(a0));

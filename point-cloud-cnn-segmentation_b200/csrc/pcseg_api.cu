@@ -705,11 +705,16 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// rows per strip of k_bn_bwd_apply: ~8 passes per block, but keep at least ~4 blocks per SM in flight
+// rows per strip of k_bn_bwd_apply: about 4 blocks per SM in total (each block ends with one atomic per column)
 static int apply_rows_per_strip(int N, int B, int C) {
     const int rpp = 256 / (C / 8);
-    int rps = rpp * 2 * 8;
-    while (rps > rpp * 2 && static_cast<long long>((N + rps - 1) / rps) * B < 4LL * num_sms()) rps /= 2;
+    const int unit = rpp * 4;                                    // rows consumed per loop iteration of a block
+    long long target_blocks = 4LL * num_sms();
+    long long strips_per_cloud = (target_blocks + B - 1) / B;
+    if (strips_per_cloud < 1) strips_per_cloud = 1;
+    int rps = static_cast<int>((N + strips_per_cloud - 1) / strips_per_cloud);
+    rps = ((rps + unit - 1) / unit) * unit;
+    if (rps < unit) rps = unit;
     return rps;
 }
 

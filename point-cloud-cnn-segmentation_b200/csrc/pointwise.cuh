@@ -559,10 +559,10 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
         }
     }
     const size_t base = static_cast<size_t>(cloud) * N;
-    for (int r = r0 + rslot; r < r1; r += 2 * rpp) {
-        uint4 yw[2], zw[2];
+    for (int r = r0 + rslot; r < r1; r += 4 * rpp) {
+        uint4 yw[4], zw[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int rr = r + u * rpp;
             if (rr < r1) {
                 yw[u] = *reinterpret_cast<const uint4*>(y + (base + rr) * ld_y + c0);
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int rr = r + u * rpp;
             if (rr >= r1) break;
             const uint32_t ys[4] = {yw[u].x, yw[u].y, yw[u].z, yw[u].w};
