@@ -29,6 +29,8 @@ WORKLOADS = {
     "cfg3_train": (16, 131072, "train"),
     "cfg2_eval": (8, 16384, "eval"),
     "cfg3_eval": (16, 131072, "eval"),
+    "cfg4": (8, 65536, "train"),          # configs[3] at 8 GPUs: global 64 x 64k -> 8 clouds x 65 536 per GPU
+    "cfg5_eval": (1, 1048576, "eval"),    # configs[4]: one 1M-point scene, inference
 }
 NUM_CLASSES = 5
 DROPOUT_P = 0.3
@@ -36,6 +38,10 @@ DROPOUT_P = 0.3
 FWD_FLOP_PER_PT = 2 * (1392896 + 128 * NUM_CLASSES)
 TRAIN_FLOP_PER_PT = 3 * FWD_FLOP_PER_PT - 512
 GFEAT_FLOP_PER_PT = 2 * 1024 * 1024          # one global_feat GEMM (forward, dgrad or wgrad), per point
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the three global_feat GEMMs at 8 x 16 384 points, from the
+# committed `ncu --set full` capture profiles/r01_ncu_full_gemm_cfg2_train.txt (MB): fwd 270.7+222.9, dgrad 539.0+239.1,
+# wgrad 541.1+3.6.  Algorithmic minimum: fwd a5 268 + y6 268; dgrad dy6 268 + y5 268 + dz5 268; wgrad dy6 268 + a5 268.
+NCU_TRAFFIC_MB_CFG2 = {5: 493.6, 21: 778.1, 37: 544.7}
 
 
 def measured_peaks():
@@ -70,7 +76,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample (used to cut the samples that fall inside the timed region)"""
+        return len(self.lines)
+
+    def stop(self, lo=0, hi=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -80,7 +90,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        hi = len(self.lines) if hi is None else hi
+        lines = self.lines[lo:hi] if hi > lo else self.lines[max(0, lo - 2):hi + 2]
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -241,6 +253,8 @@ def run_ours(args, B, N, mode):
 
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                 # started early: nvidia-smi needs ~100s of ms before its first sample
     for _ in range(warmup):
         step_resident()
     barrier()
@@ -248,17 +262,16 @@ def run_ours(args, B, N, mode):
     eng = model._get_engine(dev)
     if mode == "train":
         profile_enable(eng, B, N, True)
-    sampler = ClockSampler(local_rank)
     launches0 = pcseg_b200.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
     barrier()
+    mark0 = sampler.mark()
     e0.record()
     for _ in range(steps):
         step_resident()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    mark1 = sampler.mark()
     launches = pcseg_b200.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     prof = profile_read(eng, B, N) if mode == "train" else {}
@@ -274,6 +287,7 @@ def run_ours(args, B, N, mode):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(mark0, mark1)             # samples taken during the device-timed region (neighbours if it was < 100 ms)
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -302,7 +316,8 @@ def run_ours(args, B, N, mode):
         achieved = GFEAT_FLOP_PER_PT * B * N / (ms / n * 1e-3) / 1e12
         share = sum(prof.get(tg, (0, 1))[0] for tg in (5, 21, 37)) / ms_total
         roof = {"bound": "tensor", "kernel": names[tag], "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                "frac": achieved / peaks["bf16_sustained"],
+                "traffic": (NCU_TRAFFIC_MB_CFG2[tag] * 1e6 if (B, N) == (8, 16384) else None), "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": peaks["source"] + " bf16 sustained",
                 "ms_per_launch": ms / n, "global_feat_gemms_share_of_step": share}
     step_tflops = flop_per_pt * B * N / (ms_per_step * 1e-3) / 1e12        # per GPU
 
@@ -334,8 +349,8 @@ def run_ours(args, B, N, mode):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -267,6 +267,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int et = threadIdx.x - 128;             // 0..EPI_THREADS-1
         const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
         const bool elected = (et == 0);
+        const uint32_t out_s = smem_u32(out_stage);   // 32-bit shared-space addresses (explicit LDS/STS below)
+        const uint32_t y_s = smem_u32(y_stage);
+        const uint32_t comb_s = smem_u32(comb);
         int iter = 0;
         uint32_t sub_it = 0;                          // global 64-column sub-tile counter (buffer parity)
 
@@ -400,15 +403,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX) {
                         float o[CW];
 #pragma unroll
-                        for (int i = 0; i < CW; ++i) {
-                            float x = __uint_as_float(v[i]) + __ldg(p.bias + c0 + i);
-                            if (cb_row) x += __ldg(cb_row + c0 + i);
-                            o[i] = valid ? fmaxf(x, 0.f) : 0.f;
+                        for (int i = 0; i < CW; i += 4) {
+                            const float4 b4v = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+                            o[i] = __uint_as_float(v[i]) + b4v.x;
+                            o[i + 1] = __uint_as_float(v[i + 1]) + b4v.y;
+                            o[i + 2] = __uint_as_float(v[i + 2]) + b4v.z;
+                            o[i + 3] = __uint_as_float(v[i + 3]) + b4v.w;
+                        }
+                        if (cb_row != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < CW; i += 4) {
+                                const float4 c4v = __ldg(reinterpret_cast<const float4*>(cb_row + c0 + i));
+                                o[i] += c4v.x; o[i + 1] += c4v.y; o[i + 2] += c4v.z; o[i + 3] += c4v.w;
+                            }
                         }
                         if constexpr (EPI == EPI_BIAS_RELU) {
+                            // rows beyond M are clipped by the TMA store: no masking needed
 #pragma unroll
-                            for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                            for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(fmaxf(o[2 * i], 0.f), fmaxf(o[2 * i + 1], 0.f));
                         } else {
+#pragma unroll
+                            for (int i = 0; i < CW; ++i) o[i] = valid ? fmaxf(o[i], 0.f) : 0.f;
                             if (uniform_cloud) {
                                 const float r = warp_colreduce<CW, true>(o);
                                 if (CW == 32 || (lane & 1) == 0) comb_b[ew * 64 + cq * CW + (CW == 32 ? lane : (lane >> 1))] = r;
@@ -419,28 +434,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             }
                         }
                     } else if constexpr (EPI == EPI_STATS || EPI == EPI_STATS_POOL) {
-                        // pass 1 (row-mapped): accumulator (+ per-cloud term) -> bf16 -> staging tile
-                        float o[CW];
+                        // pass 1 (row-mapped): accumulator (+ per-cloud term) -> bf16 -> staging tile.
+                        // Rows beyond M have exactly-zero accumulators (TMA zero fill), so they add nothing to the sums.
+                        if (cb_row != nullptr) {
+                            if (valid) {
 #pragma unroll
-                        for (int i = 0; i < CW; ++i) {
-                            float x = __uint_as_float(v[i]);
-                            if (cb_row) x += __ldg(cb_row + c0 + i);
-                            o[i] = valid ? x : 0.f;
+                                for (int i = 0; i < CW; i += 4) {
+                                    const float4 c4v = __ldg(reinterpret_cast<const float4*>(cb_row + c0 + i));
+                                    v[i] = __float_as_uint(__uint_as_float(v[i]) + c4v.x);
+                                    v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + c4v.y);
+                                    v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + c4v.z);
+                                    v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + c4v.w);
+                                }
+                            }
                         }
 #pragma unroll
-                        for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                        for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
                     } else if constexpr (EPI == EPI_DGRAD) {
                         // pass 1 (row-mapped): dA * 1/(1-p) -> bf16 -> staging tile (masking happens column-mapped in pass 2)
+                        if (p.drop_thr16 != 0u) {
 #pragma unroll
-                        for (int i = 0; i < CW / 2; ++i)
-                            packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.keep_scale, __uint_as_float(v[2 * i + 1]) * p.keep_scale);
+                            for (int i = 0; i < CW / 2; ++i)
+                                packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.keep_scale, __uint_as_float(v[2 * i + 1]) * p.keep_scale);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        }
                     }
                     if constexpr (Cfg::HAS_OUT) {
-                        uint8_t* orow = out_stage + buf * 16384 + row * 128;
+                        const uint32_t orow = out_s + buf * 16384 + row * 128;
 #pragma unroll
                         for (int j = 0; j < CW / 8; ++j)
-                            *reinterpret_cast<uint4*>(orow + (((cq * (CW / 8) + j) ^ (row & 7)) << 4)) =
-                                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            sts128(orow + (((cq * (CW / 8) + j) ^ (row & 7)) << 4),
+                                   make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]));
                         fence_proxy_async_smem();
                         if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
                     }
@@ -453,7 +479,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         const int rg = pw >> 3;
                         const int colbase = n0 + sub * 64 + chunk * 8;
                         const int rbase = rg * (128 / NH) + lane;
-                        uint8_t* tile_s = out_stage + buf * 16384;
+                        const uint32_t tile_s = out_s + buf * 16384;
                         float s1[8], s2[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
@@ -465,13 +491,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 sc[e] = bp.x;
                                 sh[e] = bp.y;
                             }
-                            const uint8_t* ytile = y_stage + buf * 16384;
+                            const uint32_t ytile = y_s + buf * 16384;
 #pragma unroll
                             for (int i = 0; i < RPT; ++i) {
                                 const int r = rbase + 32 * i;
                                 const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
-                                const uint4 dw = *reinterpret_cast<const uint4*>(tile_s + off);
-                                const uint4 yw = *reinterpret_cast<const uint4*>(ytile + off);
+                                const uint4 dw = lds128(tile_s + off);
+                                const uint4 yw = lds128(ytile + off);
                                 const uint32_t ds[4] = {dw.x, dw.y, dw.z, dw.w};
                                 const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w};
                                 uint32_t keep = 0xFFu;
@@ -489,8 +515,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     s1[e] += dz[e];
                                     s2[e] = fmaf(dz[e], yv, s2[e]);
                                 }
-                                *reinterpret_cast<uint4*>(tile_s + off) = make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]),
-                                                                                      pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
+                                sts128(tile_s + off, make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]),
+                                                                pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7])));
                             }
                         } else {
                             float bestv[8], sg[8];
@@ -507,7 +533,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                             for (int i = 0; i < RPT; ++i) {
                                 const int r = rbase + 32 * i;
-                                const uint4 xw = *reinterpret_cast<const uint4*>(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                const uint4 xw = lds128(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4));
                                 const uint32_t xs[4] = {xw.x, xw.y, xw.z, xw.w};
                                 const bool row_ok = (m0 + r) < p.M;
 #pragma unroll
@@ -592,7 +618,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if ((lane & 1) == 0) {
                                 const int qn = lane >> 4;
                                 const int colk = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                                comb[(rg * 2 + qn) * BN + sub * 64 + chunk * 8 + colk] += t[0];      // unique owner: no race
+                                const uint32_t ca = comb_s + 4u * ((rg * 2 + qn) * BN + sub * 64 + chunk * 8 + colk);
+                                sts_f32(ca, lds_f32(ca) + t[0]);      // unique owner: no race
                             }
                         }
                         if constexpr (EPI == EPI_DGRAD) {

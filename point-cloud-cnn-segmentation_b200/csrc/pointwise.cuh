@@ -288,6 +288,9 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
                                                   const float* __restrict__ W4, const float* __restrict__ b4, int C,
                                                   float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
+    // one warp handles PP consecutive points per iteration (independent dependency chains hide the shuffle latency);
+    // lane = 4 channels
+    constexpr int PP = 4;
     __shared__ double red_d[8][2];
     __shared__ unsigned long long red_u[8][2];
     const int lane = threadIdx.x & 31;
@@ -302,63 +305,66 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
     for (int k = 0; k < MAXC; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) w[k][e] = (k < C) ? W4[k * 128 + lane * 4 + e] : 0.f;
-    float bias_k = (lane < C) ? __ldg(b4 + lane) : 0.f;
-    float cw_l = (class_w != nullptr && lane < C) ? __ldg(class_w + lane) : 1.f;
+    const float bias_k = (lane < C) ? __ldg(b4 + lane) : 0.f;
+    const float cw_l = (class_w != nullptr && lane < C) ? __ldg(class_w + lane) : 1.f;
     double loss_num = 0.0, w_sum = 0.0;
     unsigned long long correct = 0, nvalid = 0;
-    uint2 yw_next = make_uint2(0, 0);
-    long long lab_next = -1;
-    if (warp_g < P) {
-        yw_next = *reinterpret_cast<const uint2*>(ys3 + warp_g * 128 + lane * 4);
-        if (labels != nullptr && lane == 0) lab_next = labels[warp_g];
-    }
-    for (long pnt = warp_g; pnt < P; pnt += nwarps) {
-        const uint2 yw = yw_next;
-        const long long lab = lab_next;
-        const long nxt = pnt + nwarps;
-        if (nxt < P) {                                   // prefetch the next point before the dependent math
-            yw_next = *reinterpret_cast<const uint2*>(ys3 + nxt * 128 + lane * 4);
-            if (labels != nullptr && lane == 0) lab_next = labels[nxt];
-        }
-        float a[4];
-        a[0] = fmaxf(fmaf(bp[0].x, bf16_lo(yw.x), bp[0].y), 0.f);
-        a[1] = fmaxf(fmaf(bp[1].x, bf16_hi(yw.x), bp[1].y), 0.f);
-        a[2] = fmaxf(fmaf(bp[2].x, bf16_lo(yw.y), bp[2].y), 0.f);
-        a[3] = fmaxf(fmaf(bp[3].x, bf16_hi(yw.y), bp[3].y), 0.f);
-        // lane k ends up holding logit k (k < C): reduce each class over the warp, keep it on lane k
-        float zmine = 0.f;
+    for (long p0 = warp_g * PP; p0 < P; p0 += nwarps * PP) {
+        uint2 yw[PP];
+        long long lab[PP];
 #pragma unroll
-        for (int k = 0; k < MAXC; ++k) {
-            if (k < C) {
-                float s = a[0] * w[k][0];
-                s = fmaf(a[1], w[k][1], s);
-                s = fmaf(a[2], w[k][2], s);
-                s = fmaf(a[3], w[k][3], s);
-                s = warp_sum(s);
-                if (lane == k) zmine = s;
+        for (int u = 0; u < PP; ++u) {
+            const long pnt = p0 + u;
+            yw[u] = (pnt < P) ? *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4) : make_uint2(0, 0);
+            lab[u] = (labels != nullptr && pnt < P && lane == 0) ? labels[pnt] : -1;
+        }
+        float zmine[PP];
+#pragma unroll
+        for (int u = 0; u < PP; ++u) {
+            float a[4];
+            a[0] = fmaxf(fmaf(bp[0].x, bf16_lo(yw[u].x), bp[0].y), 0.f);
+            a[1] = fmaxf(fmaf(bp[1].x, bf16_hi(yw[u].x), bp[1].y), 0.f);
+            a[2] = fmaxf(fmaf(bp[2].x, bf16_lo(yw[u].y), bp[2].y), 0.f);
+            a[3] = fmaxf(fmaf(bp[3].x, bf16_hi(yw[u].y), bp[3].y), 0.f);
+            float zm = 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                if (k < C) {
+                    float s = a[0] * w[k][0];
+                    s = fmaf(a[1], w[k][1], s);
+                    s = fmaf(a[2], w[k][2], s);
+                    s = fmaf(a[3], w[k][3], s);
+                    s = warp_sum(s);
+                    if (lane == k) zm = s;          // lane k keeps logit k
+                }
             }
+            zmine[u] = zm + bias_k;
         }
-        zmine += bias_k;
-        if (lane < C) logits[pnt * C + lane] = zmine;
-        if (labels != nullptr) {
-            const long long labv = __shfl_sync(0xffffffffu, lab, 0);
-            if (labv >= 0) {                             // warp-uniform
-                float zm = (lane < C) ? zmine : -INFINITY;
-                float zmax = zm;
 #pragma unroll
-                for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));   // C <= 8 lanes
-                const unsigned am_mask = __ballot_sync(0xffffffffu, lane < C && zm == zmax);
-                const int am = __ffs(am_mask) - 1;       // first maximum, like torch.argmax
-                float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
+        for (int u = 0; u < PP; ++u) {
+            const long pnt = p0 + u;
+            if (pnt >= P) break;
+            if (lane < C) logits[pnt * C + lane] = zmine[u];
+            if (labels != nullptr) {
+                const long long labv = __shfl_sync(0xffffffffu, lab[u], 0);
+                if (labv >= 0) {                             // warp-uniform
+                    const float zm = (lane < C) ? zmine[u] : -INFINITY;
+                    float zmax = zm;
 #pragma unroll
-                for (int o = 4; o >= 1; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
-                const float zl = __shfl_sync(0xffffffffu, zmine, static_cast<int>(labv));
-                const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(labv));
-                if (lane == 0) {
-                    loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(ex) - zl);
-                    w_sum += wl;
-                    correct += (am == labv);
-                    nvalid += 1;
+                    for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));   // C <= 8 lanes
+                    const unsigned am_mask = __ballot_sync(0xffffffffu, lane < C && zm == zmax);
+                    const int am = __ffs(am_mask) - 1;       // first maximum, like torch.argmax
+                    float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
+#pragma unroll
+                    for (int o = 4; o >= 1; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                    const float zl = __shfl_sync(0xffffffffu, zmine[u], static_cast<int>(labv));
+                    const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(labv));
+                    if (lane == 0) {
+                        loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(ex) - zl);
+                        w_sum += wl;
+                        correct += (am == labv);
+                        nvalid += 1;
+                    }
                 }
             }
         }
@@ -423,63 +429,63 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
     const float cw_l = (class_w != nullptr && lane < C) ? __ldg(class_w + lane) : 1.f;
     const float* zsrc = fused ? logits : dlogits;
 
-    uint2 yw_next = make_uint2(0, 0);
-    float z_next = 0.f;
-    long long lab_next = -1;
-    if (warp_g < P) {
-        yw_next = *reinterpret_cast<const uint2*>(ys3 + warp_g * 128 + lane * 4);
-        if (lane < C) z_next = zsrc[warp_g * C + lane];
-        if (fused && lane == 0) lab_next = labels[warp_g];
-    }
-    for (long pnt = warp_g; pnt < P; pnt += nwarps) {
-        const uint2 yw = yw_next;
-        const float zin = z_next;
-        const long long lab0 = lab_next;
-        const long nxt = pnt + nwarps;
-        if (nxt < P) {
-            yw_next = *reinterpret_cast<const uint2*>(ys3 + nxt * 128 + lane * 4);
-            if (lane < C) z_next = zsrc[nxt * C + lane];
-            if (fused && lane == 0) lab_next = labels[nxt];
+    constexpr int PP = 1;                             // points per warp iteration (2 spills registers at 2 blocks/SM)
+    for (long p0 = warp_g * PP; p0 < P; p0 += nwarps * PP) {
+        uint2 yw[PP];
+        float zin[PP];
+        long long lab0[PP];
+#pragma unroll
+        for (int u = 0; u < PP; ++u) {
+            const long pnt = p0 + u;
+            const bool ok = pnt < P;
+            yw[u] = ok ? *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4) : make_uint2(0, 0);
+            zin[u] = (ok && lane < C) ? zsrc[pnt * C + lane] : 0.f;
+            lab0[u] = (ok && fused && lane == 0) ? labels[pnt] : -1;
         }
-        float dl_mine = zin;                              // lane k holds dlogit k
-        if (fused) {
-            const long long lab = __shfl_sync(0xffffffffu, lab0, 0);
-            if (lab >= 0) {
-                const float zm = (lane < C) ? zin : -INFINITY;
-                float zmax = zm;
 #pragma unroll
-                for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-                const float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
-                float se = ex;
+        for (int u = 0; u < PP; ++u) {
+            const long pnt = p0 + u;
+            if (pnt >= P) break;
+            float dl_mine = zin[u];                           // lane k holds dlogit k
+            if (fused) {
+                const long long lab = __shfl_sync(0xffffffffu, lab0[u], 0);
+                if (lab >= 0) {
+                    const float zm = (lane < C) ? zin[u] : -INFINITY;
+                    float zmax = zm;
 #pragma unroll
-                for (int o = 4; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-                const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(lab));
-                dl_mine = wl * inv_wsum * (ex / se - (lane == lab ? 1.f : 0.f));
-            } else {
-                dl_mine = 0.f;
+                    for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                    const float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
+                    float se = ex;
+#pragma unroll
+                    for (int o = 4; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+                    const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(lab));
+                    dl_mine = wl * inv_wsum * (ex / se - (lane == lab ? 1.f : 0.f));
+                } else {
+                    dl_mine = 0.f;
+                }
             }
-        }
-        if (lane >= C) dl_mine = 0.f;
-        dbk += dl_mine;
-        float dl[MAXC];
+            if (lane >= C) dl_mine = 0.f;
+            dbk += dl_mine;
+            float dl[MAXC];
 #pragma unroll
-        for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __shfl_sync(0xffffffffu, dl_mine, k) : 0.f;
-        const float yv[4] = {bf16_lo(yw.x), bf16_hi(yw.x), bf16_lo(yw.y), bf16_hi(yw.y)};
-        float dz[4];
+            for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __shfl_sync(0xffffffffu, dl_mine, k) : 0.f;
+            const float yv[4] = {bf16_lo(yw[u].x), bf16_hi(yw[u].x), bf16_lo(yw[u].y), bf16_hi(yw[u].y)};
+            float dz[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float t = fmaf(bp[e].x, yv[e], bp[e].y);
-            const float a = fmaxf(t, 0.f);
-            float da = 0.f;
+            for (int e = 0; e < 4; ++e) {
+                const float t = fmaf(bp[e].x, yv[e], bp[e].y);
+                const float a = fmaxf(t, 0.f);
+                float da = 0.f;
 #pragma unroll
-            for (int k = 0; k < MAXC; ++k) {
-                if (k < C) { da = fmaf(dl[k], w[k][e], da); dw[k][e] = fmaf(dl[k], a, dw[k][e]); }
+                for (int k = 0; k < MAXC; ++k) {
+                    if (k < C) { da = fmaf(dl[k], w[k][e], da); dw[k][e] = fmaf(dl[k], a, dw[k][e]); }
+                }
+                dz[e] = (t > 0.f) ? round_bf16(da) : 0.f;
+                s1[e] += dz[e];
+                s2[e] = fmaf(dz[e], fmaf(bp[e].z, yv[e], bp[e].w), s2[e]);
             }
-            dz[e] = (t > 0.f) ? round_bf16(da) : 0.f;
-            s1[e] += dz[e];
-            s2[e] = fmaf(dz[e], fmaf(bp[e].z, yv[e], bp[e].w), s2[e]);
+            *reinterpret_cast<uint2*>(dz_out + pnt * 128 + lane * 4) = make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
         }
-        *reinterpret_cast<uint2*>(dz_out + pnt * 128 + lane * 4) = make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
     }
     // block reduction over the 8 warps, then one atomic per value per block
     float* r = red[warp];

@@ -165,6 +165,26 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- explicit shared-space accesses
+// (the dynamic smem base is re-aligned through an integer cast, after which the compiler can only emit generic
+//  LD/ST with 64-bit address arithmetic; these keep the epilogue on 32-bit LDS/STS)
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (tcgen05), 128-byte swizzle, version 1 (Blackwell).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
@@ -198,11 +218,12 @@ __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w 
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// Philox4x32-10 counter-based RNG (dropout masks are regenerated in backward from (seed, index)).
+// Philox4x32-7 counter-based RNG (7 rounds is the smallest Crush-resistant variant of Salmon et al.); dropout masks
+// are regenerated in backward from (seed, element index), never stored.
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < 7; ++i) {
         uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
         uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
