@@ -28,7 +28,7 @@ enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EP
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int EPI_WARPS = 8;     // 16 was measured slightly slower (epilogues are issue-bound, not latency-bound)
+constexpr int EPI_WARPS = 8;     // 16 measured slower overall (only global_feat fwd+pool gains)
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 128 + EPI_THREADS;
 constexpr int MAX_CLASSES = 8;    // compile-time cap on num_classes for the fused head kernels

@@ -68,6 +68,15 @@ class PointNetSegmentation(nn.Module):
         self._fwd_token = 0
         self._manual_version = 0   # bumped when the arena is modified behind autograd's back (fused optimizer)
 
+    def __getstate__(self):
+        """copy.deepcopy / pickling: the engine (ctypes handles, workspaces) and the arena bookkeeping are per-instance
+        run-time state and are rebuilt lazily on the next forward."""
+        state = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        state = dict(state)
+        state["_engine"] = None
+        state["_flat"] = None
+        return state
+
     # ------------------------------------------------------------------ flat arenas
     def _param_list(self):
         ps = []

@@ -1,0 +1,134 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes (where the fp64 oracle is too slow)
+plus behavioural checks of the training loop."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointnet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(C, seed, train=False):
+    import pcseg_b200
+    m = pcseg_b200.PointNetSegmentation(C)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in orc.synth_state(C, seed).items()})
+    m = m.cuda()
+    return m.train() if train else m.eval()
+
+
+def test_eval_point_permutation_equivariance_full_size():
+    """cfg2 shape (8 x 16 384): permuting the points of every cloud permutes the logits, bit for bit (a point's logits
+    depend on the other points only through the order-independent max-pool, pcs.py:114)."""
+    m = _model(5, 1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(8, 16384, 4, device="cuda", generator=g)
+    perm = torch.stack([torch.randperm(16384, device="cuda", generator=g) for _ in range(8)])
+    with torch.no_grad():
+        a = m(x)
+        b = m(torch.gather(x, 1, perm[:, :, None].expand(-1, -1, 4)))
+    assert torch.equal(torch.gather(a, 1, perm[:, :, None].expand(-1, -1, 5)), b)
+
+
+def test_eval_clouds_are_independent_full_size():
+    """In eval mode a cloud's logits do not depend on the other clouds of the batch (pcs.py:98-133 has no cross-cloud op
+    once BatchNorm uses running statistics)."""
+    m = _model(5, 2)
+    x = torch.rand(8, 16384, 4, device="cuda")
+    with torch.no_grad():
+        full = m(x).clone()
+        for b in (0, 5):
+            assert torch.equal(m(x[b:b + 1].contiguous())[0], full[b])
+
+
+def test_eval_large_scene_and_argmax_consistency():
+    """cfg5 shape: one 1M-point cloud; integer output (labels) must equal argmax of the returned logits exactly."""
+    m = _model(5, 3)
+    x = torch.rand(1, 1 << 20, 4, device="cuda")
+    with torch.no_grad():
+        logits, labels = m.predict(x)
+    assert torch.isfinite(logits).all()
+    assert torch.equal(labels, logits.argmax(-1))
+    # a strided sample against the fp64 oracle needs the global feature of the whole cloud -> check a small prefix cloud
+    xs = x[:, :4096].contiguous()
+    with torch.no_grad():
+        got = m(xs).cpu().numpy()
+    ref = orc.forward_eval(orc.synth_state(5, 3), xs.cpu().numpy(), dtype=np.float32)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-2
+
+
+def test_eval_zero_padded_rows_enter_the_max_pool():
+    """Padding contract (pcs.py:53-61): padded rows are real zero inputs; appending them can only change
+    a cloud's logits through the max-pool, and replacing them by copies of an existing point must not change anything."""
+    m = _model(3, 4)
+    x = torch.rand(2, 1000, 4, device="cuda")
+    xp = torch.cat([x, x[:, :24]], dim=1).contiguous()             # duplicate points: max-pool unchanged
+    with torch.no_grad():
+        a = m(x)
+        b = m(xp)
+    assert torch.equal(a, b[:, :1000])
+
+
+def test_training_reduces_loss_like_the_cpu_port():
+    """30 fused steps (forward + weighted CE + backward + Adam, dropout off) on a learnable synthetic task: the loss must
+    fall, and track the torch-CPU port of the reference step started from the same weights."""
+    import pcseg_b200
+    from oracle.torch_port import TorchCpuPort
+    C, B, N = 3, 4, 512
+    rng = np.random.default_rng(0)
+    x = rng.random((B, N, 4), dtype=np.float32)
+    labels = (x[..., 0] * 3).astype(np.int64).clip(0, C - 1)      # class = slab along the first coordinate
+    labels[0, 400:] = -1
+    x[0, 400:] = 0
+    sd = orc.synth_state(C, 77)
+    # start from reference-style BN state (gamma 1, beta 0) so that both runs are well conditioned
+    for k in list(sd):
+        if k.startswith("bn") and k.endswith(".weight"):
+            sd[k] = np.ones_like(sd[k])
+        if k.startswith("bn") and k.endswith(".bias"):
+            sd[k] = np.zeros_like(sd[k])
+    cw = np.array([1.0, 0.7, 1.3], np.float32)
+    m = pcseg_b200.PointNetSegmentation(C)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    m = m.cuda().train()
+    m.dropout.p = 0.0
+    tr = pcseg_b200.FusedTrainer(m, class_weights=cw, lr=1e-3, weight_decay=1e-4)
+    xt, lt = torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda()
+    ours = [float(tr.step(xt, lt)["loss"].item()) for _ in range(30)]
+
+    torch.set_num_threads(4)
+    port = TorchCpuPort(C, state=sd)
+    ref = [port.train_step(torch.from_numpy(x), torch.from_numpy(labels), torch.from_numpy(cw), dropout_p=0.0) for _ in range(30)]
+    assert ours[-1] < 0.7 * ours[0], ours
+    assert abs(ours[0] - ref[0]) < 2e-2 * ref[0]
+    # trajectories stay close (bf16 forward noise makes them drift apart slowly)
+    assert max(abs(a - b) for a, b in zip(ours, ref)) < 0.15 * ref[0], (ours[::5], ref[::5])
+    # the running statistics and step counters moved like the reference's
+    assert int(m.bn1.num_batches_tracked.item()) == int(sd["bn1.num_batches_tracked"]) + 30
+
+
+def test_deepcopy_and_state_dict_roundtrip_after_training():
+    import pcseg_b200
+    m = _model(5, 6, train=True)
+    x = torch.rand(2, 256, 4, device="cuda")
+    m(x).sum().backward()
+    clone = copy.deepcopy(m)
+    m.eval(); clone.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), clone(x))
+    fresh = pcseg_b200.PointNetSegmentation(5).cuda().eval()
+    fresh.load_state_dict(m.state_dict(), strict=True)
+    with torch.no_grad():
+        assert torch.equal(m(x), fresh(x))
+
+
+def test_eval_is_deterministic_and_input_dtype_agnostic():
+    m = _model(5, 8)
+    x = torch.rand(3, 777, 4, device="cuda")
+    with torch.no_grad():
+        a = m(x)
+        b = m(x.double())                       # converted to fp32 like any torch module input would be
+        c = m(x.transpose(0, 1).contiguous().transpose(0, 1))     # non-contiguous view
+    assert torch.equal(a, b) and torch.equal(a, c)
