@@ -693,8 +693,8 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     TRY(timed_gemm(c, c->fw[8], 8, s));
     TRY(finalize(8));
     {
-        int grid = static_cast<int>((P + 7) / 8);
-        if (grid > num_sms() * 8) grid = num_sms() * 8;
+        int grid = static_cast<int>((P + 31) / 32);          // 8 warps x 4 points per block iteration
+        if (grid > num_sms() * 4) grid = num_sms() * 4;
         k_head_fwd<MAX_CLASSES><<<grid, 256, 0, s>>>(c->y[8], P, c->bnp[8], params + L.off[18], params + L.off[19], c->C, logits, labels,
                                                     class_w, reinterpret_cast<CeAccum*>(ce));
         LAUNCH_OK("k_head_fwd");
@@ -769,11 +769,18 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
 
     if (phase != 2) {
     {   // seg_conv4 + loss gradient
-        int grid = static_cast<int>((P + 7) / 8);
+        int grid = static_cast<int>((P + 31) / 32);
         if (grid > num_sms() * 2) grid = num_sms() * 2;
-        k_head_bwd<MAX_CLASSES><<<grid, 256, 0, s>>>(c->y[8], P, c->bnp[8], params + L.off[18], c->C, dlogits, logits, labels, class_w,
-                                                    wsum_total, c->dz[8], grads + L.off[18], grads + L.off[19],
-                                                    c->stats_b + c->stat_off[8]);
+#define HEAD_BWD(NC_)                                                                                                         \
+    case NC_:                                                                                                                 \
+        k_head_bwd<NC_><<<grid, 256, 0, s>>>(c->y[8], P, c->bnp[8], params + L.off[18], dlogits, logits, labels, class_w, wsum_total, \
+                                             c->dz[8], grads + L.off[18], grads + L.off[19], c->stats_b + c->stat_off[8]);  \
+        break;
+        switch (c->C) {
+            HEAD_BWD(1) HEAD_BWD(2) HEAD_BWD(3) HEAD_BWD(4) HEAD_BWD(5) HEAD_BWD(6) HEAD_BWD(7) HEAD_BWD(8)
+            default: return fail("pcseg_backward: unsupported num_classes %d", c->C);
+        }
+#undef HEAD_BWD
         LAUNCH_OK("k_head_bwd");
     }
     // seg_conv3

@@ -283,93 +283,106 @@ struct CeAccum {
     unsigned long long valid;     // labels != -1
 };
 
+// Layout of both head kernels: 8 lanes per point (4 points per warp), 16 channels per lane; the channel reduction needs
+// only 3 shuffle steps per class and every warp instruction works on 4 points.  seg_conv4 weights are staged in shared
+// memory as [class][128] and read with 16-byte LDS (lanes of the same point read disjoint 64-byte slices).
 template <int MAXC>
 __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restrict__ ys3, long P, const float4* __restrict__ bnp,
                                                   const float* __restrict__ W4, const float* __restrict__ b4, int C,
                                                   float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
-    // one warp handles PP consecutive points per iteration (independent dependency chains hide the shuffle latency);
-    // lane = 4 channels
-    constexpr int PP = 4;
+    __shared__ __align__(16) float w_s[MAXC * 128];
     __shared__ double red_d[8][2];
     __shared__ unsigned long long red_u[8][2];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const int sub = lane & 7;                  // 16-channel slice of the point
+    const int grp = lane >> 3;                 // point slot inside the warp
+    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) w_s[i] = W4[i];
+    float sc[16], sh[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const float4 bp = __ldg(bnp + sub * 16 + e);
+        sc[e] = bp.x;
+        sh[e] = bp.y;
+    }
+    const float bias_k = (sub < C) ? __ldg(b4 + sub) : 0.f;
+    const float cw_k = (class_w != nullptr && sub < C) ? __ldg(class_w + sub) : 1.f;
+    __syncthreads();
     const long warp_g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
-    float w[MAXC][4];
-    float4 bp[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) bp[e] = __ldg(bnp + lane * 4 + e);
-#pragma unroll
-    for (int k = 0; k < MAXC; ++k)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) w[k][e] = (k < C) ? W4[k * 128 + lane * 4 + e] : 0.f;
-    const float bias_k = (lane < C) ? __ldg(b4 + lane) : 0.f;
-    const float cw_l = (class_w != nullptr && lane < C) ? __ldg(class_w + lane) : 1.f;
     double loss_num = 0.0, w_sum = 0.0;
     unsigned long long correct = 0, nvalid = 0;
-    for (long p0 = warp_g * PP; p0 < P; p0 += nwarps * PP) {
-        uint2 yw[PP];
-        long long lab[PP];
-#pragma unroll
-        for (int u = 0; u < PP; ++u) {
-            const long pnt = p0 + u;
-            yw[u] = (pnt < P) ? *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4) : make_uint2(0, 0);
-            lab[u] = (labels != nullptr && pnt < P && lane == 0) ? labels[pnt] : -1;
+    for (long p0 = warp_g * 4; p0 < P; p0 += nwarps * 4) {
+        const long pnt = p0 + grp;
+        const bool ok = pnt < P;
+        uint4 y0 = make_uint4(0, 0, 0, 0), y1 = y0;
+        if (ok) {
+            const uint4* src = reinterpret_cast<const uint4*>(ys3 + pnt * 128 + sub * 16);
+            y0 = src[0];
+            y1 = src[1];
         }
-        float zmine[PP];
+        const long long lab = (ok && labels != nullptr && sub == 0) ? labels[pnt] : -1;
+        const uint32_t ws[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+        float a[16];
 #pragma unroll
-        for (int u = 0; u < PP; ++u) {
-            float a[4];
-            a[0] = fmaxf(fmaf(bp[0].x, bf16_lo(yw[u].x), bp[0].y), 0.f);
-            a[1] = fmaxf(fmaf(bp[1].x, bf16_hi(yw[u].x), bp[1].y), 0.f);
-            a[2] = fmaxf(fmaf(bp[2].x, bf16_lo(yw[u].y), bp[2].y), 0.f);
-            a[3] = fmaxf(fmaf(bp[3].x, bf16_hi(yw[u].y), bp[3].y), 0.f);
-            float zm = 0.f;
+        for (int e = 0; e < 16; ++e) {
+            const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
+            a[e] = fmaxf(fmaf(sc[e], yv, sh[e]), 0.f);
+        }
+        float zmine = 0.f;                     // lane `sub` == k keeps logit k of its point
 #pragma unroll
-            for (int k = 0; k < MAXC; ++k) {
-                if (k < C) {
-                    float s = a[0] * w[k][0];
-                    s = fmaf(a[1], w[k][1], s);
-                    s = fmaf(a[2], w[k][2], s);
-                    s = fmaf(a[3], w[k][3], s);
-                    s = warp_sum(s);
-                    if (lane == k) zm = s;          // lane k keeps logit k
+        for (int k = 0; k < MAXC; ++k) {
+            if (k < C) {
+                const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 16);
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w4 = wk[q];
+                    s = fmaf(a[4 * q], w4.x, s);
+                    s = fmaf(a[4 * q + 1], w4.y, s);
+                    s = fmaf(a[4 * q + 2], w4.z, s);
+                    s = fmaf(a[4 * q + 3], w4.w, s);
                 }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (sub == k) zmine = s;
             }
-            zmine[u] = zm + bias_k;
         }
+        zmine += bias_k;
+        if (ok && sub < C) logits[pnt * C + sub] = zmine;
+        if (labels != nullptr) {
+            const long long labv = __shfl_sync(0xffffffffu, lab, grp * 8);       // label of this lane's point
+            const float zm = (sub < C) ? zmine : -INFINITY;
+            float zmax = zm;
 #pragma unroll
-        for (int u = 0; u < PP; ++u) {
-            const long pnt = p0 + u;
-            if (pnt >= P) break;
-            if (lane < C) logits[pnt * C + lane] = zmine[u];
-            if (labels != nullptr) {
-                const long long labv = __shfl_sync(0xffffffffu, lab[u], 0);
-                if (labv >= 0) {                             // warp-uniform
-                    const float zm = (lane < C) ? zmine[u] : -INFINITY;
-                    float zmax = zm;
+            for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+            const unsigned am_mask = (__ballot_sync(0xffffffffu, sub < C && zm == zmax) >> (grp * 8)) & 0xFFu;
+            const int am = __ffs(am_mask) - 1;          // first maximum, like torch.argmax
+            float ex = (sub < C) ? __expf(zm - zmax) : 0.f;
 #pragma unroll
-                    for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));   // C <= 8 lanes
-                    const unsigned am_mask = __ballot_sync(0xffffffffu, lane < C && zm == zmax);
-                    const int am = __ffs(am_mask) - 1;       // first maximum, like torch.argmax
-                    float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
-#pragma unroll
-                    for (int o = 4; o >= 1; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
-                    const float zl = __shfl_sync(0xffffffffu, zmine[u], static_cast<int>(labv));
-                    const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(labv));
-                    if (lane == 0) {
-                        loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(ex) - zl);
-                        w_sum += wl;
-                        correct += (am == labv);
-                        nvalid += 1;
-                    }
-                }
+            for (int o = 4; o >= 1; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+            const int src_lane = grp * 8 + static_cast<int>(labv >= 0 ? labv : 0);
+            const float zl = __shfl_sync(0xffffffffu, zmine, src_lane);
+            const float wl = __shfl_sync(0xffffffffu, cw_k, src_lane);
+            if (sub == 0 && ok && labv >= 0) {
+                loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(ex) - zl);
+                w_sum += wl;
+                correct += (am == labv);
+                nvalid += 1;
             }
         }
     }
     if (labels != nullptr) {
+        // lanes 0, 8, 16, 24 hold partials: fold them into lane 0, then one atomic set per block
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            loss_num += __shfl_xor_sync(0xffffffffu, loss_num, o);
+            w_sum += __shfl_xor_sync(0xffffffffu, w_sum, o);
+            correct += __shfl_xor_sync(0xffffffffu, correct, o);
+            nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+        }
         if (lane == 0) { red_d[warp][0] = loss_num; red_d[warp][1] = w_sum; red_u[warp][0] = correct; red_u[warp][1] = nvalid; }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -402,100 +415,134 @@ __global__ void k_label_weight_sum(const long long* __restrict__ labels, long P,
 // dlogits either given (autograd path) or recomputed from logits/labels/class_w/inv_wsum (fused CE).
 // One warp per point; lane = 4 channels.
 // ---------------------------------------------------------------------------------------------
-template <int MAXC>
+// NC = exact number of classes (compile-time, so the per-lane dW4 accumulators are NC x 16 registers)
+template <int NC>
 __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restrict__ ys3, long P, const float4* __restrict__ bnp,
-                                                  const float* __restrict__ W4, int C, const float* __restrict__ dlogits,
+                                                  const float* __restrict__ W4, const float* __restrict__ dlogits,
                                                   const float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, const double* __restrict__ wsum_total,
                                                   __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dW4,
                                                   float* __restrict__ db4, double* __restrict__ stats) {
+    constexpr int MAXC = NC;
+    constexpr int C = NC;
+    // 8 lanes per point, 16 channels per lane (see k_head_fwd).  Per-lane accumulators: dW4[k][16 ch], sum dz[16], sum dz*yhat[16].
+    __shared__ __align__(16) float w_s[MAXC * 128];
     __shared__ float red[8][MAXC * 128 + 2 * 128 + MAXC];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const long warp_g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
-    float w[MAXC][4], dw[MAXC][4];
-    float dbk = 0.f;                                   // lane k accumulates db4[k]
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 bp[4];
+    const int sub = lane & 7;
+    const int grp = lane >> 3;
+    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) w_s[i] = W4[i];
+    float sc[16], sh[16];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) bp[e] = __ldg(bnp + lane * 4 + e);
+    for (int e = 0; e < 16; ++e) {
+        const float4 b4v = __ldg(bnp + sub * 16 + e);
+        sc[e] = b4v.x;
+        sh[e] = b4v.y;
+    }
+    float dw[MAXC][16];
+    float s1[16], s2[16];
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k)
+    for (int e = 0; e < 16; ++e) {
+        s1[e] = s2[e] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { w[k][e] = (k < C) ? W4[k * 128 + lane * 4 + e] : 0.f; dw[k][e] = 0.f; }
+        for (int k = 0; k < MAXC; ++k) dw[k][e] = 0.f;
+    }
+    float dbk = 0.f;                                   // lane with sub == k accumulates db4[k]
     const bool fused = (dlogits == nullptr);
     const float inv_wsum = (wsum_total != nullptr) ? static_cast<float>(1.0 / *wsum_total) : 0.f;
-    const float cw_l = (class_w != nullptr && lane < C) ? __ldg(class_w + lane) : 1.f;
+    const float cw_k = (class_w != nullptr && sub < C) ? __ldg(class_w + sub) : 1.f;
     const float* zsrc = fused ? logits : dlogits;
-
-    constexpr int PP = 1;                             // points per warp iteration (2 spills registers at 2 blocks/SM)
-    for (long p0 = warp_g * PP; p0 < P; p0 += nwarps * PP) {
-        uint2 yw[PP];
-        float zin[PP];
-        long long lab0[PP];
-#pragma unroll
-        for (int u = 0; u < PP; ++u) {
-            const long pnt = p0 + u;
-            const bool ok = pnt < P;
-            yw[u] = ok ? *reinterpret_cast<const uint2*>(ys3 + pnt * 128 + lane * 4) : make_uint2(0, 0);
-            zin[u] = (ok && lane < C) ? zsrc[pnt * C + lane] : 0.f;
-            lab0[u] = (ok && fused && lane == 0) ? labels[pnt] : -1;
+    __syncthreads();
+    const long warp_g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+    for (long p0 = warp_g * 4; p0 < P; p0 += nwarps * 4) {
+        const long pnt = p0 + grp;
+        const bool ok = pnt < P;
+        uint4 y0 = make_uint4(0, 0, 0, 0), y1 = y0;
+        float zin = 0.f;
+        long long lab0 = -1;
+        if (ok) {
+            const uint4* src = reinterpret_cast<const uint4*>(ys3 + pnt * 128 + sub * 16);
+            y0 = src[0];
+            y1 = src[1];
+            if (sub < C) zin = zsrc[pnt * C + sub];
+            if (fused && sub == 0) lab0 = labels[pnt];
         }
+        float dl_mine = zin;                               // lane with sub == k holds dlogit k of its point
+        if (fused) {
+            const long long lab = __shfl_sync(0xffffffffu, lab0, grp * 8);
+            const float zm = (sub < C) ? zin : -INFINITY;
+            float zmax = zm;
 #pragma unroll
-        for (int u = 0; u < PP; ++u) {
-            const long pnt = p0 + u;
-            if (pnt >= P) break;
-            float dl_mine = zin[u];                           // lane k holds dlogit k
-            if (fused) {
-                const long long lab = __shfl_sync(0xffffffffu, lab0[u], 0);
-                if (lab >= 0) {
-                    const float zm = (lane < C) ? zin[u] : -INFINITY;
-                    float zmax = zm;
+            for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+            const float ex = (sub < C) ? __expf(zm - zmax) : 0.f;
+            float se = ex;
 #pragma unroll
-                    for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-                    const float ex = (lane < C) ? __expf(zm - zmax) : 0.f;
-                    float se = ex;
+            for (int o = 4; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+            const float wl = __shfl_sync(0xffffffffu, cw_k, grp * 8 + static_cast<int>(lab >= 0 ? lab : 0));
+            dl_mine = (lab >= 0) ? wl * inv_wsum * (ex / se - (sub == lab ? 1.f : 0.f)) : 0.f;
+        }
+        if (sub >= C || !ok) dl_mine = 0.f;
+        dbk += dl_mine;
+        float dl[MAXC];
 #pragma unroll
-                    for (int o = 4; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-                    const float wl = __shfl_sync(0xffffffffu, cw_l, static_cast<int>(lab));
-                    dl_mine = wl * inv_wsum * (ex / se - (lane == lab ? 1.f : 0.f));
-                } else {
-                    dl_mine = 0.f;
+        for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __shfl_sync(0xffffffffu, dl_mine, grp * 8 + k) : 0.f;
+        const uint32_t ws[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+        float dz[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
+            const float t = fmaf(sc[e], yv, sh[e]);
+            const float a = fmaxf(t, 0.f);
+            float da = 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                if (k < C) {
+                    da = fmaf(dl[k], w_s[k * 128 + sub * 16 + e], da);
+                    dw[k][e] = fmaf(dl[k], a, dw[k][e]);
                 }
             }
-            if (lane >= C) dl_mine = 0.f;
-            dbk += dl_mine;
-            float dl[MAXC];
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __shfl_sync(0xffffffffu, dl_mine, k) : 0.f;
-            const float yv[4] = {bf16_lo(yw[u].x), bf16_hi(yw[u].x), bf16_lo(yw[u].y), bf16_hi(yw[u].y)};
-            float dz[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float t = fmaf(bp[e].x, yv[e], bp[e].y);
-                const float a = fmaxf(t, 0.f);
-                float da = 0.f;
-#pragma unroll
-                for (int k = 0; k < MAXC; ++k) {
-                    if (k < C) { da = fmaf(dl[k], w[k][e], da); dw[k][e] = fmaf(dl[k], a, dw[k][e]); }
-                }
-                dz[e] = (t > 0.f) ? round_bf16(da) : 0.f;
-                s1[e] += dz[e];
-                s2[e] = fmaf(dz[e], fmaf(bp[e].z, yv[e], bp[e].w), s2[e]);
-            }
-            *reinterpret_cast<uint2*>(dz_out + pnt * 128 + lane * 4) = make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
+            dz[e] = (t > 0.f) ? round_bf16(da) : 0.f;
+            s1[e] += dz[e];
+            s2[e] = fmaf(dz[e], yv, s2[e]);                 // sum dz*y; turned into sum dz*yhat below
+        }
+        if (ok) {
+            uint4* dst = reinterpret_cast<uint4*>(dz_out + pnt * 128 + sub * 16);
+            dst[0] = make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
+            dst[1] = make_uint4(pack_bf16x2(dz[8], dz[9]), pack_bf16x2(dz[10], dz[11]), pack_bf16x2(dz[12], dz[13]), pack_bf16x2(dz[14], dz[15]));
         }
     }
-    // block reduction over the 8 warps, then one atomic per value per block
+    // fold the 4 point slots of a warp (lanes with equal `sub`), then the 8 warps through shared memory
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k)
+                if (k < C) dw[k][e] += __shfl_xor_sync(0xffffffffu, dw[k][e], o);
+        }
+    }
+    dbk += __shfl_xor_sync(0xffffffffu, dbk, 8);
+    dbk += __shfl_xor_sync(0xffffffffu, dbk, 16);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {                       // sum dz*yhat = invstd * sum dz*y + (-mean*invstd) * sum dz
+        const float4 b4v = __ldg(bnp + sub * 16 + e);
+        s2[e] = fmaf(b4v.z, s2[e], b4v.w * s1[e]);
+    }
     float* r = red[warp];
+    if (grp == 0) {
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k)
+        for (int e = 0; e < 16; ++e) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) r[k * 128 + lane * 4 + e] = dw[k][e];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { r[MAXC * 128 + lane * 4 + e] = s1[e]; r[MAXC * 128 + 128 + lane * 4 + e] = s2[e]; }
-    if (lane < MAXC) r[MAXC * 128 + 256 + lane] = dbk;
+            for (int k = 0; k < MAXC; ++k) r[k * 128 + sub * 16 + e] = dw[k][e];
+            r[MAXC * 128 + sub * 16 + e] = s1[e];
+            r[MAXC * 128 + 128 + sub * 16 + e] = s2[e];
+        }
+        if (sub < MAXC) r[MAXC * 128 + 256 + sub] = dbk;
+    }
     __syncthreads();
     const int total = MAXC * 128 + 256 + MAXC;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
