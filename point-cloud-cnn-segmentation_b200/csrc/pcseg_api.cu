@@ -641,17 +641,25 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     CUDA_OK(cudaMemsetAsync(c->keys, 0, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long), s));
     if (ce) CUDA_OK(cudaMemsetAsync(ce, 0, sizeof(pcseg_ce_accum), s));
 
-    auto finalize = [&](int i) -> int {
-        const int co = cv[i].cout;
-        k_bn_finalize<<<(co + 127) / 128, 128, 0, s>>>(c->stats_f + c->stat_off[i], co, static_cast<double>(P), params + L.off[20 + 2 * i],
-                                                       params + L.off[21 + 2 * i], params + L.off[2 * i + 1], BN_EPS, BN_MOMENTUM,
-                                                       bnbuf + L.bn_off[i][0], bnbuf + L.bn_off[i][1], c->bnp[i]);
-        LAUNCH_OK("k_bn_finalize");
-        return 0;
+    auto fin_args = [&](int i) {
+        BnFinalizeArgs f;
+        f.stats = c->stats_f + c->stat_off[i];
+        f.gamma = params + L.off[20 + 2 * i];
+        f.beta = params + L.off[21 + 2 * i];
+        f.conv_bias = params + L.off[2 * i + 1];
+        f.rmean = bnbuf + L.bn_off[i][0];
+        f.rvar = bnbuf + L.bn_off[i][1];
+        f.bnp = c->bnp[i];
+        f.n = static_cast<double>(P);
+        f.eps = BN_EPS;
+        f.momentum = BN_MOMENTUM;
+        f.C = cv[i].cout;
+        return f;
     };
+    // BN finalize of layer i is folded into this kernel (block 0 publishes bnp + running statistics)
     auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         const int co = cv[i].cout;
-        k_bn_relu<<<strip_grid(P, co), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, c->bnp[i], sd, thr, ks);
+        k_bn_relu<<<strip_grid(P, co), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, thr, ks);
         LAUNCH_OK("k_bn_relu");
         return 0;
     };
@@ -662,7 +670,6 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         k_ingest<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(x), static_cast<int>(P), params + L.off[0], nullptr, nullptr,
                                            c->y[0], c->stats_f + c->stat_off[0]);
         LAUNCH_OK("k_ingest");
-        TRY(finalize(0));
         TRY(bn_relu(0, 0, 0, 1.f));
     }
     for (int i = 1; i <= 5; ++i) {
@@ -673,29 +680,25 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         } else {
             TRY(timed_gemm(c, c->fw[i], i, s));
         }
-        TRY(finalize(i));
         if (i < 5) TRY(bn_relu(i, 0, 0, 1.f));
     }
     {   // global max-pool of relu(bn(y6)) with arg-index
         const int total = c->B * 1024;
-        k_maxpool_finish<<<(total + 255) / 256, 256, 0, s>>>(c->keys, total, 1024, c->bnp[5], c->gmax, c->ystar, c->argidx);
+        k_maxpool_finish<<<(total + 255) / 256, 256, 0, s>>>(c->keys, total, 1024, fin_args(5), c->gmax, c->ystar, c->argidx);
         LAUNCH_OK("k_maxpool_finish");
         const int warps = c->B * 512;
         k_cloud_bias<<<(warps * 32 + 255) / 256, 256, 0, s>>>(params + L.off[12] + 64, 1088, c->gmax, c->B, 512, 1024, nullptr, nullptr, c->cb);
         LAUNCH_OK("k_cloud_bias");
     }
     TRY(timed_gemm(c, c->fw[6], 6, s));
-    TRY(finalize(6));
     TRY(bn_relu(6, seed + 1, c->thr16, c->keep_scale));
     TRY(timed_gemm(c, c->fw[7], 7, s));
-    TRY(finalize(7));
     TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
     TRY(timed_gemm(c, c->fw[8], 8, s));
-    TRY(finalize(8));
     {
         int grid = static_cast<int>((P + 31) / 32);          // 8 warps x 4 points per block iteration
         if (grid > num_sms() * 4) grid = num_sms() * 4;
-        k_head_fwd<MAX_CLASSES><<<grid, 256, 0, s>>>(c->y[8], P, c->bnp[8], params + L.off[18], params + L.off[19], c->C, logits, labels,
+        k_head_fwd<MAX_CLASSES><<<grid, 256, 0, s>>>(c->y[8], P, fin_args(8), params + L.off[18], params + L.off[19], c->C, logits, labels,
                                                     class_w, reinterpret_cast<CeAccum*>(ce));
         LAUNCH_OK("k_head_fwd");
     }
@@ -737,18 +740,23 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         CUDA_OK(cudaMemsetAsync(c->dcb, 0, static_cast<size_t>(B) * 512 * sizeof(float), s));
     }
 
-    auto coef = [&](int i) -> int {
-        const int co = cv[i].cout;
-        k_bn_bwd_coef<<<(co + 127) / 128, 128, 0, s>>>(c->stats_b + c->stat_off[i], co, static_cast<double>(P), c->bnp[i], c->coef[i],
-                                                       grads + L.off[20 + 2 * i], grads + L.off[21 + 2 * i]);
-        LAUNCH_OK("k_bn_bwd_coef");
-        return 0;
+    auto bwd_args = [&](int i) {
+        BnBwdArgs b;
+        b.stats = c->stats_b + c->stat_off[i];
+        b.bnp = c->bnp[i];
+        b.coef = c->coef[i];
+        b.dgamma = grads + L.off[20 + 2 * i];
+        b.dbeta = grads + L.off[21 + 2 * i];
+        b.n = static_cast<double>(P);
+        b.C = cv[i].cout;
+        return b;
     };
+    auto coef = [&](int) -> int { return 0; };     // BN-backward coefficients are evaluated inside k_bn_bwd_apply
     auto apply = [&](int i, bf16* dy_out, int ld_dy, float* dcb) -> int {
         const int co = cv[i].cout;
         const int rps = apply_rows_per_strip(N, B, co);
         dim3 grid((N + rps - 1) / rps, B);
-        k_bn_bwd_apply<false><<<grid, 256, 0, s>>>(c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, c->coef[i],
+        k_bn_bwd_apply<false><<<grid, 256, 0, s>>>(c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, bwd_args(i),
                                                   grads + L.off[2 * i + 1], dcb, nullptr, nullptr);
         LAUNCH_OK("k_bn_bwd_apply");
         return 0;
@@ -811,7 +819,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     {
         const int rps = apply_rows_per_strip(N, B, 1024);
         dim3 grid((N + rps - 1) / rps, B);
-        k_bn_bwd_apply<true><<<grid, 256, 0, s>>>(nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, c->coef[5], grads + L.off[11],
+        k_bn_bwd_apply<true><<<grid, 256, 0, s>>>(nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5), grads + L.off[11],
                                                  nullptr, c->argidx, c->dzv);
         LAUNCH_OK("k_bn_bwd_apply<sparse>");
     }

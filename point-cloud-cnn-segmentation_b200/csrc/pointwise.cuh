@@ -126,35 +126,57 @@ __global__ void __launch_bounds__(256) k_ingest(const float4* __restrict__ x, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// Train-mode BatchNorm finalize (one thread per channel).
+// Train-mode BatchNorm finalize, folded into the kernels that consume the normalisation (no launch of its own).
 //   stats = {sum y, sum y^2} over n rows (conv bias excluded) ->
-//   bnp[c] = {scale = gamma*invstd, shift = beta - mean*scale, invstd, -mean*invstd}
-//   running_mean/var updated with momentum, unbiased variance, bias re-added to the mean.
+//   {scale = gamma*invstd, shift = beta - mean*scale, invstd, -mean*invstd}
+// Every consumer thread evaluates `bn_from_stats` for the channels it needs; block 0 of the consumer also stores the
+// result (later kernels and backward read it) and updates running_mean / running_var (momentum, unbiased variance,
+// conv bias re-added to the mean).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_bn_finalize(const double* __restrict__ stats, int C, double n, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
-                              float* __restrict__ rmean, float* __restrict__ rvar, float4* __restrict__ bnp) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const double mean = stats[c] / n;
-    double var = stats[C + c] / n - mean * mean;
+struct BnFinalizeArgs {
+    const double* stats;      // [2][C]
+    const float* gamma;
+    const float* beta;
+    const float* conv_bias;
+    float* rmean;             // running statistics (updated by block 0), may be null
+    float* rvar;
+    float4* bnp;              // [C] output copy for later kernels
+    double n;
+    float eps, momentum;
+    int C;
+};
+__device__ __forceinline__ float4 bn_from_stats(const BnFinalizeArgs& f, int c) {
+    // only the cancellation-prone part (E[y^2] - mean^2) is done in fp64: this runs in every consumer thread
+    const double inv_n = 1.0 / f.n;              // uniform, hoisted by the compiler
+    const double mean = f.stats[c] * inv_n;
+    double var = fma(-mean, mean, f.stats[f.C + c] * inv_n);
     if (var < 0.0) var = 0.0;
-    const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
-    const float sc = static_cast<float>(gamma[c] * invstd);
-    bnp[c] = make_float4(sc, static_cast<float>(beta[c] - mean * gamma[c] * invstd), static_cast<float>(invstd),
-                         static_cast<float>(-mean * invstd));
-    if (rmean != nullptr) {
-        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
-        rmean[c] = static_cast<float>((1.0 - momentum) * rmean[c] + momentum * (mean + conv_bias[c]));
-        rvar[c] = static_cast<float>((1.0 - momentum) * rvar[c] + momentum * unb);
+    const float invstd = rsqrtf(static_cast<float>(var) + f.eps);
+    const float meanf = static_cast<float>(mean);
+    const float sc = f.gamma[c] * invstd;
+    return make_float4(sc, fmaf(-meanf, sc, f.beta[c]), invstd, -meanf * invstd);
+}
+__device__ __forceinline__ void bn_publish(const BnFinalizeArgs& f, bool first_block) {
+    if (!first_block) return;
+    for (int c = threadIdx.x; c < f.C; c += blockDim.x) {
+        f.bnp[c] = bn_from_stats(f, c);
+        if (f.rmean != nullptr) {
+            const double mean = f.stats[c] / f.n;
+            double var = f.stats[f.C + c] / f.n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double unb = f.n > 1.0 ? var * f.n / (f.n - 1.0) : var;
+            f.rmean[c] = static_cast<float>((1.0 - f.momentum) * f.rmean[c] + f.momentum * (mean + f.conv_bias[c]));
+            f.rvar[c] = static_cast<float>((1.0 - f.momentum) * f.rvar[c] + f.momentum * unb);
+        }
     }
 }
 
 // a = relu(scale*y + shift) (* dropout keep / (1-p)).  Each thread owns 8 fixed channels (scale/shift live in
 // registers) and walks down the rows of its block's strip; 4 independent 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
-                                                 int ld_a, long P, int C, const float4* __restrict__ bnp,
+                                                 int ld_a, long P, int C, const BnFinalizeArgs fin,
                                                  unsigned long long seed, unsigned int thr16, float keep_scale) {
+    bn_publish(fin, blockIdx.x == 0);
     const int tpr = C >> 3;                       // threads per row (C <= 2048)
     const int rpp = 256 / tpr;                    // rows per pass
     const int c0 = (threadIdx.x % tpr) << 3;
@@ -162,7 +184,7 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const float4 bp = __ldg(bnp + c0 + e);
+        const float4 bp = bn_from_stats(fin, c0 + e);
         sc[e] = bp.x;
         sh[e] = bp.y;
     }
@@ -239,13 +261,14 @@ __global__ void __launch_bounds__(256) k_maxpool_scan(const __nv_bfloat16* __res
     }
 }
 // decode keys -> g (post BN+ReLU), ystar (pre-BN extremum), argidx (row within cloud)
-__global__ void k_maxpool_finish(const unsigned long long* __restrict__ keys, int total, int C, const float4* __restrict__ bnp,
+__global__ void k_maxpool_finish(const unsigned long long* __restrict__ keys, int total, int C, const BnFinalizeArgs fin,
                                  float* __restrict__ g, float* __restrict__ ystar, int* __restrict__ argidx) {
+    bn_publish(fin, blockIdx.x == 0);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = i % C;
     const unsigned long long k = keys[i];
-    const float4 bp = __ldg(bnp + c);
+    const float4 bp = bn_from_stats(fin, c);
     const float sg = bp.x >= 0.f ? 1.f : -1.f;
     const float yv = sg * float_from_orderable(static_cast<uint32_t>(k >> 32));
     argidx[i] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFull));
@@ -287,7 +310,7 @@ struct CeAccum {
 // only 3 shuffle steps per class and every warp instruction works on 4 points.  seg_conv4 weights are staged in shared
 // memory as [class][128] and read with 16-byte LDS (lanes of the same point read disjoint 64-byte slices).
 template <int MAXC>
-__global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restrict__ ys3, long P, const float4* __restrict__ bnp,
+__global__ void __launch_bounds__(256, 3) k_head_fwd(const __nv_bfloat16* __restrict__ ys3, long P, const BnFinalizeArgs fin,
                                                   const float* __restrict__ W4, const float* __restrict__ b4, int C,
                                                   float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
@@ -298,11 +321,12 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
     const int warp = threadIdx.x >> 5;
     const int sub = lane & 7;                  // 16-channel slice of the point
     const int grp = lane >> 3;                 // point slot inside the warp
+    bn_publish(fin, blockIdx.x == 0);
     for (int i = threadIdx.x; i < C * 128; i += blockDim.x) w_s[i] = W4[i];
     float sc[16], sh[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-        const float4 bp = __ldg(bnp + sub * 16 + e);
+        const float4 bp = bn_from_stats(fin, sub * 16 + e);
         sc[e] = bp.x;
         sh[e] = bp.y;
     }
@@ -335,15 +359,13 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
         for (int k = 0; k < MAXC; ++k) {
             if (k < C) {
                 const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 16);
-                float s = 0.f;
+                float sq[4];                                // 4 independent chains (ILP) instead of one 16-deep chain
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 w4 = wk[q];
-                    s = fmaf(a[4 * q], w4.x, s);
-                    s = fmaf(a[4 * q + 1], w4.y, s);
-                    s = fmaf(a[4 * q + 2], w4.z, s);
-                    s = fmaf(a[4 * q + 3], w4.w, s);
+                    sq[q] = fmaf(a[4 * q + 3], w4.w, fmaf(a[4 * q + 2], w4.z, fmaf(a[4 * q + 1], w4.y, a[4 * q] * w4.x)));
                 }
+                float s = (sq[0] + sq[1]) + (sq[2] + sq[3]);
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -489,21 +511,29 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) dl[k] = (k < C) ? __shfl_sync(0xffffffffu, dl_mine, grp * 8 + k) : 0.f;
         const uint32_t ws[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-        float dz[16];
+        float dz[16], da[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) da[e] = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w4 = wk[q];
+                da[4 * q] = fmaf(dl[k], w4.x, da[4 * q]);
+                da[4 * q + 1] = fmaf(dl[k], w4.y, da[4 * q + 1]);
+                da[4 * q + 2] = fmaf(dl[k], w4.z, da[4 * q + 2]);
+                da[4 * q + 3] = fmaf(dl[k], w4.w, da[4 * q + 3]);
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
             const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
             const float t = fmaf(sc[e], yv, sh[e]);
             const float a = fmaxf(t, 0.f);
-            float da = 0.f;
 #pragma unroll
-            for (int k = 0; k < MAXC; ++k) {
-                if (k < C) {
-                    da = fmaf(dl[k], w_s[k * 128 + sub * 16 + e], da);
-                    dw[k][e] = fmaf(dl[k], a, dw[k][e]);
-                }
-            }
-            dz[e] = (t > 0.f) ? round_bf16(da) : 0.f;
+            for (int k = 0; k < MAXC; ++k) dw[k][e] = fmaf(dl[k], a, dw[k][e]);
+            dz[e] = (t > 0.f) ? round_bf16(da[e]) : 0.f;
             s1[e] += dz[e];
             s2[e] = fmaf(dz[e], yv, s2[e]);                 // sum dz*y; turned into sum dz*yhat below
         }
@@ -561,21 +591,32 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm backward.
-//   coefficients (one thread per channel):  dy = A*dz + Bc*y + Cc   with
+//   coefficients (evaluated inside k_bn_bwd_apply, no launch of their own):  dy = A*dz + Bc*y + Cc   with
 //     A = scale, Bc = -scale*c2*invstd, Cc = -scale*(c1 + c2*(-mean*invstd)),  c1 = sum dz / n, c2 = sum dz*yhat / n
 //   also writes dgamma = sum dz*yhat, dbeta = sum dz.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_bn_bwd_coef(const double* __restrict__ stats, int C, double n, const float4* __restrict__ bnp,
-                              float4* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const double sdz = stats[c], sdzy = stats[C + c];
-    const double c1 = sdz / n, c2 = sdzy / n;
-    const float4 bp = bnp[c];
-    const double A = bp.x;
-    coef[c] = make_float4(static_cast<float>(A), static_cast<float>(-A * c2 * bp.z), static_cast<float>(-A * (c1 + c2 * bp.w)), 0.f);
-    dgamma[c] = static_cast<float>(sdzy);
-    dbeta[c] = static_cast<float>(sdz);
+struct BnBwdArgs {
+    const double* stats;      // [2][C] {sum dz, sum dz*yhat}
+    const float4* bnp;        // [C] forward normalisation
+    float4* coef;             // [C] output copy {A, Bc, Cc, 0} (inspection / tests)
+    float* dgamma;            // parameter gradients written by block (0, 0)
+    float* dbeta;
+    double n;
+    int C;
+};
+__device__ __forceinline__ float4 bn_bwd_coef(const BnBwdArgs& f, int c) {
+    const double inv_n = 1.0 / f.n;
+    const float c1 = static_cast<float>(f.stats[c] * inv_n), c2 = static_cast<float>(f.stats[f.C + c] * inv_n);
+    const float4 bp = f.bnp[c];
+    return make_float4(bp.x, -bp.x * c2 * bp.z, -bp.x * fmaf(c2, bp.w, c1), 0.f);
+}
+__device__ __forceinline__ void bn_bwd_publish(const BnBwdArgs& f, bool first_block) {
+    if (!first_block) return;
+    for (int c = threadIdx.x; c < f.C; c += blockDim.x) {
+        f.coef[c] = bn_bwd_coef(f, c);
+        f.dgamma[c] = static_cast<float>(f.stats[f.C + c]);
+        f.dbeta[c] = static_cast<float>(f.stats[c]);
+    }
 }
 
 // dy = A*dz + Bc*y + Cc, bf16 out (pitch ld_dy); column sums of dy -> dbias (fp32 atomics) and,
@@ -587,10 +628,11 @@ template <bool SPARSE>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, int ld_dz,
                                                       const __nv_bfloat16* __restrict__ y, int ld_y,
                                                       __nv_bfloat16* __restrict__ dy, int ld_dy, int N /*rows per cloud*/, int C,
-                                                      int rows_per_strip, const float4* __restrict__ coef,
+                                                      int rows_per_strip, const BnBwdArgs bw,
                                                       float* __restrict__ dbias, float* __restrict__ dcb,
                                                       const int* __restrict__ argidx, const float* __restrict__ dzv) {
     __shared__ float red[256 * 8];
+    bn_bwd_publish(bw, blockIdx.x == 0 && blockIdx.y == 0);
     const int tpr = C >> 3;
     const int rpp = 256 / tpr;
     const int c0 = (threadIdx.x % tpr) << 3;
@@ -603,7 +645,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
     float dv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const float4 cf = __ldg(coef + c0 + e);
+        const float4 cf = bn_bwd_coef(bw, c0 + e);
         cA[e] = cf.x; cB[e] = cf.y; cC[e] = cf.z;
         acc[e] = 0.f;
         if (SPARSE) {

@@ -15,3 +15,16 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The CUDA library is git-ignored and normally travels with the tree; build it if it is missing or stale."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_pcseg_build", os.path.join(ROOT, "point-cloud-cnn-segmentation_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        mod.build()
+    except Exception as e:          # no nvcc: the tests that need the library will fail loudly on import
+        print("pcseg_b200 build skipped:", e)
