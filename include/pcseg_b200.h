@@ -40,6 +40,18 @@ typedef struct pcseg_ce_accum {
     unsigned long long valid;    /* labels != -1                                            */
 } pcseg_ce_accum;
 
+/* Device-resident per-step state (32 bytes).  Lets a whole training step be captured in a CUDA graph: the dropout
+ * seed, the Adam step count / bias corrections and the learning rate are read from device memory by the kernels
+ * instead of being baked into launch arguments.  pcseg_step_advance moves it to the next step. */
+typedef struct pcseg_step_state {
+    unsigned long long seed;     /* added to the `seed` argument of pcseg_forward_train                     */
+    long long step;              /* optimizer step count (1 after the first pcseg_step_advance)             */
+    float lr;                    /* learning rate; the host may rewrite it between steps (StepLR, pcs.py:218) */
+    float bias_corr1;            /* 1 - beta1^step                                                          */
+    float bias_corr2_sqrt;       /* sqrt(1 - beta2^step)                                                    */
+    float reserved;
+} pcseg_step_state;
+
 const char* pcseg_last_error(void);
 const char* pcseg_version(void);
 
@@ -69,10 +81,10 @@ int pcseg_forward_eval(pcseg_ctx* ctx, const float* x, float* logits, long long*
 /* Training forward: pcs.py:98-133 under train() (batch statistics, running-stat update, dropout).
  * bn_buffers is updated in place.  dropout_p = 0 disables dropout.  If labels != NULL the weighted
  * cross-entropy of pcs.py:216,247-251 is accumulated into *ce (device, zeroed by this call);
- * class_w may be NULL (all ones). */
+ * class_w may be NULL (all ones).  state (device, may be NULL): its seed is added to `seed`. */
 int pcseg_forward_train(pcseg_ctx* ctx, const float* x, const float* params, float* bn_buffers,
                         unsigned long long seed, float dropout_p, float* logits, const long long* labels,
-                        const float* class_w, pcseg_ce_accum* ce, void* stream);
+                        const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream);
 
 /* Backward of the training forward: loss.backward(), pcs.py:254.  Gradients of all 38 parameter
  * tensors are written (not accumulated) into `grads`, laid out like `params`.
@@ -90,7 +102,11 @@ int pcseg_backward(pcseg_ctx* ctx, const float* x, const float* params, const fl
 /* optimizer.step() of torch.optim.Adam(lr, weight_decay) on the flat arena, pcs.py:217,255. */
 int pcseg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                     int step, float lr, float beta1, float beta2, float eps, float weight_decay,
-                    float grad_scale, void* stream);
+                    float grad_scale, const pcseg_step_state* state, void* stream);
+
+/* state (device): seed += odd constant, step += 1, bias corrections recomputed.  If state is non-NULL in
+ * pcseg_adam_step, `step` and `lr` are taken from it instead of from the arguments. */
+int pcseg_step_advance(pcseg_step_state* state, float beta1, float beta2, void* stream);
 
 /* Stand-alone GEMM entry used by the unit tests of the tcgen05 kernel (bf16 in, fp32 accumulate).
  *   layout 0: D[M,N] = A[M,K] * B[N,K]^T         (A, B row-major, K contiguous), bf16 out = relu(D + bias)

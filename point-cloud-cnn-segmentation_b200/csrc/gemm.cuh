@@ -46,7 +46,8 @@ struct GemmParams {
     const float4* bnp;           // [N] {scale, shift, invstd, -mean*invstd} of the layer whose output is being masked
     float* out_f32;              // wgrad destination
     int ldc;                     // wgrad destination pitch (elements)
-    unsigned long long seed;     // dropout
+    unsigned long long seed;     // dropout (effective seed = seed + *seed_ptr when seed_ptr != nullptr)
+    const unsigned long long* seed_ptr;
     unsigned int drop_thr16;     // 0 = no dropout
     float keep_scale;            // 1/(1-p)
     const float* w4;             // [C][128] fp32
@@ -267,6 +268,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int et = threadIdx.x - 128;             // 0..EPI_THREADS-1
         const uint32_t lane_sel = static_cast<uint32_t>(ew * 32) << 16;
         const bool elected = (et == 0);
+        const unsigned long long seed_eff = p.seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
+        (void)seed_eff;
         const uint32_t out_s = smem_u32(out_stage);   // 32-bit shared-space addresses (explicit LDS/STS below)
         const uint32_t y_s = smem_u32(y_stage);
         const uint32_t comb_s = smem_u32(comb);
@@ -503,7 +506,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 uint32_t keep = 0xFFu;
                                 if (p.drop_thr16 != 0u) {
                                     const unsigned long long e0 = static_cast<unsigned long long>(m0 + r) * p.N + colbase;
-                                    keep = dropout_keep8(p.seed, e0 >> 3, p.drop_thr16);
+                                    keep = dropout_keep8(seed_eff, e0 >> 3, p.drop_thr16);
                                 }
                                 float dz[8];
 #pragma unroll

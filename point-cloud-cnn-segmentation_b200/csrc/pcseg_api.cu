@@ -15,6 +15,7 @@ using namespace pcseg;
 
 static_assert(PCSEG_MAX_CLASSES == MAX_CLASSES, "header / kernel class cap mismatch");
 static_assert(sizeof(pcseg_ce_accum) == sizeof(CeAccum), "CE accumulator layout mismatch");
+static_assert(sizeof(pcseg_step_state) == sizeof(StepState) && sizeof(StepState) == 32, "step state layout mismatch");
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -311,6 +312,7 @@ struct pcseg_ctx {
     float* dzv = nullptr;
     GemmOp fw[NUM_BN], dg[NUM_BN], wg_op[NUM_BN];
     unsigned long long seed = 0;
+    const unsigned long long* seed_ptr = nullptr;
     unsigned int thr16 = 0;
     float keep_scale = 1.f;
     // optional per-GEMM event timing
@@ -603,7 +605,7 @@ static int ew_grid(long long work_items) {
 
 extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* params, float* bnbuf, unsigned long long seed,
                                    float dropout_p, float* logits, const long long* labels, const float* class_w,
-                                   pcseg_ce_accum* ce, void* stream) {
+                                   pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
     if (!c || !c->bound || !c->train) return fail("pcseg_forward_train: context not bound in train mode");
     if (!x || !params || !bnbuf || !logits) return fail("pcseg_forward_train: null tensor");
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train: dropout_p out of range");
@@ -613,6 +615,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     const ConvDef* cv = L.conv;
     const long long P = c->P;
     c->seed = seed;
+    c->seed_ptr = state ? &state->seed : nullptr;
     c->thr16 = static_cast<unsigned int>(dropout_p * 65536.0f + 0.5f);
     c->keep_scale = c->thr16 ? 1.f / (1.f - static_cast<float>(c->thr16) / 65536.f) : 1.f;
 
@@ -659,7 +662,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     // BN finalize of layer i is folded into this kernel (block 0 publishes bnp + running statistics)
     auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         const int co = cv[i].cout;
-        k_bn_relu<<<strip_grid(P, co), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, thr, ks);
+        k_bn_relu<<<strip_grid(P, co), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks);
         LAUNCH_OK("k_bn_relu");
         return 0;
     };
@@ -770,6 +773,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     auto dgrad = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         GemmOp op = c->dg[i];
         op.p.seed = sd;
+        op.p.seed_ptr = c->seed_ptr;
         op.p.drop_thr16 = thr;
         op.p.keep_scale = ks;
         return timed_gemm(c, op, 16 + i, s);
@@ -860,13 +864,22 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
 }
 
 extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, float* v, long long n, int step, float lr, float b1,
-                               float b2, float eps, float wd, float grad_scale, void* stream) {
-    if (!params || !grads || !m || !v || n <= 0 || step < 1) return fail("pcseg_adam_step: bad arguments");
+                               float b2, float eps, float wd, float grad_scale, const pcseg_step_state* state, void* stream) {
+    if (!params || !grads || !m || !v || n <= 0 || (step < 1 && !state)) return fail("pcseg_adam_step: bad arguments");
+    if (step < 1) step = 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const float bc1 = 1.f - powf(b1, static_cast<float>(step));
     const float bc2 = 1.f - powf(b2, static_cast<float>(step));
-    k_adam<<<ew_grid(n), 256, 0, s>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale);
+    k_adam<<<ew_grid(n), 256, 0, s>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale,
+                                      reinterpret_cast<const StepState*>(state));
     LAUNCH_OK("k_adam");
+    return 0;
+}
+
+extern "C" int pcseg_step_advance(pcseg_step_state* state, float b1, float b2, void* stream) {
+    if (!state) return fail("pcseg_step_advance: null state");
+    k_step_advance<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<StepState*>(state), b1, b2);
+    LAUNCH_OK("k_step_advance");
     return 0;
 }
 

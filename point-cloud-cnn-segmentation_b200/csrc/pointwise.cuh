@@ -175,8 +175,10 @@ __device__ __forceinline__ void bn_publish(const BnFinalizeArgs& f, bool first_b
 // registers) and walks down the rows of its block's strip; 4 independent 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
                                                  int ld_a, long P, int C, const BnFinalizeArgs fin,
-                                                 unsigned long long seed, unsigned int thr16, float keep_scale) {
+                                                 unsigned long long seed_arg, const unsigned long long* __restrict__ seed_ptr,
+                                                 unsigned int thr16, float keep_scale) {
     bn_publish(fin, blockIdx.x == 0);
+    const unsigned long long seed = seed_arg + (seed_ptr != nullptr ? *seed_ptr : 0ull);
     const int tpr = C >> 3;                       // threads per row (C <= 2048)
     const int rpp = 256 / tpr;                    // rows per pass
     const int c0 = (threadIdx.x % tpr) << 3;
@@ -789,9 +791,26 @@ __global__ void __launch_bounds__(256) k_ingest_bwd(const __nv_bfloat16* __restr
 // Fused Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias correction).
 // grad_scale lets data-parallel ranks fold an averaging factor in (1.0 when grads are already summed).
 // ---------------------------------------------------------------------------------------------
+struct StepState {                 // == pcseg_step_state
+    unsigned long long seed;
+    long long step;
+    float lr, bias_corr1, bias_corr2_sqrt, reserved;
+};
+__global__ void k_step_advance(StepState* st, float b1, float b2) {
+    st->seed += 0x9E3779B97F4A7C15ull;
+    const long long t = st->step + 1;
+    st->step = t;
+    st->bias_corr1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), static_cast<double>(t)));
+    st->bias_corr2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), static_cast<double>(t))));
+}
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
-                                              float bc1, float bc2_sqrt, float grad_scale) {
+                                              float bc1, float bc2_sqrt, float grad_scale, const StepState* __restrict__ st) {
+    if (st != nullptr) {
+        lr = st->lr;
+        bc1 = st->bias_corr1;
+        bc2_sqrt = st->bias_corr2_sqrt;
+    }
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
         const float pv = p[i];
         const float gv = fmaf(wd, pv, g[i] * grad_scale);

@@ -90,13 +90,13 @@ class Engine:
         return (logits, labels) if want_labels else logits
 
     # ---- train
-    def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None):
+    def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None, state=None):
         B, N, _ = x.shape
         b = self.binding(B, N, True)
         logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(lib.pcseg_forward_train(b.handle, ptr(x), ptr(flat_params), ptr(flat_bn), C.c_ulonglong(seed & (2**64 - 1)),
-                                          C.c_float(dropout_p), ptr(logits), ptr(labels), ptr(class_w), ptr(ce), self._stream()),
+                                          C.c_float(dropout_p), ptr(logits), ptr(labels), ptr(class_w), ptr(ce), ptr(state), self._stream()),
                   "pcseg_forward_train")
         return logits
 
@@ -107,10 +107,14 @@ class Engine:
             check(lib.pcseg_backward(b.handle, ptr(x), ptr(flat_params), ptr(dlogits), ptr(logits), ptr(labels), ptr(class_w),
                                      ptr(wsum), ptr(flat_grads), phase, self._stream()), "pcseg_backward")
 
-    def adam(self, flat_params, flat_grads, m, v, step, lr, betas, eps, weight_decay, grad_scale=1.0):
+    def adam(self, flat_params, flat_grads, m, v, step, lr, betas, eps, weight_decay, grad_scale=1.0, state=None):
         with torch.cuda.device(self.device):
             check(lib.pcseg_adam_step(ptr(flat_params), ptr(flat_grads), ptr(m), ptr(v), flat_params.numel(), step, lr, betas[0],
-                                      betas[1], eps, weight_decay, grad_scale, self._stream()), "pcseg_adam_step")
+                                      betas[1], eps, weight_decay, grad_scale, ptr(state), self._stream()), "pcseg_adam_step")
+
+    def step_advance(self, state, betas):
+        with torch.cuda.device(self.device):
+            check(lib.pcseg_step_advance(ptr(state), betas[0], betas[1], self._stream()), "pcseg_step_advance")
 
 
 DEBUG_KINDS = {"y": 0, "act": 1, "dz": 2, "dy": 3, "bnp": 4, "coef": 5, "stats_f": 6, "stats_b": 7, "g": 8, "ystar": 9,

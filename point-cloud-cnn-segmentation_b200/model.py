@@ -160,12 +160,13 @@ class PointNetSegmentation(nn.Module):
             raise RuntimeError("pcseg_b200: input must be a CUDA tensor (sm_100a kernels only, no CPU fallback)")
         return x.contiguous().float()
 
-    def _run_train_forward(self, x, labels=None, class_w=None, ce=None):
+    def _run_train_forward(self, x, labels=None, class_w=None, ce=None, state=None):
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
         p = float(self.dropout.p) if self.dropout.training else 0.0
-        seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p > 0 else 0
-        logits = eng.forward_train(x, f["params"], f["bn"], seed, p, labels, class_w, ce)
+        # with a device-resident step state the dropout seed lives on the GPU (CUDA-graph friendly)
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) if (p > 0 and state is None) else 0
+        logits = eng.forward_train(x, f["params"], f["bn"], seed, p, labels, class_w, ce, state)
         torch._foreach_add_([getattr(self, n).num_batches_tracked for n in _BNS], 1)
         self._fwd_token += 1
         self._manual_version += 1      # running statistics changed

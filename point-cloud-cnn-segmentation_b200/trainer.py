@@ -18,7 +18,7 @@ from .trainer_protocol import GradSync, grad_buckets  # noqa: E402
 
 class FusedTrainer:
     def __init__(self, model: PointNetSegmentation, class_weights=None, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 weight_decay=1e-4, process_group=None, device=None, overlap=True):
+                 weight_decay=1e-4, process_group=None, device=None, overlap=True, use_cuda_graph=True):
         self.model = model
         self.device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         self.model.to(self.device)
@@ -35,34 +35,44 @@ class FusedTrainer:
         self.world = self.sync.world
         self.distributed = self.world > 1
         self.overlap = overlap
-        # 32-byte CE accumulator {loss_num f64, w_sum f64, correct u64, valid u64} + all-reducible copy
+        # 32-byte CE accumulator {loss_num f64, w_sum f64, correct u64, valid u64}
         self.ce_raw = torch.zeros(32, dtype=torch.uint8, device=self.device)
         self.ce_f64 = self.ce_raw.view(torch.float64)
         self.ce_i64 = self.ce_raw.view(torch.int64)
         self.wsum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # device-resident step state (pcseg_step_state): dropout seed, Adam step / bias corrections, learning rate
+        self.state = torch.zeros(32, dtype=torch.uint8, device=self.device)
+        seed0 = int(torch.empty((), dtype=torch.int64).random_().item())
+        self.state.view(torch.int64)[0] = seed0
+        self.state.view(torch.float32)[4] = lr
+        # static outputs of a step
+        self.out_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.out_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.loss_num = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.early, self.late = grad_buckets(self.flat["offs"], n)
-        self.comm_stream = torch.cuda.Stream(device=self.device) if self.distributed else None
         self.last_logits = None
+        # CUDA graph of the whole step (captured on the third step of a given batch shape)
+        self.use_cuda_graph = use_cuda_graph
+        self.profiling = False          # set by the bench's per-kernel event timing: forces eager launches
+        self._graph = None
+        self._graph_key = None
+        self._eager_steps_at_key = 0
+        self._static_x = None
+        self._static_labels = None
 
     def set_lr(self, lr):
         self.lr = lr
+        self.state.view(torch.float32)[4] = lr
 
-    @torch.no_grad()
-    def step(self, points, labels):
-        """One optimizer step on this rank's shard.  points (B,N,4) fp32 and labels (B,N) int64 (-1 = pad) on
-        the device.  Returns dict of device tensors: loss (global weighted mean), correct, valid."""
-        m = self.model
-        if not m.training:
-            raise RuntimeError("FusedTrainer.step needs model.train()")
-        x = m._check_input(points)
-        labels = labels.contiguous()
-        f = self.flat = m._ensure_flat(self.device)
-        logits = m._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw)
+    # ------------------------------------------------------------------ one step, device work only (capturable)
+    def _body(self, x, labels):
+        m, eng, f = self.model, self.engine, self.flat
+        eng.step_advance(self.state, self.betas)
+        logits = m._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw, state=self.state)
         self.last_logits = logits
         self.wsum.copy_(self.ce_f64[1:2])
         self.sync.g = f["grads"]
         self.sync.reduce_normaliser(self.wsum)
-        eng = self.engine
         kw = dict(logits=logits, labels=labels, class_w=self.class_w, wsum=self.wsum)
         if self.distributed and self.overlap:
             eng.backward(x, f["params"], f["grads"], phase=1, **kw)
@@ -74,18 +84,59 @@ class FusedTrainer:
             eng.backward(x, f["params"], f["grads"], phase=0, **kw)
             self.sync.launch([(0, f["grads"].numel())])
             self.sync.wait()
-        self.step_count += 1
-        eng.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps,
-                 self.weight_decay)
-        m._manual_version += 1
-        stats = self.ce_raw.clone()
+        eng.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, 1, self.lr, self.betas, self.eps, self.weight_decay,
+                 state=self.state)
+        self.loss_num.copy_(self.ce_f64[0:1])
         if self.distributed:
-            sf = stats.view(torch.float64)[:1].clone()
-            dist.all_reduce(sf, op=dist.ReduceOp.SUM, group=self.pg)
-            loss = sf[0] / self.wsum[0]
+            self.sync.reduce_normaliser(self.loss_num)
+        torch.div(self.loss_num, self.wsum, out=self.out_loss)
+        self.out_counts.copy_(self.ce_i64[2:4])
+
+    def _try_capture(self, x, labels):
+        try:
+            self._static_x = x.clone()
+            self._static_labels = labels.clone()
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(self._static_x, self._static_labels)
+            self._graph = g
+            return True
+        except Exception as e:                      # capture not possible (e.g. collective backend): stay eager
+            self._graph = None
+            self.use_cuda_graph = False
+            self._capture_error = repr(e)
+            torch.cuda.synchronize(self.device)
+            return False
+
+    @torch.no_grad()
+    def step(self, points, labels):
+        """One optimizer step on this rank's shard.  points (B,N,4) fp32 and labels (B,N) int64 (-1 = pad) on
+        the device.  Returns dict of device tensors: loss (global weighted mean), correct, valid."""
+        m = self.model
+        if not m.training:
+            raise RuntimeError("FusedTrainer.step needs model.train()")
+        x = m._check_input(points)
+        labels = labels.contiguous()
+        self.flat = m._ensure_flat(self.device)
+        key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr())
+        use_graph = self.use_cuda_graph and not self.profiling
+        if use_graph and self._graph is not None and self._graph_key == key:
+            self._static_x.copy_(x, non_blocking=True)
+            self._static_labels.copy_(labels, non_blocking=True)
+            self._graph.replay()
         else:
-            loss = stats.view(torch.float64)[0] / self.wsum[0]
-        return dict(loss=loss, correct=stats.view(torch.int64)[2], valid=stats.view(torch.int64)[3])
+            if key != self._graph_key:
+                self._graph, self._graph_key, self._eager_steps_at_key = None, key, 0
+            if use_graph and self._graph is None and self._eager_steps_at_key >= 2 and self._try_capture(x, labels):
+                self._graph.replay()                # the capture only recorded the work: run it now
+            else:
+                self._body(x, labels)
+                self._eager_steps_at_key += 1
+        self.step_count += 1
+        m._fwd_token += 1
+        m._manual_version += 1
+        return dict(loss=self.out_loss[0], correct=self.out_counts[0], valid=self.out_counts[1])
 
     def sync_bn_buffers(self, src=0):
         """DataParallel keeps replica 0's running statistics; broadcast them when a checkpoint is written."""

@@ -132,3 +132,39 @@ def test_eval_is_deterministic_and_input_dtype_agnostic():
         b = m(x.double())                       # converted to fp32 like any torch module input would be
         c = m(x.transpose(0, 1).contiguous().transpose(0, 1))     # non-contiguous view
     assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """FusedTrainer replays a captured CUDA graph from the third step on; it must train exactly like eager launches
+    (same kernels, device-resident seed / Adam state), up to atomics-order noise."""
+    import pcseg_b200
+    C, B, N = 5, 4, 640
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.random((B, N, 4), dtype=np.float32)).cuda()
+    labels = torch.from_numpy(rng.integers(0, C, (B, N)).astype(np.int64)).cuda()
+    losses = {}
+    params = {}
+    for use_graph in (False, True):
+        m = _model(C, 21, train=True)
+        m.dropout.p = 0.0
+        tr = pcseg_b200.FusedTrainer(m, class_weights=torch.ones(C), use_cuda_graph=use_graph)
+        losses[use_graph] = [float(tr.step(x, labels)["loss"].item()) for _ in range(8)]
+        params[use_graph] = tr.flat["params"].clone()
+        assert (tr._graph is not None) == use_graph
+        assert int(m.bn1.num_batches_tracked.item()) == 7 + 8
+        assert int(tr.state.view(torch.int64)[1].item()) == 8           # device-side Adam step counter
+    # two EAGER runs already differ by ~0.5 % after a few steps (fp64 atomics order -> last-bit differences in the batch
+    # statistics -> individual bf16 roundings flip -> amplified by the ill-conditioned train-mode network)
+    assert abs(losses[False][0] - losses[True][0]) < 1e-5 * abs(losses[False][0])
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) < 2e-2 * abs(a), (losses[False], losses[True])
+    assert (params[False] - params[True]).abs().max().item() < 1.7e-2        # 8 Adam steps of lr = 1e-3 each way
+    # dropout masks must differ from step to step under graph replay (seed advances on the device)
+    m = _model(C, 22, train=True)
+    tr = pcseg_b200.FusedTrainer(m, class_weights=torch.ones(C))
+    outs = []
+    for _ in range(5):
+        tr.step(x, labels)
+        outs.append(tr.last_logits.clone())
+    assert tr._graph is not None
+    assert (outs[-1] - outs[-2]).abs().max().item() > 1e-4
