@@ -64,50 +64,83 @@ class FusedTrainer:
         self.lr = lr
         self.state.view(torch.float32)[4] = lr
 
-    # ------------------------------------------------------------------ one step, device work only (capturable)
-    def _body(self, x, labels):
-        m, eng, f = self.model, self.engine, self.flat
-        eng.step_advance(self.state, self.betas)
-        logits = m._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw, state=self.state)
-        self.last_logits = logits
+    # ------------------------------------------------------------------ one step = 4 capturable segments + collectives
+    # Collectives are never captured (they run eagerly between the graph segments), so the same code serves one GPU and
+    # data-parallel ranks:  [forward] -> all-reduce(sum w) -> [backward phase 1] -> async all-reduce(bucket 1)
+    #                       -> [backward phase 2] -> all-reduce(bucket 2), wait -> [Adam + outputs] -> all-reduce(loss num)
+    def _seg_forward(self, x, labels):
+        self.engine.step_advance(self.state, self.betas)
+        self.last_logits = self.model._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw, state=self.state)
         self.wsum.copy_(self.ce_f64[1:2])
-        self.sync.g = f["grads"]
-        self.sync.reduce_normaliser(self.wsum)
-        kw = dict(logits=logits, labels=labels, class_w=self.class_w, wsum=self.wsum)
-        if self.distributed and self.overlap:
-            eng.backward(x, f["params"], f["grads"], phase=1, **kw)
-            self.sync.launch(self.early)                    # NCCL runs on its own stream while phase 2 computes
-            eng.backward(x, f["params"], f["grads"], phase=2, **kw)
-            self.sync.launch(self.late)
-            self.sync.wait()
-        else:
-            eng.backward(x, f["params"], f["grads"], phase=0, **kw)
-            self.sync.launch([(0, f["grads"].numel())])
-            self.sync.wait()
-        eng.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, 1, self.lr, self.betas, self.eps, self.weight_decay,
-                 state=self.state)
+
+    def _seg_backward(self, x, labels, phase):
+        f = self.flat
+        self.engine.backward(x, f["params"], f["grads"], phase=phase, logits=self.last_logits, labels=labels, class_w=self.class_w,
+                             wsum=self.wsum)
+
+    def _seg_tail(self, x, labels):
+        f = self.flat
+        self.engine.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, 1, self.lr, self.betas, self.eps, self.weight_decay,
+                         state=self.state)
         self.loss_num.copy_(self.ce_f64[0:1])
-        if self.distributed:
-            self.sync.reduce_normaliser(self.loss_num)
-        torch.div(self.loss_num, self.wsum, out=self.out_loss)
         self.out_counts.copy_(self.ce_i64[2:4])
 
+    def _segments(self):
+        if self.distributed and self.overlap:
+            return [self._seg_forward, lambda x, l: self._seg_backward(x, l, 1), lambda x, l: self._seg_backward(x, l, 2), self._seg_tail]
+        return [self._seg_forward, lambda x, l: self._seg_backward(x, l, 0), None, self._seg_tail]
+
+    def _collective_after(self, i):
+        """eager collectives that follow segment i"""
+        f = self.flat
+        self.sync.g = f["grads"]
+        if i == 0:
+            self.sync.reduce_normaliser(self.wsum)
+        elif i == 1:
+            if self.distributed and self.overlap:
+                self.sync.launch(self.early)                # NCCL runs on its own stream while phase 2 computes
+            else:
+                self.sync.launch([(0, f["grads"].numel())])
+                self.sync.wait()
+        elif i == 2:
+            if self.distributed and self.overlap:
+                self.sync.launch(self.late)
+                self.sync.wait()
+        elif i == 3:
+            self.sync.reduce_normaliser(self.loss_num)
+            torch.div(self.loss_num, self.wsum, out=self.out_loss)
+
+    def _run_step(self, x, labels, graphs=None):
+        for i, seg in enumerate(self._segments()):
+            if seg is not None:
+                if graphs is not None:
+                    graphs[i].replay()
+                else:
+                    seg(x, labels)
+            self._collective_after(i)
+
     def _try_capture(self, x, labels):
+        """Record the four segments (no execution).  Returns the list of graphs or None."""
         try:
             self._static_x = x.clone()
             self._static_labels = labels.clone()
             torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._body(self._static_x, self._static_labels)
-            self._graph = g
-            return True
-        except Exception as e:                      # capture not possible (e.g. collective backend): stay eager
-            self._graph = None
+            graphs, pool = [], None
+            for seg in self._segments():
+                if seg is None:
+                    graphs.append(None)
+                    continue
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    seg(self._static_x, self._static_labels)
+                pool = g.pool()
+                graphs.append(g)
+            return graphs
+        except Exception as e:                      # stay eager
             self.use_cuda_graph = False
             self._capture_error = repr(e)
             torch.cuda.synchronize(self.device)
-            return False
+            return None
 
     @torch.no_grad()
     def step(self, points, labels):
@@ -121,18 +154,17 @@ class FusedTrainer:
         self.flat = m._ensure_flat(self.device)
         key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr())
         use_graph = self.use_cuda_graph and not self.profiling
-        if use_graph and self._graph is not None and self._graph_key == key:
+        if key != self._graph_key:
+            self._graph, self._graph_key, self._eager_steps_at_key = None, key, 0
+        if use_graph and self._graph is None and self._eager_steps_at_key >= 2:
+            self._graph = self._try_capture(x, labels)          # recording only; the replay below runs this step
+        if use_graph and self._graph is not None:
             self._static_x.copy_(x, non_blocking=True)
             self._static_labels.copy_(labels, non_blocking=True)
-            self._graph.replay()
+            self._run_step(self._static_x, self._static_labels, self._graph)
         else:
-            if key != self._graph_key:
-                self._graph, self._graph_key, self._eager_steps_at_key = None, key, 0
-            if use_graph and self._graph is None and self._eager_steps_at_key >= 2 and self._try_capture(x, labels):
-                self._graph.replay()                # the capture only recorded the work: run it now
-            else:
-                self._body(x, labels)
-                self._eager_steps_at_key += 1
+            self._run_step(x, labels)
+            self._eager_steps_at_key += 1
         self.step_count += 1
         m._fwd_token += 1
         m._manual_version += 1
