@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "pcseg_api.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("gemm.cuh", "pointwise.cuh", "ptx.cuh")] + [
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("gemm.cuh", "head_chain.cuh", "pointwise.cuh", "ptx.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "pcseg_b200.h")]
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpcseg_b200.so")

@@ -4,11 +4,13 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "gemm.cuh"
+#include "head_chain.cuh"
 #include "pointwise.cuh"
 
 using namespace pcseg;
@@ -292,6 +294,9 @@ struct pcseg_ctx {
     bf16* wk[NUM_BN] = {};        // bf16 [Cout][Cin] forward weights (index = conv index; [6] = point-feature part [512][64])
     bf16* act[NUM_BN] = {};       // eval: activations a_l; train: post-BN/ReLU activations
     GemmOp ev[NUM_BN];            // eval forward GEMMs (index = conv index 1..8)
+    CUtensorMap hcA1, hcB1, hcB2, hcB3;   // fused inference head (head_chain_kernel)
+    HeadChainParams hcp;
+    bool use_head_chain = true;
     // ---- train
     bf16* y[NUM_BN] = {};         // pre-BN conv outputs
     bf16* dz[NUM_BN] = {};        // gradient wrt BN output (after ReLU / dropout mask)
@@ -460,6 +465,25 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         c->ev[8].p.w4 = c->w4;
         c->ev[8].p.b4 = c->b4;
         c->ev[8].p.num_classes = c->C;
+        // fused head: seg_conv1..4 in one kernel (PCSEG_EVAL_CHAIN=0 selects the layer-by-layer kernels above)
+        TRY(make_tmap(&c->hcA1, c->act[1], 64, P, 64, 64, 128));
+        TRY(make_tmap(&c->hcB1, c->wk[6], 64, 512, 64, 64, 256));
+        TRY(make_tmap(&c->hcB2, c->wk[7], 512, 256, 512, 64, 256));
+        TRY(make_tmap(&c->hcB3, c->wk[8], 256, 128, 256, 64, 128));
+        memset(&c->hcp, 0, sizeof(c->hcp));
+        c->hcp.M = static_cast<int>(P);
+        c->hcp.num_tiles = static_cast<int>((P + 127) / 128);
+        c->hcp.pts_per_cloud = N;
+        c->hcp.cloud_bias = c->cb;
+        c->hcp.bias2 = c->delta[7];
+        c->hcp.bias3 = c->delta[8];
+        c->hcp.w4 = c->w4;
+        c->hcp.b4 = c->b4;
+        c->hcp.num_classes = c->C;
+        {
+            const char* e = getenv("PCSEG_EVAL_CHAIN");
+            c->use_head_chain = !(e && e[0] == '0');
+        }
     } else {
         // ---- forward: y_i = a_{i-1} W_i^T, statistics in the epilogue
         for (int i = 1; i <= 5; ++i) {
@@ -573,11 +597,24 @@ extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, l
         k_cloud_bias<<<(warps * 32 + 255) / 256, 256, 0, s>>>(c->wg, 1024, c->gmax, c->B, 512, 1024, c->alpha[6], c->delta[6], c->cb);
         LAUNCH_OK("k_cloud_bias");
     }
-    TRY(launch_gemm(c->ev[6], s));
-    TRY(launch_gemm(c->ev[7], s));
-    GemmOp head = c->ev[8];
-    head.p.logits = logits;
-    TRY(launch_gemm(head, s));
+    if (c->use_head_chain) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HC_SMEM_BYTES));
+            attr_set = true;
+        }
+        HeadChainParams hp = c->hcp;
+        hp.logits = logits;
+        const int grid = hp.num_tiles < num_sms() ? hp.num_tiles : num_sms();
+        head_chain_kernel<<<grid, HC_THREADS, HC_SMEM_BYTES, s>>>(c->hcA1, c->hcB1, c->hcB2, c->hcB3, hp);
+        LAUNCH_OK("head_chain_kernel");
+    } else {
+        TRY(launch_gemm(c->ev[6], s));
+        TRY(launch_gemm(c->ev[7], s));
+        GemmOp head = c->ev[8];
+        head.p.logits = logits;
+        TRY(launch_gemm(head, s));
+    }
     if (labels_out) {
         k_argmax<<<static_cast<int>((P + 255) / 256), 256, 0, s>>>(logits, P, c->C, labels_out);
         LAUNCH_OK("k_argmax");
