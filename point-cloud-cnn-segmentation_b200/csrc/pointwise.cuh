@@ -53,13 +53,34 @@ struct ConvertJobs {
     int count;
 };
 __global__ void __launch_bounds__(256) k_convert_multi(const ConvertJobs jobs) {
+    // blockIdx.y = job; 32x32 tiles through shared memory so that both the fp32 reads and the (possibly transposed)
+    // bf16 writes are coalesced
+    __shared__ float tile[32][33];
     const ConvertJob j = jobs.job[blockIdx.y];
-    const int n = j.rows * j.cols;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-        const int r = idx / j.cols, c = idx % j.cols;
-        const float v = j.src[static_cast<size_t>(r) * j.ld_src + c];
-        if (j.transpose) j.dst[static_cast<size_t>(c) * j.ld_dst + r] = __float2bfloat16_rn(v);
-        else j.dst[static_cast<size_t>(r) * j.ld_dst + c] = __float2bfloat16_rn(v);
+    const int tiles_c = (j.cols + 31) >> 5, tiles_r = (j.rows + 31) >> 5;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+        const int r0 = (t / tiles_c) << 5, c0 = (t % tiles_c) << 5;
+#pragma unroll
+        for (int i = ty; i < 32; i += 8) {
+            const int r = r0 + i, c = c0 + tx;
+            tile[i][tx] = (r < j.rows && c < j.cols) ? j.src[static_cast<size_t>(r) * j.ld_src + c] : 0.f;
+        }
+        __syncthreads();
+        if (j.transpose) {
+#pragma unroll
+            for (int i = ty; i < 32; i += 8) {
+                const int c = c0 + i, r = r0 + tx;
+                if (r < j.rows && c < j.cols) j.dst[static_cast<size_t>(c) * j.ld_dst + r] = __float2bfloat16_rn(tile[tx][i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = ty; i < 32; i += 8) {
+                const int r = r0 + i, c = c0 + tx;
+                if (r < j.rows && c < j.cols) j.dst[static_cast<size_t>(r) * j.ld_dst + c] = __float2bfloat16_rn(tile[i][tx]);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -324,7 +345,12 @@ __global__ void __launch_bounds__(256, 3) k_head_fwd(const __nv_bfloat16* __rest
     const int sub = lane & 7;                  // 16-channel slice of the point
     const int grp = lane >> 3;                 // point slot inside the warp
     bn_publish(fin, blockIdx.x == 0);
-    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) w_s[i] = W4[i];
+    // bank-conflict-free layout [class][q][sub][4]: logical channel = sub*16 + q*4 + j (lanes of a point read 8 distinct
+    // 16-byte chunks that cover all 32 banks)
+    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) {
+        const int k = i >> 7, c = i & 127;
+        w_s[k * 128 + ((c >> 2) & 3) * 32 + (c >> 4) * 4 + (c & 3)] = W4[i];
+    }
     float sc[16], sh[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -360,11 +386,11 @@ __global__ void __launch_bounds__(256, 3) k_head_fwd(const __nv_bfloat16* __rest
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
             if (k < C) {
-                const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 16);
+                const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 4);
                 float sq[4];                                // 4 independent chains (ILP) instead of one 16-deep chain
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 w4 = wk[q];
+                    const float4 w4 = wk[q * 8];
                     sq[q] = fmaf(a[4 * q + 3], w4.w, fmaf(a[4 * q + 2], w4.z, fmaf(a[4 * q + 1], w4.y, a[4 * q] * w4.x)));
                 }
                 float s = (sq[0] + sq[1]) + (sq[2] + sq[3]);
@@ -456,7 +482,12 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
     const int warp = threadIdx.x >> 5;
     const int sub = lane & 7;
     const int grp = lane >> 3;
-    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) w_s[i] = W4[i];
+    // bank-conflict-free layout [class][q][sub][4]: logical channel = sub*16 + q*4 + j (lanes of a point read 8 distinct
+    // 16-byte chunks that cover all 32 banks)
+    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) {
+        const int k = i >> 7, c = i & 127;
+        w_s[k * 128 + ((c >> 2) & 3) * 32 + (c >> 4) * 4 + (c & 3)] = W4[i];
+    }
     float sc[16], sh[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -518,10 +549,10 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
         for (int e = 0; e < 16; ++e) da[e] = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
-            const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 16);
+            const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 4);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 w4 = wk[q];
+                const float4 w4 = wk[q * 8];
                 da[4 * q] = fmaf(dl[k], w4.x, da[4 * q]);
                 da[4 * q + 1] = fmaf(dl[k], w4.y, da[4 * q + 1]);
                 da[4 * q + 2] = fmaf(dl[k], w4.z, da[4 * q + 2]);
