@@ -28,9 +28,9 @@ enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EP
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int EPI_WARPS = 8;     // 16 measured slower overall (only global_feat fwd+pool gains)
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int GEMM_THREADS = 128 + EPI_THREADS;
+// Epilogue warps per kernel variant: 8 everywhere except the train-mode global_feat forward (stats + fused max-pool), whose
+// epilogue is the longest and measurably profits from 16 (282 vs 296 us); 16 everywhere was slower overall.
+constexpr int epi_warps_for(int epi) { return epi == 6 /* EPI_STATS_POOL */ ? 16 : 8; }
 constexpr int MAX_CLASSES = 8;    // compile-time cap on num_classes for the fused head kernels
 
 struct GemmParams {
@@ -48,6 +48,7 @@ struct GemmParams {
     int ldc;                     // wgrad destination pitch (elements)
     unsigned long long seed;     // dropout (effective seed = seed + *seed_ptr when seed_ptr != nullptr)
     const unsigned long long* seed_ptr;
+    const unsigned char* keep_bytes;   // [M][N/8] dropout keep masks written by the forward pass (1 bit per element); null = regenerate
     unsigned int drop_thr16;     // 0 = no dropout
     float keep_scale;            // 1/(1-p)
     const float* w4;             // [C][128] fp32
@@ -60,6 +61,9 @@ struct GemmParams {
 
 template <int BN, int EPI, bool MN>
 struct GemmCfg {
+    static constexpr int EPI_WARPS = epi_warps_for(EPI);
+    static constexpr int EPI_THREADS = EPI_WARPS * 32;
+    static constexpr int THREADS = 128 + EPI_THREADS;
     static constexpr int STAGE_A = GEMM_BM * GEMM_BK * 2;
     static constexpr int STAGE_B = BN * GEMM_BK * 2;
     static constexpr int STAGE = STAGE_A + STAGE_B;
@@ -67,7 +71,7 @@ struct GemmCfg {
     static constexpr bool HAS_Y = (EPI == EPI_DGRAD);
     static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
     static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
-    static constexpr int COMB_BYTES = (EPI == EPI_LOGITS) ? (EPI_WARPS / 4 - 1) * 128 * MAX_CLASSES * 4 + 1024
+    static constexpr int COMB_BYTES = (EPI == EPI_LOGITS) ? (epi_warps_for(EPI) / 4 - 1) * 128 * MAX_CLASSES * 4 + 1024
                                                              : 4096;   // column accumulators / colmax exchange / logits partials
     static constexpr int W4_BYTES = (EPI == EPI_LOGITS) ? (MAX_CLASSES * 128 + MAX_CLASSES) * 4 : 0;
     static constexpr int BAR_BYTES = 256;
@@ -111,11 +115,14 @@ __device__ __forceinline__ float warp_colreduce(float (&v)[CW]) {
 }
 
 template <int BN, int EPI, bool MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, EPI, MN>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmY,
             const GemmParams p) {
     using Cfg = GemmCfg<BN, EPI, MN>;
+    constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+    constexpr int EPI_THREADS = Cfg::EPI_THREADS;
+    constexpr int GEMM_THREADS = Cfg::THREADS;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int SUBS = BN / 64;           // 64-column epilogue sub-tiles
     static_assert(BN % 64 == 0, "BN must be a multiple of 64");
@@ -505,8 +512,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w};
                                 uint32_t keep = 0xFFu;
                                 if (p.drop_thr16 != 0u) {
-                                    const unsigned long long e0 = static_cast<unsigned long long>(m0 + r) * p.N + colbase;
-                                    keep = dropout_keep8(seed_eff, e0 >> 3, p.drop_thr16);
+                                    if (p.keep_bytes != nullptr) {
+                                        keep = (m0 + r < p.M) ? __ldg(p.keep_bytes + static_cast<size_t>(m0 + r) * (p.N >> 3) + (colbase >> 3)) : 0u;
+                                    } else {
+                                        const unsigned long long e0 = static_cast<unsigned long long>(m0 + r) * p.N + colbase;
+                                        keep = dropout_keep8(seed_eff, e0 >> 3, p.drop_thr16);
+                                    }
                                 }
                                 float dz[8];
 #pragma unroll

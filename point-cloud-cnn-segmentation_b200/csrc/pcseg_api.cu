@@ -171,7 +171,7 @@ int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
     const int tiles = op.p.num_m_tiles * op.p.num_n_tiles * op.p.num_splits;
     int grid = tiles < num_sms() ? tiles : num_sms();
     if (!MN) grid = (grid / op.p.num_n_tiles) * op.p.num_n_tiles;   // every CTA keeps one n_tile (per-CTA column accumulators)
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmY, op.p);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmY, op.p);
     LAUNCH_OK("gemm_kernel");
     return 0;
 }
@@ -302,6 +302,7 @@ struct pcseg_ctx {
     bf16* dz[NUM_BN] = {};        // gradient wrt BN output (after ReLU / dropout mask)
     bf16* dy[NUM_BN] = {};        // gradient wrt conv output
     bf16* dycat = nullptr;        // [P][576] = [dy(conv3) | dy(seg_conv1)]
+    unsigned char* keepb[NUM_BN] = {};   // dropout keep masks of seg_conv1 / seg_conv2 outputs, 1 bit per element
     bf16* wt[NUM_BN] = {};        // bf16 transposed weights [Cin][Cout] for dgrad (index = conv index)
     bf16* wcat = nullptr;         // [64][576] = [W3^T | Wpf^T]
     double* stats_f = nullptr;    // forward  stats, per layer [2][C] at stat_off
@@ -699,7 +700,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     // BN finalize of layer i is folded into this kernel (block 0 publishes bnp + running statistics)
     auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         const int co = cv[i].cout;
-        k_bn_relu<<<strip_grid(P, co), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks);
+        k_bn_relu<<<strip_grid(P, co), 256, 0, s>>>(c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks, nullptr);
         LAUNCH_OK("k_bn_relu");
         return 0;
     };
@@ -809,6 +810,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     };
     auto dgrad = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         GemmOp op = c->dg[i];
+        op.p.keep_bytes = nullptr;      // stored keep masks were measured SLOWER than regenerating Philox (uncoalesced byte loads)
         op.p.seed = sd;
         op.p.seed_ptr = c->seed_ptr;
         op.p.drop_thr16 = thr;

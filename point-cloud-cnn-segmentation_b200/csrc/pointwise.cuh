@@ -197,7 +197,7 @@ __device__ __forceinline__ void bn_publish(const BnFinalizeArgs& f, bool first_b
 __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
                                                  int ld_a, long P, int C, const BnFinalizeArgs fin,
                                                  unsigned long long seed_arg, const unsigned long long* __restrict__ seed_ptr,
-                                                 unsigned int thr16, float keep_scale) {
+                                                 unsigned int thr16, float keep_scale, unsigned char* __restrict__ keep_out) {
     bn_publish(fin, blockIdx.x == 0);
     const unsigned long long seed = seed_arg + (seed_ptr != nullptr ? *seed_ptr : 0ull);
     const int tpr = C >> 3;                       // threads per row (C <= 2048)
@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
             if (rr >= r_end) break;
             const uint32_t ws[4] = {yw[u].x, yw[u].y, yw[u].z, yw[u].w};
             uint32_t keep = 0xFFu;
-            if (thr16 != 0u) keep = dropout_keep8(seed, (static_cast<unsigned long long>(rr) * C + c0) >> 3, thr16);
+            if (thr16 != 0u) {
+                keep = dropout_keep8(seed, (static_cast<unsigned long long>(rr) * C + c0) >> 3, thr16);
+                if (keep_out != nullptr) keep_out[rr * (C >> 3) + (c0 >> 3)] = static_cast<unsigned char>(keep);   // re-used by backward
+            }
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
