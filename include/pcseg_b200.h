@@ -108,6 +108,14 @@ int pcseg_adam_step(float* params, const float* grads, float* exp_avg, float* ex
  * pcseg_adam_step, `step` and `lr` are taken from it instead of from the arguments. */
 int pcseg_step_advance(pcseg_step_state* state, float beta1, float beta2, void* stream);
 
+/* Validation metrics in one pass over logits (pcs.py:292-304 loss / accuracy, pcs.py:319-343 F1 inputs):
+ * *ce accumulates the weighted-CE sums and accuracy counters (caller zeroes it), confusion is a C x C matrix
+ * (rows = true class, columns = argmax prediction; int64, caller zeroes it), pred_out (optional) receives the
+ * argmax labels.  labels == -1 are ignored (pcs.py:54, 216). */
+int pcseg_eval_metrics(const float* logits, const long long* labels, long long num_points, int num_classes,
+                       const float* class_w, pcseg_ce_accum* ce, unsigned long long* confusion,
+                       long long* pred_out, void* stream);
+
 /* Stand-alone GEMM entry used by the unit tests of the tcgen05 kernel (bf16 in, fp32 accumulate).
  *   layout 0: D[M,N] = A[M,K] * B[N,K]^T         (A, B row-major, K contiguous), bf16 out = relu(D + bias)
  *   layout 1: D[M,N] = A[K,M]^T * B[K,N]         (A, B row-major, K = rows),     fp32 out += D (split-K atomics)

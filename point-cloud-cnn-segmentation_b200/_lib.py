@@ -10,7 +10,7 @@ EXPORTS = [
     "pcseg_last_error", "pcseg_version", "pcseg_create", "pcseg_destroy", "pcseg_param_count", "pcseg_param_offset",
     "pcseg_param_numel", "pcseg_bn_buffer_count", "pcseg_bn_buffer_offset", "pcseg_workspace_bytes", "pcseg_bind",
     "pcseg_prepare_eval", "pcseg_forward_eval", "pcseg_forward_train", "pcseg_backward", "pcseg_adam_step",
-    "pcseg_gemm_test", "pcseg_launch_count", "pcseg_debug_copy", "pcseg_step_advance", "pcseg_profile_enable", "pcseg_profile_read", "pcseg_profile_reset",
+    "pcseg_gemm_test", "pcseg_launch_count", "pcseg_debug_copy", "pcseg_step_advance", "pcseg_eval_metrics", "pcseg_profile_enable", "pcseg_profile_read", "pcseg_profile_reset",
 ]
 
 
@@ -47,6 +47,7 @@ def _load():
     lib.pcseg_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.pcseg_adam_step.argtypes = [vp, vp, vp, vp, ll, i32, f32, f32, f32, f32, f32, f32, vp, vp]
     lib.pcseg_step_advance.argtypes = [vp, f32, f32, vp]
+    lib.pcseg_eval_metrics.argtypes = [vp, vp, ll, i32, vp, vp, vp, vp, vp]
     lib.pcseg_gemm_test.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
     lib.pcseg_launch_count.restype = ll
     lib.pcseg_profile_enable.argtypes = [vp, i32]

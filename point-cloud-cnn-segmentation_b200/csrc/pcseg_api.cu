@@ -915,6 +915,18 @@ extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, floa
     return 0;
 }
 
+extern "C" int pcseg_eval_metrics(const float* logits, const long long* labels, long long P, int C, const float* class_w,
+                                  pcseg_ce_accum* ce, unsigned long long* confusion, long long* pred_out, void* stream) {
+    if (!logits || P <= 0 || C < 1 || C > MAX_CLASSES) return fail("pcseg_eval_metrics: bad arguments");
+    if (!labels && !pred_out) return fail("pcseg_eval_metrics: nothing to compute (no labels, no pred_out)");
+    int grid = static_cast<int>((P + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    k_eval_metrics<MAX_CLASSES><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, P, C, class_w,
+                                                                                      reinterpret_cast<CeAccum*>(ce), confusion, pred_out);
+    LAUNCH_OK("k_eval_metrics");
+    return 0;
+}
+
 extern "C" int pcseg_step_advance(pcseg_step_state* state, float b1, float b2, void* stream) {
     if (!state) return fail("pcseg_step_advance: null state");
     k_step_advance<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<StepState*>(state), b1, b2);

@@ -857,6 +857,69 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     }
 }
 
+// Validation metrics in one pass over the logits (pcs.py:292-304, 319-343): weighted-CE sums, accuracy counters and the
+// C x C confusion matrix (rows = true class, columns = predicted class) from which F1 scores follow on the host.
+// One thread per point; block-level reduction, then one atomic per counter per block.
+template <int MAXC>
+__global__ void __launch_bounds__(256) k_eval_metrics(const float* __restrict__ logits, const long long* __restrict__ labels, long P, int C,
+                                                      const float* __restrict__ class_w, CeAccum* __restrict__ ce,
+                                                      unsigned long long* __restrict__ confusion, long long* __restrict__ pred_out) {
+    __shared__ unsigned int conf_s[MAXC * MAXC];
+    __shared__ double red_d[8][2];
+    __shared__ unsigned long long red_u[8][2];
+    for (int i = threadIdx.x; i < MAXC * MAXC; i += blockDim.x) conf_s[i] = 0u;
+    __syncthreads();
+    double loss_num = 0.0, w_sum = 0.0;
+    unsigned long long correct = 0, nvalid = 0;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < P; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        float z[MAXC];
+        float zmax = -INFINITY;
+        int am = 0;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            z[k] = (k < C) ? logits[i * C + k] : -INFINITY;
+            if (z[k] > zmax) { zmax = z[k]; am = k; }          // first maximum, like torch.argmax
+        }
+        if (pred_out != nullptr) pred_out[i] = am;
+        const long long lab = labels != nullptr ? labels[i] : -1;
+        if (lab >= 0) {
+            float se = 0.f, zl = 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k)
+                if (k < C) { se += __expf(z[k] - zmax); if (k == lab) zl = z[k]; }
+            const float wl = class_w ? class_w[lab] : 1.f;
+            loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(se) - zl);
+            w_sum += wl;
+            correct += (am == lab);
+            nvalid += 1;
+            atomicAdd(&conf_s[static_cast<int>(lab) * MAXC + am], 1u);
+        }
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+        loss_num += __shfl_xor_sync(0xffffffffu, loss_num, o);
+        w_sum += __shfl_xor_sync(0xffffffffu, w_sum, o);
+        correct += __shfl_xor_sync(0xffffffffu, correct, o);
+        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red_d[warp][0] = loss_num; red_d[warp][1] = w_sum; red_u[warp][0] = correct; red_u[warp][1] = nvalid; }
+    __syncthreads();
+    if (threadIdx.x == 0 && ce != nullptr) {
+        double a0 = 0.0, a1 = 0.0;
+        unsigned long long u0 = 0, u1 = 0;
+        for (int w = 0; w < 8; ++w) { a0 += red_d[w][0]; a1 += red_d[w][1]; u0 += red_u[w][0]; u1 += red_u[w][1]; }
+        atomicAdd(&ce->loss_num, a0);
+        atomicAdd(&ce->w_sum, a1);
+        atomicAdd(&ce->correct, u0);
+        atomicAdd(&ce->valid, u1);
+    }
+    if (confusion != nullptr)
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+            const unsigned int v = conf_s[(i / C) * MAXC + (i % C)];
+            if (v) atomicAdd(confusion + i, static_cast<unsigned long long>(v));
+        }
+}
+
 // argmax over classes (first maximum wins, like torch.argmax on ties)
 __global__ void k_argmax(const float* __restrict__ logits, long P, int C, long long* __restrict__ out) {
     const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;

@@ -112,6 +112,17 @@ class Engine:
             check(lib.pcseg_adam_step(ptr(flat_params), ptr(flat_grads), ptr(m), ptr(v), flat_params.numel(), step, lr, betas[0],
                                       betas[1], eps, weight_decay, grad_scale, ptr(state), self._stream()), "pcseg_adam_step")
 
+    def eval_metrics(self, logits, labels, class_w=None, want_pred=False):
+        """Weighted CE sums, accuracy counters and confusion matrix of eval-mode logits (one kernel, no host sync)."""
+        P = logits.shape[0] * logits.shape[1]
+        ce = torch.zeros(32, dtype=torch.uint8, device=self.device)
+        conf = torch.zeros((self.C, self.C), dtype=torch.int64, device=self.device)
+        pred = torch.empty(logits.shape[:2], dtype=torch.int64, device=self.device) if want_pred else None
+        with torch.cuda.device(self.device):
+            check(lib.pcseg_eval_metrics(ptr(logits), ptr(labels), P, self.C, ptr(class_w), ptr(ce), ptr(conf), ptr(pred), self._stream()),
+                  "pcseg_eval_metrics")
+        return ce, conf, pred
+
     def step_advance(self, state, betas):
         with torch.cuda.device(self.device):
             check(lib.pcseg_step_advance(ptr(state), betas[0], betas[1], self._stream()), "pcseg_step_advance")

@@ -200,6 +200,37 @@ class PointNetSegmentation(nn.Module):
         return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), want_labels=True)
 
 
+    @torch.no_grad()
+    def evaluate(self, x, labels, class_weights=None):
+        """One validation batch without host synchronisation: replaces the per-batch loss / accuracy code of
+        pcs.py:289-304 and the second F1 sweep of pcs.py:319-343.  Returns device tensors: logits, loss (weighted-mean CE),
+        correct, valid and the C x C confusion matrix (rows = true class, columns = prediction)."""
+        x = self._check_input(x)
+        if self.training:
+            raise RuntimeError("evaluate() is an eval-mode call; use model.eval() first")
+        f = self._ensure_flat(x.device)
+        eng = self._get_engine(x.device)
+        logits = eng.forward_eval(x, f["params"], f["bn"], self._weights_key())
+        cw = None if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float32, device=x.device).contiguous()
+        ce, conf, _ = eng.eval_metrics(logits, labels.contiguous(), cw)
+        f64, i64 = ce.view(torch.float64), ce.view(torch.int64)
+        return dict(logits=logits, loss=f64[0] / f64[1], correct=i64[2], valid=i64[3], confusion=conf)
+
+
+def f1_scores(confusion):
+    """Per-class F1, macro F1 and weighted F1 from a confusion matrix (what sklearn.f1_score returns at pcs.py:341-343)."""
+    conf = confusion.to(torch.float64)
+    tp = conf.diag()
+    support = conf.sum(dim=1)
+    predicted = conf.sum(dim=0)
+    denom = support + predicted
+    f1 = torch.where(denom > 0, 2 * tp / denom.clamp(min=1), torch.zeros_like(tp))
+    present = (support + predicted) > 0
+    macro = f1[present].mean() if present.any() else f1.sum() * 0
+    weighted = (f1 * support).sum() / support.sum().clamp(min=1)
+    return f1, macro, weighted
+
+
 def load_checkpoint(path, map_location=None):
     """Load a `best_model.pth` written by the reference (pcs.py:373-382): reads `num_classes` and
     `model_state_dict`, strips a DataParallel `module.` prefix if present (pcs.py:410-428)."""

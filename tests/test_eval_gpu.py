@@ -90,3 +90,30 @@ def test_forward_rejects_bad_input():
         m(torch.rand(10, 4, device="cuda"))            # same tuple-unpack error as pcs.py:100
     with pytest.raises(RuntimeError):
         m(torch.rand(1, 10, 4))                         # CPU tensor: no fallback
+
+
+def test_evaluate_metrics_match_torch_and_sklearn():
+    """model.evaluate: weighted-CE loss, accuracy counters and confusion matrix (integer, exact) of one validation batch
+    (pcs.py:289-304, 319-343) against torch / sklearn applied to the SAME logits."""
+    import pcseg_b200
+    from sklearn.metrics import confusion_matrix, f1_score
+    C = 5
+    m = _model(C, orc.synth_state(C, 12))
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy(rng.random((3, 700, 4), dtype=np.float32)).cuda()
+    labels = torch.from_numpy(rng.integers(-1, C, (3, 700)).astype(np.int64)).cuda()
+    cw = torch.tensor([0.5, 1.0, 2.0, 0.75, 0.75], device="cuda")
+    out = m.evaluate(x, labels, cw)
+    logits = out["logits"]
+    ref_loss = torch.nn.functional.cross_entropy(logits.view(-1, C), labels.view(-1), weight=cw, ignore_index=-1)
+    assert abs(out["loss"].item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
+    valid = labels >= 0
+    pred = logits.argmax(-1)
+    assert int(out["valid"].item()) == int(valid.sum().item())
+    assert int(out["correct"].item()) == int(((pred == labels) & valid).sum().item())
+    yt, yp = labels[valid].cpu().numpy(), pred[valid].cpu().numpy()
+    assert np.array_equal(out["confusion"].cpu().numpy(), confusion_matrix(yt, yp, labels=list(range(C))))
+    f1, macro, weighted = pcseg_b200.f1_scores(out["confusion"])
+    np.testing.assert_allclose(f1.cpu().numpy(), f1_score(yt, yp, average=None, labels=list(range(C))), atol=1e-12)
+    assert abs(macro.item() - f1_score(yt, yp, average="macro")) < 1e-12
+    assert abs(weighted.item() - f1_score(yt, yp, average="weighted")) < 1e-12
