@@ -707,7 +707,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
 
     {   // conv1 on CUDA cores
         int grid = static_cast<int>((P + 31) / 32);
-        if (grid > num_sms() * 8) grid = num_sms() * 8;
+        if (grid > num_sms() * 2) grid = num_sms() * 2;     // every block ends with 128 fp64 atomics on the same addresses
         k_ingest<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(x), static_cast<int>(P), params + L.off[0], nullptr, nullptr,
                                            c->y[0], c->stats_f + c->stat_off[0]);
         LAUNCH_OK("k_ingest");
@@ -753,7 +753,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
 static int apply_rows_per_strip(int N, int B, int C) {
     const int rpp = 256 / (C / 8);
     const int unit = rpp * 4;                                    // rows consumed per loop iteration of a block
-    long long target_blocks = 4LL * num_sms();
+    long long target_blocks = 2LL * num_sms();      // == resident blocks (102 regs x 256 threads -> 2 per SM): one wave, half the atomics
     long long strips_per_cloud = (target_blocks + B - 1) / B;
     if (strips_per_cloud < 1) strips_per_cloud = 1;
     int rps = static_cast<int>((N + strips_per_cloud - 1) / strips_per_cloud);
@@ -895,7 +895,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     TRY(apply(0, c->dy[0], 64, nullptr));
     {
         int grid = static_cast<int>((P + 31) / 32);
-        if (grid > num_sms() * 4) grid = num_sms() * 4;
+        if (grid > num_sms() * 2) grid = num_sms() * 2;
         k_ingest_bwd<<<grid, 256, 0, s>>>(c->dy[0], reinterpret_cast<const float4*>(x), P, grads + L.off[0]);
         LAUNCH_OK("k_ingest_bwd");
     }
