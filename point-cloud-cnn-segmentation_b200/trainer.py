@@ -170,6 +170,35 @@ class FusedTrainer:
         m._manual_version += 1
         return dict(loss=self.out_loss[0], correct=self.out_counts[0], valid=self.out_counts[1])
 
+    # ------------------------------------------------------------------ host-fed training (pinned memory -> device)
+    def prefetch(self, points_host, labels_host):
+        """Start the host->device copy of the NEXT batch on a side stream (double buffered) so that it overlaps the
+        current step; replaces the synchronous `.to(device)` of pcs.py:237-238.  Returns a ticket for `step_prefetched`."""
+        if not hasattr(self, "_h2d_stream"):
+            self._h2d_stream = torch.cuda.Stream(device=self.device)
+            self._h2d_slots = [None, None]
+            self._h2d_next = 0
+        slot = self._h2d_next
+        self._h2d_next ^= 1
+        buf = self._h2d_slots[slot]
+        if buf is None or buf[0].shape != points_host.shape or buf[1].shape != labels_host.shape:
+            buf = [torch.empty(points_host.shape, dtype=torch.float32, device=self.device),
+                   torch.empty(labels_host.shape, dtype=torch.int64, device=self.device), torch.cuda.Event(), torch.cuda.Event()]
+            self._h2d_slots[slot] = buf
+        with torch.cuda.stream(self._h2d_stream):
+            self._h2d_stream.wait_event(buf[3])          # the step that last read this slot has finished
+            buf[0].copy_(points_host, non_blocking=True)
+            buf[1].copy_(labels_host, non_blocking=True)
+            buf[2].record(self._h2d_stream)
+        return slot
+
+    def step_prefetched(self, ticket):
+        buf = self._h2d_slots[ticket]
+        torch.cuda.current_stream(self.device).wait_event(buf[2])
+        out = self.step(buf[0], buf[1])
+        buf[3].record(torch.cuda.current_stream(self.device))
+        return out
+
     def sync_bn_buffers(self, src=0):
         """DataParallel keeps replica 0's running statistics; broadcast them when a checkpoint is written."""
         if self.distributed:

@@ -168,3 +168,32 @@ def test_cuda_graph_step_equals_eager_step():
         outs.append(tr.last_logits.clone())
     assert tr._graph is not None
     assert (outs[-1] - outs[-2]).abs().max().item() > 1e-4
+
+
+def test_prefetched_host_batches_train_like_device_batches():
+    """FusedTrainer.prefetch / step_prefetched (pinned host -> device on a copy stream, double buffered) feeds the same
+    data as passing device tensors."""
+    import pcseg_b200
+    C, B, N = 3, 2, 384
+    rng = np.random.default_rng(9)
+    batches = [(torch.from_numpy(rng.random((B, N, 4), dtype=np.float32)).pin_memory(),
+                torch.from_numpy(rng.integers(-1, C, (B, N)).astype(np.int64)).pin_memory()) for _ in range(5)]
+    losses = []
+    for mode in ("device", "prefetch"):
+        m = _model(C, 31, train=True)
+        m.dropout.p = 0.0
+        tr = pcseg_b200.FusedTrainer(m, class_weights=torch.ones(C), use_cuda_graph=False)
+        out = []
+        if mode == "device":
+            for xb, lb in batches:
+                out.append(float(tr.step(xb.cuda(), lb.cuda())["loss"].item()))
+        else:
+            ticket = tr.prefetch(*batches[0])
+            for i in range(len(batches)):
+                nxt = tr.prefetch(*batches[i + 1]) if i + 1 < len(batches) else None
+                out.append(float(tr.step_prefetched(ticket)["loss"].item()))
+                ticket = nxt
+        losses.append(out)
+    assert abs(losses[0][0] - losses[1][0]) < 1e-6 * abs(losses[0][0])
+    for a, b in zip(*losses):
+        assert abs(a - b) < 2e-2 * abs(a), losses
