@@ -114,6 +114,40 @@ __device__ __forceinline__ float warp_colreduce(float (&v)[CW]) {
     return v[0];
 }
 
+// DGRAD epilogue, pass 2 for one thread: RPT rows x 8 columns of the staged dA tile are masked in place with the ReLU
+// (and dropout) mask of the layer below and accumulated into s1 = sum dz, s2 = sum dz*y.
+template <bool DROP, int RPT>
+__device__ __forceinline__ void dgrad_pass2_rows(uint32_t tile_s, uint32_t ytile, int rbase, int chunk, const float (&sc)[8],
+                                                 const float (&sh)[8], float (&s1)[8], float (&s2)[8], unsigned long long seed_eff,
+                                                 unsigned int thr16, long long row0, int ncols, int colbase) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
+        const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+        const uint4 dw = lds128(tile_s + off);
+        const uint4 yw = lds128(ytile + off);
+        const uint32_t ds[4] = {dw.x, dw.y, dw.z, dw.w};
+        const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w};
+        uint32_t keep = 0xFFu;
+        if (DROP) {
+            const unsigned long long e0 = static_cast<unsigned long long>(row0 + r) * ncols + colbase;
+            keep = dropout_keep8(seed_eff, e0 >> 3, thr16);
+        }
+        float dz[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float yv = (e & 1) ? bf16_hi(ys[e >> 1]) : bf16_lo(ys[e >> 1]);
+            const float da = (e & 1) ? bf16_hi(ds[e >> 1]) : bf16_lo(ds[e >> 1]);
+            bool on = fmaf(sc[e], yv, sh[e]) > 0.f;
+            if (DROP) on = on && ((keep >> e) & 1u);
+            dz[e] = on ? da : 0.f;
+            s1[e] += dz[e];
+            s2[e] = fmaf(dz[e], yv, s2[e]);
+        }
+        sts128(tile_s + off, make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7])));
+    }
+}
+
 template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(GemmCfg<BN, EPI, MN>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -480,6 +514,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         fence_proxy_async_smem();
                         if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
                     }
+                    // per-column parameters of pass 2 are fetched BEFORE the barrier so that their latency hides behind it
+                    float p2a[8], p2b[8];
+                    if constexpr (EPI == EPI_DGRAD) {
+                        const int colbase_pre = n0 + sub * 64 + ((warp_idx - 4) & 7) * 8;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bp = __ldg(p.bnp + colbase_pre + e);
+                            p2a[e] = bp.x;
+                            p2b[e] = bp.y;
+                        }
+                    } else if constexpr (EPI == EPI_STATS_POOL) {
+                        const int colbase_pre = n0 + sub * 64 + ((warp_idx - 4) & 7) * 8;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) p2a[e] = (__ldg(p.gamma + colbase_pre + e) >= 0.f) ? 1.f : -1.f;
+                    }
                     named_bar_sync(1, EPI_THREADS);
                     if constexpr (COLACC) {
                         // pass 2 (column-mapped): warp pw owns 16-byte chunk (pw & 7) = 8 columns of row group (pw >> 3);
@@ -494,46 +543,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                         for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
                         if constexpr (EPI == EPI_DGRAD) {
-                            float sc[8], sh[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 bp = __ldg(p.bnp + colbase + e);
-                                sc[e] = bp.x;
-                                sh[e] = bp.y;
-                            }
                             const uint32_t ytile = y_s + buf * 16384;
-#pragma unroll
-                            for (int i = 0; i < RPT; ++i) {
-                                const int r = rbase + 32 * i;
-                                const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
-                                const uint4 dw = lds128(tile_s + off);
-                                const uint4 yw = lds128(ytile + off);
-                                const uint32_t ds[4] = {dw.x, dw.y, dw.z, dw.w};
-                                const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w};
-                                uint32_t keep = 0xFFu;
-                                if (p.drop_thr16 != 0u) {
-                                    if (p.keep_bytes != nullptr) {
-                                        keep = (m0 + r < p.M) ? __ldg(p.keep_bytes + static_cast<size_t>(m0 + r) * (p.N >> 3) + (colbase >> 3)) : 0u;
-                                    } else {
-                                        const unsigned long long e0 = static_cast<unsigned long long>(m0 + r) * p.N + colbase;
-                                        keep = dropout_keep8(seed_eff, e0 >> 3, p.drop_thr16);
-                                    }
-                                }
-                                float dz[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const float yv = (e & 1) ? bf16_hi(ys[e >> 1]) : bf16_lo(ys[e >> 1]);
-                                    const float da = (e & 1) ? bf16_hi(ds[e >> 1]) : bf16_lo(ds[e >> 1]);
-                                    const bool on = (fmaf(sc[e], yv, sh[e]) > 0.f) && ((keep >> e) & 1u);
-                                    dz[e] = on ? da : 0.f;
-                                    s1[e] += dz[e];
-                                    s2[e] = fmaf(dz[e], yv, s2[e]);
-                                }
-                                sts128(tile_s + off, make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]),
-                                                                pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7])));
-                            }
+                            if (p.drop_thr16 != 0u)
+                                dgrad_pass2_rows<true, RPT>(tile_s, ytile, rbase, chunk, p2a, p2b, s1, s2, seed_eff, p.drop_thr16, m0, p.N, colbase);
+                            else
+                                dgrad_pass2_rows<false, RPT>(tile_s, ytile, rbase, chunk, p2a, p2b, s1, s2, 0ull, 0u, m0, p.N, colbase);
                         } else {
-                            float bestv[8], sg[8];
+                            float bestv[8];
+                            const float (&sg)[8] = p2a;
                             int besti[8];
                             const int row0_in_cloud = (EPI == EPI_STATS_POOL) ? (m0 % p.pts_per_cloud) : 0;   // uniform tiles only
                             if constexpr (EPI == EPI_STATS_POOL) {
@@ -541,7 +558,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 for (int e = 0; e < 8; ++e) {
                                     bestv[e] = -INFINITY;
                                     besti[e] = 0;
-                                    sg[e] = (__ldg(p.gamma + colbase + e) >= 0.f) ? 1.f : -1.f;
                                 }
                             }
 #pragma unroll
