@@ -151,7 +151,8 @@ class FusedTrainer:
             raise RuntimeError("FusedTrainer.step needs model.train()")
         x = m._check_input(points)
         labels = labels.contiguous()
-        self.flat = m._ensure_flat(self.device)
+        if not m._flat_quick_ok(self.device):
+            self.flat = m._ensure_flat(self.device)
         key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr())
         use_graph = self.use_cuda_graph and not self.profiling
         if key != self._graph_key:
