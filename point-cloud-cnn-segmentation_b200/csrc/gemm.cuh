@@ -203,6 +203,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
+    pdl_wait();          // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
     if (EPI == EPI_LOGITS) {
         for (int i = threadIdx.x; i < p.num_classes * 128; i += GEMM_THREADS) w4s[i] = p.w4[i];
         for (int i = threadIdx.x; i < p.num_classes; i += GEMM_THREADS) w4s[MAX_CLASSES * 128 + i] = p.b4[i];
@@ -701,6 +702,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     }
 
+    // this CTA's work is done: let the next kernel of the stream start launching (it still waits for the whole grid in
+    // its own griddepcontrol.wait).  Triggering at kernel start instead was measured slower in training: the dependent
+    // kernel's CTAs then sit resident on the SMs for the whole GEMM.
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     if (warp_idx == 2) {

@@ -85,6 +85,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
+    pdl_wait();
     for (int i = threadIdx.x; i < p.num_classes * 128; i += HC_THREADS) w4s[i] = p.w4[i];
     for (int i = threadIdx.x; i < p.num_classes; i += HC_THREADS) w4s[MAX_CLASSES * 128 + i] = p.b4[i];
     tc_fence_before();
@@ -280,6 +281,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         }
     }
 
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     if (warp_idx == 2) {

@@ -18,6 +18,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // dst[r][c] (bf16, pitch ld_dst) = alpha[r] * src[r][c] (fp32, pitch ld_src); alpha may be null.
 __global__ void k_convert_rows(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
                                int rows, int cols, const float* __restrict__ alpha) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * cols) return;
     const int r = idx / cols, c = idx % cols;
@@ -28,6 +30,8 @@ __global__ void k_convert_rows(const float* __restrict__ src, int ld_src, __nv_b
 // dst[c][r] (bf16, pitch ld_dst) = src[r][c]: transposed copy used as the dgrad B operand.
 __global__ void k_convert_transpose(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
                                     int rows, int cols) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -53,6 +57,8 @@ struct ConvertJobs {
     int count;
 };
 __global__ void __launch_bounds__(256) k_convert_multi(const ConvertJobs jobs) {
+    pdl_launch_dependents();
+    pdl_wait();
     // blockIdx.y = job; 32x32 tiles through shared memory so that both the fp32 reads and the (possibly transposed)
     // bf16 writes are coalesced
     __shared__ float tile[32][33];
@@ -88,6 +94,8 @@ __global__ void __launch_bounds__(256) k_convert_multi(const ConvertJobs jobs) {
 __global__ void k_fold_bn(const float* __restrict__ conv_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ rmean, const float* __restrict__ rvar, float eps, int C,
                           float* __restrict__ alpha, float* __restrict__ delta) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float a2 = gamma[c] / sqrtf(rvar[c] + eps);
@@ -104,6 +112,8 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(256) k_ingest(const float4* __restrict__ x, int P, const float* __restrict__ W /*[64][4]*/,
                                                 const float* __restrict__ alpha, const float* __restrict__ delta,
                                                 __nv_bfloat16* __restrict__ out, double* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[2][32][64];   // per point-slot partial sums (TRAIN only)
     const int cg = threadIdx.x & 7;    // channel group: channels cg*8 .. cg*8+7
     const int slot = threadIdx.x >> 3; // 0..31
@@ -198,6 +208,8 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
                                                  int ld_a, long P, int C, const BnFinalizeArgs fin,
                                                  unsigned long long seed_arg, const unsigned long long* __restrict__ seed_ptr,
                                                  unsigned int thr16, float keep_scale, unsigned char* __restrict__ keep_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     bn_publish(fin, blockIdx.x == 0);
     const unsigned long long seed = seed_arg + (seed_ptr != nullptr ? *seed_ptr : 0ull);
     const int tpr = C >> 3;                       // threads per row (C <= 2048)
@@ -259,6 +271,8 @@ __device__ __forceinline__ float float_from_orderable(uint32_t k) {
 // grid: (C/64, strips, clouds); block 256 = 8 warps; lane -> 2 channels, warp -> rows r = warp, warp+8, ...
 __global__ void __launch_bounds__(256) k_maxpool_scan(const __nv_bfloat16* __restrict__ y, int C, int N, int rows_per_strip,
                                                       const float4* __restrict__ bnp, unsigned long long* __restrict__ keys) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ unsigned long long red[8][64];
     const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
     const int warp = threadIdx.x >> 5;
@@ -289,6 +303,8 @@ __global__ void __launch_bounds__(256) k_maxpool_scan(const __nv_bfloat16* __res
 // decode keys -> g (post BN+ReLU), ystar (pre-BN extremum), argidx (row within cloud)
 __global__ void k_maxpool_finish(const unsigned long long* __restrict__ keys, int total, int C, const BnFinalizeArgs fin,
                                  float* __restrict__ g, float* __restrict__ ystar, int* __restrict__ argidx) {
+    pdl_launch_dependents();
+    pdl_wait();
     bn_publish(fin, blockIdx.x == 0);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -309,6 +325,8 @@ __global__ void k_maxpool_finish(const unsigned long long* __restrict__ keys, in
 __global__ void __launch_bounds__(256) k_cloud_bias(const float* __restrict__ Wg, int ldw, const float* __restrict__ g, int clouds,
                                                     int Nout, int K, const float* __restrict__ alpha,
                                                     const float* __restrict__ delta, float* __restrict__ cb) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= clouds * Nout) return;
@@ -340,6 +358,8 @@ __global__ void __launch_bounds__(256, 3) k_head_fwd(const __nv_bfloat16* __rest
                                                   const float* __restrict__ W4, const float* __restrict__ b4, int C,
                                                   float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(16) float w_s[MAXC * 128];
     __shared__ double red_d[8][2];
     __shared__ unsigned long long red_u[8][2];
@@ -454,6 +474,8 @@ __global__ void __launch_bounds__(256, 3) k_head_fwd(const __nv_bfloat16* __rest
 // before backward (and before the cross-rank all-reduce of the normaliser).
 __global__ void k_label_weight_sum(const long long* __restrict__ labels, long P, const float* __restrict__ class_w,
                                    double* __restrict__ wsum) {
+    pdl_launch_dependents();
+    pdl_wait();
     double s = 0.0;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < P; i += static_cast<long>(gridDim.x) * blockDim.x) {
         const long long l = labels[i];
@@ -476,6 +498,8 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
                                                   const float* __restrict__ class_w, const double* __restrict__ wsum_total,
                                                   __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dW4,
                                                   float* __restrict__ db4, double* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int MAXC = NC;
     constexpr int C = NC;
     // 8 lanes per point, 16 channels per lane (see k_head_fwd).  Per-lane accumulators: dW4[k][16 ch], sum dz[16], sum dz*yhat[16].
@@ -667,6 +691,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
                                                       int rows_per_strip, const BnBwdArgs bw,
                                                       float* __restrict__ dbias, float* __restrict__ dcb,
                                                       const int* __restrict__ argidx, const float* __restrict__ dzv) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[256 * 8];
     bn_bwd_publish(bw, blockIdx.x == 0 && blockIdx.y == 0);
     const int tpr = C >> 3;
@@ -744,6 +770,8 @@ __global__ void __launch_bounds__(256) k_cloud_bwd_dg(const float* __restrict__ 
                                                       int Nn /*512*/, int J /*1024*/, const float* __restrict__ g,
                                                       const float* __restrict__ ystar, const float4* __restrict__ bnp6,
                                                       float* __restrict__ dzv, double* __restrict__ stats6) {
+    pdl_launch_dependents();
+    pdl_wait();
     // grid: (J/32, clouds); block 256 = 8 warps; lane -> output j, warp -> 1/8 of the Nn-long reduction.
     // stats6 must be zeroed by the caller.
     __shared__ float part[8][32];
@@ -777,6 +805,8 @@ __global__ void __launch_bounds__(256) k_cloud_bwd_dg(const float* __restrict__ 
 }
 __global__ void __launch_bounds__(256) k_cloud_bwd_dw(const float* __restrict__ dcb, const float* __restrict__ g, int clouds, int Nn,
                                                       int J, float* __restrict__ dWg, int ldw) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = blockIdx.y;
     if (j >= J) return;
@@ -788,6 +818,8 @@ __global__ void __launch_bounds__(256) k_cloud_bwd_dw(const float* __restrict__ 
 // dW1[c][k] = sum_p dy1[p][c] * x[p][k]   (64 x 4).  8 threads per point, 8 channels each.
 __global__ void __launch_bounds__(256) k_ingest_bwd(const __nv_bfloat16* __restrict__ dy1, const float4* __restrict__ x, long P,
                                                     float* __restrict__ dW1) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32][64 * 4];
     const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
     float acc[8][4];
@@ -831,6 +863,8 @@ struct StepState {                 // == pcseg_step_state
     float lr, bias_corr1, bias_corr2_sqrt, reserved;
 };
 __global__ void k_step_advance(StepState* st, float b1, float b2) {
+    pdl_launch_dependents();
+    pdl_wait();
     st->seed += 0x9E3779B97F4A7C15ull;
     const long long t = st->step + 1;
     st->step = t;
@@ -840,6 +874,8 @@ __global__ void k_step_advance(StepState* st, float b1, float b2) {
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
                                               float bc1, float bc2_sqrt, float grad_scale, const StepState* __restrict__ st) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (st != nullptr) {
         lr = st->lr;
         bc1 = st->bias_corr1;
@@ -864,6 +900,8 @@ template <int MAXC>
 __global__ void __launch_bounds__(256) k_eval_metrics(const float* __restrict__ logits, const long long* __restrict__ labels, long P, int C,
                                                       const float* __restrict__ class_w, CeAccum* __restrict__ ce,
                                                       unsigned long long* __restrict__ confusion, long long* __restrict__ pred_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ unsigned int conf_s[MAXC * MAXC];
     __shared__ double red_d[8][2];
     __shared__ unsigned long long red_u[8][2];
@@ -922,6 +960,8 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const float* __restrict__ 
 
 // argmax over classes (first maximum wins, like torch.argmax on ties)
 __global__ void k_argmax(const float* __restrict__ logits, long P, int C, long long* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
     if (i >= P) return;
     const float* z = logits + i * C;

@@ -70,6 +70,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library starts with pdl_launch_dependents() (the next kernel in the stream may begin its own
+// prologue as SMs free up) and executes pdl_wait() before it touches memory written by earlier kernels.  Because every
+// kernel waits before it can finish, completion stays transitive along the stream.  Both are no-ops for kernels launched
+// without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- named barriers
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
