@@ -165,15 +165,16 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long inner, long long outer,
     return 0;
 }
 
-int g_num_sms = 0;
+int g_num_sms[64] = {};
 int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& n = g_num_sms[dev & 63];
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
     }
-    return g_num_sms;
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -190,11 +191,13 @@ struct GemmOp {
 template <int BN, int EPI, bool MN>
 int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
     using Cfg = GemmCfg<BN, EPI, MN>;
-    static bool attr_set = false;
+    static unsigned long long attr_set_mask = 0;       // per device: the attribute is a per-device function property
     auto kern = gemm_kernel<BN, EPI, MN>;
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set_mask & (1ull << (dev & 63)))) {
         CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
+        attr_set_mask |= 1ull << (dev & 63);
     }
     const int tiles = op.p.num_m_tiles * op.p.num_n_tiles * op.p.num_splits;
     int grid = tiles < num_sms() ? tiles : num_sms();
@@ -627,10 +630,12 @@ extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, l
         LAUNCH_OK("k_cloud_bias");
     }
     if (c->use_head_chain) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned long long attr_set_mask = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!(attr_set_mask & (1ull << (dev & 63)))) {
             CUDA_OK(cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HC_SMEM_BYTES));
-            attr_set = true;
+            attr_set_mask |= 1ull << (dev & 63);
         }
         HeadChainParams hp = c->hcp;
         hp.logits = logits;

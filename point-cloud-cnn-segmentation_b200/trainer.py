@@ -169,7 +169,9 @@ class FusedTrainer:
         self.step_count += 1
         m._fwd_token += 1
         m._manual_version += 1
-        return dict(loss=self.out_loss[0], correct=self.out_counts[0], valid=self.out_counts[1])
+        # clones: the static output buffers are overwritten by the next step (graph replay)
+        loss, counts = self.out_loss.clone(), self.out_counts.clone()
+        return dict(loss=loss[0], correct=counts[0], valid=counts[1])
 
     # ------------------------------------------------------------------ host-fed training (pinned memory -> device)
     def prefetch(self, points_host, labels_host):
