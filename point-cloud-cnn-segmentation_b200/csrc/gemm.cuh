@@ -48,7 +48,6 @@ struct GemmParams {
     int ldc;                     // wgrad destination pitch (elements)
     unsigned long long seed;     // dropout (effective seed = seed + *seed_ptr when seed_ptr != nullptr)
     const unsigned long long* seed_ptr;
-    const unsigned char* keep_bytes;   // [M][N/8] dropout keep masks written by the forward pass (1 bit per element); null = regenerate
     unsigned int drop_thr16;     // 0 = no dropout
     float keep_scale;            // 1/(1-p)
     const float* w4;             // [C][128] fp32

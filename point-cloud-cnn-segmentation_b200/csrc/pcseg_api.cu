@@ -333,7 +333,6 @@ struct pcseg_ctx {
     bf16* dz[NUM_BN] = {};        // gradient wrt BN output (after ReLU / dropout mask)
     bf16* dy[NUM_BN] = {};        // gradient wrt conv output
     bf16* dycat = nullptr;        // [P][576] = [dy(conv3) | dy(seg_conv1)]
-    unsigned char* keepb[NUM_BN] = {};   // dropout keep masks of seg_conv1 / seg_conv2 outputs, 1 bit per element
     bf16* wt[NUM_BN] = {};        // bf16 transposed weights [Cin][Cout] for dgrad (index = conv index)
     bf16* wcat = nullptr;         // [64][576] = [W3^T | Wpf^T]
     double* stats_f = nullptr;    // forward  stats, per layer [2][C] at stat_off
@@ -733,7 +732,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     // BN finalize of layer i is folded into this kernel (block 0 publishes bnp + running statistics)
     auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         const int co = cv[i].cout;
-        pdl_launch(k_bn_relu, strip_grid(P, co), 256, 0, s, c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks, nullptr);
+        pdl_launch(k_bn_relu, strip_grid(P, co), 256, 0, s, c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks);
         LAUNCH_OK("k_bn_relu");
         return 0;
     };
@@ -843,7 +842,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     };
     auto dgrad = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
         GemmOp op = c->dg[i];
-        op.p.keep_bytes = nullptr;      // stored keep masks were measured SLOWER than regenerating Philox (uncoalesced byte loads)
+        // (storing the keep masks in forward and re-loading them here was measured slower than regenerating Philox)
         op.p.seed = sd;
         op.p.seed_ptr = c->seed_ptr;
         op.p.drop_thr16 = thr;

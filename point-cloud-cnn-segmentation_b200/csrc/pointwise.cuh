@@ -207,7 +207,7 @@ __device__ __forceinline__ void bn_publish(const BnFinalizeArgs& f, bool first_b
 __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
                                                  int ld_a, long P, int C, const BnFinalizeArgs fin,
                                                  unsigned long long seed_arg, const unsigned long long* __restrict__ seed_ptr,
-                                                 unsigned int thr16, float keep_scale, unsigned char* __restrict__ keep_out) {
+                                                 unsigned int thr16, float keep_scale) {
     pdl_launch_dependents();
     pdl_wait();
     bn_publish(fin, blockIdx.x == 0);
@@ -239,10 +239,7 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
             if (rr >= r_end) break;
             const uint32_t ws[4] = {yw[u].x, yw[u].y, yw[u].z, yw[u].w};
             uint32_t keep = 0xFFu;
-            if (thr16 != 0u) {
-                keep = dropout_keep8(seed, (static_cast<unsigned long long>(rr) * C + c0) >> 3, thr16);
-                if (keep_out != nullptr) keep_out[rr * (C >> 3) + (c0 >> 3)] = static_cast<unsigned char>(keep);   // re-used by backward
-            }
+            if (thr16 != 0u) keep = dropout_keep8(seed, (static_cast<unsigned long long>(rr) * C + c0) >> 3, thr16);
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -258,8 +255,9 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
 
 // ---------------------------------------------------------------------------------------------
 // Train-mode global max-pool over points of relu(bn(y6)).  Because bn is monotone per channel
-// the arg-extremum of the pre-BN value decides: max(y) if scale >= 0 else min(y).
-// Packed 64-bit key = (orderable(sign*y) << 32) | ~index, reduced with atomicMax: ties -> lowest index.
+// the arg-extremum of the pre-BN value decides: max(y) if gamma >= 0 else min(y).  The scan itself is fused into the
+// global_feat GEMM epilogue (EPI_STATS_POOL): packed 64-bit key = (orderable(sign*y) << 32) | ~index, reduced with
+// atomicMax (ties -> lowest index); k_maxpool_finish decodes the keys.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t float_orderable(float f) {
     const uint32_t b = __float_as_uint(f);
@@ -267,38 +265,6 @@ __device__ __forceinline__ uint32_t float_orderable(float f) {
 }
 __device__ __forceinline__ float float_from_orderable(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
-}
-// grid: (C/64, strips, clouds); block 256 = 8 warps; lane -> 2 channels, warp -> rows r = warp, warp+8, ...
-__global__ void __launch_bounds__(256) k_maxpool_scan(const __nv_bfloat16* __restrict__ y, int C, int N, int rows_per_strip,
-                                                      const float4* __restrict__ bnp, unsigned long long* __restrict__ keys) {
-    pdl_launch_dependents();
-    pdl_wait();
-    __shared__ unsigned long long red[8][64];
-    const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
-    const int warp = threadIdx.x >> 5;
-    const int cloud = blockIdx.z;
-    const int r0 = blockIdx.y * rows_per_strip;
-    const int r1 = min(r0 + rows_per_strip, N);
-    const float sg0 = (__ldg(bnp + c).x >= 0.f) ? 1.f : -1.f;
-    const float sg1 = (__ldg(bnp + c + 1).x >= 0.f) ? 1.f : -1.f;
-    unsigned long long k0 = 0ull, k1 = 0ull;
-    const __nv_bfloat16* base = y + (static_cast<size_t>(cloud) * N) * C + c;
-    for (int r = r0 + warp; r < r1; r += 8) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(base + static_cast<size_t>(r) * C);
-        const unsigned long long inv = 0xFFFFFFFFu - static_cast<uint32_t>(r);
-        const unsigned long long a0 = (static_cast<unsigned long long>(float_orderable(sg0 * bf16_lo(w))) << 32) | inv;
-        const unsigned long long a1 = (static_cast<unsigned long long>(float_orderable(sg1 * bf16_hi(w))) << 32) | inv;
-        k0 = a0 > k0 ? a0 : k0;
-        k1 = a1 > k1 ? a1 : k1;
-    }
-    red[warp][(threadIdx.x & 31) * 2] = k0;
-    red[warp][(threadIdx.x & 31) * 2 + 1] = k1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        unsigned long long k = red[0][threadIdx.x];
-        for (int w = 1; w < 8; ++w) k = red[w][threadIdx.x] > k ? red[w][threadIdx.x] : k;
-        atomicMax(keys + static_cast<size_t>(cloud) * C + blockIdx.x * 64 + threadIdx.x, k);
-    }
 }
 // decode keys -> g (post BN+ReLU), ystar (pre-BN extremum), argidx (row within cloud)
 __global__ void k_maxpool_finish(const unsigned long long* __restrict__ keys, int total, int C, const BnFinalizeArgs fin,
@@ -468,21 +434,6 @@ __global__ void __launch_bounds__(256, 3) k_head_fwd(const __nv_bfloat16* __rest
             atomicAdd(&ce->valid, u1);
         }
     }
-}
-
-// Weighted-CE forward only (labels -> sum of class weights); used to get the global normaliser
-// before backward (and before the cross-rank all-reduce of the normaliser).
-__global__ void k_label_weight_sum(const long long* __restrict__ labels, long P, const float* __restrict__ class_w,
-                                   double* __restrict__ wsum) {
-    pdl_launch_dependents();
-    pdl_wait();
-    double s = 0.0;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < P; i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const long long l = labels[i];
-        if (l >= 0) s += class_w ? class_w[l] : 1.f;
-    }
-    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(wsum, s);
 }
 
 // ---------------------------------------------------------------------------------------------
