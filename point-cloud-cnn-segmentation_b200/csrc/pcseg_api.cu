@@ -371,12 +371,12 @@ static int timed_gemm(pcseg_ctx* c, const GemmOp& op, int tag, cudaStream_t s) {
 }
 
 static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes_out) {
+    // Shape-independent buffers (weights, per-channel vectors) come first so that their addresses do not depend on
+    // (B, N): bindings of different batch shapes can then share one caller-owned workspace and keep prepared weights.
     Carver k(ws);
     const size_t P = static_cast<size_t>(B) * N;
     const ConvDef* cv = c->L.conv;
     c->zeros1024 = k.take<float>(1024);
-    c->gmax = k.take<float>(static_cast<size_t>(B) * 1024);
-    c->cb = k.take<float>(static_cast<size_t>(B) * 512);
     c->w1 = k.take<float>(256);
     c->w4 = k.take<float>(MAX_CLASSES * 128);
     c->b4 = k.take<float>(MAX_CLASSES);
@@ -389,13 +389,7 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
         const int cin = (i == 6) ? 64 : cv[i].cin;
         c->wk[i] = k.take<bf16>(static_cast<size_t>(cv[i].cout) * cin);
     }
-    if (!train) {
-        // a1..a5, a_s1, a_s2 (global_feat output is reduced in-kernel; seg_conv3 output feeds the fused logits epilogue)
-        for (int i = 0; i < NUM_BN; ++i) {
-            if (i == 5 || i == 8) continue;
-            c->act[i] = k.take<bf16>(P * cv[i].cout);
-        }
-    } else {
+    if (train) {
         size_t so = 0;
         for (int i = 0; i < NUM_BN; ++i) { c->stat_off[i] = so; so += 2 * static_cast<size_t>(cv[i].cout); }
         c->stat_total = so;
@@ -405,16 +399,27 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
             c->bnp[i] = k.take<float4>(cv[i].cout);
             c->coef[i] = k.take<float4>(cv[i].cout);
         }
-        c->keys = k.take<unsigned long long>(static_cast<size_t>(B) * 1024);
-        c->ystar = k.take<float>(static_cast<size_t>(B) * 1024);
-        c->argidx = k.take<int>(static_cast<size_t>(B) * 1024);
-        c->dcb = k.take<float>(static_cast<size_t>(B) * 512);
-        c->dzv = k.take<float>(static_cast<size_t>(B) * 1024);
         for (int i = 1; i < NUM_BN; ++i) {
             const int cin = (i == 6) ? 64 : cv[i].cin;
             c->wt[i] = k.take<bf16>(static_cast<size_t>(cv[i].cout) * cin);
         }
         c->wcat = k.take<bf16>(64 * 576);
+    }
+    // ---- shape-dependent buffers
+    c->gmax = k.take<float>(static_cast<size_t>(B) * 1024);
+    c->cb = k.take<float>(static_cast<size_t>(B) * 512);
+    if (!train) {
+        // a1..a5, a_s1, a_s2 (global_feat output is reduced in-kernel; seg_conv3 output feeds the fused logits epilogue)
+        for (int i = 0; i < NUM_BN; ++i) {
+            if (i == 5 || i == 8) continue;
+            c->act[i] = k.take<bf16>(P * cv[i].cout);
+        }
+    } else {
+        c->keys = k.take<unsigned long long>(static_cast<size_t>(B) * 1024);
+        c->ystar = k.take<float>(static_cast<size_t>(B) * 1024);
+        c->argidx = k.take<int>(static_cast<size_t>(B) * 1024);
+        c->dcb = k.take<float>(static_cast<size_t>(B) * 512);
+        c->dzv = k.take<float>(static_cast<size_t>(B) * 1024);
         c->dycat = k.take<bf16>(P * 576);
         for (int i = 0; i < NUM_BN; ++i) {
             c->y[i] = k.take<bf16>(P * cv[i].cout);

@@ -25,19 +25,24 @@ def bn_layout():
 
 
 class _Binding:
-    def __init__(self, num_classes, B, N, train, device):
+    """One C context bound to one batch shape.  The device workspace is owned by the Engine and SHARED by all bindings of
+    the same mode (activations only have to live from a forward to its backward)."""
+
+    def __init__(self, num_classes, B, N, train):
         self.handle = C.c_void_p()
         check(lib.pcseg_create(C.byref(self.handle), num_classes), "pcseg_create")
-        nbytes = int(lib.pcseg_workspace_bytes(B, N, num_classes, int(train)))
-        if nbytes <= 0:
+        self.shape = (B, N, bool(train))
+        self.nbytes = int(lib.pcseg_workspace_bytes(B, N, num_classes, int(train)))
+        if self.nbytes <= 0:
             raise ValueError(f"unsupported shape B={B} N={N} C={num_classes}")
-        # torch caching-allocator blocks are 512-byte aligned; over-allocate and align to 1024
-        self.storage = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-        base = self.storage.data_ptr()
-        self.ws_ptr = (base + 1023) & ~1023
-        check(lib.pcseg_bind(self.handle, B, N, C.c_void_p(self.ws_ptr), nbytes, int(train)), "pcseg_bind")
+        self.ws_ptr = None
         self.eval_key = None
-        self.nbytes = nbytes
+
+    def bind(self, ws_ptr, ws_bytes):
+        B, N, train = self.shape
+        check(lib.pcseg_bind(self.handle, B, N, C.c_void_p(ws_ptr), ws_bytes, int(train)), "pcseg_bind")
+        self.ws_ptr = ws_ptr
+        self.eval_key = None
 
     def __del__(self):
         try:
@@ -48,9 +53,11 @@ class _Binding:
 
 
 class Engine:
-    """One per (module, device).  Caches a few (B, N, mode) bindings."""
+    """One per (module, device).  Keeps one grow-only workspace per mode (train / eval) and a cache of per-shape
+    bindings into it, so variable-length batches (every DataLoader batch of the reference has its own max_points,
+    pcs.py:50) neither re-allocate device memory nor thrash: a new shape only costs the host-side TMA descriptor setup."""
 
-    def __init__(self, num_classes, device, max_bindings=4):
+    def __init__(self, num_classes, device, max_bindings=32):
         if not (1 <= num_classes <= MAX_CLASSES):
             raise ValueError(f"num_classes must be in 1..{MAX_CLASSES}")
         self.C = num_classes
@@ -59,22 +66,42 @@ class Engine:
             raise RuntimeError("pcseg_b200 runs on CUDA (sm_100a) devices only; there is no CPU fallback")
         self.bindings = OrderedDict()
         self.max_bindings = max_bindings
+        self._ws = {True: None, False: None}          # mode -> (storage tensor, aligned ptr, usable bytes)
 
-    def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+    def _workspace(self, train, need):
+        ws = self._ws[train]
+        if ws is None or ws[2] < need:
+            # grow-only; all bindings of this mode point into the old block and are dropped
+            for key in [k for k in self.bindings if k[2] == train]:
+                del self.bindings[key]
+            self._ws[train] = None
+            del ws
+            # torch caching-allocator blocks are 512-byte aligned; over-allocate and align to 1024
+            storage = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            ptr_aligned = (storage.data_ptr() + 1023) & ~1023
+            self._ws[train] = (storage, ptr_aligned, need)
+        return self._ws[train]
 
     def binding(self, B, N, train):
-        key = (B, N, bool(train))
+        train = bool(train)
+        key = (B, N, train)
         b = self.bindings.get(key)
         if b is None:
-            with torch.cuda.device(self.device):
-                b = _Binding(self.C, B, N, train, self.device)
+            b = _Binding(self.C, B, N, train)
+        _, ws_ptr, ws_bytes = self._workspace(train, b.nbytes)
+        if key not in self.bindings:                 # (the workspace may just have dropped every cached binding)
             self.bindings[key] = b
             while len(self.bindings) > self.max_bindings:
                 self.bindings.popitem(last=False)
         else:
             self.bindings.move_to_end(key)
+        if b.ws_ptr != ws_ptr:
+            with torch.cuda.device(self.device):
+                b.bind(ws_ptr, ws_bytes)
         return b
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- eval
     def forward_eval(self, x, flat_params, flat_bn, weights_key, want_labels=False):

@@ -153,7 +153,8 @@ class FusedTrainer:
         labels = labels.contiguous()
         if not m._flat_quick_ok(self.device):
             self.flat = m._ensure_flat(self.device)
-        key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr())
+        ws_ptr = self.engine.binding(x.shape[0], x.shape[1], True).ws_ptr       # (also keeps the binding hot in the LRU)
+        key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr(), ws_ptr)
         use_graph = self.use_cuda_graph and not self.profiling
         if key != self._graph_key:
             self._graph, self._graph_key, self._eager_steps_at_key = None, key, 0

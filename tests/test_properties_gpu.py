@@ -231,3 +231,43 @@ def test_training_with_dropout_converges_and_eval_improves():
     for bn in (m.bn1, m.bn_global, m.bn_seg3):
         assert torch.isfinite(bn.running_mean).all() and (bn.running_var > 0).all()
         assert int(bn.num_batches_tracked.item()) == 150
+
+
+def test_variable_length_batches_share_one_workspace():
+    """Every DataLoader batch of the reference has its own max_points (pcs.py:50).  Bindings of different shapes share one
+    grow-only workspace; results must equal those of a fresh model, for interleaved eval and training shapes."""
+    import pcseg_b200
+    C = 5
+    sd = orc.synth_state(C, 41)
+    shapes = [(2, 300), (3, 1000), (2, 300), (1, 77), (3, 1000), (4, 512)]
+    rng = np.random.default_rng(5)
+    xs = [torch.from_numpy(rng.random((b, n, 4), dtype=np.float32)).cuda() for b, n in shapes]
+
+    def fresh():
+        m = pcseg_b200.PointNetSegmentation(C)
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+        return m.cuda()
+
+    shared = fresh().eval()
+    with torch.no_grad():
+        outs = [shared(x).clone() for x in xs]
+        eng = shared._get_engine(xs[0].device)
+        assert len({b.ws_ptr for b in eng.bindings.values()}) == 1          # one workspace, many bindings
+        for x, o in zip(xs, outs):
+            assert torch.equal(fresh().eval()(x), o)
+
+    # training: forward/backward pairs of different shapes, gradients equal a fresh model's
+    shared = fresh().train()
+    shared.dropout.p = 0.0
+    for x in xs[:4]:
+        for m in (shared, fresh().train()):
+            m.dropout.p = 0.0
+            m.zero_grad()
+            m(x).square().mean().backward()
+            g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+            if m is shared:
+                g_shared = g.clone()
+                # undo the running-stat update so that the next shape starts from the same state as a fresh model
+                shared.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+        cos = torch.nn.functional.cosine_similarity(g_shared, g, dim=0).item()
+        assert cos > 0.9995, cos
