@@ -774,10 +774,18 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
     TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
     TRY(timed_gemm(c, c->fw[8], 8, s));
     {
-        int grid = static_cast<int>((P + 31) / 32);          // 8 warps x 4 points per block iteration
+        int grid = static_cast<int>((P + 255) / 256);        // one thread per point
         if (grid > num_sms() * 4) grid = num_sms() * 4;
-        pdl_launch(k_head_fwd<MAX_CLASSES>, grid, 256, 0, s, c->y[8], P, fin_args(8), params + L.off[18], params + L.off[19], c->C, logits, labels,
-                                                    class_w, reinterpret_cast<CeAccum*>(ce));
+#define HEAD_FWD(NC_)                                                                                                          \
+    case NC_:                                                                                                                  \
+        pdl_launch(k_head_fwd<NC_>, grid, 256, 0, s, c->y[8], P, fin_args(8), params + L.off[18], params + L.off[19], logits, labels, \
+                   class_w, reinterpret_cast<CeAccum*>(ce));                                                                  \
+        break;
+        switch (c->C) {
+            HEAD_FWD(1) HEAD_FWD(2) HEAD_FWD(3) HEAD_FWD(4) HEAD_FWD(5) HEAD_FWD(6) HEAD_FWD(7) HEAD_FWD(8)
+            default: return fail("pcseg_forward_train: unsupported num_classes %d", c->C);
+        }
+#undef HEAD_FWD
         LAUNCH_OK("k_head_fwd");
     }
     return 0;

@@ -316,113 +316,105 @@ struct CeAccum {
     unsigned long long valid;     // labels != -1
 };
 
-// Layout of both head kernels: 8 lanes per point (4 points per warp), 16 channels per lane; the channel reduction needs
-// only 3 shuffle steps per class and every warp instruction works on 4 points.  seg_conv4 weights are staged in shared
-// memory as [class][128] and read with 16-byte LDS (lanes of the same point read disjoint 64-byte slices).
-template <int MAXC>
-__global__ void __launch_bounds__(256, 3) k_head_fwd(const __nv_bfloat16* __restrict__ ys3, long P, const BnFinalizeArgs fin,
-                                                  const float* __restrict__ W4, const float* __restrict__ b4, int C,
+// Train-mode head forward, ONE THREAD PER POINT: the point's 128 pre-BN values are streamed with 16-byte loads (a
+// warp touches 32 different rows per instruction, but consecutive instructions hit the same lines in L1, so DRAM traffic
+// stays at the algorithmic 256 B/point), BN + ReLU + the 128 x NC mat-vec run on private registers with no shuffles,
+// and the weighted-CE terms are accumulated per thread and reduced once per block.
+template <int NC>
+__global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restrict__ ys3, long P, const BnFinalizeArgs fin,
+                                                  const float* __restrict__ W4, const float* __restrict__ b4,
                                                   float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ __align__(16) float w_s[MAXC * 128];
+    constexpr int NCP = (NC + 3) & ~3;                  // weights per channel padded to a multiple of 4 floats
+    __shared__ __align__(16) float w_s[128 * NCP];      // [channel][class]
+    __shared__ float2 bn_s[128];                        // {scale, shift}
     __shared__ double red_d[8][2];
     __shared__ unsigned long long red_u[8][2];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int sub = lane & 7;                  // 16-channel slice of the point
-    const int grp = lane >> 3;                 // point slot inside the warp
     bn_publish(fin, blockIdx.x == 0);
-    // bank-conflict-free layout [class][q][sub][4]: logical channel = sub*16 + q*4 + j (lanes of a point read 8 distinct
-    // 16-byte chunks that cover all 32 banks)
-    for (int i = threadIdx.x; i < C * 128; i += blockDim.x) {
-        const int k = i >> 7, c = i & 127;
-        w_s[k * 128 + ((c >> 2) & 3) * 32 + (c >> 4) * 4 + (c & 3)] = W4[i];
+    if (threadIdx.x < 128) {
+        const float4 bp = bn_from_stats(fin, threadIdx.x);
+        bn_s[threadIdx.x] = make_float2(bp.x, bp.y);
     }
-    float sc[16], sh[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const float4 bp = bn_from_stats(fin, sub * 16 + e);
-        sc[e] = bp.x;
-        sh[e] = bp.y;
+    for (int i = threadIdx.x; i < 128 * NCP; i += blockDim.x) {
+        const int c = i / NCP, k = i % NCP;
+        w_s[i] = (k < NC) ? W4[k * 128 + c] : 0.f;
     }
-    const float bias_k = (sub < C) ? __ldg(b4 + sub) : 0.f;
-    const float cw_k = (class_w != nullptr && sub < C) ? __ldg(class_w + sub) : 1.f;
     __syncthreads();
-    const long warp_g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+    float bias[NC], cw[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        bias[k] = __ldg(b4 + k);
+        cw[k] = class_w != nullptr ? __ldg(class_w + k) : 1.f;
+    }
     double loss_num = 0.0, w_sum = 0.0;
     unsigned long long correct = 0, nvalid = 0;
-    for (long p0 = warp_g * 4; p0 < P; p0 += nwarps * 4) {
-        const long pnt = p0 + grp;
-        const bool ok = pnt < P;
-        uint4 y0 = make_uint4(0, 0, 0, 0), y1 = y0;
-        if (ok) {
-            const uint4* src = reinterpret_cast<const uint4*>(ys3 + pnt * 128 + sub * 16);
-            y0 = src[0];
-            y1 = src[1];
-        }
-        const long long lab = (ok && labels != nullptr && sub == 0) ? labels[pnt] : -1;
-        const uint32_t ws[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-        float a[16];
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+    for (long pnt = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; pnt < P; pnt += stride) {
+        const uint4* row = reinterpret_cast<const uint4*>(ys3 + pnt * 128);
+        float z[NC];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
-            a[e] = fmaxf(fmaf(sc[e], yv, sh[e]), 0.f);
-        }
-        float zmine = 0.f;                     // lane `sub` == k keeps logit k of its point
+        for (int k = 0; k < NC; ++k) z[k] = bias[k];
 #pragma unroll
-        for (int k = 0; k < MAXC; ++k) {
-            if (k < C) {
-                const float4* wk = reinterpret_cast<const float4*>(w_s + k * 128 + sub * 4);
-                float sq[4];                                // 4 independent chains (ILP) instead of one 16-deep chain
+        for (int j0 = 0; j0 < 16; j0 += 4) {
+            uint4 v[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 w4 = wk[q * 8];
-                    sq[q] = fmaf(a[4 * q + 3], w4.w, fmaf(a[4 * q + 2], w4.z, fmaf(a[4 * q + 1], w4.y, a[4 * q] * w4.x)));
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(row + j0 + u);      // 4 independent 16-byte loads in flight
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t ws[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = (j0 + u) * 8 + e;
+                    const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
+                    const float2 b2 = bn_s[c];
+                    const float a = fmaxf(fmaf(b2.x, yv, b2.y), 0.f);
+                    const float4* wc = reinterpret_cast<const float4*>(w_s + c * NCP);
+#pragma unroll
+                    for (int q = 0; q < NCP / 4; ++q) {
+                        const float4 w4 = wc[q];                      // broadcast: every lane reads the same address
+                        if (4 * q < NC) z[4 * q] = fmaf(a, w4.x, z[4 * q]);
+                        if (4 * q + 1 < NC) z[4 * q + 1] = fmaf(a, w4.y, z[4 * q + 1]);
+                        if (4 * q + 2 < NC) z[4 * q + 2] = fmaf(a, w4.z, z[4 * q + 2]);
+                        if (4 * q + 3 < NC) z[4 * q + 3] = fmaf(a, w4.w, z[4 * q + 3]);
+                    }
                 }
-                float s = (sq[0] + sq[1]) + (sq[2] + sq[3]);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                if (sub == k) zmine = s;
             }
         }
-        zmine += bias_k;
-        if (ok && sub < C) logits[pnt * C + sub] = zmine;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) logits[pnt * NC + k] = z[k];
         if (labels != nullptr) {
-            const long long labv = __shfl_sync(0xffffffffu, lab, grp * 8);       // label of this lane's point
-            const float zm = (sub < C) ? zmine : -INFINITY;
-            float zmax = zm;
+            const long long lab = labels[pnt];
+            if (lab >= 0) {
+                float zmax = z[0];
+                int am = 0;
 #pragma unroll
-            for (int o = 4; o >= 1; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-            const unsigned am_mask = (__ballot_sync(0xffffffffu, sub < C && zm == zmax) >> (grp * 8)) & 0xFFu;
-            const int am = __ffs(am_mask) - 1;          // first maximum, like torch.argmax
-            float ex = (sub < C) ? __expf(zm - zmax) : 0.f;
+                for (int k = 1; k < NC; ++k)
+                    if (z[k] > zmax) { zmax = z[k]; am = k; }        // first maximum, like torch.argmax
+                float se = 0.f, zl = 0.f, wl = 1.f;
 #pragma unroll
-            for (int o = 4; o >= 1; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
-            const int src_lane = grp * 8 + static_cast<int>(labv >= 0 ? labv : 0);
-            const float zl = __shfl_sync(0xffffffffu, zmine, src_lane);
-            const float wl = __shfl_sync(0xffffffffu, cw_k, src_lane);
-            if (sub == 0 && ok && labv >= 0) {
-                loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(ex) - zl);
+                for (int k = 0; k < NC; ++k) {
+                    se += __expf(z[k] - zmax);
+                    if (k == lab) { zl = z[k]; wl = cw[k]; }
+                }
+                loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(se) - zl);
                 w_sum += wl;
-                correct += (am == labv);
+                correct += (am == lab);
                 nvalid += 1;
             }
         }
     }
     if (labels != nullptr) {
-        // lanes 0, 8, 16, 24 hold partials: fold them into lane 0, then one atomic set per block
 #pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
+        for (int o = 16; o >= 1; o >>= 1) {
             loss_num += __shfl_xor_sync(0xffffffffu, loss_num, o);
             w_sum += __shfl_xor_sync(0xffffffffu, w_sum, o);
             correct += __shfl_xor_sync(0xffffffffu, correct, o);
             nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
         }
-        if (lane == 0) { red_d[warp][0] = loss_num; red_d[warp][1] = w_sum; red_u[warp][0] = correct; red_u[warp][1] = nvalid; }
+        const int warp = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { red_d[warp][0] = loss_num; red_d[warp][1] = w_sum; red_u[warp][0] = correct; red_u[warp][1] = nvalid; }
         __syncthreads();
         if (threadIdx.x == 0) {
             double a0 = 0.0, a1 = 0.0;
