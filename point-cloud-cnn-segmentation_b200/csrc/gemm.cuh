@@ -5,7 +5,11 @@
 //   warp 0      : TMA producer (A and B tiles, 128B-swizzled, mbarrier complete_tx)
 //   warp 1      : MMA issuer   (one lane issues tcgen05.mma, tcgen05.commit frees smem stages)
 //   warp 2      : TMEM allocator
-//   warps 4..11 : epilogue     (tcgen05.ld -> fused math -> swizzled smem -> TMA store / reductions)
+//   warps 4..11 : epilogue     (tcgen05.ld -> fused math -> swizzled smem -> TMA store / reductions); 4..19 for the
+//                 stats + max-pool variant.  STATS / DGRAD epilogues work in two passes per 64-column sub-tile: pass 1 is
+//                 row-mapped (TMEM lane = row) and only converts accumulators to bf16 into the staging tile, pass 2 is
+//                 column-mapped over that tile (a warp owns 8 columns, per-column parameters in registers) and does the
+//                 masking and the column reductions into per-CTA shared-memory accumulators (n_tile is fixed per CTA).
 //
 // Operand layouts:
 //   MN == false : A is [M x K] row-major (K contiguous), B is [N x K] row-major  (forward, dgrad)
