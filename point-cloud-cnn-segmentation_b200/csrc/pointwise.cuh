@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
         for (int k = 0; k < NC; ++k) logits[pnt * NC + k] = z[k];
         if (labels != nullptr) {
             const long long lab = labels[pnt];
-            if (lab >= 0) {
+            if (lab >= 0 && lab < NC) {
                 float zmax = z[0];
                 int am = 0;
 #pragma unroll
@@ -505,8 +505,8 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
             float se = ex;
 #pragma unroll
             for (int o = 4; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-            const float wl = __shfl_sync(0xffffffffu, cw_k, grp * 8 + static_cast<int>(lab >= 0 ? lab : 0));
-            dl_mine = (lab >= 0) ? wl * inv_wsum * (ex / se - (sub == lab ? 1.f : 0.f)) : 0.f;
+            const float wl = __shfl_sync(0xffffffffu, cw_k, grp * 8 + static_cast<int>((lab >= 0 && lab < C) ? lab : 0));
+            dl_mine = (lab >= 0 && lab < C) ? wl * inv_wsum * (ex / se - (sub == lab ? 1.f : 0.f)) : 0.f;
         }
         if (sub >= C || !ok) dl_mine = 0.f;
         dbk += dl_mine;
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const float* __restrict__ 
         }
         if (pred_out != nullptr) pred_out[i] = am;
         const long long lab = labels != nullptr ? labels[i] : -1;
-        if (lab >= 0) {
+        if (lab >= 0 && lab < C) {      // labels outside [0, C) would be an error in the reference; here they are ignored
             float se = 0.f, zl = 0.f;
 #pragma unroll
             for (int k = 0; k < MAXC; ++k)
