@@ -78,6 +78,15 @@ int pcseg_prepare_eval(pcseg_ctx* ctx, const float* params, const float* bn_buff
  * labels_out (optional, int64 (B,N)) receives argmax over classes, pcs.py:452. */
 int pcseg_forward_eval(pcseg_ctx* ctx, const float* x, float* logits, long long* labels_out, void* stream);
 
+/* Ragged (un-padded) execution of a zero-padded batch, SURVEY §8(f) rank 1.  x is the reference's padded batch
+ * (B, N, 4) as built by collate_fn (pcs.py:44-63); lengths (HOST array, B ints) gives the number of real points
+ * of every cloud -- rows lengths[b] .. N-1 of cloud b are the zero pad rows of pcs.py:53-56 (their content is not
+ * read).  Only the real rows plus one representative pad row per cloud are computed; the result is the one the
+ * padded batch gives: logits (B, N, C) bit-identical to pcseg_forward_eval on the same padded x, pad rows filled
+ * with their cloud's pad-row logits.  The context must be bound to (B, N) as usual. */
+int pcseg_forward_eval_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, float* logits, long long* labels_out,
+                              void* stream);
+
 /* Training forward: pcs.py:98-133 under train() (batch statistics, running-stat update, dropout).
  * bn_buffers is updated in place.  dropout_p = 0 disables dropout.  If labels != NULL the weighted
  * cross-entropy of pcs.py:216,247-251 is accumulated into *ce (device, zeroed by this call);
@@ -85,6 +94,18 @@ int pcseg_forward_eval(pcseg_ctx* ctx, const float* x, float* logits, long long*
 int pcseg_forward_train(pcseg_ctx* ctx, const float* x, const float* params, float* bn_buffers,
                         unsigned long long seed, float dropout_p, float* logits, const long long* labels,
                         const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream);
+
+/* Ragged training forward (see pcseg_forward_eval_ragged).  The pad rows of the reference are real inputs of the
+ * train-mode BatchNorm statistics: the representative pad row of every cloud enters every batch
+ * sum, the max-pool and the gradients with multiplicity N - lengths[b], so that losses, logits of real points,
+ * running statistics and parameter gradients equal those of the padded batch up to summation order (bf16 rounding
+ * noise) when dropout is off.  With dropout the pad rows of one cloud share ONE mask instead of N - lengths[b]
+ * independent ones: the BN batch sums of seg_conv2/3 are then an unbiased but noisier estimate of the padded ones.
+ * labels is the padded (B, N) tensor (entries of pad rows are ignored and treated as -1).  pcseg_backward after this
+ * call runs on the packed rows as well; it requires the fused loss gradient (dlogits == NULL). */
+int pcseg_forward_train_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, const float* params, float* bn_buffers,
+                               unsigned long long seed, float dropout_p, float* logits, const long long* labels,
+                               const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream);
 
 /* Backward of the training forward: loss.backward(), pcs.py:254.  Gradients of all 38 parameter
  * tensors are written (not accumulated) into `grads`, laid out like `params`.

@@ -45,6 +45,8 @@ struct GemmParams {
     const float* bias;           // [N]
     const float* cloud_bias;     // [clouds][N] or nullptr
     int pts_per_cloud;           // rows per cloud (for cloud_bias / colmax)
+    const int* tile_cloud;       // ragged (packed) execution: cloud of every 128-row tile, or nullptr (dense: row / pts_per_cloud)
+    const int* cloud_off;        // ragged: first packed row of every cloud (tiles never straddle clouds)
     unsigned int* colmax;        // [clouds][N] float bits (values >= 0)
     double* stats;               // [2][N]
     const float4* bnp;           // [N] {scale, shift, invstd, -mean*invstd} of the layer whose output is being masked
@@ -426,12 +428,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
             } else {
-                const int cloud = (p.pts_per_cloud > 0 && valid) ? grow / p.pts_per_cloud : 0;
+                const bool ragged = p.tile_cloud != nullptr;
+                const int tile_cl = ragged ? __ldg(p.tile_cloud + (m0 >> 7)) : (p.pts_per_cloud > 0 ? m0 / p.pts_per_cloud : 0);
+                const int cloud = ragged ? tile_cl : ((p.pts_per_cloud > 0 && valid) ? grow / p.pts_per_cloud : 0);
                 const float* cb_row = (p.cloud_bias != nullptr) ? p.cloud_bias + static_cast<size_t>(cloud) * p.N : nullptr;
                 bool uniform_cloud = true;
                 if constexpr (EPI == EPI_COLMAX || EPI == EPI_STATS_POOL) {
                     const int last = min(m0 + GEMM_BM, p.M) - 1;
-                    uniform_cloud = (m0 / p.pts_per_cloud) == (last / p.pts_per_cloud);
+                    uniform_cloud = ragged || (m0 / p.pts_per_cloud) == (last / p.pts_per_cloud);
                 }
                 const bool pool_uniform = uniform_cloud;
 #pragma unroll 1
@@ -556,7 +560,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             float bestv[8];
                             const float (&sg)[8] = p2a;
                             int besti[8];
-                            const int row0_in_cloud = (EPI == EPI_STATS_POOL) ? (m0 % p.pts_per_cloud) : 0;   // uniform tiles only
+                            const int row0_in_cloud = (EPI != EPI_STATS_POOL) ? 0                            // uniform tiles only
+                                                      : (ragged ? m0 - __ldg(p.cloud_off + tile_cl) : m0 % p.pts_per_cloud);
                             if constexpr (EPI == EPI_STATS_POOL) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
@@ -623,7 +628,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     }
                                     if ((lane & 3) == 0 && best[0] != 0ull) {
                                         const int colk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                                        atomicMax(p.pool_keys + static_cast<size_t>(m0 / p.pts_per_cloud) * p.N + colbase + colk, best[0]);
+                                        atomicMax(p.pool_keys + static_cast<size_t>(tile_cl) * p.N + colbase + colk, best[0]);
                                     }
                                 }
                             }
@@ -671,7 +676,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if constexpr (EPI == EPI_COLMAX) {
                         if (uniform_cloud && et < 64) {
                             const float s = fmaxf(fmaxf(comb_b[et], comb_b[64 + et]), fmaxf(comb_b[128 + et], comb_b[192 + et]));
-                            const int cl = m0 / p.pts_per_cloud;
+                            const int cl = tile_cl;
                             const int col = n0 + sub * 64 + et;
                             if (col < p.N && s > 0.f) atomicMax(p.colmax + static_cast<size_t>(cl) * p.N + col, __float_as_uint(s));
                         }

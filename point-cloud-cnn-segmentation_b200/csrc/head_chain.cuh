@@ -21,6 +21,7 @@ struct HeadChainParams {
     int M;                       // points
     int num_tiles;               // ceil(M / 128)
     int pts_per_cloud;
+    const int* tile_cloud;       // ragged (packed) execution: cloud of every 128-row tile, or nullptr
     const float* cloud_bias;     // [clouds][512]  folded seg_conv1 bias + global-feature term
     const float* bias2;          // [256] folded seg_conv2 / bn_seg2
     const float* bias3;          // [128] folded seg_conv3 / bn_seg3
@@ -194,7 +195,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
             const uint32_t par = it & 1;
             const int grow = tile * 128 + row;
             const bool valid = grow < p.M;
-            const int cloud = valid ? grow / p.pts_per_cloud : 0;
+            const int cloud = p.tile_cloud ? __ldg(p.tile_cloud + tile) : (valid ? grow / p.pts_per_cloud : 0);
             const float* cb_row = p.cloud_bias + static_cast<size_t>(cloud) * 512;
             // ---- epilogue 1: relu(D1 + cb) -> ACT [128 x 512]
             mbar_wait(&d_full[0], par);

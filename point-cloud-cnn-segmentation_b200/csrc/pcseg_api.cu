@@ -324,10 +324,27 @@ struct pcseg_ctx {
     float* wg = nullptr;          // seg_conv1.weight[:, 64:] dense copy [512][1024] fp32
     bf16* wk[NUM_BN] = {};        // bf16 [Cout][Cin] forward weights (index = conv index; [6] = point-feature part [512][64])
     bf16* act[NUM_BN] = {};       // eval: activations a_l; train: post-BN/ReLU activations
-    GemmOp ev[NUM_BN];            // eval forward GEMMs (index = conv index 1..8)
-    CUtensorMap hcA1, hcB1, hcB2, hcB3;   // fused inference head (head_chain_kernel)
-    HeadChainParams hcp;
+    // GEMM operations come in two sets: [0] the dense (B, N) batch, [1] the packed ragged batch (same buffers, tensor
+    // maps spanning the whole row capacity, row counts patched per call by rag_plan)
+    struct OpSet {
+        GemmOp ev[NUM_BN];            // eval forward GEMMs (index = conv index 1..8)
+        CUtensorMap hcA1;             // fused inference head (head_chain_kernel): point_feat operand
+        HeadChainParams hcp;
+        GemmOp fw[NUM_BN], dg[NUM_BN], wg_op[NUM_BN];   // training
+    };
+    OpSet ops[2];
+    CUtensorMap hcB1, hcB2, hcB3;
     bool use_head_chain = true;
+    // ---- ragged execution (k_pack_rows): device tables, packed input / logits / labels, row multiplicities
+    long long cap_rows = 0;       // B * ceil128(N): rows every point-major buffer can hold
+    int* meta = nullptr;          // len[B] | off[B+1] | tile_cloud[cap_rows/128]
+    float* xpack = nullptr;       // [cap_rows][4]
+    float* lpack = nullptr;       // [cap_rows][C]
+    long long* labpack = nullptr; // [cap_rows]      (train)
+    float* rowmult = nullptr;     // [cap_rows]      (train)
+    std::vector<int> meta_host;
+    long long rag_rows = 0;       // packed rows of the current ragged batch
+    bool rag_active = false;      // the latest training forward was ragged (backward follows it)
     // ---- train
     bf16* y[NUM_BN] = {};         // pre-BN conv outputs
     bf16* dz[NUM_BN] = {};        // gradient wrt BN output (after ReLU / dropout mask)
@@ -346,7 +363,6 @@ struct pcseg_ctx {
     int* argidx = nullptr;
     float* dcb = nullptr;
     float* dzv = nullptr;
-    GemmOp fw[NUM_BN], dg[NUM_BN], wg_op[NUM_BN];
     unsigned long long seed = 0;
     const unsigned long long* seed_ptr = nullptr;
     unsigned int thr16 = 0;
@@ -374,7 +390,9 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
     // Shape-independent buffers (weights, per-channel vectors) come first so that their addresses do not depend on
     // (B, N): bindings of different batch shapes can then share one caller-owned workspace and keep prepared weights.
     Carver k(ws);
-    const size_t P = static_cast<size_t>(B) * N;
+    // rows are sized for the packed ragged layout as well: every cloud rounded up to a multiple of 128 rows
+    const size_t P = static_cast<size_t>(B) * ((static_cast<size_t>(N) + 127) / 128 * 128);
+    c->cap_rows = static_cast<long long>(P);
     const ConvDef* cv = c->L.conv;
     c->zeros1024 = k.take<float>(1024);
     c->w1 = k.take<float>(256);
@@ -408,6 +426,13 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
     // ---- shape-dependent buffers
     c->gmax = k.take<float>(static_cast<size_t>(B) * 1024);
     c->cb = k.take<float>(static_cast<size_t>(B) * 512);
+    c->meta = k.take<int>(2 * static_cast<size_t>(B) + 1 + P / 128);
+    c->xpack = k.take<float>(P * 4);
+    c->lpack = k.take<float>(P * c->C);
+    if (train) {
+        c->labpack = k.take<long long>(P);
+        c->rowmult = k.take<float>(P);
+    }
     if (!train) {
         // a1..a5, a_s1, a_s2 (global_feat output is reduced in-kernel; seg_conv3 output feeds the fused logits epilogue)
         for (int i = 0; i < NUM_BN; ++i) {
@@ -474,48 +499,57 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
     carve(c, ws, B, N, c->train, &need);
     if (static_cast<long long>(need) > ws_bytes) return fail("pcseg_bind: workspace too small (%lld < %zu)", ws_bytes, need);
     const ConvDef* cv = c->L.conv;
-    const long long P = c->P;
     c->bound = false;
     c->eval_ready = false;
+    c->rag_active = false;
+    for (int set = 0; set < 2; ++set) {
+    pcseg_ctx::OpSet& O = c->ops[set];
+    const bool rag = set == 1;
+    const long long P = rag ? c->cap_rows : c->P;       // rows spanned by the tensor maps (ragged: patched per call)
+    const int* tile_cloud = rag ? c->meta + 2 * B + 1 : nullptr;
+    const int* cloud_off = rag ? c->meta + B : nullptr;
     if (!c->train) {
         // conv2..conv5
         for (int i = 1; i <= 4; ++i) {
-            TRY(setup_gemm_kmajor(&c->ev[i], EPI_BIAS_RELU, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
+            TRY(setup_gemm_kmajor(&O.ev[i], EPI_BIAS_RELU, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
                                   c->act[i], cv[i].cout, nullptr, 0));
-            c->ev[i].p.bias = c->delta[i];
+            O.ev[i].p.bias = c->delta[i];
         }
         // global_feat + max-pool
-        TRY(setup_gemm_kmajor(&c->ev[5], EPI_COLMAX, c->act[4], 1024, c->wk[5], 1024, P, 1024, 1024, nullptr, 0, nullptr, 0));
-        c->ev[5].p.bias = c->delta[5];
-        c->ev[5].p.colmax = reinterpret_cast<unsigned int*>(c->gmax);
-        c->ev[5].p.pts_per_cloud = N;
+        TRY(setup_gemm_kmajor(&O.ev[5], EPI_COLMAX, c->act[4], 1024, c->wk[5], 1024, P, 1024, 1024, nullptr, 0, nullptr, 0));
+        O.ev[5].p.bias = c->delta[5];
+        O.ev[5].p.colmax = reinterpret_cast<unsigned int*>(c->gmax);
+        O.ev[5].p.pts_per_cloud = N;
+        O.ev[5].p.tile_cloud = tile_cloud;
         // seg_conv1: point-feature part + per-cloud bias
-        TRY(setup_gemm_kmajor(&c->ev[6], EPI_BIAS_RELU, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->act[6], 512, nullptr, 0));
-        c->ev[6].p.bias = c->zeros1024;
-        c->ev[6].p.cloud_bias = c->cb;
-        c->ev[6].p.pts_per_cloud = N;
-        TRY(setup_gemm_kmajor(&c->ev[7], EPI_BIAS_RELU, c->act[6], 512, c->wk[7], 512, P, 256, 512, c->act[7], 256, nullptr, 0));
-        c->ev[7].p.bias = c->delta[7];
-        TRY(setup_gemm_kmajor(&c->ev[8], EPI_LOGITS, c->act[7], 256, c->wk[8], 256, P, 128, 256, nullptr, 0, nullptr, 0));
-        c->ev[8].p.bias = c->delta[8];
-        c->ev[8].p.w4 = c->w4;
-        c->ev[8].p.b4 = c->b4;
-        c->ev[8].p.num_classes = c->C;
+        TRY(setup_gemm_kmajor(&O.ev[6], EPI_BIAS_RELU, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->act[6], 512, nullptr, 0));
+        O.ev[6].p.bias = c->zeros1024;
+        O.ev[6].p.cloud_bias = c->cb;
+        O.ev[6].p.pts_per_cloud = N;
+        O.ev[6].p.tile_cloud = tile_cloud;
+        TRY(setup_gemm_kmajor(&O.ev[7], EPI_BIAS_RELU, c->act[6], 512, c->wk[7], 512, P, 256, 512, c->act[7], 256, nullptr, 0));
+        O.ev[7].p.bias = c->delta[7];
+        TRY(setup_gemm_kmajor(&O.ev[8], EPI_LOGITS, c->act[7], 256, c->wk[8], 256, P, 128, 256, nullptr, 0, nullptr, 0));
+        O.ev[8].p.bias = c->delta[8];
+        O.ev[8].p.w4 = c->w4;
+        O.ev[8].p.b4 = c->b4;
+        O.ev[8].p.num_classes = c->C;
         // fused head: seg_conv1..4 in one kernel (PCSEG_EVAL_CHAIN=0 selects the layer-by-layer kernels above)
-        TRY(make_tmap(&c->hcA1, c->act[1], 64, P, 64, 64, 128));
-        TRY(make_tmap(&c->hcB1, c->wk[6], 64, 512, 64, 64, 256));
-        TRY(make_tmap(&c->hcB2, c->wk[7], 512, 256, 512, 64, 256));
-        TRY(make_tmap(&c->hcB3, c->wk[8], 256, 128, 256, 64, 128));
-        memset(&c->hcp, 0, sizeof(c->hcp));
-        c->hcp.M = static_cast<int>(P);
-        c->hcp.num_tiles = static_cast<int>((P + 127) / 128);
-        c->hcp.pts_per_cloud = N;
-        c->hcp.cloud_bias = c->cb;
-        c->hcp.bias2 = c->delta[7];
-        c->hcp.bias3 = c->delta[8];
-        c->hcp.w4 = c->w4;
-        c->hcp.b4 = c->b4;
-        c->hcp.num_classes = c->C;
+        TRY(make_tmap(&O.hcA1, c->act[1], 64, P, 64, 64, 128));
+        if (!rag) TRY(make_tmap(&c->hcB1, c->wk[6], 64, 512, 64, 64, 256));
+        if (!rag) TRY(make_tmap(&c->hcB2, c->wk[7], 512, 256, 512, 64, 256));
+        if (!rag) TRY(make_tmap(&c->hcB3, c->wk[8], 256, 128, 256, 64, 128));
+        memset(&O.hcp, 0, sizeof(O.hcp));
+        O.hcp.M = static_cast<int>(P);
+        O.hcp.num_tiles = static_cast<int>((P + 127) / 128);
+        O.hcp.pts_per_cloud = N;
+        O.hcp.tile_cloud = tile_cloud;
+        O.hcp.cloud_bias = c->cb;
+        O.hcp.bias2 = c->delta[7];
+        O.hcp.bias3 = c->delta[8];
+        O.hcp.w4 = c->w4;
+        O.hcp.b4 = c->b4;
+        O.hcp.num_classes = c->C;
         {
             const char* e = getenv("PCSEG_EVAL_CHAIN");
             c->use_head_chain = !(e && e[0] == '0');
@@ -523,27 +557,30 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
     } else {
         // ---- forward: y_i = a_{i-1} W_i^T, statistics in the epilogue
         for (int i = 1; i <= 5; ++i) {
-            TRY(setup_gemm_kmajor(&c->fw[i], i == 5 ? EPI_STATS_POOL : EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P,
+            TRY(setup_gemm_kmajor(&O.fw[i], i == 5 ? EPI_STATS_POOL : EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P,
                                   cv[i].cout, cv[i].cin, c->y[i], cv[i].cout, nullptr, 0));
-            c->fw[i].p.stats = c->stats_f + c->stat_off[i];
+            O.fw[i].p.stats = c->stats_f + c->stat_off[i];
         }
-        c->fw[5].p.pool_keys = c->keys;          // train-mode max-pool fused into global_feat's epilogue
-        c->fw[5].p.pts_per_cloud = N;
-        TRY(setup_gemm_kmajor(&c->fw[6], EPI_STATS, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->y[6], 512, nullptr, 0));
-        c->fw[6].p.stats = c->stats_f + c->stat_off[6];
-        c->fw[6].p.cloud_bias = c->cb;
-        c->fw[6].p.pts_per_cloud = N;
+        O.fw[5].p.pool_keys = c->keys;          // train-mode max-pool fused into global_feat's epilogue
+        O.fw[5].p.pts_per_cloud = N;
+        O.fw[5].p.tile_cloud = tile_cloud;
+        O.fw[5].p.cloud_off = cloud_off;
+        TRY(setup_gemm_kmajor(&O.fw[6], EPI_STATS, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->y[6], 512, nullptr, 0));
+        O.fw[6].p.stats = c->stats_f + c->stat_off[6];
+        O.fw[6].p.cloud_bias = c->cb;
+        O.fw[6].p.pts_per_cloud = N;
+        O.fw[6].p.tile_cloud = tile_cloud;
         for (int i = 7; i <= 8; ++i) {
-            TRY(setup_gemm_kmajor(&c->fw[i], EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
+            TRY(setup_gemm_kmajor(&O.fw[i], EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
                                   c->y[i], cv[i].cout, nullptr, 0));
-            c->fw[i].p.stats = c->stats_f + c->stat_off[i];
+            O.fw[i].p.stats = c->stats_f + c->stat_off[i];
         }
         // ---- backward data gradients: dz_{i-1} = (dy_i W_i) masked by layer i-1
         auto dgrad = [&](int i, const bf16* dyA, int lda, int K, const bf16* Bw, int prev) -> int {
-            TRY(setup_gemm_kmajor(&c->dg[i], EPI_DGRAD, dyA, lda, Bw, K, P, cv[prev].cout, K, c->dz[prev], cv[prev].cout,
+            TRY(setup_gemm_kmajor(&O.dg[i], EPI_DGRAD, dyA, lda, Bw, K, P, cv[prev].cout, K, c->dz[prev], cv[prev].cout,
                                   c->y[prev], cv[prev].cout));
-            c->dg[i].p.stats = c->stats_b + c->stat_off[prev];
-            c->dg[i].p.bnp = c->bnp[prev];
+            O.dg[i].p.stats = c->stats_b + c->stat_off[prev];
+            O.dg[i].p.bnp = c->bnp[prev];
             return 0;
         };
         TRY(dgrad(8, c->dy[8], 128, 128, c->wt[8], 7));
@@ -555,7 +592,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         TRY(dgrad(1, c->dy[1], 64, 64, c->wt[1], 0));
         // ---- backward weight gradients (destinations patched with the grads arena at call time)
         auto wgrad = [&](int i, const bf16* dyA, int lda, const bf16* aB, int ldb, int cin) -> int {
-            return setup_gemm_wgrad(&c->wg_op[i], dyA, lda, cv[i].cout, aB, ldb, cin, P, nullptr, cv[i].cin);
+            return setup_gemm_wgrad(&O.wg_op[i], dyA, lda, cv[i].cout, aB, ldb, cin, P, nullptr, cv[i].cin);
         };
         TRY(wgrad(8, c->dy[8], 128, c->act[7], 256, 256));
         TRY(wgrad(7, c->dy[7], 256, c->act[6], 512, 512));
@@ -566,6 +603,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         TRY(wgrad(2, c->dycat, 576, c->act[1], 64, 64));
         TRY(wgrad(1, c->dy[1], 64, c->act[0], 64, 64));
     }
+    }   // op sets
     c->bound = true;
     return 0;
 }
@@ -613,21 +651,92 @@ extern "C" int pcseg_prepare_eval(pcseg_ctx* c, const float* params, const float
     return 0;
 }
 
-extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, long long* labels_out, void* stream) {
-    if (!c || !c->bound || c->train) return fail("pcseg_forward_eval: context not bound in eval mode");
-    if (!c->eval_ready) return fail("pcseg_forward_eval: call pcseg_prepare_eval first");
-    if (!x || !logits) return fail("pcseg_forward_eval: null tensor");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const long long P = c->P;
+// ------------------------------------------------------------------------------------------------
+// ragged batches: host-side plan of the packed layout (see k_pack_rows) + upload of the device tables
+// ------------------------------------------------------------------------------------------------
+static RaggedMeta rag_meta(const pcseg_ctx* c) {
+    RaggedMeta m;
+    m.len = c->meta;
+    m.off = c->meta + c->B;
+    m.tile_cloud = c->meta + 2 * c->B + 1;
+    m.B = c->B;
+    m.Nmax = c->N;
+    m.rows = static_cast<int>(c->rag_rows);
+    return m;
+}
+static void patch_rows(GemmOp& op, long long rows) {
+    if (!op.ready) return;
+    if (op.mn) {          // weight gradient: the points are the reduction dimension
+        op.p.K = static_cast<int>(rows);
+        const int total_kb = static_cast<int>(rows / 64);
+        int splits = num_sms() / (op.p.num_m_tiles * op.p.num_n_tiles);
+        if (splits < 1) splits = 1;
+        if (splits > total_kb) splits = total_kb;
+        op.p.kb_per_split = (total_kb + splits - 1) / splits;
+        op.p.num_splits = (total_kb + op.p.kb_per_split - 1) / op.p.kb_per_split;
+    } else {
+        op.p.M = static_cast<int>(rows);
+        op.p.num_m_tiles = static_cast<int>(rows / 128);
+    }
+}
+static int rag_plan(pcseg_ctx* c, const int* lengths, cudaStream_t s) {
+    const int B = c->B, N = c->N;
+    std::vector<int>& h = c->meta_host;
+    h.assign(2 * static_cast<size_t>(B) + 1 + static_cast<size_t>(c->cap_rows / 128), 0);
+    long long off = 0;
+    for (int b = 0; b < B; ++b) {
+        const int L = lengths[b];
+        if (L < 0 || L > N) return fail("ragged batch: lengths[%d]=%d outside 0..%d", b, L, N);
+        const long long alloc = (static_cast<long long>(L) + (L < N ? 1 : 0) + 127) / 128 * 128;
+        h[b] = L;
+        h[B + b] = static_cast<int>(off);
+        for (long long t = off / 128; t < (off + alloc) / 128; ++t) h[2 * B + 1 + t] = b;
+        off += alloc;
+    }
+    h[2 * B] = static_cast<int>(off);
+    if (off > c->cap_rows) return fail("internal: packed rows %lld exceed the capacity %lld", off, c->cap_rows);
+    c->rag_rows = off;
+    // (pageable source: the copy is staged before the call returns, meta_host may be rewritten by the next plan)
+    CUDA_OK(cudaMemcpyAsync(c->meta, h.data(), (2 * static_cast<size_t>(B) + 1 + off / 128) * sizeof(int), cudaMemcpyHostToDevice, s));
+    pcseg_ctx::OpSet& O = c->ops[1];
+    for (int i = 0; i < NUM_BN; ++i) {
+        patch_rows(O.ev[i], off);
+        patch_rows(O.fw[i], off);
+        patch_rows(O.dg[i], off);
+        patch_rows(O.wg_op[i], off);
+    }
+    O.hcp.M = static_cast<int>(off);
+    O.hcp.num_tiles = static_cast<int>(off / 128);
+    return 0;
+}
+static int rag_pack(pcseg_ctx* c, const float* x, const long long* labels, bool train, cudaStream_t s) {
+    int grid = static_cast<int>((c->rag_rows + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    pdl_launch(k_pack_rows, grid, 256, 0, s, reinterpret_cast<const float4*>(x), labels, rag_meta(c), reinterpret_cast<float4*>(c->xpack),
+               train ? c->labpack : static_cast<long long*>(nullptr), train ? c->rowmult : static_cast<float*>(nullptr));
+    LAUNCH_OK("k_pack_rows");
+    return 0;
+}
+static int rag_unpack_logits(pcseg_ctx* c, float* logits, cudaStream_t s) {
+    const long long total = c->P * c->C;
+    int grid = static_cast<int>((total + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    pdl_launch(k_unpack_logits, grid, 256, 0, s, static_cast<const float*>(c->lpack), rag_meta(c), c->C, logits);
+    LAUNCH_OK("k_unpack_logits");
+    return 0;
+}
+
+// rows = points to process (dense: B*N; ragged: packed rows), x / logits in that row space
+static int forward_eval_rows(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows, const float* x, float* logits, cudaStream_t s) {
     CUDA_OK(cudaMemsetAsync(c->gmax, 0, static_cast<size_t>(c->B) * 1024 * sizeof(float), s));
     {
-        int grid = static_cast<int>((P + 31) / 32);
+        int grid = static_cast<int>((rows + 31) / 32);
         if (grid > num_sms() * 8) grid = num_sms() * 8;
-        pdl_launch(k_ingest<false>, grid, 256, 0, s, reinterpret_cast<const float4*>(x), static_cast<int>(P), c->w1, c->alpha[0], c->delta[0],
+        pdl_launch(k_ingest<false>, grid, 256, 0, s, reinterpret_cast<const float4*>(x), static_cast<int>(rows), c->w1, c->alpha[0], c->delta[0],
                                             c->act[0], nullptr);
         LAUNCH_OK("k_ingest");
     }
-    for (int i = 1; i <= 5; ++i) TRY(launch_gemm(c->ev[i], s));
+    for (int i = 1; i <= 5; ++i) TRY(launch_gemm(O.ev[i], s));
     {
         const int warps = c->B * 512;
         pdl_launch(k_cloud_bias, (warps * 32 + 255) / 256, 256, 0, s, c->wg, 1024, c->gmax, c->B, 512, 1024, c->alpha[6], c->delta[6], c->cb);
@@ -641,22 +750,47 @@ extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, l
             CUDA_OK(cudaFuncSetAttribute(head_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HC_SMEM_BYTES));
             attr_set_mask |= 1ull << (dev & 63);
         }
-        HeadChainParams hp = c->hcp;
+        HeadChainParams hp = O.hcp;
         hp.logits = logits;
         const int grid = hp.num_tiles < num_sms() ? hp.num_tiles : num_sms();
-        pdl_launch(head_chain_kernel, grid, HC_THREADS, HC_SMEM_BYTES, s, c->hcA1, c->hcB1, c->hcB2, c->hcB3, hp);
+        pdl_launch(head_chain_kernel, grid, HC_THREADS, HC_SMEM_BYTES, s, O.hcA1, c->hcB1, c->hcB2, c->hcB3, hp);
         LAUNCH_OK("head_chain_kernel");
     } else {
-        TRY(launch_gemm(c->ev[6], s));
-        TRY(launch_gemm(c->ev[7], s));
-        GemmOp head = c->ev[8];
+        TRY(launch_gemm(O.ev[6], s));
+        TRY(launch_gemm(O.ev[7], s));
+        GemmOp head = O.ev[8];
         head.p.logits = logits;
         TRY(launch_gemm(head, s));
     }
-    if (labels_out) {
-        pdl_launch(k_argmax, static_cast<int>((P + 255) / 256), 256, 0, s, logits, P, c->C, labels_out);
-        LAUNCH_OK("k_argmax");
-    }
+    return 0;
+}
+static int argmax_labels(pcseg_ctx* c, const float* logits, long long* labels_out, cudaStream_t s) {
+    pdl_launch(k_argmax, static_cast<int>((c->P + 255) / 256), 256, 0, s, logits, c->P, c->C, labels_out);
+    LAUNCH_OK("k_argmax");
+    return 0;
+}
+
+extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, long long* labels_out, void* stream) {
+    if (!c || !c->bound || c->train) return fail("pcseg_forward_eval: context not bound in eval mode");
+    if (!c->eval_ready) return fail("pcseg_forward_eval: call pcseg_prepare_eval first");
+    if (!x || !logits) return fail("pcseg_forward_eval: null tensor");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TRY(forward_eval_rows(c, c->ops[0], c->P, x, logits, s));
+    if (labels_out) TRY(argmax_labels(c, logits, labels_out, s));
+    return 0;
+}
+
+extern "C" int pcseg_forward_eval_ragged(pcseg_ctx* c, const float* x, const int* lengths, float* logits, long long* labels_out,
+                                         void* stream) {
+    if (!c || !c->bound || c->train) return fail("pcseg_forward_eval_ragged: context not bound in eval mode");
+    if (!c->eval_ready) return fail("pcseg_forward_eval_ragged: call pcseg_prepare_eval first");
+    if (!x || !logits || !lengths) return fail("pcseg_forward_eval_ragged: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TRY(rag_plan(c, lengths, s));
+    TRY(rag_pack(c, x, nullptr, false, s));
+    TRY(forward_eval_rows(c, c->ops[1], c->rag_rows, c->xpack, c->lpack, s));
+    TRY(rag_unpack_logits(c, logits, s));
+    if (labels_out) TRY(argmax_labels(c, logits, labels_out, s));
     return 0;
 }
 
@@ -678,17 +812,14 @@ static int ew_grid(long long work_items) {
     return static_cast<int>(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
-extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* params, float* bnbuf, unsigned long long seed,
-                                   float dropout_p, float* logits, const long long* labels, const float* class_w,
-                                   pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
-    if (!c || !c->bound || !c->train) return fail("pcseg_forward_train: context not bound in train mode");
-    if (!x || !params || !bnbuf || !logits) return fail("pcseg_forward_train: null tensor");
-    if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train: dropout_p out of range");
-    if (labels && !ce) return fail("pcseg_forward_train: labels given without a CE accumulator");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+// P = rows to process (dense: B*N; ragged: packed rows); BN statistics are always normalised by the logical B*N rows
+static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, const float* params, float* bnbuf, unsigned long long seed,
+                              float dropout_p, float* logits, const long long* labels, const float* class_w,
+                              pcseg_ce_accum* ce, const pcseg_step_state* state, cudaStream_t s) {
+    pcseg_ctx::OpSet& O = c->ops[rag ? 1 : 0];
     const Layout& L = c->L;
     const ConvDef* cv = L.conv;
-    const long long P = c->P;
+    const long long P = rag ? c->rag_rows : c->P;
     c->seed = seed;
     c->seed_ptr = state ? &state->seed : nullptr;
     c->thr16 = static_cast<unsigned int>(dropout_p * 65536.0f + 0.5f);
@@ -728,7 +859,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         f.rmean = bnbuf + L.bn_off[i][0];
         f.rvar = bnbuf + L.bn_off[i][1];
         f.bnp = c->bnp[i];
-        f.n = static_cast<double>(P);
+        f.n = static_cast<double>(c->P);
         f.eps = BN_EPS;
         f.momentum = BN_MOMENTUM;
         f.C = cv[i].cout;
@@ -742,22 +873,34 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         return 0;
     };
 
+    // ragged: weight the representative pad rows by their multiplicity and drop the filler rows from the batch sums
+    auto stats_fix = [&](int i) -> int {
+        if (!rag) return 0;
+        const int co = cv[i].cout;
+        pdl_launch(k_stats_fix, dim3((co + 255) / 256, c->B), 256, 0, s, static_cast<const bf16*>(c->y[i]), co, co, rag_meta(c),
+                   static_cast<const float*>(c->rowmult), c->stats_f + c->stat_off[i]);
+        LAUNCH_OK("k_stats_fix");
+        return 0;
+    };
+
     {   // conv1 on CUDA cores
         int grid = static_cast<int>((P + 31) / 32);
         if (grid > num_sms() * 2) grid = num_sms() * 2;     // every block ends with 128 fp64 atomics on the same addresses
         pdl_launch(k_ingest<true>, grid, 256, 0, s, reinterpret_cast<const float4*>(x), static_cast<int>(P), params + L.off[0], nullptr, nullptr,
                                            c->y[0], c->stats_f + c->stat_off[0]);
         LAUNCH_OK("k_ingest");
+        TRY(stats_fix(0));
         TRY(bn_relu(0, 0, 0, 1.f));
     }
     for (int i = 1; i <= 5; ++i) {
         if (i == 5) {
-            GemmOp op = c->fw[5];
+            GemmOp op = O.fw[5];
             op.p.gamma = params + L.off[20 + 2 * 5];
             TRY(timed_gemm(c, op, 5, s));
         } else {
-            TRY(timed_gemm(c, c->fw[i], i, s));
+            TRY(timed_gemm(c, O.fw[i], i, s));
         }
+        TRY(stats_fix(i));
         if (i < 5) TRY(bn_relu(i, 0, 0, 1.f));
     }
     {   // global max-pool of relu(bn(y6)) with arg-index
@@ -768,11 +911,14 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         pdl_launch(k_cloud_bias, (warps * 32 + 255) / 256, 256, 0, s, params + L.off[12] + 64, 1088, c->gmax, c->B, 512, 1024, nullptr, nullptr, c->cb);
         LAUNCH_OK("k_cloud_bias");
     }
-    TRY(timed_gemm(c, c->fw[6], 6, s));
+    TRY(timed_gemm(c, O.fw[6], 6, s));
+    TRY(stats_fix(6));
     TRY(bn_relu(6, seed + 1, c->thr16, c->keep_scale));
-    TRY(timed_gemm(c, c->fw[7], 7, s));
+    TRY(timed_gemm(c, O.fw[7], 7, s));
+    TRY(stats_fix(7));
     TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
-    TRY(timed_gemm(c, c->fw[8], 8, s));
+    TRY(timed_gemm(c, O.fw[8], 8, s));
+    TRY(stats_fix(8));
     {
         int grid = static_cast<int>((P + 255) / 256);        // one thread per point
         if (grid > num_sms() * 4) grid = num_sms() * 4;
@@ -789,6 +935,33 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
         LAUNCH_OK("k_head_fwd");
     }
     return 0;
+}
+
+extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* params, float* bnbuf, unsigned long long seed,
+                                   float dropout_p, float* logits, const long long* labels, const float* class_w,
+                                   pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
+    if (!c || !c->bound || !c->train) return fail("pcseg_forward_train: context not bound in train mode");
+    if (!x || !params || !bnbuf || !logits) return fail("pcseg_forward_train: null tensor");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train: dropout_p out of range");
+    if (labels && !ce) return fail("pcseg_forward_train: labels given without a CE accumulator");
+    c->rag_active = false;
+    return forward_train_rows(c, false, x, params, bnbuf, seed, dropout_p, logits, labels, class_w, ce, state,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pcseg_forward_train_ragged(pcseg_ctx* c, const float* x, const int* lengths, const float* params, float* bnbuf,
+                                          unsigned long long seed, float dropout_p, float* logits, const long long* labels,
+                                          const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
+    if (!c || !c->bound || !c->train) return fail("pcseg_forward_train_ragged: context not bound in train mode");
+    if (!x || !lengths || !params || !bnbuf || !logits) return fail("pcseg_forward_train_ragged: null argument");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train_ragged: dropout_p out of range");
+    if (labels && !ce) return fail("pcseg_forward_train_ragged: labels given without a CE accumulator");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TRY(rag_plan(c, lengths, s));
+    TRY(rag_pack(c, x, labels, true, s));
+    c->rag_active = true;
+    TRY(forward_train_rows(c, true, c->xpack, params, bnbuf, seed, dropout_p, c->lpack, labels ? c->labpack : nullptr, class_w, ce, state, s));
+    return rag_unpack_logits(c, logits, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -817,8 +990,18 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Layout& L = c->L;
     const ConvDef* cv = L.conv;
-    const long long P = c->P;
-    const int B = c->B, N = c->N;
+    const bool rag = c->rag_active;      // the forward this backward belongs to ran on the packed ragged batch
+    pcseg_ctx::OpSet& O = c->ops[rag ? 1 : 0];
+    const long long P = rag ? c->rag_rows : c->P;
+    const int B = c->B;
+    const int N = rag ? static_cast<int>((c->N + 127) / 128 * 128) : c->N;     // (upper bound of the) rows per cloud
+    const int* rag_off = rag ? c->meta + B : nullptr;
+    if (rag) {
+        if (dlogits) return fail("pcseg_backward: a ragged forward needs the fused loss gradient (logits + labels), not dlogits");
+        x = c->xpack;
+        logits = c->lpack;
+        labels = c->labpack;
+    }
 
     if (phase != 2) {
         CUDA_OK(cudaMemsetAsync(grads, 0, static_cast<size_t>(L.total) * sizeof(float), s));
@@ -833,7 +1016,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         b.coef = c->coef[i];
         b.dgamma = grads + L.off[20 + 2 * i];
         b.dbeta = grads + L.off[21 + 2 * i];
-        b.n = static_cast<double>(P);
+        b.n = static_cast<double>(c->P);
         b.C = cv[i].cout;
         return b;
     };
@@ -842,19 +1025,23 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         const int co = cv[i].cout;
         const int rps = apply_rows_per_strip(N, B, co);
         dim3 grid((N + rps - 1) / rps, B);
-        pdl_launch(k_bn_bwd_apply<false>, grid, 256, 0, s, c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, bwd_args(i),
-                                                  grads + L.off[2 * i + 1], dcb, nullptr, nullptr);
+        if (rag)
+            pdl_launch(k_bn_bwd_apply<false, true>, grid, 256, 0, s, c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, bwd_args(i),
+                       grads + L.off[2 * i + 1], dcb, nullptr, nullptr, rag_off, c->rowmult);
+        else
+            pdl_launch(k_bn_bwd_apply<false, false>, grid, 256, 0, s, c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, bwd_args(i),
+                       grads + L.off[2 * i + 1], dcb, nullptr, nullptr, nullptr, nullptr);
         LAUNCH_OK("k_bn_bwd_apply");
         return 0;
     };
     auto wgrad = [&](int i, float* dst, int ldc) -> int {
-        GemmOp op = c->wg_op[i];
+        GemmOp op = O.wg_op[i];
         op.p.out_f32 = dst;
         op.p.ldc = ldc;
         return timed_gemm(c, op, 32 + i, s);
     };
     auto dgrad = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
-        GemmOp op = c->dg[i];
+        GemmOp op = O.dg[i];
         // (storing the keep masks in forward and re-loading them here was measured slower than regenerating Philox)
         op.p.seed = sd;
         op.p.seed_ptr = c->seed_ptr;
@@ -907,8 +1094,12 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     {
         const int rps = apply_rows_per_strip(N, B, 1024);
         dim3 grid((N + rps - 1) / rps, B);
-        pdl_launch(k_bn_bwd_apply<true>, grid, 256, 0, s, nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5), grads + L.off[11],
-                                                 nullptr, c->argidx, c->dzv);
+        if (rag)
+            pdl_launch(k_bn_bwd_apply<true, true>, grid, 256, 0, s, nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5),
+                       grads + L.off[11], nullptr, c->argidx, c->dzv, rag_off, c->rowmult);
+        else
+            pdl_launch(k_bn_bwd_apply<true, false>, grid, 256, 0, s, nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5),
+                       grads + L.off[11], nullptr, c->argidx, c->dzv, nullptr, nullptr);
         LAUNCH_OK("k_bn_bwd_apply<sparse>");
     }
     TRY(wgrad(5, grads + L.off[10], 1024));

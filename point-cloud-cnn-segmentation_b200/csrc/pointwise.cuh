@@ -627,13 +627,17 @@ __device__ __forceinline__ void bn_bwd_publish(const BnBwdArgs& f, bool first_bl
 // SPARSE variant (max-pool backward): dz[p][c] = (row_in_cloud == argidx[cloud][c]) ? dzv[cloud][c] : 0.
 // grid: (strips per cloud, clouds); every thread owns 8 fixed channels (coefficients in registers) and walks
 // down the rows of its strip, two rows in flight.
-template <bool SPARSE>
+// RAG variant (packed ragged batches, see k_pack_rows): cloud b owns packed rows rag_off[b] .. rag_off[b+1]; the
+// affine term is weighted by the row multiplicity (gradients of the representative pad row are carried pre-multiplied,
+// filler rows carry none).
+template <bool SPARSE, bool RAG>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, int ld_dz,
                                                       const __nv_bfloat16* __restrict__ y, int ld_y,
                                                       __nv_bfloat16* __restrict__ dy, int ld_dy, int N /*rows per cloud*/, int C,
                                                       int rows_per_strip, const BnBwdArgs bw,
                                                       float* __restrict__ dbias, float* __restrict__ dcb,
-                                                      const int* __restrict__ argidx, const float* __restrict__ dzv) {
+                                                      const int* __restrict__ argidx, const float* __restrict__ dzv,
+                                                      const int* __restrict__ rag_off, const float* __restrict__ rowmult) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[256 * 8];
@@ -643,6 +647,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
     const int c0 = (threadIdx.x % tpr) << 3;
     const int rslot = threadIdx.x / tpr;
     const int cloud = blockIdx.y;
+    const size_t base = RAG ? static_cast<size_t>(rag_off[cloud]) : static_cast<size_t>(cloud) * N;
+    if (RAG) N = rag_off[cloud + 1] - rag_off[cloud];
     const int r0 = blockIdx.x * rows_per_strip;
     const int r1 = min(r0 + rows_per_strip, N);
     float cA[8], cB[8], cC[8], acc[8];
@@ -658,13 +664,14 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
             dv[e] = dzv[static_cast<size_t>(cloud) * C + c0 + e];
         }
     }
-    const size_t base = static_cast<size_t>(cloud) * N;
     for (int r = r0 + rslot; r < r1; r += 4 * rpp) {
         uint4 yw[4], zw[4];
+        float mw[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int rr = r + u * rpp;
             if (rr < r1) {
+                if (RAG) mw[u] = rowmult[base + rr];
                 yw[u] = *reinterpret_cast<const uint4*>(y + (base + rr) * ld_y + c0);
                 if (!SPARSE) zw[u] = *reinterpret_cast<const uint4*>(dz + (base + rr) * ld_dz + c0);
             }
@@ -682,7 +689,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
                 float dze;
                 if (SPARSE) dze = (arg[e] == rr) ? dv[e] : 0.f;
                 else dze = (e & 1) ? bf16_hi(zs[e >> 1]) : bf16_lo(zs[e >> 1]);
-                const float v = round_bf16(fmaf(cA[e], dze, fmaf(cB[e], yv, cC[e])));
+                const float aff = fmaf(cB[e], yv, cC[e]);
+                const float v = round_bf16(fmaf(cA[e], dze, RAG ? mw[u] * aff : aff));
                 o[e] = v;
                 acc[e] += v;
             }
@@ -899,6 +907,90 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const float* __restrict__ 
             const unsigned int v = conf_s[(i / C) * MAXC + (i % C)];
             if (v) atomicAdd(confusion + i, static_cast<unsigned long long>(v));
         }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ragged (un-padded) execution of a zero-padded batch (reference collate_fn, pcs.py:44-63).
+// The real rows of every cloud are packed into a matrix whose clouds start at multiples of 128 rows, so that a GEMM
+// tile never straddles two clouds.  Cloud b (length L, padded length Nmax) owns packed rows off[b] .. off[b+1]:
+//   rows 0 .. L-1        the real points                                     multiplicity 1
+//   row  L   (L < Nmax)  ONE representative of the Nmax-L identical pad rows  multiplicity Nmax-L
+//   rows after that      filler up to the next multiple of 128               multiplicity 0
+// Filler rows are zero rows when the cloud has pad rows (they tie with the representative: max-pool unaffected, first
+// index wins) and copies of the last real row otherwise (they tie with it).  Inference needs nothing else.  Training
+// weights the representative row by its multiplicity in every reduction over points: k_stats_fix corrects the BN batch
+// sums after the GEMM epilogues, and the backward pass carries the representative's gradient pre-multiplied (every
+// backward op is linear in it; k_bn_bwd_apply<., true> scales the affine BN term).
+// meta (int32, device): len[B] | off[B+1] | tile_cloud[rows/128]
+// ---------------------------------------------------------------------------------------------
+struct RaggedMeta {
+    const int* len;
+    const int* off;
+    const int* tile_cloud;
+    int B, Nmax, rows;
+};
+
+__global__ void __launch_bounds__(256) k_pack_rows(const float4* __restrict__ x, const long long* __restrict__ labels, const RaggedMeta m,
+                                                   float4* __restrict__ xpack, long long* __restrict__ labpack,
+                                                   float* __restrict__ rowmult) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m.rows; r += gridDim.x * blockDim.x) {
+        const int c = m.tile_cloud[r >> 7];
+        const int i = r - m.off[c];
+        const int L = m.len[c];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        long long lab = -1;
+        float mult = 0.f;
+        if (i < L) {
+            const size_t src = static_cast<size_t>(c) * m.Nmax + i;
+            v = __ldg(x + src);
+            if (labels != nullptr) lab = labels[src];
+            mult = 1.f;
+        } else if (L < m.Nmax) {
+            mult = (i == L) ? static_cast<float>(m.Nmax - L) : 0.f;
+        } else {
+            v = __ldg(x + static_cast<size_t>(c) * m.Nmax + (m.Nmax - 1));
+        }
+        xpack[r] = v;
+        if (labpack != nullptr) labpack[r] = lab;
+        if (rowmult != nullptr) rowmult[r] = mult;
+    }
+}
+
+// packed logits -> the reference's padded (B, Nmax, C) tensor; every pad row receives its cloud's pad-row logits
+__global__ void __launch_bounds__(256) k_unpack_logits(const float* __restrict__ lp, const RaggedMeta m, int C, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long total = static_cast<long>(m.B) * m.Nmax * C;
+    for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long row = idx / C;
+        const int k = static_cast<int>(idx - row * C);
+        const int b = static_cast<int>(row / m.Nmax);
+        const int i = static_cast<int>(row - static_cast<long>(b) * m.Nmax);
+        const int src = m.off[b] + min(i, m.len[b]);
+        out[idx] = lp[static_cast<size_t>(src) * C + k];
+    }
+}
+
+// BN batch sums of a packed layer: add (multiplicity - 1) * {y, y^2} of every non-real row.  grid (ceil(C/256), B).
+__global__ void __launch_bounds__(256) k_stats_fix(const __nv_bfloat16* __restrict__ y, int ld, int C, const RaggedMeta m,
+                                                   const float* __restrict__ rowmult, double* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    const int r0 = m.off[b] + m.len[b], r1 = m.off[b + 1];
+    if (col >= C || r0 >= r1) return;
+    double a1 = 0.0, a2 = 0.0;
+    for (int r = r0; r < r1; ++r) {
+        const double w = static_cast<double>(rowmult[r]) - 1.0;
+        const double v = static_cast<double>(__bfloat162float(y[static_cast<size_t>(r) * ld + col]));
+        a1 += w * v;
+        a2 += w * v * v;
+    }
+    atomicAdd(stats + col, a1);
+    atomicAdd(stats + C + col, a2);
 }
 
 // argmax over classes (first maximum wins, like torch.argmax on ties)

@@ -52,6 +52,21 @@ class _Binding:
             pass
 
 
+def host_lengths(lengths, B, N):
+    """Per-cloud point counts of a zero-padded batch as a ctypes int array (None stays None).  Accepts a list, a numpy
+    array or a tensor (a CUDA tensor costs one device->host read); the reference's collate_fn (pcs.py:44-63) knows
+    them on the host: `masks.sum(1)`."""
+    if lengths is None:
+        return None
+    vals = lengths.detach().cpu().tolist() if torch.is_tensor(lengths) else [int(v) for v in lengths]
+    if len(vals) != B:
+        raise ValueError(f"lengths has {len(vals)} entries for a batch of {B} clouds")
+    vals = [int(v) for v in vals]
+    if any(v < 0 or v > N for v in vals):
+        raise ValueError(f"lengths must be within 0..{N}")
+    return (C.c_int * B)(*vals)
+
+
 class Engine:
     """One per (module, device).  Keeps one grow-only workspace per mode (train / eval) and a cache of per-shape
     bindings into it, so variable-length batches (every DataLoader batch of the reference has its own max_points,
@@ -104,8 +119,9 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- eval
-    def forward_eval(self, x, flat_params, flat_bn, weights_key, want_labels=False):
+    def forward_eval(self, x, flat_params, flat_bn, weights_key, want_labels=False, lengths=None):
         B, N, _ = x.shape
+        lengths = host_lengths(lengths, B, N)
         b = self.binding(B, N, False)
         with torch.cuda.device(self.device):
             if b.eval_key != weights_key:
@@ -113,15 +129,25 @@ class Engine:
                 b.eval_key = weights_key
             logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
             labels = torch.empty((B, N), dtype=torch.int64, device=self.device) if want_labels else None
-            check(lib.pcseg_forward_eval(b.handle, ptr(x), ptr(logits), ptr(labels), self._stream()), "pcseg_forward_eval")
+            if lengths is not None:
+                check(lib.pcseg_forward_eval_ragged(b.handle, ptr(x), lengths, ptr(logits), ptr(labels), self._stream()),
+                      "pcseg_forward_eval_ragged")
+            else:
+                check(lib.pcseg_forward_eval(b.handle, ptr(x), ptr(logits), ptr(labels), self._stream()), "pcseg_forward_eval")
         return (logits, labels) if want_labels else logits
 
     # ---- train
-    def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None, state=None):
+    def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None, state=None, lengths=None):
         B, N, _ = x.shape
         b = self.binding(B, N, True)
+        lengths = host_lengths(lengths, B, N)
         logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
+            if lengths is not None:
+                check(lib.pcseg_forward_train_ragged(b.handle, ptr(x), lengths, ptr(flat_params), ptr(flat_bn),
+                                                     C.c_ulonglong(seed & (2**64 - 1)), C.c_float(dropout_p), ptr(logits), ptr(labels),
+                                                     ptr(class_w), ptr(ce), ptr(state), self._stream()), "pcseg_forward_train_ragged")
+                return logits
             check(lib.pcseg_forward_train(b.handle, ptr(x), ptr(flat_params), ptr(flat_bn), C.c_ulonglong(seed & (2**64 - 1)),
                                           C.c_float(dropout_p), ptr(logits), ptr(labels), ptr(class_w), ptr(ce), ptr(state), self._stream()),
                   "pcseg_forward_train")

@@ -173,13 +173,13 @@ class PointNetSegmentation(nn.Module):
             raise RuntimeError("pcseg_b200: input must be a CUDA tensor (sm_100a kernels only, no CPU fallback)")
         return x.contiguous().float()
 
-    def _run_train_forward(self, x, labels=None, class_w=None, ce=None, state=None):
+    def _run_train_forward(self, x, labels=None, class_w=None, ce=None, state=None, lengths=None):
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
         p = float(self.dropout.p) if self.dropout.training else 0.0
         # with a device-resident step state the dropout seed lives on the GPU (CUDA-graph friendly)
         seed = int(torch.empty((), dtype=torch.int64).random_().item()) if (p > 0 and state is None) else 0
-        logits = eng.forward_train(x, f["params"], f["bn"], seed, p, labels, class_w, ce, state)
+        logits = eng.forward_train(x, f["params"], f["bn"], seed, p, labels, class_w, ce, state, lengths=lengths)
         torch._foreach_add_([getattr(self, n).num_batches_tracked for n in _BNS], 1)
         self._fwd_token += 1
         self._manual_version += 1      # running statistics changed
@@ -191,30 +191,35 @@ class PointNetSegmentation(nn.Module):
         eng.backward(x, f["params"], f["grads"], dlogits=dlogits)
         return [g.clone() for g in self.grad_views()]
 
-    def forward(self, x):
+    def forward(self, x, lengths=None):
+        """`lengths` (optional, B ints: real points per cloud of a zero-padded batch, pcs.py:44-63) selects ragged
+        execution: pad rows cost nothing and the result is the one of the padded batch (see include/pcseg_b200.h)."""
         x = self._check_input(x)
         if self.training:
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                if lengths is not None:
+                    raise NotImplementedError("ragged training runs through FusedTrainer.step(points, labels, lengths=...): "
+                                              "the packed backward needs the fused loss gradient")
                 self._ensure_flat(x.device)
                 return _SegTrainFn.apply(self, x, *self._param_list())
-            return self._run_train_forward(x)
+            return self._run_train_forward(x, lengths=lengths)
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
-        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key())
+        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), lengths=lengths)
 
     @torch.no_grad()
-    def predict(self, x):
+    def predict(self, x, lengths=None):
         """Fused inference + argmax (pcs.py:450-452): returns (logits, labels int64 (B, N))."""
         x = self._check_input(x)
         if self.training:
             raise RuntimeError("predict() is an eval-mode call; use model.eval() first")
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
-        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), want_labels=True)
+        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), want_labels=True, lengths=lengths)
 
 
     @torch.no_grad()
-    def evaluate(self, x, labels, class_weights=None):
+    def evaluate(self, x, labels, class_weights=None, lengths=None):
         """One validation batch without host synchronisation: replaces the per-batch loss / accuracy code of
         pcs.py:289-304 and the second F1 sweep of pcs.py:319-343.  Returns device tensors: logits, loss (weighted-mean CE),
         correct, valid and the C x C confusion matrix (rows = true class, columns = prediction)."""
@@ -223,11 +228,17 @@ class PointNetSegmentation(nn.Module):
             raise RuntimeError("evaluate() is an eval-mode call; use model.eval() first")
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
-        logits = eng.forward_eval(x, f["params"], f["bn"], self._weights_key())
+        logits = eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), lengths=lengths)
         cw = None if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float32, device=x.device).contiguous()
         ce, conf, _ = eng.eval_metrics(logits, labels.contiguous(), cw)
         f64, i64 = ce.view(torch.float64), ce.view(torch.int64)
         return dict(logits=logits, loss=f64[0] / f64[1], correct=i64[2], valid=i64[3], confusion=conf)
+
+
+def lengths_from_masks(masks):
+    """Real points per cloud from the `masks` tensor of the reference's collate_fn (pcs.py:58-63: True on the first
+    len(points) rows of every cloud)."""
+    return masks.sum(dim=1).to(torch.int64).cpu().tolist()
 
 
 def f1_scores(confusion):

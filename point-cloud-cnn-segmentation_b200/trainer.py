@@ -59,6 +59,7 @@ class FusedTrainer:
         self._eager_steps_at_key = 0
         self._static_x = None
         self._static_labels = None
+        self._lengths = None            # per-cloud point counts of the current batch (ragged execution) or None
 
     def set_lr(self, lr):
         self.lr = lr
@@ -70,7 +71,8 @@ class FusedTrainer:
     #                       -> [backward phase 2] -> all-reduce(bucket 2), wait -> [Adam + outputs] -> all-reduce(loss num)
     def _seg_forward(self, x, labels):
         self.engine.step_advance(self.state, self.betas)
-        self.last_logits = self.model._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw, state=self.state)
+        self.last_logits = self.model._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw, state=self.state,
+                                                         lengths=self._lengths)
         self.wsum.copy_(self.ce_f64[1:2])
 
     def _seg_backward(self, x, labels, phase):
@@ -143,9 +145,11 @@ class FusedTrainer:
             return None
 
     @torch.no_grad()
-    def step(self, points, labels):
+    def step(self, points, labels, lengths=None):
         """One optimizer step on this rank's shard.  points (B,N,4) fp32 and labels (B,N) int64 (-1 = pad) on
-        the device.  Returns dict of device tensors: loss (global weighted mean), correct, valid."""
+        the device.  Returns dict of device tensors: loss (global weighted mean), correct, valid.
+        lengths (optional, B host ints = real points per cloud, `masks.sum(1)` of pcs.py:58-63) runs the step on the
+        un-padded points only (ragged execution; launched eagerly, packed shapes change from batch to batch)."""
         m = self.model
         if not m.training:
             raise RuntimeError("FusedTrainer.step needs model.train()")
@@ -155,7 +159,8 @@ class FusedTrainer:
             self.flat = m._ensure_flat(self.device)
         ws_ptr = self.engine.binding(x.shape[0], x.shape[1], True).ws_ptr       # (also keeps the binding hot in the LRU)
         key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr(), ws_ptr)
-        use_graph = self.use_cuda_graph and not self.profiling
+        self._lengths = lengths
+        use_graph = self.use_cuda_graph and not self.profiling and lengths is None
         if key != self._graph_key:
             self._graph, self._graph_key, self._eager_steps_at_key = None, key, 0
         if use_graph and self._graph is None and self._eager_steps_at_key >= 2:
