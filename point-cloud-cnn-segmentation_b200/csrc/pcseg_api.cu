@@ -284,6 +284,8 @@ int setup_gemm_wgrad(GemmOp* op, const void* A, int lda, int Mc, const void* B, 
 // ------------------------------------------------------------------------------------------------
 // workspace carving
 // ------------------------------------------------------------------------------------------------
+constexpr int RAG_MAX_STRIPS = 1024;
+
 struct Carver {
     uint8_t* base;
     size_t off = 0;
@@ -337,13 +339,14 @@ struct pcseg_ctx {
     bool use_head_chain = true;
     // ---- ragged execution (k_pack_rows): device tables, packed input / logits / labels, row multiplicities
     long long cap_rows = 0;       // B * ceil128(N): rows every point-major buffer can hold
-    int* meta = nullptr;          // len[B] | off[B+1] | tile_cloud[cap_rows/128]
+    int* meta = nullptr;          // len[B] | off[B+1] | tile_cloud[rows/128] | strips[rag_strips][4]
     float* xpack = nullptr;       // [cap_rows][4]
     float* lpack = nullptr;       // [cap_rows][C]
     long long* labpack = nullptr; // [cap_rows]      (train)
     float* rowmult = nullptr;     // [cap_rows]      (train)
     std::vector<int> meta_host;
     long long rag_rows = 0;       // packed rows of the current ragged batch
+    int rag_strips = 0;           // row strips of k_bn_bwd_apply<., true> (planned per batch)
     bool rag_active = false;      // the latest training forward was ragged (backward follows it)
     // ---- train
     bf16* y[NUM_BN] = {};         // pre-BN conv outputs
@@ -426,7 +429,7 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
     // ---- shape-dependent buffers
     c->gmax = k.take<float>(static_cast<size_t>(B) * 1024);
     c->cb = k.take<float>(static_cast<size_t>(B) * 512);
-    c->meta = k.take<int>(2 * static_cast<size_t>(B) + 1 + P / 128);
+    c->meta = k.take<int>(2 * static_cast<size_t>(B) + 1 + P / 128 + 4 * (static_cast<size_t>(RAG_MAX_STRIPS) + B));
     c->xpack = k.take<float>(P * 4);
     c->lpack = k.take<float>(P * c->C);
     if (train) {
@@ -682,7 +685,7 @@ static void patch_rows(GemmOp& op, long long rows) {
 static int rag_plan(pcseg_ctx* c, const int* lengths, cudaStream_t s) {
     const int B = c->B, N = c->N;
     std::vector<int>& h = c->meta_host;
-    h.assign(2 * static_cast<size_t>(B) + 1 + static_cast<size_t>(c->cap_rows / 128), 0);
+    h.assign(2 * static_cast<size_t>(B) + 1 + static_cast<size_t>(c->cap_rows / 128) + 4 * (static_cast<size_t>(RAG_MAX_STRIPS) + B), 0);
     long long off = 0;
     for (int b = 0; b < B; ++b) {
         const int L = lengths[b];
@@ -696,8 +699,28 @@ static int rag_plan(pcseg_ctx* c, const int* lengths, cudaStream_t s) {
     h[2 * B] = static_cast<int>(off);
     if (off > c->cap_rows) return fail("internal: packed rows %lld exceed the capacity %lld", off, c->cap_rows);
     c->rag_rows = off;
+    // row strips for the BN-backward kernels: about two blocks per SM over the packed rows, never across clouds
+    size_t w = 2 * static_cast<size_t>(B) + 1 + static_cast<size_t>(off / 128);
+    {
+        int target = 2 * num_sms();
+        if (target > RAG_MAX_STRIPS) target = RAG_MAX_STRIPS;
+        const long long tiles = off / 128;
+        const long long tps = (tiles + target - 1) / target;        // tiles per strip
+        int n = 0;
+        for (int b = 0; b < B; ++b) {
+            const long long r_begin = h[B + b], r_end = (b + 1 < B) ? h[B + b + 1] : off;
+            for (long long r = r_begin; r < r_end; r += tps * 128, ++n) {
+                h[w + 4 * n] = b;
+                h[w + 4 * n + 1] = static_cast<int>(r);
+                h[w + 4 * n + 2] = static_cast<int>(r + tps * 128 < r_end ? r + tps * 128 : r_end);
+                h[w + 4 * n + 3] = static_cast<int>(r_begin);
+            }
+        }
+        c->rag_strips = n;
+        w += 4 * static_cast<size_t>(n);
+    }
     // (pageable source: the copy is staged before the call returns, meta_host may be rewritten by the next plan)
-    CUDA_OK(cudaMemcpyAsync(c->meta, h.data(), (2 * static_cast<size_t>(B) + 1 + off / 128) * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(c->meta, h.data(), w * sizeof(int), cudaMemcpyHostToDevice, s));
     pcseg_ctx::OpSet& O = c->ops[1];
     for (int i = 0; i < NUM_BN; ++i) {
         patch_rows(O.ev[i], off);
@@ -877,7 +900,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
     auto stats_fix = [&](int i) -> int {
         if (!rag) return 0;
         const int co = cv[i].cout;
-        pdl_launch(k_stats_fix, dim3((co + 255) / 256, c->B), 256, 0, s, static_cast<const bf16*>(c->y[i]), co, co, rag_meta(c),
+        pdl_launch(k_stats_fix, dim3((co + 31) / 32, c->B), 256, 0, s, static_cast<const bf16*>(c->y[i]), co, co, rag_meta(c),
                    static_cast<const float*>(c->rowmult), c->stats_f + c->stat_off[i]);
         LAUNCH_OK("k_stats_fix");
         return 0;
@@ -995,7 +1018,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     const long long P = rag ? c->rag_rows : c->P;
     const int B = c->B;
     const int N = rag ? static_cast<int>((c->N + 127) / 128 * 128) : c->N;     // (upper bound of the) rows per cloud
-    const int* rag_off = rag ? c->meta + B : nullptr;
+    const int* rag_strips = rag ? c->meta + 2 * B + 1 + c->rag_rows / 128 : nullptr;
     if (rag) {
         if (dlogits) return fail("pcseg_backward: a ragged forward needs the fused loss gradient (logits + labels), not dlogits");
         x = c->xpack;
@@ -1026,8 +1049,8 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         const int rps = apply_rows_per_strip(N, B, co);
         dim3 grid((N + rps - 1) / rps, B);
         if (rag)
-            pdl_launch(k_bn_bwd_apply<false, true>, grid, 256, 0, s, c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, bwd_args(i),
-                       grads + L.off[2 * i + 1], dcb, nullptr, nullptr, rag_off, c->rowmult);
+            pdl_launch(k_bn_bwd_apply<false, true>, c->rag_strips, 256, 0, s, c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, bwd_args(i),
+                       grads + L.off[2 * i + 1], dcb, nullptr, nullptr, rag_strips, c->rowmult);
         else
             pdl_launch(k_bn_bwd_apply<false, false>, grid, 256, 0, s, c->dz[i], co, c->y[i], co, dy_out, ld_dy, N, co, rps, bwd_args(i),
                        grads + L.off[2 * i + 1], dcb, nullptr, nullptr, nullptr, nullptr);
@@ -1095,8 +1118,8 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         const int rps = apply_rows_per_strip(N, B, 1024);
         dim3 grid((N + rps - 1) / rps, B);
         if (rag)
-            pdl_launch(k_bn_bwd_apply<true, true>, grid, 256, 0, s, nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5),
-                       grads + L.off[11], nullptr, c->argidx, c->dzv, rag_off, c->rowmult);
+            pdl_launch(k_bn_bwd_apply<true, true>, c->rag_strips, 256, 0, s, nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5),
+                       grads + L.off[11], nullptr, c->argidx, c->dzv, rag_strips, c->rowmult);
         else
             pdl_launch(k_bn_bwd_apply<true, false>, grid, 256, 0, s, nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5),
                        grads + L.off[11], nullptr, c->argidx, c->dzv, nullptr, nullptr);

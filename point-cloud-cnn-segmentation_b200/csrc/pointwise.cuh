@@ -627,9 +627,10 @@ __device__ __forceinline__ void bn_bwd_publish(const BnBwdArgs& f, bool first_bl
 // SPARSE variant (max-pool backward): dz[p][c] = (row_in_cloud == argidx[cloud][c]) ? dzv[cloud][c] : 0.
 // grid: (strips per cloud, clouds); every thread owns 8 fixed channels (coefficients in registers) and walks
 // down the rows of its strip, two rows in flight.
-// RAG variant (packed ragged batches, see k_pack_rows): cloud b owns packed rows rag_off[b] .. rag_off[b+1]; the
-// affine term is weighted by the row multiplicity (gradients of the representative pad row are carried pre-multiplied,
-// filler rows carry none).
+// RAG variant (packed ragged batches, see k_pack_rows): 1-D grid over the strips planned on the host (rag_strips[blk] =
+// {cloud, first row, end row, first row of the cloud} in packed rows, strips sized by the batch's real row count so that short clouds do not idle
+// blocks); the affine term is weighted by the row multiplicity (gradients of the representative pad row are carried
+// pre-multiplied, filler rows carry none).
 template <bool SPARSE, bool RAG>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, int ld_dz,
                                                       const __nv_bfloat16* __restrict__ y, int ld_y,
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
                                                       int rows_per_strip, const BnBwdArgs bw,
                                                       float* __restrict__ dbias, float* __restrict__ dcb,
                                                       const int* __restrict__ argidx, const float* __restrict__ dzv,
-                                                      const int* __restrict__ rag_off, const float* __restrict__ rowmult) {
+                                                      const int* __restrict__ rag_strips, const float* __restrict__ rowmult) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[256 * 8];
@@ -646,11 +647,11 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
     const int rpp = 256 / tpr;
     const int c0 = (threadIdx.x % tpr) << 3;
     const int rslot = threadIdx.x / tpr;
-    const int cloud = blockIdx.y;
-    const size_t base = RAG ? static_cast<size_t>(rag_off[cloud]) : static_cast<size_t>(cloud) * N;
-    if (RAG) N = rag_off[cloud + 1] - rag_off[cloud];
-    const int r0 = blockIdx.x * rows_per_strip;
-    const int r1 = min(r0 + rows_per_strip, N);
+    const int cloud = RAG ? rag_strips[4 * blockIdx.x] : blockIdx.y;
+    const size_t base = RAG ? 0 : static_cast<size_t>(cloud) * N;                 // RAG: strip bounds are packed rows already
+    const int r0 = RAG ? rag_strips[4 * blockIdx.x + 1] : blockIdx.x * rows_per_strip;
+    const int r1 = RAG ? rag_strips[4 * blockIdx.x + 2] : min(r0 + rows_per_strip, N);
+    const int arg_base = RAG ? rag_strips[4 * blockIdx.x + 3] : 0;                // argidx is relative to the cloud
     float cA[8], cB[8], cC[8], acc[8];
     int arg[8];
     float dv[8];
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
         cA[e] = cf.x; cB[e] = cf.y; cC[e] = cf.z;
         acc[e] = 0.f;
         if (SPARSE) {
-            arg[e] = argidx[static_cast<size_t>(cloud) * C + c0 + e];
+            arg[e] = argidx[static_cast<size_t>(cloud) * C + c0 + e] + arg_base;
             dv[e] = dzv[static_cast<size_t>(cloud) * C + c0 + e];
         }
     }
@@ -973,24 +974,36 @@ __global__ void __launch_bounds__(256) k_unpack_logits(const float* __restrict__
     }
 }
 
-// BN batch sums of a packed layer: add (multiplicity - 1) * {y, y^2} of every non-real row.  grid (ceil(C/256), B).
+// BN batch sums of a packed layer: add (multiplicity - 1) * {y, y^2} of every non-real row (at most 128 per cloud).
+// grid (C/32, B), block 256 = 32 columns x 8 row slots.
 __global__ void __launch_bounds__(256) k_stats_fix(const __nv_bfloat16* __restrict__ y, int ld, int C, const RaggedMeta m,
                                                    const float* __restrict__ rowmult, double* __restrict__ stats) {
     pdl_launch_dependents();
     pdl_wait();
-    const int col = blockIdx.x * 256 + threadIdx.x;
+    __shared__ double red[2][8][32];
+    const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
     const int b = blockIdx.y;
     const int r0 = m.off[b] + m.len[b], r1 = m.off[b + 1];
-    if (col >= C || r0 >= r1) return;
+    if (r0 >= r1) return;                                   // (uniform over the block)
     double a1 = 0.0, a2 = 0.0;
-    for (int r = r0; r < r1; ++r) {
-        const double w = static_cast<double>(rowmult[r]) - 1.0;
-        const double v = static_cast<double>(__bfloat162float(y[static_cast<size_t>(r) * ld + col]));
-        a1 += w * v;
-        a2 += w * v * v;
+    if (col < C) {
+        for (int r = r0 + slot; r < r1; r += 8) {
+            const double w = static_cast<double>(rowmult[r]) - 1.0;
+            const double v = static_cast<double>(__bfloat162float(y[static_cast<size_t>(r) * ld + col]));
+            a1 += w * v;
+            a2 += w * v * v;
+        }
     }
-    atomicAdd(stats + col, a1);
-    atomicAdd(stats + C + col, a2);
+    red[0][slot][lane] = a1;
+    red[1][slot][lane] = a2;
+    __syncthreads();
+    if (slot < 2 && col < C) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[slot][k][lane];
+        atomicAdd(stats + slot * C + col, t);
+    }
 }
 
 // argmax over classes (first maximum wins, like torch.argmax on ties)

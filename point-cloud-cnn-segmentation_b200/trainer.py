@@ -159,6 +159,8 @@ class FusedTrainer:
             self.flat = m._ensure_flat(self.device)
         ws_ptr = self.engine.binding(x.shape[0], x.shape[1], True).ws_ptr       # (also keeps the binding hot in the LRU)
         key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr(), ws_ptr)
+        if lengths is not None and all(int(v) == x.shape[1] for v in (lengths.tolist() if torch.is_tensor(lengths) else lengths)):
+            lengths = None                                      # nothing padded: dense (CUDA-graph) path
         self._lengths = lengths
         use_graph = self.use_cuda_graph and not self.profiling and lengths is None
         if key != self._graph_key:
