@@ -356,8 +356,18 @@ def run_ours(args, B, N, mode):
     if args.gpus == 1 and not args.no_cpu_baseline:
         cpu_value, _, cpu_sample = time_cpu(mode, B, N, C, steps=2, warmup=1, budget_s=8.0)
         cpu = {"value": cpu_value, "unit": "points/s", "cores": cores, "kind": "port", "sample": cpu_sample}
+        # the reference network through stock torch eager (cuDNN / cuBLAS fp32) on this same B200,
+        # on a bounded sample of the workload (whole clouds; the reference keeps ~37 KB of saved tensors per point)
+        from oracle.torch_port import time_stock_torch_on_gpu
+        tb = max(1, min(B, 262144 // N)) if N <= 262144 else 1
+        tn = min(N, 262144)
+        te = time_stock_torch_on_gpu(mode, tb, tn, C, steps=10, warmup=3, device=dev)
+        torch_eager = {"tf32": te["tf32"], "ieee_fp32": te["ieee"], "unit": "points/s", "kind": "port",
+                       "sample": f"{tb} cloud(s) x {tn} points per step, 10 timed steps, stock nn.Conv1d/BatchNorm1d eager in the "
+                                 f"reference's channel-major layout, {mode}"}
     else:
         cpu = None
+        torch_eager = None
 
     line = {
         "metric": metric_name(mode), "value": value, "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -369,7 +379,7 @@ def run_ours(args, B, N, mode):
                    "parallelism": f"dp{world}" if world > 1 else "single"},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_total / steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "torch_eager_same_gpu": torch_eager,
         "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
         "gemm_kernels": kernels,
     }

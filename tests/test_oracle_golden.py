@@ -145,3 +145,25 @@ def test_torch_cpu_port_matches_reference(path):
         ref = gold["g/" + name] if ("g/" + name) in gold.files else None
         if ref is not None:
             np.testing.assert_allclose(g, ref, atol=1e-3 * np.abs(ref).max() + 1e-6)
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_stock_torch_model_matches_reference(path):
+    """the channel-major stock-torch restatement that bench.py times on the B200 (torch eager) against the same vectors"""
+    import torch
+    from oracle.torch_port import StockTorchModel
+    gold = np.load(path)
+    C, seed = int(gold["C"]), int(gold["seed"])
+    m = StockTorchModel(C, state=orc.synth_state(C, seed))
+    x = torch.from_numpy(gold["x"])
+    m.eval()
+    with torch.no_grad():
+        le = m(x).numpy()
+    np.testing.assert_allclose(le, gold["eval_logits"], rtol=0, atol=2e-5)
+    m.train()
+    m.dropout.p = 0.0
+    lt = m(x)
+    np.testing.assert_allclose(lt.detach().numpy(), gold["train_logits"], rtol=0, atol=5e-5)
+    loss = torch.nn.functional.cross_entropy(lt.contiguous().view(-1, C), torch.from_numpy(gold["labels"]).view(-1),
+                                             weight=torch.from_numpy(gold["class_w"]), ignore_index=-1)
+    assert abs(loss.item() - float(gold["loss"])) < 1e-5
