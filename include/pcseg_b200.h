@@ -78,6 +78,14 @@ int pcseg_prepare_eval(pcseg_ctx* ctx, const float* params, const float* bn_buff
  * labels_out (optional, int64 (B,N)) receives argmax over classes, pcs.py:452. */
 int pcseg_forward_eval(pcseg_ctx* ctx, const float* x, float* logits, long long* labels_out, void* stream);
 
+/* Point-sharded inference of clouds that are split over several GPUs ("within one cloud"): every rank
+ * holds the same B clouds but its own slice of their points.  part 1 runs pcs.py:103-114 on the local points and leaves
+ * the local max-pool result in the context; the caller reduces it over the ranks with MAX (e.g. ncclAllReduce on the
+ * pointer returned by pcseg_pooled_feature: B x 1024 fp32, all values >= 0) and calls part 2 (pcs.py:117-131 + argmax)
+ * for the local points.  The logits of a point are bit-identical to those of the un-sharded cloud. */
+int pcseg_forward_eval_part(pcseg_ctx* ctx, const float* x, float* logits, long long* labels_out, int part, void* stream);
+int pcseg_pooled_feature(pcseg_ctx* ctx, float** pooled);
+
 /* Ragged (un-padded) execution of a zero-padded batch, SURVEY §8(f) rank 1.  x is the reference's padded batch
  * (B, N, 4) as built by collate_fn (pcs.py:44-63); lengths (HOST array, B ints) gives the number of real points
  * of every cloud -- rows lengths[b] .. N-1 of cloud b are the zero pad rows of pcs.py:53-56 (their content is not

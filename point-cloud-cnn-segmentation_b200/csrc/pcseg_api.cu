@@ -750,7 +750,8 @@ static int rag_unpack_logits(pcseg_ctx* c, float* logits, cudaStream_t s) {
 }
 
 // rows = points to process (dense: B*N; ragged: packed rows), x / logits in that row space
-static int forward_eval_rows(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows, const float* x, float* logits, cudaStream_t s) {
+// part 1: ingest .. global_feat + max-pool (the pooled feature of every cloud is left in c->gmax)
+static int forward_eval_trunk(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows, const float* x, cudaStream_t s) {
     CUDA_OK(cudaMemsetAsync(c->gmax, 0, static_cast<size_t>(c->B) * 1024 * sizeof(float), s));
     {
         int grid = static_cast<int>((rows + 31) / 32);
@@ -760,6 +761,10 @@ static int forward_eval_rows(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows, 
         LAUNCH_OK("k_ingest");
     }
     for (int i = 1; i <= 5; ++i) TRY(launch_gemm(O.ev[i], s));
+    return 0;
+}
+// part 2: per-cloud seg_conv1 term from the pooled feature, segmentation head, logits
+static int forward_eval_head(pcseg_ctx* c, pcseg_ctx::OpSet& O, float* logits, cudaStream_t s) {
     {
         const int warps = c->B * 512;
         pdl_launch(k_cloud_bias, (warps * 32 + 255) / 256, 256, 0, s, c->wg, 1024, c->gmax, c->B, 512, 1024, c->alpha[6], c->delta[6], c->cb);
@@ -787,6 +792,10 @@ static int forward_eval_rows(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows, 
     }
     return 0;
 }
+static int forward_eval_rows(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows, const float* x, float* logits, cudaStream_t s) {
+    TRY(forward_eval_trunk(c, O, rows, x, s));
+    return forward_eval_head(c, O, logits, s);
+}
 static int argmax_labels(pcseg_ctx* c, const float* logits, long long* labels_out, cudaStream_t s) {
     pdl_launch(k_argmax, static_cast<int>((c->P + 255) / 256), 256, 0, s, logits, c->P, c->C, labels_out);
     LAUNCH_OK("k_argmax");
@@ -800,6 +809,28 @@ extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, l
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TRY(forward_eval_rows(c, c->ops[0], c->P, x, logits, s));
     if (labels_out) TRY(argmax_labels(c, logits, labels_out, s));
+    return 0;
+}
+
+extern "C" int pcseg_forward_eval_part(pcseg_ctx* c, const float* x, float* logits, long long* labels_out, int part, void* stream) {
+    if (!c || !c->bound || c->train) return fail("pcseg_forward_eval_part: context not bound in eval mode");
+    if (!c->eval_ready) return fail("pcseg_forward_eval_part: call pcseg_prepare_eval first");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (part == 1) {
+        if (!x) return fail("pcseg_forward_eval_part: null input");
+        return forward_eval_trunk(c, c->ops[0], c->P, x, s);
+    }
+    if (part == 2) {
+        if (!logits) return fail("pcseg_forward_eval_part: null logits");
+        TRY(forward_eval_head(c, c->ops[0], logits, s));
+        if (labels_out) TRY(argmax_labels(c, logits, labels_out, s));
+        return 0;
+    }
+    return fail("pcseg_forward_eval_part: part must be 1 or 2");
+}
+extern "C" int pcseg_pooled_feature(pcseg_ctx* c, float** pooled) {
+    if (!c || !c->bound || !pooled) return fail("pcseg_pooled_feature: context not bound");
+    *pooled = c->gmax;
     return 0;
 }
 

@@ -138,6 +138,27 @@ class Engine:
                 check(lib.pcseg_forward_eval(b.handle, ptr(x), ptr(logits), ptr(labels), self._stream()), "pcseg_forward_eval")
         return (logits, labels) if want_labels else logits
 
+    def forward_eval_sharded(self, x, flat_params, flat_bn, weights_key, reduce_max, want_labels=False):
+        """Inference on this rank's slice of the points of B clouds: trunk, `reduce_max(pooled)` (the caller's MAX
+        all-reduce over the ranks that hold the other slices, in place on a (B, 1024) fp32 tensor), head."""
+        B, N, _ = x.shape
+        b = self.binding(B, N, False)
+        with torch.cuda.device(self.device):
+            if b.eval_key != weights_key:
+                check(lib.pcseg_prepare_eval(b.handle, ptr(flat_params), ptr(flat_bn), self._stream()), "pcseg_prepare_eval")
+                b.eval_key = weights_key
+            check(lib.pcseg_forward_eval_part(b.handle, ptr(x), None, None, 1, self._stream()), "pcseg_forward_eval_part")
+            pooled_ptr = C.c_void_p()
+            check(lib.pcseg_pooled_feature(b.handle, C.byref(pooled_ptr)), "pcseg_pooled_feature")
+            storage = self._ws[False][0]
+            off = pooled_ptr.value - storage.data_ptr()
+            pooled = storage[off:off + B * 1024 * 4].view(torch.float32).view(B, 1024)      # a view of the workspace
+            reduce_max(pooled)
+            logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
+            labels = torch.empty((B, N), dtype=torch.int64, device=self.device) if want_labels else None
+            check(lib.pcseg_forward_eval_part(b.handle, None, ptr(logits), ptr(labels), 2, self._stream()), "pcseg_forward_eval_part")
+        return (logits, labels) if want_labels else logits
+
     # ---- train
     def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None, state=None, lengths=None):
         B, N, _ = x.shape

@@ -219,6 +219,25 @@ class PointNetSegmentation(nn.Module):
 
 
     @torch.no_grad()
+    def predict_point_sharded(self, x_local, group=None, reduce_max=None):
+        """Inference of clouds whose POINTS are split over the ranks of `group` (one 1M-point scene on several
+        GPUs): x_local (B, N_local, 4) is this rank's slice of the same B clouds (slices may differ in length).  The only
+        exchange is a MAX all-reduce of the (B, 1024) pooled feature between global_feat and seg_conv1 (pcs.py:114-117);
+        returns (logits, labels) of the local points, bit-identical to the un-sharded forward.  `reduce_max` overrides
+        the collective (tests)."""
+        import torch.distributed as dist
+        x = self._check_input(x_local)
+        if self.training:
+            raise RuntimeError("predict_point_sharded() is an eval-mode call; use model.eval() first")
+        f = self._ensure_flat(x.device)
+        eng = self._get_engine(x.device)
+        if reduce_max is None:
+            def reduce_max(pooled):
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                    dist.all_reduce(pooled, op=dist.ReduceOp.MAX, group=group)
+        return eng.forward_eval_sharded(x, f["params"], f["bn"], self._weights_key(), reduce_max, want_labels=True)
+
+    @torch.no_grad()
     def evaluate(self, x, labels, class_weights=None, lengths=None):
         """One validation batch without host synchronisation: replaces the per-batch loss / accuracy code of
         pcs.py:289-304 and the second F1 sweep of pcs.py:319-343.  Returns device tensors: logits, loss (weighted-mean CE),

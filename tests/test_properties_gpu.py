@@ -271,3 +271,23 @@ def test_variable_length_batches_share_one_workspace():
                 shared.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
         cos = torch.nn.functional.cosine_similarity(g_shared, g, dim=0).item()
         assert cos > 0.9995, cos
+
+
+def test_point_sharded_inference_is_bit_identical():
+    """SURVEY §8(e), one cloud over several GPUs: slices of the points of the same clouds, the pooled feature reduced with
+    MAX between them (here: the collective is emulated on one GPU), give bit-identical logits and labels."""
+    m = _model(5, 31)
+    x = torch.rand(2, 3000, 4, device="cuda")
+    with torch.no_grad():
+        full, full_lab = m.predict(x)
+    shards = [x[:, :1000].contiguous(), x[:, 1000:1001].contiguous(), x[:, 1001:].contiguous()]
+    pooled = []
+    for xs in shards:                                   # pass 1: every "rank" computes its local pooled feature
+        m.predict_point_sharded(xs, reduce_max=lambda p: pooled.append(p.clone()))
+    gmax = torch.stack(pooled).max(dim=0)[0]
+    outs = [m.predict_point_sharded(xs, reduce_max=lambda p: p.copy_(gmax)) for xs in shards]
+    assert torch.equal(torch.cat([o[0] for o in outs], dim=1), full)
+    assert torch.equal(torch.cat([o[1] for o in outs], dim=1), full_lab)
+    # without the exchange a slice only sees its own points
+    alone = m.predict_point_sharded(shards[0], reduce_max=lambda p: None)[0]
+    assert torch.equal(alone, m(shards[0]))
