@@ -107,9 +107,11 @@ def _bn_eval(y, sd, bn, dt):
     return (y - m) / np.sqrt(v + BN_EPS) * g + b
 
 
-def forward_eval(sd, x, dtype=np.float64):
+def forward_eval(sd, x, dtype=np.float64, pooled=None, return_pooled=False):
     """Inference forward, pcs.py:98-133 under model.eval() (pcs.py:432,450-451).
-    x: (B, N, Cin) -> logits (B, N, num_classes)."""
+    x: (B, N, Cin) -> logits (B, N, num_classes).
+    pooled / return_pooled: the (B, 1024) max-pool result of pcs.py:114 can be handed in / out, which is all that
+    point-sharded inference exchanges (tests of the multi-GPU protocol)."""
     B, N, cin = x.shape
     a = x.reshape(B * N, cin).astype(dtype)
     point_feat = None
@@ -119,13 +121,17 @@ def forward_eval(sd, x, dtype=np.float64):
         if conv == "conv2":
             point_feat = a                                              # pcs.py:107
     g = a.reshape(B, N, -1).max(axis=1)                                # pcs.py:114
+    g_local = g
+    if pooled is not None:
+        g = np.asarray(pooled, dtype)
     gexp = np.repeat(g[:, None, :], N, axis=1).reshape(B * N, -1)      # pcs.py:117
     a = np.concatenate([point_feat, gexp], axis=1)                     # pcs.py:120
     for conv, bn, _, _ in HEAD:
         W, b = _w(sd, conv, dtype)
         a = np.maximum(_bn_eval(a @ W.T + b, sd, bn, dtype), 0)       # pcs.py:123-127 (dropout = identity in eval)
     W, b = _w(sd, "seg_conv4", dtype)
-    return (a @ W.T + b).reshape(B, N, -1)                              # pcs.py:128-131
+    logits = (a @ W.T + b).reshape(B, N, -1)                            # pcs.py:128-131
+    return (logits, g_local) if return_pooled else logits
 
 
 def _bn_train(y, sd, bn, dt):

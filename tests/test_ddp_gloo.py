@@ -118,3 +118,45 @@ def test_grad_buckets_partition_the_arena():
             mask[a:b] = True
         for t, (o, n) in enumerate(offs):
             assert mask[o:o + n].all() == (10 <= t <= 19 or t >= 30), t
+
+
+def _shard_worker(rank, world, port_no, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = port_no
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pointnet_oracle as orc
+    C, B, N = 3, 2, 200
+    sd = orc.synth_state(C, 5)
+    x = np.random.default_rng(1).random((B, N, 4))
+    cut = [0, 77, N]                                                 # unequal slices of the points of the same clouds
+    xs = x[:, cut[rank]:cut[rank + 1]]
+    _, pooled = orc.forward_eval(sd, xs, return_pooled=True)         # part 1 on the local points
+    t = torch.from_numpy(np.ascontiguousarray(pooled))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                         # the one exchange (model.predict_point_sharded)
+    logits = orc.forward_eval(sd, xs, pooled=t.numpy())              # part 2 on the local points
+    q.put((rank, logits))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_point_sharded_inference_protocol():
+    """SURVEY §8(e) within-one-cloud sharding: slices of the points + MAX all-reduce of the pooled feature == the whole cloud"""
+    sys.path.insert(0, ROOT)
+    from oracle import pointnet_oracle as orc
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = str(31500 + (os.getpid() % 2000))
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port_no, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    C, B, N = 3, 2, 200
+    x = np.random.default_rng(1).random((B, N, 4))
+    ref = orc.forward_eval(orc.synth_state(C, 5), x)
+    np.testing.assert_allclose(np.concatenate([got[0], got[1]], axis=1), ref, rtol=0, atol=1e-10)
