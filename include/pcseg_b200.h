@@ -91,9 +91,12 @@ int pcseg_pooled_feature(pcseg_ctx* ctx, float** pooled);
  * of every cloud -- rows lengths[b] .. N-1 of cloud b are the zero pad rows of pcs.py:53-56 (their content is not
  * read).  Only the real rows plus one representative pad row per cloud are computed; the result is the one the
  * padded batch gives: logits (B, N, C) bit-identical to pcseg_forward_eval on the same padded x, pad rows filled
- * with their cloud's pad-row logits.  The context must be bound to (B, N) as usual. */
-int pcseg_forward_eval_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, float* logits, long long* labels_out,
-                              void* stream);
+ * with their cloud's pad-row logits.
+ * nmax = the padded length N of THIS batch (x is (B, nmax, 4), logits (B, nmax, C)); it may be anything up to the N the
+ * context is bound to (0 = exactly N), so that one binding of a generous capacity serves batches whose longest cloud
+ * changes from batch to batch (pcs.py:50) without re-binding. */
+int pcseg_forward_eval_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, int nmax, float* logits,
+                              long long* labels_out, void* stream);
 
 /* Training forward: pcs.py:98-133 under train() (batch statistics, running-stat update, dropout).
  * bn_buffers is updated in place.  dropout_p = 0 disables dropout.  If labels != NULL the weighted
@@ -111,7 +114,7 @@ int pcseg_forward_train(pcseg_ctx* ctx, const float* x, const float* params, flo
  * independent ones: the BN batch sums of seg_conv2/3 are then an unbiased but noisier estimate of the padded ones.
  * labels is the padded (B, N) tensor (entries of pad rows are ignored and treated as -1).  pcseg_backward after this
  * call runs on the packed rows as well; it requires the fused loss gradient (dlogits == NULL). */
-int pcseg_forward_train_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, const float* params, float* bn_buffers,
+int pcseg_forward_train_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, int nmax, const float* params, float* bn_buffers,
                                unsigned long long seed, float dropout_p, float* logits, const long long* labels,
                                const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream);
 

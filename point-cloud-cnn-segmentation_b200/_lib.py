@@ -47,8 +47,8 @@ def _load():
     lib.pcseg_forward_train.argtypes = [vp, vp, vp, vp, u64, f32, vp, vp, vp, vp, vp, vp]
     lib.pcseg_forward_eval_part.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.pcseg_pooled_feature.argtypes = [vp, C.POINTER(vp)]
-    lib.pcseg_forward_eval_ragged.argtypes = [vp, vp, C.POINTER(i32), vp, vp, vp]
-    lib.pcseg_forward_train_ragged.argtypes = [vp, vp, C.POINTER(i32), vp, vp, u64, f32, vp, vp, vp, vp, vp, vp]
+    lib.pcseg_forward_eval_ragged.argtypes = [vp, vp, C.POINTER(i32), i32, vp, vp, vp]
+    lib.pcseg_forward_train_ragged.argtypes = [vp, vp, C.POINTER(i32), i32, vp, vp, u64, f32, vp, vp, vp, vp, vp, vp]
     lib.pcseg_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.pcseg_adam_step.argtypes = [vp, vp, vp, vp, ll, i32, f32, f32, f32, f32, f32, f32, vp, vp]
     lib.pcseg_step_advance.argtypes = [vp, f32, f32, vp]

@@ -345,6 +345,7 @@ struct pcseg_ctx {
     long long* labpack = nullptr; // [cap_rows]      (train)
     float* rowmult = nullptr;     // [cap_rows]      (train)
     std::vector<int> meta_host;
+    int rag_N = 0;                // padded length of the current ragged batch (<= N of the binding)
     long long rag_rows = 0;       // packed rows of the current ragged batch
     int rag_strips = 0;           // row strips of k_bn_bwd_apply<., true> (planned per batch)
     bool rag_active = false;      // the latest training forward was ragged (backward follows it)
@@ -663,7 +664,7 @@ static RaggedMeta rag_meta(const pcseg_ctx* c) {
     m.off = c->meta + c->B;
     m.tile_cloud = c->meta + 2 * c->B + 1;
     m.B = c->B;
-    m.Nmax = c->N;
+    m.Nmax = c->rag_N;
     m.rows = static_cast<int>(c->rag_rows);
     return m;
 }
@@ -682,8 +683,11 @@ static void patch_rows(GemmOp& op, long long rows) {
         op.p.num_m_tiles = static_cast<int>(rows / 128);
     }
 }
-static int rag_plan(pcseg_ctx* c, const int* lengths, cudaStream_t s) {
-    const int B = c->B, N = c->N;
+static int rag_plan(pcseg_ctx* c, const int* lengths, int nmax, cudaStream_t s) {
+    if (nmax <= 0) nmax = c->N;
+    if (nmax > c->N) return fail("ragged batch: padded length %d exceeds the bound capacity %d", nmax, c->N);
+    c->rag_N = nmax;
+    const int B = c->B, N = nmax;
     std::vector<int>& h = c->meta_host;
     h.assign(2 * static_cast<size_t>(B) + 1 + static_cast<size_t>(c->cap_rows / 128) + 4 * (static_cast<size_t>(RAG_MAX_STRIPS) + B), 0);
     long long off = 0;
@@ -741,7 +745,7 @@ static int rag_pack(pcseg_ctx* c, const float* x, const long long* labels, bool 
     return 0;
 }
 static int rag_unpack_logits(pcseg_ctx* c, float* logits, cudaStream_t s) {
-    const long long total = c->P * c->C;
+    const long long total = static_cast<long long>(c->B) * c->rag_N * c->C;
     int grid = static_cast<int>((total + 255) / 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
     pdl_launch(k_unpack_logits, grid, 256, 0, s, static_cast<const float*>(c->lpack), rag_meta(c), c->C, logits);
@@ -796,8 +800,8 @@ static int forward_eval_rows(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows, 
     TRY(forward_eval_trunk(c, O, rows, x, s));
     return forward_eval_head(c, O, logits, s);
 }
-static int argmax_labels(pcseg_ctx* c, const float* logits, long long* labels_out, cudaStream_t s) {
-    pdl_launch(k_argmax, static_cast<int>((c->P + 255) / 256), 256, 0, s, logits, c->P, c->C, labels_out);
+static int argmax_labels(pcseg_ctx* c, long long P, const float* logits, long long* labels_out, cudaStream_t s) {
+    pdl_launch(k_argmax, static_cast<int>((P + 255) / 256), 256, 0, s, logits, P, c->C, labels_out);
     LAUNCH_OK("k_argmax");
     return 0;
 }
@@ -808,7 +812,7 @@ extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, l
     if (!x || !logits) return fail("pcseg_forward_eval: null tensor");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TRY(forward_eval_rows(c, c->ops[0], c->P, x, logits, s));
-    if (labels_out) TRY(argmax_labels(c, logits, labels_out, s));
+    if (labels_out) TRY(argmax_labels(c, c->P, logits, labels_out, s));
     return 0;
 }
 
@@ -823,7 +827,7 @@ extern "C" int pcseg_forward_eval_part(pcseg_ctx* c, const float* x, float* logi
     if (part == 2) {
         if (!logits) return fail("pcseg_forward_eval_part: null logits");
         TRY(forward_eval_head(c, c->ops[0], logits, s));
-        if (labels_out) TRY(argmax_labels(c, logits, labels_out, s));
+        if (labels_out) TRY(argmax_labels(c, c->P, logits, labels_out, s));
         return 0;
     }
     return fail("pcseg_forward_eval_part: part must be 1 or 2");
@@ -834,17 +838,17 @@ extern "C" int pcseg_pooled_feature(pcseg_ctx* c, float** pooled) {
     return 0;
 }
 
-extern "C" int pcseg_forward_eval_ragged(pcseg_ctx* c, const float* x, const int* lengths, float* logits, long long* labels_out,
-                                         void* stream) {
+extern "C" int pcseg_forward_eval_ragged(pcseg_ctx* c, const float* x, const int* lengths, int nmax, float* logits,
+                                         long long* labels_out, void* stream) {
     if (!c || !c->bound || c->train) return fail("pcseg_forward_eval_ragged: context not bound in eval mode");
     if (!c->eval_ready) return fail("pcseg_forward_eval_ragged: call pcseg_prepare_eval first");
     if (!x || !logits || !lengths) return fail("pcseg_forward_eval_ragged: null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    TRY(rag_plan(c, lengths, s));
+    TRY(rag_plan(c, lengths, nmax, s));
     TRY(rag_pack(c, x, nullptr, false, s));
     TRY(forward_eval_rows(c, c->ops[1], c->rag_rows, c->xpack, c->lpack, s));
     TRY(rag_unpack_logits(c, logits, s));
-    if (labels_out) TRY(argmax_labels(c, logits, labels_out, s));
+    if (labels_out) TRY(argmax_labels(c, static_cast<long long>(c->B) * c->rag_N, logits, labels_out, s));
     return 0;
 }
 
@@ -913,7 +917,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         f.rmean = bnbuf + L.bn_off[i][0];
         f.rvar = bnbuf + L.bn_off[i][1];
         f.bnp = c->bnp[i];
-        f.n = static_cast<double>(c->P);
+        f.n = static_cast<double>(rag ? static_cast<long long>(c->B) * c->rag_N : c->P);
         f.eps = BN_EPS;
         f.momentum = BN_MOMENTUM;
         f.C = cv[i].cout;
@@ -1003,7 +1007,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
                               static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int pcseg_forward_train_ragged(pcseg_ctx* c, const float* x, const int* lengths, const float* params, float* bnbuf,
+extern "C" int pcseg_forward_train_ragged(pcseg_ctx* c, const float* x, const int* lengths, int nmax, const float* params, float* bnbuf,
                                           unsigned long long seed, float dropout_p, float* logits, const long long* labels,
                                           const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
     if (!c || !c->bound || !c->train) return fail("pcseg_forward_train_ragged: context not bound in train mode");
@@ -1011,7 +1015,7 @@ extern "C" int pcseg_forward_train_ragged(pcseg_ctx* c, const float* x, const in
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train_ragged: dropout_p out of range");
     if (labels && !ce) return fail("pcseg_forward_train_ragged: labels given without a CE accumulator");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    TRY(rag_plan(c, lengths, s));
+    TRY(rag_plan(c, lengths, nmax, s));
     TRY(rag_pack(c, x, labels, true, s));
     c->rag_active = true;
     TRY(forward_train_rows(c, true, c->xpack, params, bnbuf, seed, dropout_p, c->lpack, labels ? c->labpack : nullptr, class_w, ce, state, s));
@@ -1048,7 +1052,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     pcseg_ctx::OpSet& O = c->ops[rag ? 1 : 0];
     const long long P = rag ? c->rag_rows : c->P;
     const int B = c->B;
-    const int N = rag ? static_cast<int>((c->N + 127) / 128 * 128) : c->N;     // (upper bound of the) rows per cloud
+    const int N = c->N;                   // rows per cloud (dense launches only: the ragged ones walk planned strips)
     const int* rag_strips = rag ? c->meta + 2 * B + 1 + c->rag_rows / 128 : nullptr;
     if (rag) {
         if (dlogits) return fail("pcseg_backward: a ragged forward needs the fused loss gradient (logits + labels), not dlogits");
@@ -1070,7 +1074,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         b.coef = c->coef[i];
         b.dgamma = grads + L.off[20 + 2 * i];
         b.dbeta = grads + L.off[21 + 2 * i];
-        b.n = static_cast<double>(c->P);
+        b.n = static_cast<double>(rag ? static_cast<long long>(c->B) * c->rag_N : c->P);
         b.C = cv[i].cout;
         return b;
     };

@@ -69,6 +69,13 @@ def host_lengths(lengths, B, N):
     return (C.c_int * B)(*vals)
 
 
+def ragged_capacity(N, step=4096):
+    """Ragged calls bind a padded length rounded up to a multiple of `step`: the padded length of a DataLoader batch is
+    its longest cloud (pcs.py:50) and changes every batch, the binding (TMA descriptors) is reused as long as the
+    capacity bucket does not change.  Costs nothing at run time: only real rows are computed."""
+    return (N + step - 1) // step * step
+
+
 class Engine:
     """One per (module, device).  Keeps one grow-only workspace per mode (train / eval) and a cache of per-shape
     bindings into it, so variable-length batches (every DataLoader batch of the reference has its own max_points,
@@ -124,7 +131,7 @@ class Engine:
     def forward_eval(self, x, flat_params, flat_bn, weights_key, want_labels=False, lengths=None):
         B, N, _ = x.shape
         lengths = host_lengths(lengths, B, N)
-        b = self.binding(B, N, False)
+        b = self.binding(B, N if lengths is None else ragged_capacity(N), False)
         with torch.cuda.device(self.device):
             if b.eval_key != weights_key:
                 check(lib.pcseg_prepare_eval(b.handle, ptr(flat_params), ptr(flat_bn), self._stream()), "pcseg_prepare_eval")
@@ -132,7 +139,7 @@ class Engine:
             logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
             labels = torch.empty((B, N), dtype=torch.int64, device=self.device) if want_labels else None
             if lengths is not None:
-                check(lib.pcseg_forward_eval_ragged(b.handle, ptr(x), lengths, ptr(logits), ptr(labels), self._stream()),
+                check(lib.pcseg_forward_eval_ragged(b.handle, ptr(x), lengths, N, ptr(logits), ptr(labels), self._stream()),
                       "pcseg_forward_eval_ragged")
             else:
                 check(lib.pcseg_forward_eval(b.handle, ptr(x), ptr(logits), ptr(labels), self._stream()), "pcseg_forward_eval")
@@ -162,12 +169,13 @@ class Engine:
     # ---- train
     def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None, state=None, lengths=None):
         B, N, _ = x.shape
-        b = self.binding(B, N, True)
         lengths = host_lengths(lengths, B, N)
+        b = self.binding(B, N if lengths is None else ragged_capacity(N), True)
+        self._train_binding = b              # backward runs on the binding of the latest training forward
         logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             if lengths is not None:
-                check(lib.pcseg_forward_train_ragged(b.handle, ptr(x), lengths, ptr(flat_params), ptr(flat_bn),
+                check(lib.pcseg_forward_train_ragged(b.handle, ptr(x), lengths, N, ptr(flat_params), ptr(flat_bn),
                                                      C.c_ulonglong(seed & (2**64 - 1)), C.c_float(dropout_p), ptr(logits), ptr(labels),
                                                      ptr(class_w), ptr(ce), ptr(state), self._stream()), "pcseg_forward_train_ragged")
                 return logits
@@ -178,7 +186,9 @@ class Engine:
 
     def backward(self, x, flat_params, flat_grads, dlogits=None, logits=None, labels=None, class_w=None, wsum=None, phase=0):
         B, N, _ = x.shape
-        b = self.binding(B, N, True)
+        b = getattr(self, "_train_binding", None)
+        if b is None or b.shape[0] != B or b.shape[1] < N or b.ws_ptr is None or self.bindings.get(b.shape) is not b:
+            b = self.binding(B, N, True)
         with torch.cuda.device(self.device):
             check(lib.pcseg_backward(b.handle, ptr(x), ptr(flat_params), ptr(dlogits), ptr(logits), ptr(labels), ptr(class_w),
                                      ptr(wsum), ptr(flat_grads), phase, self._stream()), "pcseg_backward")

@@ -157,12 +157,20 @@ class FusedTrainer:
         labels = labels.contiguous()
         if not m._flat_quick_ok(self.device):
             self.flat = m._ensure_flat(self.device)
-        ws_ptr = self.engine.binding(x.shape[0], x.shape[1], True).ws_ptr       # (also keeps the binding hot in the LRU)
-        key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr(), ws_ptr)
         if lengths is not None and all(int(v) == x.shape[1] for v in (lengths.tolist() if torch.is_tensor(lengths) else lengths)):
             lengths = None                                      # nothing padded: dense (CUDA-graph) path
         self._lengths = lengths
-        use_graph = self.use_cuda_graph and not self.profiling and lengths is None
+        if lengths is not None:
+            # packed step: launched eagerly on a capacity-bucketed binding (engine.ragged_capacity); graphs are left alone
+            self._run_step(x, labels)
+            self.step_count += 1
+            m._fwd_token += 1
+            m._manual_version += 1
+            loss, counts = self.out_loss.clone(), self.out_counts.clone()
+            return dict(loss=loss[0], correct=counts[0], valid=counts[1])
+        ws_ptr = self.engine.binding(x.shape[0], x.shape[1], True).ws_ptr       # (also keeps the binding hot in the LRU)
+        key = (tuple(x.shape), float(m.dropout.p) if m.dropout.training else 0.0, self.flat["params"].data_ptr(), ws_ptr)
+        use_graph = self.use_cuda_graph and not self.profiling
         if key != self._graph_key:
             self._graph, self._graph_key, self._eager_steps_at_key = None, key, 0
         if use_graph and self._graph is None and self._eager_steps_at_key >= 2:

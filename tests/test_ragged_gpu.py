@@ -193,3 +193,22 @@ def test_ragged_and_dense_steps_interleave():
         out = tr.step(x, y, lengths=[512, 100] if i % 2 else None)
         losses.append(out["loss"].item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_ragged_batches_of_changing_padded_length_share_one_binding():
+    """every DataLoader batch is padded to ITS longest cloud (pcs.py:50): ragged calls bind a capacity bucket, not the
+    exact padded length, and still reproduce the padded batch (whose BN / max-pool semantics depend on that length)"""
+    m = _model(3, 15)
+    for N, lengths in [(1000, [1000, 400]), (1500, [7, 1500]), (3000, [2999, 3000]), (1001, [1001, 1])]:
+        x, _ = _padded_batch(2, N, lengths, 3, N)
+        with torch.no_grad():
+            assert torch.equal(m(x), m(x, lengths=lengths))
+    eval_keys = [k for k in m._engine.bindings if not k[2]]
+    assert sum(1 for k in eval_keys if k[1] == 4096) == 1           # one capacity-bucketed binding served all four
+    # training: two padded lengths through one binding, each equal to its padded step
+    for N, lengths in [(900, [900, 333, 10]), (1200, [5, 1200, 600])]:
+        _, trd, ld, gd, _ = _one_step(3, 3, N, lengths, False)
+        _, trr, lr_, gr, _ = _one_step(3, 3, N, lengths, True)
+        assert abs(ld[0] - lr_[0]) < 2e-4 * max(1.0, abs(ld[0]))
+        cos = torch.nn.functional.cosine_similarity(gd.double(), gr.double(), dim=0).item()
+        assert cos > 0.999, cos
