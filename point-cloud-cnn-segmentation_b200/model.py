@@ -166,6 +166,10 @@ class PointNetSegmentation(nn.Module):
 
     # ------------------------------------------------------------------ kernels
     def _check_input(self, x):
+        if getattr(self, "_is_replica", False):
+            raise RuntimeError("pcseg_b200.PointNetSegmentation cannot run as an nn.DataParallel replica (pcs.py:209-211): use one "
+                               "process per GPU with pcseg_b200.FusedTrainer (INTEGRATION.md, multi-GPU), which reproduces the "
+                               "DataParallel result")
         batch_size, max_points, _ = x.shape      # same unpack (and ValueError) as pcs.py:100
         if x.shape[2] != 4:
             raise RuntimeError(f"expected input with 4 channels (x, y, z, e), got {x.shape[2]}")

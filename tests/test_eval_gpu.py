@@ -92,6 +92,9 @@ def test_forward_rejects_bad_input():
         m(torch.rand(10, 4, device="cuda"))            # same tuple-unpack error as pcs.py:100
     with pytest.raises(RuntimeError):
         m(torch.rand(1, 10, 4))                         # CPU tensor: no fallback
+    replica = torch.nn.parallel.replicate(m, [0])[0]    # what nn.DataParallel (pcs.py:211) would run
+    with pytest.raises(RuntimeError, match="DataParallel"):
+        replica(torch.rand(1, 10, 4, device="cuda"))
 
 
 def test_evaluate_metrics_match_torch_and_sklearn():
