@@ -250,14 +250,23 @@ def run_ours(args, B, N, mode):
                 return model.predict_point_sharded(x_dev)[0] if sharded else model(x_dev)
 
         out_host = torch.empty((B, N), dtype=torch.int64).pin_memory()
+        pstream = None if sharded else pcseg_b200.PredictStream(model)
+        pending = [None]
 
         def step_e2e():
-            xd = x_host.to(dev, non_blocking=True)
-            with torch.no_grad():
-                _, labels = model.predict_point_sharded(xd) if sharded else model.predict(xd)
-            out_host.copy_(labels, non_blocking=True)                   # per-point predicted labels back to the host (pcs.py:452-454)
-            torch.cuda.synchronize()
-            return out_host
+            # every step: this batch's points from pinned host memory, per-point predicted labels back on the host
+            # (pcs.py:446-454).  The copies are double buffered on side streams (PredictStream): a step submits batch i
+            # and consumes the labels of batch i-1.
+            if sharded:
+                xd = x_host.to(dev, non_blocking=True)
+                with torch.no_grad():
+                    _, labels = model.predict_point_sharded(xd)
+                out_host.copy_(labels, non_blocking=True)
+                torch.cuda.synchronize()
+                return out_host
+            t = pstream.submit(x_host)
+            prev, pending[0] = pending[0], t
+            return pstream.result(prev) if prev is not None else None
         h2d = x_host.numel() * 4
         d2h = B * N * 8
         flop_per_pt = FWD_FLOP_PER_PT
@@ -318,14 +327,16 @@ def run_ours(args, B, N, mode):
         trainer.profiling = False
 
     # end-to-end: pinned host inputs copied every step, result read back every step
-    for _ in range(2):
+    for _ in range(3):
         step_e2e()
     barrier()
+    # (host-clocked: short steps are repeated at least 50 times so that the region is not a few milliseconds long)
+    e2e_steps = steps if ms_total / steps >= 5.0 else max(steps, 50)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(e2e_steps):
         step_e2e()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = (time.perf_counter() - t0) * steps / e2e_steps          # normalised to K steps
     clocks = sampler.stop(mark0, mark1)             # samples taken during the device-timed region (neighbours if it was < 100 ms)
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -389,7 +400,7 @@ def run_ours(args, B, N, mode):
                    "parallelism": (f"points of each cloud sharded over {world} ranks, MAX all-reduce of the pooled feature" if sharded
                                    else (f"dp{world}" if world > 1 else "single"))},
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms_total / steps},
+                "ms_per_step": e2e_ms_total / steps, "timed_steps": e2e_steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "torch_eager_same_gpu": torch_eager,
         "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
         "gemm_kernels": kernels,

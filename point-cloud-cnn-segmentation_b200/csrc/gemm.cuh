@@ -428,15 +428,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
             } else {
-                const bool ragged = p.tile_cloud != nullptr;
-                const int tile_cl = ragged ? __ldg(p.tile_cloud + (m0 >> 7)) : (p.pts_per_cloud > 0 ? m0 / p.pts_per_cloud : 0);
-                const int cloud = ragged ? tile_cl : ((p.pts_per_cloud > 0 && valid) ? grow / p.pts_per_cloud : 0);
-                const float* cb_row = (p.cloud_bias != nullptr) ? p.cloud_bias + static_cast<size_t>(cloud) * p.N : nullptr;
+                // cloud of this tile: dense batches divide by the rows per cloud, packed ragged batches look it up (tiles
+                // never straddle clouds there); everything per tile, nothing of it inside the column loop below
+                int tile_cl = 0, row0_in_cloud = 0;
                 bool uniform_cloud = true;
-                if constexpr (EPI == EPI_COLMAX || EPI == EPI_STATS_POOL) {
-                    const int last = min(m0 + GEMM_BM, p.M) - 1;
-                    uniform_cloud = ragged || (m0 / p.pts_per_cloud) == (last / p.pts_per_cloud);
+                if (p.tile_cloud != nullptr) {
+                    tile_cl = __ldg(p.tile_cloud + (m0 >> 7));
+                    if constexpr (EPI == EPI_STATS_POOL) row0_in_cloud = m0 - __ldg(p.cloud_off + tile_cl);
+                } else if (p.pts_per_cloud > 0) {
+                    tile_cl = m0 / p.pts_per_cloud;
+                    row0_in_cloud = m0 - tile_cl * p.pts_per_cloud;
+                    uniform_cloud = row0_in_cloud + (min(m0 + GEMM_BM, p.M) - m0) <= p.pts_per_cloud;
                 }
+                const int cloud = uniform_cloud ? tile_cl : (valid ? grow / p.pts_per_cloud : 0);
+                const float* cb_row = (p.cloud_bias != nullptr) ? p.cloud_bias + static_cast<size_t>(cloud) * p.N : nullptr;
                 const bool pool_uniform = uniform_cloud;
 #pragma unroll 1
                 for (int sub = 0; sub < SUBS; ++sub, ++sub_it) {
@@ -560,8 +565,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             float bestv[8];
                             const float (&sg)[8] = p2a;
                             int besti[8];
-                            const int row0_in_cloud = (EPI != EPI_STATS_POOL) ? 0                            // uniform tiles only
-                                                      : (ragged ? m0 - __ldg(p.cloud_off + tile_cl) : m0 % p.pts_per_cloud);
                             if constexpr (EPI == EPI_STATS_POOL) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {

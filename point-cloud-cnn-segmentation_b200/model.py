@@ -258,6 +258,58 @@ class PointNetSegmentation(nn.Module):
         return dict(logits=logits, loss=f64[0] / f64[1], correct=i64[2], valid=i64[3], confusion=conf)
 
 
+class PredictStream:
+    """Host-fed inference with the copies off the critical path (replaces the synchronous `.to(device)` ... `.cpu()` round
+    trip of pcs.py:446-454): the host->device copy of batch i+1 and the device->host copy of batch i-1's labels run on
+    side streams while batch i computes.  Double buffered: at most two batches are in flight, and `result(ticket)` of a
+    batch must be consumed before the second `submit` after it.
+
+        ps = PredictStream(model)
+        t = ps.submit(points_pinned)                 # (B, N, 4) fp32 host tensor, ideally pinned
+        labels = ps.result(t)                        # (B, N) int64 pinned host tensor (argmax labels, pcs.py:452)
+    """
+
+    def __init__(self, model):
+        if model.training:
+            raise RuntimeError("PredictStream is an eval-mode helper; use model.eval() first")
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.h2d = torch.cuda.Stream(device=self.device)
+        self.d2h = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.next = 0
+
+    @torch.no_grad()
+    def submit(self, points_host, lengths=None):
+        slot, self.next = self.next, self.next ^ 1
+        s = self.slots[slot]
+        if s is None or s["x"].shape != points_host.shape:
+            B, N, _ = points_host.shape
+            s = dict(x=torch.empty(points_host.shape, dtype=torch.float32, device=self.device),
+                     labels_host=torch.empty((B, N), dtype=torch.int64).pin_memory(),
+                     h2d_done=torch.cuda.Event(), compute_done=torch.cuda.Event(), d2h_done=torch.cuda.Event(), keep=None)
+            self.slots[slot] = s
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_event(s["compute_done"])           # the batch that last used this input buffer has been computed
+            s["x"].copy_(points_host, non_blocking=True)
+            s["h2d_done"].record(self.h2d)
+        cur.wait_event(s["h2d_done"])
+        logits, labels = self.model.predict(s["x"], lengths=lengths)
+        s["compute_done"].record(cur)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(s["compute_done"])
+            s["labels_host"].copy_(labels, non_blocking=True)
+            s["d2h_done"].record(self.d2h)
+        s["keep"] = (logits, labels)                         # alive until the copy has been consumed
+        return slot
+
+    def result(self, ticket, want_logits=False):
+        s = self.slots[ticket]
+        s["d2h_done"].synchronize()
+        return (s["labels_host"], s["keep"][0]) if want_logits else s["labels_host"]
+
+
 def lengths_from_masks(masks):
     """Real points per cloud from the `masks` tensor of the reference's collate_fn (pcs.py:58-63: True on the first
     len(points) rows of every cloud)."""

@@ -291,3 +291,33 @@ def test_point_sharded_inference_is_bit_identical():
     # without the exchange a slice only sees its own points
     alone = m.predict_point_sharded(shards[0], reduce_max=lambda p: None)[0]
     assert torch.equal(alone, m(shards[0]))
+
+
+def test_predict_stream_matches_predict():
+    """PredictStream (copies on side streams, two batches in flight) returns what predict() returns, batch after batch"""
+    import pcseg_b200
+    m = _model(5, 32)
+    ps = pcseg_b200.PredictStream(m)
+    g = torch.Generator().manual_seed(0)
+    batches = [torch.rand(2, 1500, 4, generator=g).pin_memory() for _ in range(5)]
+    expect = []
+    with torch.no_grad():
+        for xb in batches:
+            expect.append(m.predict(xb.cuda())[1].cpu())
+    prev, got = None, []
+    for xb in batches:
+        t = ps.submit(xb)
+        if prev is not None:
+            got.append(ps.result(prev).clone())
+        prev = t
+    labels, logits = ps.result(prev, want_logits=True)
+    got.append(labels.clone())
+    assert logits.shape == (2, 1500, 5)
+    for a, b in zip(expect, got):
+        assert torch.equal(a, b)
+    # ragged batch through the same stream
+    x = batches[0].clone()
+    x[1, 400:] = 0
+    t = ps.submit(x, lengths=[1500, 400])
+    with torch.no_grad():
+        assert torch.equal(ps.result(t), m.predict(x.cuda())[1].cpu())
