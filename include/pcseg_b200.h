@@ -113,7 +113,8 @@ int pcseg_forward_train(pcseg_ctx* ctx, const float* x, const float* params, flo
  * noise) when dropout is off.  With dropout the pad rows of one cloud share ONE mask instead of N - lengths[b]
  * independent ones: the BN batch sums of seg_conv2/3 are then an unbiased but noisier estimate of the padded ones.
  * labels is the padded (B, N) tensor (entries of pad rows are ignored and treated as -1).  pcseg_backward after this
- * call runs on the packed rows as well; it requires the fused loss gradient (dlogits == NULL). */
+ * call runs on the packed rows as well; a caller-supplied dlogits is the gradient of the PADDED logits (B, nmax, C): the
+ * representative pad row receives the sum over its cloud's pad rows. */
 int pcseg_forward_train_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, int nmax, const float* params, float* bn_buffers,
                                unsigned long long seed, float dropout_p, float* logits, const long long* labels,
                                const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream);

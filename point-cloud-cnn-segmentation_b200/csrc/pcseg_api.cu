@@ -495,7 +495,8 @@ extern "C" int pcseg_destroy(pcseg_ctx* c) {
 extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_bytes, int train) {
     if (!c) return fail("pcseg_bind: null ctx");
     if (B <= 0 || N <= 0) return fail("pcseg_bind: bad shape B=%d N=%d", B, N);
-    if (static_cast<long long>(B) * N >= (1LL << 31) - 256) return fail("pcseg_bind: B*N too large for 32-bit row indices");
+    if (static_cast<long long>(B) * ((static_cast<long long>(N) + 127) / 128 * 128) >= (1LL << 31) - 256)
+        return fail("pcseg_bind: B*N too large for 32-bit row indices");
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) return fail("pcseg_bind: workspace must be non-null and 1024-byte aligned");
     size_t need = 0;
     c->B = B; c->N = N; c->P = static_cast<long long>(B) * N;
@@ -1055,10 +1056,21 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     const int N = c->N;                   // rows per cloud (dense launches only: the ragged ones walk planned strips)
     const int* rag_strips = rag ? c->meta + 2 * B + 1 + c->rag_rows / 128 : nullptr;
     if (rag) {
-        if (dlogits) return fail("pcseg_backward: a ragged forward needs the fused loss gradient (logits + labels), not dlogits");
         x = c->xpack;
-        logits = c->lpack;
-        labels = c->labpack;
+        if (dlogits) {
+            // caller's gradient of the padded logits -> packed rows (the packed logits are not needed in this mode)
+            if (phase != 2) {
+                const int copy_blocks = static_cast<int>((c->rag_rows + 255) / 256);
+                pdl_launch(k_pack_dlogits, copy_blocks + B, 256, 0, s, dlogits, rag_meta(c), c->C, c->lpack);
+                LAUNCH_OK("k_pack_dlogits");
+            }
+            dlogits = c->lpack;
+            logits = nullptr;
+            labels = nullptr;
+        } else {
+            logits = c->lpack;
+            labels = c->labpack;
+        }
     }
 
     if (phase != 2) {

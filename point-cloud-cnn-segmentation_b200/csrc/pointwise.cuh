@@ -974,6 +974,45 @@ __global__ void __launch_bounds__(256) k_unpack_logits(const float* __restrict__
     }
 }
 
+// caller-supplied dlogits of the padded batch (B, Nmax, C) -> packed rows: real rows are copied, the representative pad
+// row receives the SUM over its cloud's pad rows (gradients are carried pre-multiplied), filler rows zero.
+// grid (ceil(rows / 256)) + B extra blocks: block (gridDim.x - B + b) reduces the pad rows of cloud b.
+__global__ void __launch_bounds__(256) k_pack_dlogits(const float* __restrict__ dl, const RaggedMeta m, int C, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int copy_blocks = gridDim.x - m.B;
+    if (static_cast<int>(blockIdx.x) < copy_blocks) {
+        const int r = blockIdx.x * 256 + threadIdx.x;
+        if (r >= m.rows) return;
+        const int c = m.tile_cloud[r >> 7];
+        const int i = r - m.off[c];
+        const int L = m.len[c];
+        if (i < L) {
+            const float* src = dl + (static_cast<size_t>(c) * m.Nmax + i) * C;
+            for (int k = 0; k < C; ++k) out[static_cast<size_t>(r) * C + k] = src[k];
+        } else if (!(i == L && L < m.Nmax)) {
+            for (int k = 0; k < C; ++k) out[static_cast<size_t>(r) * C + k] = 0.f;
+        }
+        return;
+    }
+    const int b = blockIdx.x - copy_blocks;
+    const int L = m.len[b];
+    if (L >= m.Nmax) return;
+    __shared__ float red[256];
+    for (int k = 0; k < C; ++k) {
+        float s = 0.f;
+        for (int i = L + threadIdx.x; i < m.Nmax; i += 256) s += dl[(static_cast<size_t>(b) * m.Nmax + i) * C + k];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if (static_cast<int>(threadIdx.x) < w) red[threadIdx.x] += red[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[static_cast<size_t>(m.off[b] + L) * C + k] = red[0];
+        __syncthreads();
+    }
+}
+
 // BN batch sums of a packed layer: add (multiplicity - 1) * {y, y^2} of every non-real row (at most 128 per cloud).
 // grid (C/32, B), block 256 = 32 columns x 8 row slots.
 __global__ void __launch_bounds__(256) k_stats_fix(const __nv_bfloat16* __restrict__ y, int ld, int C, const RaggedMeta m,

@@ -17,8 +17,8 @@ class _SegTrainFn(torch.autograd.Function):
     with the caller's dlogits (whatever loss the user put on top, e.g. pcs.py:216,251)."""
 
     @staticmethod
-    def forward(ctx, module, x, *params):
-        logits = module._run_train_forward(x)
+    def forward(ctx, module, x, lengths, *params):
+        logits = module._run_train_forward(x, lengths=lengths)
         ctx.module = module
         ctx.save_for_backward(x)
         ctx.token = module._fwd_token
@@ -32,7 +32,7 @@ class _SegTrainFn(torch.autograd.Function):
             raise RuntimeError("pcseg_b200: activations of this forward were overwritten by a later training forward; "
                                "call backward() before the next forward (as the reference loop does, pcs.py:244-254)")
         grads = module._run_backward(x, dlogits.contiguous().float())
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
 
 
 class PointNetSegmentation(nn.Module):
@@ -201,11 +201,8 @@ class PointNetSegmentation(nn.Module):
         x = self._check_input(x)
         if self.training:
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                if lengths is not None:
-                    raise NotImplementedError("ragged training runs through FusedTrainer.step(points, labels, lengths=...): "
-                                              "the packed backward needs the fused loss gradient")
                 self._ensure_flat(x.device)
-                return _SegTrainFn.apply(self, x, *self._param_list())
+                return _SegTrainFn.apply(self, x, lengths, *self._param_list())
             return self._run_train_forward(x, lengths=lengths)
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)

@@ -103,9 +103,27 @@ def test_ragged_argument_checks():
         m(x, lengths=[64])
     with pytest.raises(ValueError):
         m(x, lengths=[64, 65])
-    m.train()
-    with pytest.raises(NotImplementedError):
-        m(x, lengths=[64, 3])                                   # autograd path: ragged training goes through FusedTrainer
+
+
+def test_ragged_autograd_path_equals_the_padded_one():
+    """the reference loop itself (criterion on the module's output, loss.backward(), pcs.py:244-254) with lengths=: the
+    caller's dlogits of the padded logits are packed (pad rows summed into the representative row)"""
+    C, B, N, lengths = 3, 3, 700, [700, 250, 9]
+    x, y = _padded_batch(B, N, lengths, C, 17)
+    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 2.0, 0.5], device="cuda"), ignore_index=-1)
+    res = []
+    for ls in (None, lengths):
+        m = _model(C, 23, train=True, p_drop=0.0)
+        out = m(x, lengths=ls)
+        loss = crit(out.contiguous().view(-1, C), y.view(-1))
+        # a loss term that also touches the pad rows' logits (their gradients must be summed into the representative row)
+        loss = loss + 1e-3 * out.pow(2).mean()
+        loss.backward()
+        res.append((loss.item(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).double()))
+    assert abs(res[0][0] - res[1][0]) < 2e-4 * max(1.0, abs(res[0][0]))
+    cos = torch.nn.functional.cosine_similarity(res[0][1], res[1][1], dim=0).item()
+    assert cos > 0.999, cos
+    assert abs(res[0][1].norm().item() - res[1][1].norm().item()) < 2e-2 * res[0][1].norm().item()
 
 
 def _one_step(C, B, N, lengths, use_lengths, p_drop=0.0, steps=1, seed=21):
