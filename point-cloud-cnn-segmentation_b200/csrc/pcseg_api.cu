@@ -1090,7 +1090,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         b.C = cv[i].cout;
         return b;
     };
-    auto coef = [&](int) -> int { return 0; };     // BN-backward coefficients are evaluated inside k_bn_bwd_apply
+    // (BN-backward coefficients are evaluated inside k_bn_bwd_apply: no launch of their own)
     auto apply = [&](int i, bf16* dy_out, int ld_dy, float* dcb) -> int {
         const int co = cv[i].cout;
         const int rps = apply_rows_per_strip(N, B, co);
@@ -1137,17 +1137,14 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         LAUNCH_OK("k_head_bwd");
     }
     // seg_conv3
-    TRY(coef(8));
     TRY(apply(8, c->dy[8], 128, nullptr));
     TRY(wgrad(8, grads + L.off[16], 256));
     TRY(dgrad(8, c->seed + 2, c->thr16, c->keep_scale));
     // seg_conv2
-    TRY(coef(7));
     TRY(apply(7, c->dy[7], 256, nullptr));
     TRY(wgrad(7, grads + L.off[14], 512));
     TRY(dgrad(7, c->seed + 1, c->thr16, c->keep_scale));
     // seg_conv1: point-feature columns by GEMM, global columns per cloud
-    TRY(coef(6));
     TRY(apply(6, c->dycat + 64, 576, c->dcb));
     TRY(wgrad(6, grads + L.off[12], 1088));
     {
@@ -1160,7 +1157,6 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         LAUNCH_OK("k_cloud_bwd_dw");
     }
     // global_feat (sparse max-pool gradient folded into the BN backward)
-    TRY(coef(5));
     {
         const int rps = apply_rows_per_strip(N, B, 1024);
         dim3 grid((N + rps - 1) / rps, B);
@@ -1177,27 +1173,22 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     }   // phase != 2
     if (phase == 1) return 0;
     // conv5
-    TRY(coef(4));
     TRY(apply(4, c->dy[4], 1024, nullptr));
     TRY(wgrad(4, grads + L.off[8], 128));
     TRY(dgrad(4, 0, 0, 1.f));
     // conv4
-    TRY(coef(3));
     TRY(apply(3, c->dy[3], 128, nullptr));
     TRY(wgrad(3, grads + L.off[6], 64));
     TRY(dgrad(3, 0, 0, 1.f));
     // conv3 (its dy lives in the left 64 columns of dycat), then the skip join into conv2's output
-    TRY(coef(2));
     TRY(apply(2, c->dycat, 576, nullptr));
     TRY(wgrad(2, grads + L.off[4], 64));
     TRY(dgrad(2, 0, 0, 1.f));
     // conv2
-    TRY(coef(1));
     TRY(apply(1, c->dy[1], 64, nullptr));
     TRY(wgrad(1, grads + L.off[2], 64));
     TRY(dgrad(1, 0, 0, 1.f));
     // conv1 (no data gradient: the input does not require grad)
-    TRY(coef(0));
     TRY(apply(0, c->dy[0], 64, nullptr));
     {
         int grid = static_cast<int>((P + 31) / 32);
