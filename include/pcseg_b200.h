@@ -28,7 +28,7 @@ extern "C" {
 
 typedef struct pcseg_ctx pcseg_ctx;
 
-#define PCSEG_MAX_CLASSES 8
+#define PCSEG_MAX_CLASSES 32          /* 1..8 classes run the fused head kernels, 9..32 the wide ones */
 #define PCSEG_NUM_PARAM_TENSORS 38   /* 10 conv weight/bias pairs + 9 BN weight/bias pairs */
 #define PCSEG_NUM_BN 9
 

@@ -15,7 +15,10 @@
 
 using namespace pcseg;
 
-static_assert(PCSEG_MAX_CLASSES == MAX_CLASSES, "header / kernel class cap mismatch");
+// MAX_CLASSES (8, gemm.cuh) is the cap of the fused head kernels (head_chain_kernel, EPI_LOGITS, k_head_bwd); models with
+// 9 .. PCSEG_MAX_CLASSES classes run seg_conv3 / seg_conv4 through the wide kernels (k_head_fwd<16|32>, k_head_bwd_wide_*).
+constexpr int API_MAX_CLASSES = PCSEG_MAX_CLASSES;
+static_assert(API_MAX_CLASSES == 32 && MAX_CLASSES == 8, "class caps: fused kernels 8, wide kernels 32");
 static_assert(sizeof(pcseg_ce_accum) == sizeof(CeAccum), "CE accumulator layout mismatch");
 static_assert(sizeof(pcseg_step_state) == sizeof(StepState) && sizeof(StepState) == 32, "step state layout mismatch");
 
@@ -342,6 +345,7 @@ struct pcseg_ctx {
     int* meta = nullptr;          // len[B] | off[B+1] | tile_cloud[rows/128] | strips[rag_strips][4]
     float* xpack = nullptr;       // [cap_rows][4]
     float* lpack = nullptr;       // [cap_rows][C]
+    float* dlbuf = nullptr;       // [cap_rows][C] loss gradient wrt the logits (train, more than 8 classes only)
     long long* labpack = nullptr; // [cap_rows]      (train)
     float* rowmult = nullptr;     // [cap_rows]      (train)
     std::vector<int> meta_host;
@@ -400,8 +404,8 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
     const ConvDef* cv = c->L.conv;
     c->zeros1024 = k.take<float>(1024);
     c->w1 = k.take<float>(256);
-    c->w4 = k.take<float>(MAX_CLASSES * 128);
-    c->b4 = k.take<float>(MAX_CLASSES);
+    c->w4 = k.take<float>(API_MAX_CLASSES * 128);
+    c->b4 = k.take<float>(API_MAX_CLASSES);
     c->wg = k.take<float>(512 * 1024);
     for (int i = 0; i < NUM_BN; ++i) {
         c->alpha[i] = k.take<float>(cv[i].cout);
@@ -436,11 +440,12 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
     if (train) {
         c->labpack = k.take<long long>(P);
         c->rowmult = k.take<float>(P);
+        c->dlbuf = (c->C > MAX_CLASSES) ? k.take<float>(P * c->C) : nullptr;
     }
     if (!train) {
         // a1..a5, a_s1, a_s2 (global_feat output is reduced in-kernel; seg_conv3 output feeds the fused logits epilogue)
         for (int i = 0; i < NUM_BN; ++i) {
-            if (i == 5 || i == 8) continue;
+            if (i == 5 || (i == 8 && c->C <= MAX_CLASSES)) continue;      // (wide head: seg_conv3's output is materialised)
             c->act[i] = k.take<bf16>(P * cv[i].cout);
         }
     } else {
@@ -469,7 +474,7 @@ extern "C" long long pcseg_bn_buffer_offset(int bn, int which) {
     return (bn < 0 || bn >= NUM_BN || which < 0 || which > 1) ? -1 : make_layout(3).bn_off[bn][which];
 }
 extern "C" long long pcseg_workspace_bytes(int B, int N, int C, int train) {
-    if (B <= 0 || N <= 0 || C < 1 || C > MAX_CLASSES) return -1;
+    if (B <= 0 || N <= 0 || C < 1 || C > API_MAX_CLASSES) return -1;
     pcseg_ctx tmp;
     tmp.C = C;
     tmp.L = make_layout(C);
@@ -480,7 +485,7 @@ extern "C" long long pcseg_workspace_bytes(int B, int N, int C, int train) {
 
 extern "C" int pcseg_create(pcseg_ctx** out, int num_classes) {
     if (!out) return fail("pcseg_create: null out pointer");
-    if (num_classes < 1 || num_classes > MAX_CLASSES) return fail("num_classes=%d unsupported (1..%d)", num_classes, MAX_CLASSES);
+    if (num_classes < 1 || num_classes > API_MAX_CLASSES) return fail("num_classes=%d unsupported (1..%d)", num_classes, API_MAX_CLASSES);
     pcseg_ctx* c = new pcseg_ctx();
     c->C = num_classes;
     c->L = make_layout(num_classes);
@@ -534,11 +539,16 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         O.ev[6].p.tile_cloud = tile_cloud;
         TRY(setup_gemm_kmajor(&O.ev[7], EPI_BIAS_RELU, c->act[6], 512, c->wk[7], 512, P, 256, 512, c->act[7], 256, nullptr, 0));
         O.ev[7].p.bias = c->delta[7];
-        TRY(setup_gemm_kmajor(&O.ev[8], EPI_LOGITS, c->act[7], 256, c->wk[8], 256, P, 128, 256, nullptr, 0, nullptr, 0));
-        O.ev[8].p.bias = c->delta[8];
-        O.ev[8].p.w4 = c->w4;
-        O.ev[8].p.b4 = c->b4;
-        O.ev[8].p.num_classes = c->C;
+        if (c->C <= MAX_CLASSES) {
+            TRY(setup_gemm_kmajor(&O.ev[8], EPI_LOGITS, c->act[7], 256, c->wk[8], 256, P, 128, 256, nullptr, 0, nullptr, 0));
+            O.ev[8].p.bias = c->delta[8];
+            O.ev[8].p.w4 = c->w4;
+            O.ev[8].p.b4 = c->b4;
+            O.ev[8].p.num_classes = c->C;
+        } else {        // more than 8 classes: seg_conv3 as a plain GEMM, seg_conv4 by k_head_fwd<16|32, false>
+            TRY(setup_gemm_kmajor(&O.ev[8], EPI_BIAS_RELU, c->act[7], 256, c->wk[8], 256, P, 128, 256, c->act[8], 128, nullptr, 0));
+            O.ev[8].p.bias = c->delta[8];
+        }
         // fused head: seg_conv1..4 in one kernel (PCSEG_EVAL_CHAIN=0 selects the layer-by-layer kernels above)
         TRY(make_tmap(&O.hcA1, c->act[1], 64, P, 64, 64, 128));
         if (!rag) TRY(make_tmap(&c->hcB1, c->wk[6], 64, 512, 64, 64, 256));
@@ -557,7 +567,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         O.hcp.num_classes = c->C;
         {
             const char* e = getenv("PCSEG_EVAL_CHAIN");
-            c->use_head_chain = !(e && e[0] == '0');
+            c->use_head_chain = !(e && e[0] == '0') && c->C <= MAX_CLASSES;
         }
     } else {
         // ---- forward: y_i = a_{i-1} W_i^T, statistics in the epilogue
@@ -788,12 +798,28 @@ static int forward_eval_head(pcseg_ctx* c, pcseg_ctx::OpSet& O, float* logits, c
         const int grid = hp.num_tiles < num_sms() ? hp.num_tiles : num_sms();
         pdl_launch(head_chain_kernel, grid, HC_THREADS, HC_SMEM_BYTES, s, O.hcA1, c->hcB1, c->hcB2, c->hcB3, hp);
         LAUNCH_OK("head_chain_kernel");
-    } else {
+    } else if (c->C <= MAX_CLASSES) {
         TRY(launch_gemm(O.ev[6], s));
         TRY(launch_gemm(O.ev[7], s));
         GemmOp head = O.ev[8];
         head.p.logits = logits;
         TRY(launch_gemm(head, s));
+    } else {
+        TRY(launch_gemm(O.ev[6], s));
+        TRY(launch_gemm(O.ev[7], s));
+        TRY(launch_gemm(O.ev[8], s));
+        const long rows = O.ev[8].p.M;
+        int grid = static_cast<int>((rows + 255) / 256);
+        if (grid > num_sms() * 4) grid = num_sms() * 4;
+        BnFinalizeArgs none;
+        memset(&none, 0, sizeof(none));
+        if (c->C <= 16)
+            pdl_launch(k_head_fwd<16, false>, grid, 256, 0, s, static_cast<const bf16*>(c->act[8]), rows, none, static_cast<const float*>(c->w4),
+                       static_cast<const float*>(c->b4), c->C, logits, nullptr, nullptr, nullptr);
+        else
+            pdl_launch(k_head_fwd<32, false>, grid, 256, 0, s, static_cast<const bf16*>(c->act[8]), rows, none, static_cast<const float*>(c->w4),
+                       static_cast<const float*>(c->b4), c->C, logits, nullptr, nullptr, nullptr);
+        LAUNCH_OK("k_head_fwd<wide>");
     }
     return 0;
 }
@@ -983,11 +1009,11 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         if (grid > num_sms() * 4) grid = num_sms() * 4;
 #define HEAD_FWD(NC_)                                                                                                          \
     case NC_:                                                                                                                  \
-        pdl_launch(k_head_fwd<NC_>, grid, 256, 0, s, c->y[8], P, fin_args(8), params + L.off[18], params + L.off[19], logits, labels, \
-                   class_w, reinterpret_cast<CeAccum*>(ce));                                                                  \
+        pdl_launch(k_head_fwd<NC_, true>, grid, 256, 0, s, c->y[8], P, fin_args(8), params + L.off[18], params + L.off[19], c->C, logits, \
+                   labels, class_w, reinterpret_cast<CeAccum*>(ce));                                                          \
         break;
-        switch (c->C) {
-            HEAD_FWD(1) HEAD_FWD(2) HEAD_FWD(3) HEAD_FWD(4) HEAD_FWD(5) HEAD_FWD(6) HEAD_FWD(7) HEAD_FWD(8)
+        switch (c->C <= MAX_CLASSES ? c->C : (c->C <= 16 ? 16 : 32)) {       // class slots of the kernel
+            HEAD_FWD(1) HEAD_FWD(2) HEAD_FWD(3) HEAD_FWD(4) HEAD_FWD(5) HEAD_FWD(6) HEAD_FWD(7) HEAD_FWD(8) HEAD_FWD(16) HEAD_FWD(32)
             default: return fail("pcseg_forward_train: unsupported num_classes %d", c->C);
         }
 #undef HEAD_FWD
@@ -1121,7 +1147,22 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     };
 
     if (phase != 2) {
-    {   // seg_conv4 + loss gradient
+    if (c->C > MAX_CLASSES) {   // seg_conv4 + loss gradient, 9..32 classes: per-point kernel + column reductions
+        int grid = static_cast<int>((P + 255) / 256);
+        if (grid > num_sms() * 4) grid = num_sms() * 4;
+        const float* dl_src = dlogits ? dlogits : c->dlbuf;
+        long long rgrid = (P + 63) / 64;
+        if (rgrid > 2LL * num_sms()) rgrid = 2LL * num_sms();
+#define HEAD_BWD_WIDE(NC_)                                                                                                   \
+        pdl_launch(k_head_bwd_wide_points<NC_>, grid, 256, 0, s, c->y[8], P, c->bnp[8], params + L.off[18], c->C, dlogits, logits, labels,  \
+                   class_w, wsum_total, c->dlbuf, c->dz[8]);                                                                 \
+        LAUNCH_OK("k_head_bwd_wide_points");                                                                                 \
+        pdl_launch(k_head_bwd_wide_reduce<NC_>, static_cast<int>(rgrid), 256, 0, s, c->y[8], c->dz[8], P, c->bnp[8], c->C, dl_src,           \
+                   grads + L.off[18], grads + L.off[19], c->stats_b + c->stat_off[8]);                                      \
+        LAUNCH_OK("k_head_bwd_wide_reduce");
+        if (c->C <= 16) { HEAD_BWD_WIDE(16) } else { HEAD_BWD_WIDE(32) }
+#undef HEAD_BWD_WIDE
+    } else {   // seg_conv4 + loss gradient
         int grid = static_cast<int>((P + 31) / 32);
         if (grid > num_sms() * 2) grid = num_sms() * 2;
 #define HEAD_BWD(NC_)                                                                                                         \
@@ -1214,12 +1255,16 @@ extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, floa
 
 extern "C" int pcseg_eval_metrics(const float* logits, const long long* labels, long long P, int C, const float* class_w,
                                   pcseg_ce_accum* ce, unsigned long long* confusion, long long* pred_out, void* stream) {
-    if (!logits || P <= 0 || C < 1 || C > MAX_CLASSES) return fail("pcseg_eval_metrics: bad arguments");
+    if (!logits || P <= 0 || C < 1 || C > API_MAX_CLASSES) return fail("pcseg_eval_metrics: bad arguments");
     if (!labels && !pred_out) return fail("pcseg_eval_metrics: nothing to compute (no labels, no pred_out)");
     int grid = static_cast<int>((P + 255) / 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
-    pdl_launch(k_eval_metrics<MAX_CLASSES>, grid, 256, 0, static_cast<cudaStream_t>(stream), logits, labels, P, C, class_w,
-                                                                                      reinterpret_cast<CeAccum*>(ce), confusion, pred_out);
+    if (C <= MAX_CLASSES)
+        pdl_launch(k_eval_metrics<MAX_CLASSES>, grid, 256, 0, static_cast<cudaStream_t>(stream), logits, labels, P, C, class_w,
+                   reinterpret_cast<CeAccum*>(ce), confusion, pred_out);
+    else
+        pdl_launch(k_eval_metrics<API_MAX_CLASSES>, grid, 256, 0, static_cast<cudaStream_t>(stream), logits, labels, P, C, class_w,
+                   reinterpret_cast<CeAccum*>(ce), confusion, pred_out);
     LAUNCH_OK("k_eval_metrics");
     return 0;
 }

@@ -320,34 +320,39 @@ struct CeAccum {
 // warp touches 32 different rows per instruction, but consecutive instructions hit the same lines in L1, so DRAM traffic
 // stays at the algorithmic 256 B/point), BN + ReLU + the 128 x NC mat-vec run on private registers with no shuffles,
 // and the weighted-CE terms are accumulated per thread and reduced once per block.
-template <int NC>
+// NC <= 8: exactly NC classes (everything unrolled on compile-time bounds).  NC = 16 / 32: the wide variants for 9..32
+// classes, Crt = the actual count (padded class slots carry zero weights and are skipped by the loss / argmax / stores).
+// HAS_BN = false: the input already is the post-ReLU activation (inference, BatchNorm folded into the GEMM before).
+template <int NC, bool HAS_BN>
 __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restrict__ ys3, long P, const BnFinalizeArgs fin,
-                                                  const float* __restrict__ W4, const float* __restrict__ b4,
+                                                  const float* __restrict__ W4, const float* __restrict__ b4, int Crt,
                                                   float* __restrict__ logits, const long long* __restrict__ labels,
                                                   const float* __restrict__ class_w, CeAccum* __restrict__ ce) {
     pdl_launch_dependents();
     pdl_wait();
+    const int C = (NC <= 8) ? NC : Crt;
     constexpr int NCP = (NC + 3) & ~3;                  // weights per channel padded to a multiple of 4 floats
     __shared__ __align__(16) float w_s[128 * NCP];      // [channel][class]
     __shared__ float2 bn_s[128];                        // {scale, shift}
+    __shared__ float bias_s[NC], cw_s[NC];
     __shared__ double red_d[8][2];
     __shared__ unsigned long long red_u[8][2];
-    bn_publish(fin, blockIdx.x == 0);
-    if (threadIdx.x < 128) {
-        const float4 bp = bn_from_stats(fin, threadIdx.x);
-        bn_s[threadIdx.x] = make_float2(bp.x, bp.y);
+    if (HAS_BN) {
+        bn_publish(fin, blockIdx.x == 0);
+        if (threadIdx.x < 128) {
+            const float4 bp = bn_from_stats(fin, threadIdx.x);
+            bn_s[threadIdx.x] = make_float2(bp.x, bp.y);
+        }
     }
     for (int i = threadIdx.x; i < 128 * NCP; i += blockDim.x) {
         const int c = i / NCP, k = i % NCP;
-        w_s[i] = (k < NC) ? W4[k * 128 + c] : 0.f;
+        w_s[i] = (k < C) ? W4[k * 128 + c] : 0.f;
+    }
+    if (threadIdx.x < NC) {
+        bias_s[threadIdx.x] = (static_cast<int>(threadIdx.x) < C) ? __ldg(b4 + threadIdx.x) : 0.f;
+        cw_s[threadIdx.x] = (class_w != nullptr && static_cast<int>(threadIdx.x) < C) ? __ldg(class_w + threadIdx.x) : 1.f;
     }
     __syncthreads();
-    float bias[NC], cw[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        bias[k] = __ldg(b4 + k);
-        cw[k] = class_w != nullptr ? __ldg(class_w + k) : 1.f;
-    }
     double loss_num = 0.0, w_sum = 0.0;
     unsigned long long correct = 0, nvalid = 0;
     const long stride = static_cast<long>(gridDim.x) * blockDim.x;
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
         const uint4* row = reinterpret_cast<const uint4*>(ys3 + pnt * 128);
         float z[NC];
 #pragma unroll
-        for (int k = 0; k < NC; ++k) z[k] = bias[k];
+        for (int k = 0; k < NC; ++k) z[k] = bias_s[k];
 #pragma unroll
         for (int j0 = 0; j0 < 16; j0 += 4) {
             uint4 v[4];
@@ -368,8 +373,11 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
                 for (int e = 0; e < 8; ++e) {
                     const int c = (j0 + u) * 8 + e;
                     const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
-                    const float2 b2 = bn_s[c];
-                    const float a = fmaxf(fmaf(b2.x, yv, b2.y), 0.f);
+                    float a = yv;
+                    if (HAS_BN) {
+                        const float2 b2 = bn_s[c];
+                        a = fmaxf(fmaf(b2.x, yv, b2.y), 0.f);
+                    }
                     const float4* wc = reinterpret_cast<const float4*>(w_s + c * NCP);
 #pragma unroll
                     for (int q = 0; q < NCP / 4; ++q) {
@@ -383,20 +391,22 @@ __global__ void __launch_bounds__(256) k_head_fwd(const __nv_bfloat16* __restric
             }
         }
 #pragma unroll
-        for (int k = 0; k < NC; ++k) logits[pnt * NC + k] = z[k];
+        for (int k = 0; k < NC; ++k)
+            if (k < C) logits[pnt * C + k] = z[k];
         if (labels != nullptr) {
             const long long lab = labels[pnt];
-            if (lab >= 0 && lab < NC) {
+            if (lab >= 0 && lab < C) {
                 float zmax = z[0];
                 int am = 0;
 #pragma unroll
                 for (int k = 1; k < NC; ++k)
-                    if (z[k] > zmax) { zmax = z[k]; am = k; }        // first maximum, like torch.argmax
-                float se = 0.f, zl = 0.f, wl = 1.f;
+                    if (k < C && z[k] > zmax) { zmax = z[k]; am = k; }        // first maximum, like torch.argmax
+                float se = 0.f, zl = 0.f;
+                const float wl = cw_s[lab];
 #pragma unroll
                 for (int k = 0; k < NC; ++k) {
-                    se += __expf(z[k] - zmax);
-                    if (k == lab) { zl = z[k]; wl = cw[k]; }
+                    if (k < C) se += __expf(z[k] - zmax);
+                    if (k == lab) zl = z[k];
                 }
                 loss_num += static_cast<double>(wl) * static_cast<double>(zmax + logf(se) - zl);
                 w_sum += wl;
@@ -590,6 +600,143 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
             atomicAdd(db4 + (i - MAXC * 128 - 256), s);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head backward for 9..32 classes (k_head_bwd keeps NC x 16 gradient accumulators per lane, which stops at 8 classes).
+// Two kernels: (A) one thread per point: dlogits (fused CE gradient, or the caller's) -> dl buffer, dz of seg_conv3;
+//              (B) column reductions: dW4, db4 and the BN-backward sums, thread = (channel, half of the classes).
+// NC = 16 / 32 class slots, C = actual count.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256) k_head_bwd_wide_points(const __nv_bfloat16* __restrict__ ys3, long P, const float4* __restrict__ bnp,
+                                                              const float* __restrict__ W4, int C, const float* __restrict__ dlogits,
+                                                              const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                              const float* __restrict__ class_w, const double* __restrict__ wsum_total,
+                                                              float* __restrict__ dlbuf, __nv_bfloat16* __restrict__ dz_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ __align__(16) float w_s[128 * NC];      // [channel][class]
+    __shared__ float2 bn_s[128];
+    __shared__ float cw_s[NC];
+    for (int i = threadIdx.x; i < 128 * NC; i += blockDim.x) {
+        const int c = i / NC, k = i % NC;
+        w_s[i] = (k < C) ? W4[k * 128 + c] : 0.f;
+    }
+    if (threadIdx.x < 128) {
+        const float4 bp = __ldg(bnp + threadIdx.x);
+        bn_s[threadIdx.x] = make_float2(bp.x, bp.y);
+    }
+    if (threadIdx.x < NC) cw_s[threadIdx.x] = (class_w != nullptr && static_cast<int>(threadIdx.x) < C) ? __ldg(class_w + threadIdx.x) : 1.f;
+    __syncthreads();
+    const bool fused = (dlogits == nullptr);
+    const float inv_wsum = (wsum_total != nullptr) ? static_cast<float>(1.0 / *wsum_total) : 0.f;
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+    for (long pnt = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; pnt < P; pnt += stride) {
+        float dl[NC];
+        if (fused) {
+            const long long lab = labels[pnt];
+            float zmax = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                dl[k] = (k < C) ? logits[pnt * C + k] : -INFINITY;
+                zmax = fmaxf(zmax, dl[k]);
+            }
+            float se = 0.f;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                dl[k] = (k < C) ? __expf(dl[k] - zmax) : 0.f;
+                se += dl[k];
+            }
+            const bool okl = lab >= 0 && lab < C;
+            const float f = okl ? cw_s[okl ? lab : 0] * inv_wsum : 0.f;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) dl[k] = f * (dl[k] / se - (k == lab ? 1.f : 0.f));
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (k < C) dlbuf[pnt * C + k] = dl[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) dl[k] = (k < C) ? dlogits[pnt * C + k] : 0.f;
+        }
+        const uint4* row = reinterpret_cast<const uint4*>(ys3 + pnt * 128);
+        uint4* dst = reinterpret_cast<uint4*>(dz_out + pnt * 128);
+#pragma unroll 1
+        for (int j = 0; j < 16; ++j) {
+            const uint4 v = __ldg(row + j);
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+            float dz[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = j * 8 + e;
+                const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
+                const float2 b2 = bn_s[c];
+                const float t = fmaf(b2.x, yv, b2.y);
+                const float4* wc = reinterpret_cast<const float4*>(w_s + c * NC);
+                float da = 0.f;
+#pragma unroll
+                for (int q = 0; q < NC / 4; ++q) {
+                    const float4 w4 = wc[q];
+                    da = fmaf(dl[4 * q], w4.x, da);
+                    da = fmaf(dl[4 * q + 1], w4.y, da);
+                    da = fmaf(dl[4 * q + 2], w4.z, da);
+                    da = fmaf(dl[4 * q + 3], w4.w, da);
+                }
+                dz[e] = (t > 0.f) ? round_bf16(da) : 0.f;
+            }
+            dst[j] = make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
+        }
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) k_head_bwd_wide_reduce(const __nv_bfloat16* __restrict__ ys3, const __nv_bfloat16* __restrict__ dz,
+                                                              long P, const float4* __restrict__ bnp, int C,
+                                                              const float* __restrict__ dl /*[P][C]*/, float* __restrict__ dW4,
+                                                              float* __restrict__ db4, double* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int HALF = NC / 2;
+    constexpr int CHUNK = 64;                          // points staged per iteration
+    __shared__ float dl_s[CHUNK][NC];
+    const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const float4 bp = __ldg(bnp + c);
+    float dw[HALF];
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) dw[k] = 0.f;
+    float s1 = 0.f, s2 = 0.f, dbk = 0.f;
+    const long per_block = (P + gridDim.x - 1) / gridDim.x;
+    const long p_begin = blockIdx.x * per_block, p_end = (p_begin + per_block < P) ? p_begin + per_block : P;
+    for (long p0 = p_begin; p0 < p_end; p0 += CHUNK) {
+        const int n = static_cast<int>((p_end - p0 < CHUNK) ? p_end - p0 : CHUNK);
+        __syncthreads();
+        for (int i = threadIdx.x; i < CHUNK * NC; i += 256) {
+            const int j = i / NC, k = i % NC;
+            dl_s[j][k] = (j < n && k < C) ? dl[(p0 + j) * C + k] : 0.f;
+        }
+        __syncthreads();
+        if (static_cast<int>(threadIdx.x) < NC)
+            for (int j = 0; j < n; ++j) dbk += dl_s[j][threadIdx.x];
+        for (int j = 0; j < n; ++j) {
+            const float yv = __bfloat162float(ys3[(p0 + j) * 128 + c]);
+            const float a = fmaxf(fmaf(bp.x, yv, bp.y), 0.f);
+#pragma unroll
+            for (int k = 0; k < HALF; ++k) dw[k] = fmaf(dl_s[j][half * HALF + k], a, dw[k]);
+            if (half == 0) {
+                const float dzv = __bfloat162float(dz[(p0 + j) * 128 + c]);
+                s1 += dzv;
+                s2 = fmaf(dzv, yv, s2);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < HALF; ++k)
+        if (half * HALF + k < C) atomicAdd(dW4 + (half * HALF + k) * 128 + c, dw[k]);
+    if (half == 0) {      // sum dz*yhat = invstd * sum dz*y + (-mean*invstd) * sum dz
+        atomicAdd(stats + c, static_cast<double>(s1));
+        atomicAdd(stats + 128 + c, static_cast<double>(bp.z) * s2 + static_cast<double>(bp.w) * s1);
+    }
+    if (static_cast<int>(threadIdx.x) < C) atomicAdd(db4 + threadIdx.x, dbk);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ import torch
 
 from ._lib import lib, check, ptr
 
-MAX_CLASSES = 8
+MAX_CLASSES = 32
 NUM_PARAM_TENSORS = 38
 NUM_BN = 9
 

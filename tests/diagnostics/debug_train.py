@@ -65,7 +65,10 @@ def _blk(sd, pf, extra):
 
 
 def main():
-    for (C, B, N, seed) in [(5, 2, 96, 11), (5, 4, 512, 1), (5, 8, 2048, 2)]:
+    cases = [(5, 2, 96, 11), (5, 4, 512, 1), (5, 8, 2048, 2)]
+    if len(sys.argv) > 1:                      # e.g. "24,4,1024,1 5,4,1024,1"
+        cases = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+    for (C, B, N, seed) in cases:
         sd = orc.synth_state(C, seed)
         rng = np.random.default_rng(seed + 1)
         x = rng.random((B, N, 4), dtype=np.float32)

@@ -52,7 +52,8 @@ def test_eval_matches_golden(path):
     assert agree >= ARGMAX_AGREE
 
 
-@pytest.mark.parametrize("B,N,C", [(1, 16384, 5), (3, 1000, 3), (2, 129, 5), (5, 64, 8), (2, 4096, 5), (1, 1, 5), (1, 7, 3), (4, 31, 1)])
+@pytest.mark.parametrize("B,N,C", [(1, 16384, 5), (3, 1000, 3), (2, 129, 5), (5, 64, 8), (2, 4096, 5), (1, 1, 5), (1, 7, 3), (4, 31, 1),
+                                   (2, 1000, 9), (2, 1500, 16), (1, 2048, 32)])
 def test_eval_matches_oracle(B, N, C):
     sd = orc.synth_state(C, 100 + B + N)
     m = _model(C, sd)
@@ -97,17 +98,17 @@ def test_forward_rejects_bad_input():
         replica(torch.rand(1, 10, 4, device="cuda"))
 
 
-def test_evaluate_metrics_match_torch_and_sklearn():
+@pytest.mark.parametrize("C", [5, 13])
+def test_evaluate_metrics_match_torch_and_sklearn(C):
     """model.evaluate: weighted-CE loss, accuracy counters and confusion matrix (integer, exact) of one validation batch
     (pcs.py:289-304, 319-343) against torch / sklearn applied to the SAME logits."""
     import pcseg_b200
     from sklearn.metrics import confusion_matrix, f1_score
-    C = 5
     m = _model(C, orc.synth_state(C, 12))
     rng = np.random.default_rng(4)
     x = torch.from_numpy(rng.random((3, 700, 4), dtype=np.float32)).cuda()
     labels = torch.from_numpy(rng.integers(-1, C, (3, 700)).astype(np.int64)).cuda()
-    cw = torch.tensor([0.5, 1.0, 2.0, 0.75, 0.75], device="cuda")
+    cw = torch.tensor(([0.5, 1.0, 2.0, 0.75, 0.75] * 3)[:C], device="cuda")
     out = m.evaluate(x, labels, cw)
     logits = out["logits"]
     ref_loss = torch.nn.functional.cross_entropy(logits.view(-1, C), labels.view(-1), weight=cw, ignore_index=-1)

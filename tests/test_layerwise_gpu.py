@@ -47,7 +47,7 @@ def _diverse_clouds(B, N, rng):
     return np.stack(xs).astype(np.float32)
 
 
-@pytest.mark.parametrize("B,N,C,p_drop", [(3, 500, 5, 0.0), (4, 1024, 3, 0.3), (2, 200, 8, 0.0)])
+@pytest.mark.parametrize("B,N,C,p_drop", [(3, 500, 5, 0.0), (4, 1024, 3, 0.3), (2, 200, 8, 0.0), (2, 384, 12, 0.3), (2, 200, 32, 0.0)])
 def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop):
     import pcseg_b200
     from pcseg_b200.engine import debug_tensor

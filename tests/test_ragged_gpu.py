@@ -40,6 +40,7 @@ CASES = [
     (4, 4096, [4095, 4096, 129, 128], 5),
     (1, 100, [100], 3),                  # nothing padded, N not a multiple of 128 (filler rows are duplicates)
     (5, 777, [1, 2, 3, 776, 777], 8),
+    (3, 900, [900, 450, 2], 12),         # more than 8 classes: the wide head kernels
 ]
 
 
@@ -139,7 +140,8 @@ def _one_step(C, B, N, lengths, use_lengths, p_drop=0.0, steps=1, seed=21):
     return m, tr, losses, grads, out
 
 
-@pytest.mark.parametrize("B,N,lengths,C", [(3, 1000, [1000, 517, 64], 3), (4, 2048, [2048, 2047, 700, 1], 5), (2, 300, [300, 300], 5)])
+@pytest.mark.parametrize("B,N,lengths,C", [(3, 1000, [1000, 517, 64], 3), (4, 2048, [2048, 2047, 700, 1], 5), (2, 300, [300, 300], 5),
+                                              (3, 800, [800, 300, 31], 12)])
 def test_ragged_training_step_equals_the_padded_step(B, N, lengths, C):
     """dropout off: loss, logits, BatchNorm running statistics and every parameter gradient of the packed step equal the
     padded step's.  Not bit-exact: the batch sums are accumulated in a different order (and the filler rows are removed

@@ -113,7 +113,7 @@ def test_train_step_matches_oracle_on_golden_inputs(path):
             np.testing.assert_allclose(buf.cpu().numpy(), newbuf[name], rtol=3e-2, atol=5e-3, err_msg=name)
 
 
-@pytest.mark.parametrize("B,N,C", [(4, 512, 5), (2, 1000, 3), (8, 2048, 5), (3, 37, 2)])
+@pytest.mark.parametrize("B,N,C", [(4, 512, 5), (2, 1000, 3), (8, 2048, 5), (3, 37, 2), (4, 512, 12), (8, 2048, 24)])
 def test_train_step_matches_oracle(B, N, C):
     sd = orc.synth_state(C, 7 * B + N)
     rng = np.random.default_rng(B * N)
