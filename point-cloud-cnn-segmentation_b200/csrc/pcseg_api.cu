@@ -60,16 +60,19 @@ extern "C" long long pcseg_launch_count(void) { return g_launches; }
 
 // ------------------------------------------------------------------------------------------------
 // kernel launch with optional programmatic dependent launch (PDL): the next kernel of the stream may start its prologue
-// while this one drains; every kernel calls griddepcontrol.wait before touching data (ptx.cuh).  Measured on B200 (same
-// box A/B): inference +1.3 %, training step -3.6 %, so it is OFF by default; PCSEG_PDL=1 enables the launch attribute.
+// while this one drains; every kernel calls griddepcontrol.wait before touching data (ptx.cuh).
+// Default per entry point (g_pdl_call, set by the API functions): ON for inference and for the eagerly launched ragged
+// training step (measured: -3 % .. -9 % per call), OFF for the dense training step, which replays CUDA graphs and was
+// measured 4-5 % slower with the attribute.  PCSEG_PDL=0 / 1 forces it off / on everywhere.
 // ------------------------------------------------------------------------------------------------
+static thread_local bool g_pdl_call = false;
 static bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) {
+    static int v = -2;
+    if (v == -2) {
         const char* e = getenv("PCSEG_PDL");
-        v = (e && e[0] == '1') ? 1 : 0;
+        v = (e && e[0] == '1') ? 1 : ((e && e[0] == '0') ? 0 : -1);
     }
-    return v == 1;
+    return v >= 0 ? v == 1 : g_pdl_call;
 }
 template <typename... KArgs, typename... Args>
 static void pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
@@ -640,6 +643,7 @@ static int convert_transpose(const float* src, int ld_src, bf16* dst, int ld_dst
 }
 
 extern "C" int pcseg_prepare_eval(pcseg_ctx* c, const float* params, const float* bnbuf, void* stream) {
+    g_pdl_call = true;
     if (!c || !c->bound || c->train) return fail("pcseg_prepare_eval: context not bound in eval mode");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Layout& L = c->L;
@@ -834,6 +838,7 @@ static int argmax_labels(pcseg_ctx* c, long long P, const float* logits, long lo
 }
 
 extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, long long* labels_out, void* stream) {
+    g_pdl_call = true;
     if (!c || !c->bound || c->train) return fail("pcseg_forward_eval: context not bound in eval mode");
     if (!c->eval_ready) return fail("pcseg_forward_eval: call pcseg_prepare_eval first");
     if (!x || !logits) return fail("pcseg_forward_eval: null tensor");
@@ -844,6 +849,7 @@ extern "C" int pcseg_forward_eval(pcseg_ctx* c, const float* x, float* logits, l
 }
 
 extern "C" int pcseg_forward_eval_part(pcseg_ctx* c, const float* x, float* logits, long long* labels_out, int part, void* stream) {
+    g_pdl_call = true;
     if (!c || !c->bound || c->train) return fail("pcseg_forward_eval_part: context not bound in eval mode");
     if (!c->eval_ready) return fail("pcseg_forward_eval_part: call pcseg_prepare_eval first");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -867,6 +873,7 @@ extern "C" int pcseg_pooled_feature(pcseg_ctx* c, float** pooled) {
 
 extern "C" int pcseg_forward_eval_ragged(pcseg_ctx* c, const float* x, const int* lengths, int nmax, float* logits,
                                          long long* labels_out, void* stream) {
+    g_pdl_call = true;
     if (!c || !c->bound || c->train) return fail("pcseg_forward_eval_ragged: context not bound in eval mode");
     if (!c->eval_ready) return fail("pcseg_forward_eval_ragged: call pcseg_prepare_eval first");
     if (!x || !logits || !lengths) return fail("pcseg_forward_eval_ragged: null argument");
@@ -1025,6 +1032,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
 extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* params, float* bnbuf, unsigned long long seed,
                                    float dropout_p, float* logits, const long long* labels, const float* class_w,
                                    pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
+    g_pdl_call = false;
     if (!c || !c->bound || !c->train) return fail("pcseg_forward_train: context not bound in train mode");
     if (!x || !params || !bnbuf || !logits) return fail("pcseg_forward_train: null tensor");
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train: dropout_p out of range");
@@ -1037,6 +1045,7 @@ extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* pa
 extern "C" int pcseg_forward_train_ragged(pcseg_ctx* c, const float* x, const int* lengths, int nmax, const float* params, float* bnbuf,
                                           unsigned long long seed, float dropout_p, float* logits, const long long* labels,
                                           const float* class_w, pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
+    g_pdl_call = true;
     if (!c || !c->bound || !c->train) return fail("pcseg_forward_train_ragged: context not bound in train mode");
     if (!x || !lengths || !params || !bnbuf || !logits) return fail("pcseg_forward_train_ragged: null argument");
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train_ragged: dropout_p out of range");
@@ -1068,6 +1077,7 @@ static int apply_rows_per_strip(int N, int B, int C) {
 extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params, const float* dlogits, const float* logits,
                               const long long* labels, const float* class_w, const double* wsum_total, float* grads, int phase,
                               void* stream) {
+    g_pdl_call = c && c->rag_active;
     if (!c || !c->bound || !c->train) return fail("pcseg_backward: context not bound in train mode");
     if (phase < 0 || phase > 2) return fail("pcseg_backward: phase must be 0, 1 or 2");
     if (!x || !params || !grads) return fail("pcseg_backward: null tensor");
@@ -1242,6 +1252,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
 
 extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, float* v, long long n, int step, float lr, float b1,
                                float b2, float eps, float wd, float grad_scale, const pcseg_step_state* state, void* stream) {
+    g_pdl_call = false;
     if (!params || !grads || !m || !v || n <= 0 || (step < 1 && !state)) return fail("pcseg_adam_step: bad arguments");
     if (step < 1) step = 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1255,6 +1266,7 @@ extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, floa
 
 extern "C" int pcseg_eval_metrics(const float* logits, const long long* labels, long long P, int C, const float* class_w,
                                   pcseg_ce_accum* ce, unsigned long long* confusion, long long* pred_out, void* stream) {
+    g_pdl_call = true;
     if (!logits || P <= 0 || C < 1 || C > API_MAX_CLASSES) return fail("pcseg_eval_metrics: bad arguments");
     if (!labels && !pred_out) return fail("pcseg_eval_metrics: nothing to compute (no labels, no pred_out)");
     int grid = static_cast<int>((P + 255) / 256);
@@ -1270,6 +1282,7 @@ extern "C" int pcseg_eval_metrics(const float* logits, const long long* labels, 
 }
 
 extern "C" int pcseg_step_advance(pcseg_step_state* state, float b1, float b2, void* stream) {
+    g_pdl_call = false;
     if (!state) return fail("pcseg_step_advance: null state");
     pdl_launch(k_step_advance, 1, 1, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<StepState*>(state), b1, b2);
     LAUNCH_OK("k_step_advance");
