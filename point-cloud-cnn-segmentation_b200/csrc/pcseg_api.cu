@@ -61,11 +61,19 @@ extern "C" long long pcseg_launch_count(void) { return g_launches; }
 // ------------------------------------------------------------------------------------------------
 // kernel launch with optional programmatic dependent launch (PDL): the next kernel of the stream may start its prologue
 // while this one drains; every kernel calls griddepcontrol.wait before touching data (ptx.cuh).
-// Default per entry point (g_pdl_call, set by the API functions): ON for inference and for the eagerly launched ragged
-// training step (measured: -3 % .. -9 % per call), OFF for the dense training step, which replays CUDA graphs and was
-// measured 4-5 % slower with the attribute.  PCSEG_PDL=0 / 1 forces it off / on everywhere.
+// Default per entry point (g_pdl_call, set by the API functions): ON for every eagerly launched call (measured: -3 % ..
+// -9 % for inference and for training steps of <= 64k points, neutral for larger ones), OFF while the stream is being
+// captured: the graph-replayed training step was measured 4-5 % slower with the attribute.  PCSEG_PDL=0 / 1 forces it.
 // ------------------------------------------------------------------------------------------------
 static thread_local bool g_pdl_call = false;
+static bool stream_is_capturing(void* stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
 static bool pdl_enabled() {
     static int v = -2;
     if (v == -2) {
@@ -1032,7 +1040,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
 extern "C" int pcseg_forward_train(pcseg_ctx* c, const float* x, const float* params, float* bnbuf, unsigned long long seed,
                                    float dropout_p, float* logits, const long long* labels, const float* class_w,
                                    pcseg_ce_accum* ce, const pcseg_step_state* state, void* stream) {
-    g_pdl_call = false;
+    g_pdl_call = !stream_is_capturing(stream);
     if (!c || !c->bound || !c->train) return fail("pcseg_forward_train: context not bound in train mode");
     if (!x || !params || !bnbuf || !logits) return fail("pcseg_forward_train: null tensor");
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail("pcseg_forward_train: dropout_p out of range");
@@ -1077,7 +1085,7 @@ static int apply_rows_per_strip(int N, int B, int C) {
 extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params, const float* dlogits, const float* logits,
                               const long long* labels, const float* class_w, const double* wsum_total, float* grads, int phase,
                               void* stream) {
-    g_pdl_call = c && c->rag_active;
+    g_pdl_call = !stream_is_capturing(stream);
     if (!c || !c->bound || !c->train) return fail("pcseg_backward: context not bound in train mode");
     if (phase < 0 || phase > 2) return fail("pcseg_backward: phase must be 0, 1 or 2");
     if (!x || !params || !grads) return fail("pcseg_backward: null tensor");
@@ -1252,7 +1260,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
 
 extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, float* v, long long n, int step, float lr, float b1,
                                float b2, float eps, float wd, float grad_scale, const pcseg_step_state* state, void* stream) {
-    g_pdl_call = false;
+    g_pdl_call = !stream_is_capturing(stream);
     if (!params || !grads || !m || !v || n <= 0 || (step < 1 && !state)) return fail("pcseg_adam_step: bad arguments");
     if (step < 1) step = 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1282,7 +1290,7 @@ extern "C" int pcseg_eval_metrics(const float* logits, const long long* labels, 
 }
 
 extern "C" int pcseg_step_advance(pcseg_step_state* state, float b1, float b2, void* stream) {
-    g_pdl_call = false;
+    g_pdl_call = !stream_is_capturing(stream);
     if (!state) return fail("pcseg_step_advance: null state");
     pdl_launch(k_step_advance, 1, 1, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<StepState*>(state), b1, b2);
     LAUNCH_OK("k_step_advance");
