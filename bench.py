@@ -42,9 +42,9 @@ FWD_FLOP_PER_PT = 2 * (1392896 + 128 * NUM_CLASSES)
 TRAIN_FLOP_PER_PT = 3 * FWD_FLOP_PER_PT - 512
 GFEAT_FLOP_PER_PT = 2 * 1024 * 1024          # one global_feat GEMM (forward, dgrad or wgrad), per point
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the three global_feat GEMMs at 8 x 16 384 points, from the
-# committed `ncu --set full` capture profiles/r01_ncu_full_gemm_cfg2_train.txt (MB): fwd 270.7+222.9, dgrad 539.0+239.1,
-# wgrad 541.1+3.6.  Algorithmic minimum: fwd a5 268 + y6 268; dgrad dy6 268 + y5 268 + dz5 268; wgrad dy6 268 + a5 268.
-NCU_TRAFFIC_MB_CFG2 = {5: 493.6, 21: 778.1, 37: 544.7}
+# committed `ncu --set full` capture profiles/r01_ncu_full_gemm_cfg2_train.txt (MB): fwd 270.7+224.7, dgrad 539.1+243.1,
+# wgrad 541.1+5.2.  Algorithmic minimum: fwd a5 268 + y6 268; dgrad dy6 268 + y5 268 + dz5 268; wgrad dy6 268 + a5 268.
+NCU_TRAFFIC_MB_CFG2 = {5: 495.4, 21: 782.2, 37: 546.3}
 
 
 def measured_peaks():
