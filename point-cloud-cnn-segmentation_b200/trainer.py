@@ -39,7 +39,9 @@ class FusedTrainer:
         self.ce_raw = torch.zeros(32, dtype=torch.uint8, device=self.device)
         self.ce_f64 = self.ce_raw.view(torch.float64)
         self.ce_i64 = self.ce_raw.view(torch.int64)
-        self.wsum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # {loss numerator, sum of class weights} of the step: both are known after the forward and all-reduced together
+        self.lw = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self.loss_num, self.wsum = self.lw[0:1], self.lw[1:2]
         # device-resident step state (pcseg_step_state): dropout seed, Adam step / bias corrections, learning rate
         self.state = torch.zeros(32, dtype=torch.uint8, device=self.device)
         seed0 = int(torch.empty((), dtype=torch.int64).random_().item())
@@ -48,7 +50,6 @@ class FusedTrainer:
         # static outputs of a step
         self.out_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.out_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
-        self.loss_num = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.early, self.late = grad_buckets(self.flat["offs"], n)
         self.last_logits = None
         # CUDA graph of the whole step (captured on the third step of a given batch shape)
@@ -67,13 +68,13 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------ one step = 4 capturable segments + collectives
     # Collectives are never captured (they run eagerly between the graph segments), so the same code serves one GPU and
-    # data-parallel ranks:  [forward] -> all-reduce(sum w) -> [backward phase 1] -> async all-reduce(bucket 1)
-    #                       -> [backward phase 2] -> all-reduce(bucket 2), wait -> [Adam + outputs] -> all-reduce(loss num)
+    # data-parallel ranks:  [forward] -> all-reduce(loss num, sum w) -> [backward phase 1] -> async all-reduce(bucket 1)
+    #                       -> [backward phase 2] -> all-reduce(bucket 2), wait -> [Adam + outputs]
     def _seg_forward(self, x, labels):
         self.engine.step_advance(self.state, self.betas)
         self.last_logits = self.model._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw, state=self.state,
                                                          lengths=self._lengths)
-        self.wsum.copy_(self.ce_f64[1:2])
+        self.lw.copy_(self.ce_f64[0:2])
 
     def _seg_backward(self, x, labels, phase):
         f = self.flat
@@ -84,7 +85,7 @@ class FusedTrainer:
         f = self.flat
         self.engine.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, 1, self.lr, self.betas, self.eps, self.weight_decay,
                          state=self.state)
-        self.loss_num.copy_(self.ce_f64[0:1])
+        torch.div(self.loss_num, self.wsum, out=self.out_loss)
         self.out_counts.copy_(self.ce_i64[2:4])
 
     def _segments(self):
@@ -97,7 +98,7 @@ class FusedTrainer:
         f = self.flat
         self.sync.g = f["grads"]
         if i == 0:
-            self.sync.reduce_normaliser(self.wsum)
+            self.sync.reduce_normaliser(self.lw)
         elif i == 1:
             if self.distributed and self.overlap:
                 self.sync.launch(self.early)                # NCCL runs on its own stream while phase 2 computes
@@ -108,9 +109,6 @@ class FusedTrainer:
             if self.distributed and self.overlap:
                 self.sync.launch(self.late)
                 self.sync.wait()
-        elif i == 3:
-            self.sync.reduce_normaliser(self.loss_num)
-            torch.div(self.loss_num, self.wsum, out=self.out_loss)
 
     def _run_step(self, x, labels, graphs=None):
         for i, seg in enumerate(self._segments()):

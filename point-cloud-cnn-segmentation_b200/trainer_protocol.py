@@ -17,9 +17,10 @@ def grad_buckets(offs, total):
 class GradSync:
     """Collective protocol of the data-parallel step (backend-agnostic: NCCL on GPUs, gloo in the CPU tests).
 
-    * `reduce_normaliser`: SUM all-reduce of the scalar sum of class weights, BEFORE backward, so that every
-      rank scales its dlogits by 1 / (global sum) -- the reference computes ONE weighted-mean loss over the
-      gathered logits of all replicas (pcs.py:244-251 under nn.DataParallel).
+    * `reduce_normaliser`: SUM all-reduce of the sum of class weights (and, in the same tiny tensor, the loss numerator,
+      both known after the forward), BEFORE backward, so that every rank scales its dlogits by 1 / (global sum) -- the
+      reference computes ONE weighted-mean loss over the gathered logits of all replicas (pcs.py:244-251 under
+      nn.DataParallel).
     * `launch(ranges)` / `wait()`: asynchronous SUM all-reduce of slices of the flat gradient arena (summing
       equals DataParallel's reduce-add of replica gradients); launched per bucket so that the first bucket's
       transfer overlaps the rest of backward.
@@ -41,10 +42,22 @@ class GradSync:
         return t
 
     def launch(self, ranges):
-        if self.active:
-            for a, b in ranges:
-                if b > a:
-                    self.works.append(dist.all_reduce(self.g[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        """one asynchronous SUM all-reduce of the given slices of the arena (the slices of a bucket are coalesced into one
+        collective launch where the backend supports it)"""
+        if not self.active:
+            return
+        views = [self.g[a:b] for a, b in ranges if b > a]
+        if len(views) > 1:
+            try:
+                with dist._coalescing_manager(group=self.pg, device=self.g.device, async_ops=True) as cm:
+                    for v in views:
+                        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg)
+                self.works.append(cm)
+                return
+            except (AttributeError, RuntimeError, ValueError, TypeError):
+                pass                                           # backend without coalescing: one call per slice
+        for v in views:
+            self.works.append(dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
     def wait(self):
         for w in self.works:
