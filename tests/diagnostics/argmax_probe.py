@@ -1,7 +1,7 @@
 """argmax agreement of the CUDA inference path with the fp32 oracle on ALL points (no near-tie exclusion)"""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import pcseg_b200
 from oracle import pointnet_oracle as orc
 for (B, N, C, seed) in [(1, 16384, 5, 1), (2, 8192, 5, 2), (2, 8192, 3, 3), (4, 4096, 8, 4)]:
