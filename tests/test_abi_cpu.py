@@ -107,3 +107,39 @@ def test_module_is_a_state_dict_drop_in():
             assert torch.equal(model.state_dict()[k], v), k
     with pytest.raises(NotImplementedError):
         pcseg_b200.PointNetSegmentation(C, input_dim=3)
+
+
+def test_host_side_helpers_without_gpu():
+    """host logic that needs no device: per-cloud lengths validation, capacity buckets of ragged calls, mask -> lengths,
+    F1 scores from a confusion matrix (pcs.py:341-343) against sklearn"""
+    import numpy as np
+    import pytest
+    import torch
+    import pcseg_b200
+    from pcseg_b200.engine import host_lengths, ragged_capacity
+    from sklearn.metrics import confusion_matrix, f1_score
+
+    assert host_lengths(None, 3, 10) is None
+    assert host_lengths([10, 10, 10], 3, 10) is None                     # nothing padded -> dense path
+    arr = host_lengths(torch.tensor([10, 0, 7]), 3, 10)
+    assert list(arr) == [10, 0, 7]
+    assert list(host_lengths(np.array([1, 2, 3]), 3, 10)) == [1, 2, 3]
+    for bad in ([1, 2], [1, 2, 11], [-1, 2, 3]):
+        with pytest.raises(ValueError):
+            host_lengths(bad, 3, 10)
+    assert ragged_capacity(1) == 4096 and ragged_capacity(4096) == 4096 and ragged_capacity(4097) == 8192
+
+    masks = torch.zeros(3, 8, dtype=torch.bool)
+    masks[0, :8] = True
+    masks[1, :3] = True
+    assert pcseg_b200.lengths_from_masks(masks) == [8, 3, 0]
+
+    rng = np.random.default_rng(0)
+    C = 6
+    yt = rng.integers(0, C - 1, 500)          # class C-1 never occurs as a label ...
+    yp = rng.integers(0, C, 500)              # ... but is predicted
+    conf = torch.from_numpy(confusion_matrix(yt, yp, labels=list(range(C))))
+    f1, macro, weighted = pcseg_b200.f1_scores(conf)
+    np.testing.assert_allclose(f1.numpy(), f1_score(yt, yp, average=None, labels=list(range(C))), atol=1e-12)
+    assert abs(macro.item() - f1_score(yt, yp, average="macro")) < 1e-12
+    assert abs(weighted.item() - f1_score(yt, yp, average="weighted")) < 1e-12
