@@ -98,6 +98,14 @@ int pcseg_pooled_feature(pcseg_ctx* ctx, float** pooled);
 int pcseg_forward_eval_ragged(pcseg_ctx* ctx, const float* x, const int* lengths, int nmax, float* logits,
                               long long* labels_out, void* stream);
 
+/* Host-only planner of the packed layout used by the *_ragged calls (no CUDA call; the calls run it themselves -- it is
+ * exported for inspection, tests and for callers that want the packed row count of a batch).  meta_out (may be NULL)
+ * receives  len[B] | off[B+1] | tile_cloud[rows/128] | strips[n][4] = {cloud, first row, end row, first row of the cloud}:
+ * cloud b owns packed rows off[b] .. off[b+1] (multiples of 128): its lengths[b] real rows, then ONE representative pad
+ * row if lengths[b] < nmax, then filler.  Returns the number of ints of the plan, or -1 (pcseg_last_error). */
+long long pcseg_ragged_plan(int B, int nmax, const int* lengths, int* meta_out, long long meta_capacity,
+                            long long* rows_out, int* strips_out);
+
 /* Training forward: pcs.py:98-133 under train() (batch statistics, running-stat update, dropout).
  * bn_buffers is updated in place.  dropout_p = 0 disables dropout.  If labels != NULL the weighted
  * cross-entropy of pcs.py:216,247-251 is accumulated into *ce (device, zeroed by this call);

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpcseg_b200.so")
 EXPORTS = [
     "pcseg_last_error", "pcseg_version", "pcseg_create", "pcseg_destroy", "pcseg_param_count", "pcseg_param_offset",
     "pcseg_param_numel", "pcseg_bn_buffer_count", "pcseg_bn_buffer_offset", "pcseg_workspace_bytes", "pcseg_bind",
-    "pcseg_prepare_eval", "pcseg_forward_eval", "pcseg_forward_eval_ragged", "pcseg_forward_eval_part", "pcseg_pooled_feature", "pcseg_forward_train",
+    "pcseg_prepare_eval", "pcseg_forward_eval", "pcseg_forward_eval_ragged", "pcseg_ragged_plan", "pcseg_forward_eval_part", "pcseg_pooled_feature", "pcseg_forward_train",
     "pcseg_forward_train_ragged", "pcseg_backward", "pcseg_adam_step",
     "pcseg_gemm_test", "pcseg_launch_count", "pcseg_debug_copy", "pcseg_step_advance", "pcseg_eval_metrics", "pcseg_profile_enable", "pcseg_profile_read", "pcseg_profile_reset",
 ]
@@ -47,6 +47,8 @@ def _load():
     lib.pcseg_forward_train.argtypes = [vp, vp, vp, vp, u64, f32, vp, vp, vp, vp, vp, vp]
     lib.pcseg_forward_eval_part.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.pcseg_pooled_feature.argtypes = [vp, C.POINTER(vp)]
+    lib.pcseg_ragged_plan.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), ll, C.POINTER(ll), C.POINTER(i32)]
+    lib.pcseg_ragged_plan.restype = ll
     lib.pcseg_forward_eval_ragged.argtypes = [vp, vp, C.POINTER(i32), i32, vp, vp, vp]
     lib.pcseg_forward_train_ragged.argtypes = [vp, vp, C.POINTER(i32), i32, vp, vp, u64, f32, vp, vp, vp, vp, vp, vp]
     lib.pcseg_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]

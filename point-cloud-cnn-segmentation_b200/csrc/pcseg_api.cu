@@ -706,17 +706,13 @@ static void patch_rows(GemmOp& op, long long rows) {
         op.p.num_m_tiles = static_cast<int>(rows / 128);
     }
 }
-static int rag_plan(pcseg_ctx* c, const int* lengths, int nmax, cudaStream_t s) {
-    if (nmax <= 0) nmax = c->N;
-    if (nmax > c->N) return fail("ragged batch: padded length %d exceeds the bound capacity %d", nmax, c->N);
-    c->rag_N = nmax;
-    const int B = c->B, N = nmax;
-    std::vector<int>& h = c->meta_host;
-    h.assign(2 * static_cast<size_t>(B) + 1 + static_cast<size_t>(c->cap_rows / 128) + 4 * (static_cast<size_t>(RAG_MAX_STRIPS) + B), 0);
+// Pure host planner of the packed layout (no CUDA calls; exported as pcseg_ragged_plan so that it can be inspected and
+// tested without a device).  h must hold 2B + 1 + sum(alloc)/128 + 4 (RAG_MAX_STRIPS + B) ints; returns the ints written.
+static long long plan_ragged(int B, int N, const int* lengths, std::vector<int>& h, long long* rows_out, int* strips_out) {
     long long off = 0;
     for (int b = 0; b < B; ++b) {
         const int L = lengths[b];
-        if (L < 0 || L > N) return fail("ragged batch: lengths[%d]=%d outside 0..%d", b, L, N);
+        if (L < 0 || L > N) return fail("ragged batch: lengths[%d]=%d outside 0..%d", b, L, N), -1;
         const long long alloc = (static_cast<long long>(L) + (L < N ? 1 : 0) + 127) / 128 * 128;
         h[b] = L;
         h[B + b] = static_cast<int>(off);
@@ -724,30 +720,64 @@ static int rag_plan(pcseg_ctx* c, const int* lengths, int nmax, cudaStream_t s) 
         off += alloc;
     }
     h[2 * B] = static_cast<int>(off);
-    if (off > c->cap_rows) return fail("internal: packed rows %lld exceed the capacity %lld", off, c->cap_rows);
-    c->rag_rows = off;
     // row strips for the BN-backward kernels: about two blocks per SM over the packed rows, never across clouds
     size_t w = 2 * static_cast<size_t>(B) + 1 + static_cast<size_t>(off / 128);
-    {
-        int target = 2 * num_sms();
-        if (target > RAG_MAX_STRIPS) target = RAG_MAX_STRIPS;
-        const long long tiles = off / 128;
-        const long long tps = (tiles + target - 1) / target;        // tiles per strip
-        int n = 0;
-        for (int b = 0; b < B; ++b) {
-            const long long r_begin = h[B + b], r_end = (b + 1 < B) ? h[B + b + 1] : off;
-            for (long long r = r_begin; r < r_end; r += tps * 128, ++n) {
-                h[w + 4 * n] = b;
-                h[w + 4 * n + 1] = static_cast<int>(r);
-                h[w + 4 * n + 2] = static_cast<int>(r + tps * 128 < r_end ? r + tps * 128 : r_end);
-                h[w + 4 * n + 3] = static_cast<int>(r_begin);
-            }
+    int target = 2 * num_sms();
+    if (target > RAG_MAX_STRIPS) target = RAG_MAX_STRIPS;
+    const long long tiles = off / 128;
+    const long long tps = (tiles + target - 1) / target;        // tiles per strip
+    int n = 0;
+    for (int b = 0; b < B; ++b) {
+        const long long r_begin = h[B + b], r_end = h[B + b + 1];
+        for (long long r = r_begin; r < r_end; r += tps * 128, ++n) {
+            h[w + 4 * n] = b;
+            h[w + 4 * n + 1] = static_cast<int>(r);
+            h[w + 4 * n + 2] = static_cast<int>(r + tps * 128 < r_end ? r + tps * 128 : r_end);
+            h[w + 4 * n + 3] = static_cast<int>(r_begin);
         }
-        c->rag_strips = n;
-        w += 4 * static_cast<size_t>(n);
     }
+    *rows_out = off;
+    *strips_out = n;
+    return static_cast<long long>(w + 4 * static_cast<size_t>(n));
+}
+static size_t plan_capacity_ints(int B, int N) {
+    const size_t cap_rows = static_cast<size_t>(B) * ((static_cast<size_t>(N) + 127) / 128 * 128);
+    return 2 * static_cast<size_t>(B) + 1 + cap_rows / 128 + 4 * (static_cast<size_t>(RAG_MAX_STRIPS) + B);
+}
+
+extern "C" long long pcseg_ragged_plan(int B, int nmax, const int* lengths, int* meta_out, long long meta_capacity,
+                                       long long* rows_out, int* strips_out) {
+    if (B <= 0 || nmax <= 0 || !lengths) return fail("pcseg_ragged_plan: bad arguments"), -1;
+    std::vector<int> h(plan_capacity_ints(B, nmax), 0);
+    long long rows = 0;
+    int strips = 0;
+    const long long n = plan_ragged(B, nmax, lengths, h, &rows, &strips);
+    if (n < 0) return -1;
+    if (rows_out) *rows_out = rows;
+    if (strips_out) *strips_out = strips;
+    if (meta_out) {
+        if (meta_capacity < n) return fail("pcseg_ragged_plan: meta buffer too small (%lld < %lld ints)", meta_capacity, n), -1;
+        memcpy(meta_out, h.data(), static_cast<size_t>(n) * sizeof(int));
+    }
+    return n;
+}
+
+static int rag_plan(pcseg_ctx* c, const int* lengths, int nmax, cudaStream_t s) {
+    if (nmax <= 0) nmax = c->N;
+    if (nmax > c->N) return fail("ragged batch: padded length %d exceeds the bound capacity %d", nmax, c->N);
+    c->rag_N = nmax;
+    const int B = c->B;
+    std::vector<int>& h = c->meta_host;
+    h.assign(plan_capacity_ints(B, c->N), 0);
+    long long off = 0;
+    int nstrips = 0;
+    const long long w = plan_ragged(B, nmax, lengths, h, &off, &nstrips);
+    if (w < 0) return 1;
+    if (off > c->cap_rows) return fail("internal: packed rows %lld exceed the capacity %lld", off, c->cap_rows);
+    c->rag_rows = off;
+    c->rag_strips = nstrips;
     // (pageable source: the copy is staged before the call returns, meta_host may be rewritten by the next plan)
-    CUDA_OK(cudaMemcpyAsync(c->meta, h.data(), w * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(c->meta, h.data(), static_cast<size_t>(w) * sizeof(int), cudaMemcpyHostToDevice, s));
     pcseg_ctx::OpSet& O = c->ops[1];
     for (int i = 0; i < NUM_BN; ++i) {
         patch_rows(O.ev[i], off);

@@ -143,3 +143,48 @@ def test_host_side_helpers_without_gpu():
     np.testing.assert_allclose(f1.numpy(), f1_score(yt, yp, average=None, labels=list(range(C))), atol=1e-12)
     assert abs(macro.item() - f1_score(yt, yp, average="macro")) < 1e-12
     assert abs(weighted.item() - f1_score(yt, yp, average="weighted")) < 1e-12
+
+
+def test_ragged_plan_invariants(lib):
+    """pcseg_ragged_plan (pure host code, the layout every *_ragged call runs on): clouds start at multiples of 128 rows,
+    hold their real rows plus ONE representative pad row when they are padded, tiles map to exactly one cloud, and the
+    BN-backward strips tile the packed rows exactly once without crossing a cloud."""
+    import numpy as np
+    lib.pcseg_ragged_plan.restype = ctypes.c_longlong
+    lib.pcseg_ragged_plan.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                      ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)]
+    rng = np.random.default_rng(0)
+    cases = [(3, 1000, [1000, 517, 1]), (2, 256, [256, 0]), (1, 100, [100]), (5, 777, [1, 2, 3, 776, 777]),
+             (8, 16384, [16384] + rng.integers(1, 16384, 7).tolist()), (64, 65536, rng.integers(0, 65537, 64).tolist())]
+    for B, N, lengths in cases:
+        arr = (ctypes.c_int * B)(*lengths)
+        rows, strips = ctypes.c_longlong(), ctypes.c_int()
+        n = lib.pcseg_ragged_plan(B, N, arr, None, 0, ctypes.byref(rows), ctypes.byref(strips))
+        assert n > 0
+        meta = (ctypes.c_int * n)()
+        assert lib.pcseg_ragged_plan(B, N, arr, meta, n, None, None) == n
+        m = np.frombuffer(meta, dtype=np.int32)
+        ln, off = m[:B], m[B:2 * B + 1]
+        T = rows.value // 128
+        tile_cloud = m[2 * B + 1:2 * B + 1 + T]
+        st = m[2 * B + 1 + T:].reshape(-1, 4)
+        assert list(ln) == lengths and off[0] == 0 and off[B] == rows.value
+        assert rows.value <= B * ((N + 127) // 128 * 128)
+        for b in range(B):
+            alloc = off[b + 1] - off[b]
+            need = lengths[b] + (1 if lengths[b] < N else 0)
+            assert off[b] % 128 == 0 and alloc % 128 == 0 and need <= alloc < need + 128 and alloc >= 128
+            assert (tile_cloud[off[b] // 128:off[b + 1] // 128] == b).all()
+        assert len(st) == strips.value
+        covered = np.zeros(rows.value, dtype=np.int32)
+        for cl, r0, r1, base in st:
+            assert off[cl] <= r0 < r1 <= off[cl + 1] and base == off[cl] and r0 % 128 == 0
+            covered[r0:r1] += 1
+        assert (covered == 1).all()
+    # errors: length out of range, meta buffer too small
+    bad = (ctypes.c_int * 2)(5, 11)
+    assert lib.pcseg_ragged_plan(2, 10, bad, None, 0, None, None) == -1
+    ok = (ctypes.c_int * 2)(5, 10)
+    small = (ctypes.c_int * 4)()
+    assert lib.pcseg_ragged_plan(2, 10, ok, small, 4, None, None) == -1
+    assert b"too small" in lib.pcseg_last_error()
