@@ -23,6 +23,10 @@
 //   EPI_DGRAD     : dz = acc * relu'(bn(y)) * dropout; column sum dz, sum dz*yhat     -> bf16 store + fp64 atomics
 //   EPI_WGRAD     : split-K partial tile                                              -> fp32 red.add
 //   EPI_LOGITS    : logits = W4 * relu(acc + bias) + b4  (BN == 128 == all channels)  -> fp32 store
+//
+// cloud(row): dense batches hold pts_per_cloud consecutive rows per cloud (row / pts_per_cloud; a tile may straddle two
+// clouds); packed ragged batches (pointwise.cuh, k_pack_rows) start every cloud at a multiple of 128 rows and look the
+// cloud of a tile up in tile_cloud[].  Either way the lookup happens once per tile, outside the column loop.
 #pragma once
 #include "ptx.cuh"
 
