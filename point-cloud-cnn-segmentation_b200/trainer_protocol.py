@@ -31,6 +31,10 @@ class GradSync:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.works = []
+        # slices of a bucket go out as ONE collective launch on NCCL (ncclGroupStart/End); other backends (gloo in the CPU
+        # tests) get one call per slice -- a coalescing attempt that fails half-way leaves the group unusable
+        self._coalesce = (self.world > 1 and hasattr(dist, "_coalescing_manager")
+                          and "nccl" in str(dist.get_backend(process_group)).lower())
 
     @property
     def active(self):
@@ -47,15 +51,12 @@ class GradSync:
         if not self.active:
             return
         views = [self.g[a:b] for a, b in ranges if b > a]
-        if len(views) > 1:
-            try:
-                with dist._coalescing_manager(group=self.pg, device=self.g.device, async_ops=True) as cm:
-                    for v in views:
-                        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg)
-                self.works.append(cm)
-                return
-            except (AttributeError, RuntimeError, ValueError, TypeError):
-                pass                                           # backend without coalescing: one call per slice
+        if len(views) > 1 and self._coalesce:
+            with dist._coalescing_manager(group=self.pg, device=self.g.device, async_ops=True) as cm:
+                for v in views:
+                    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg)
+            self.works.append(cm)
+            return
         for v in views:
             self.works.append(dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 

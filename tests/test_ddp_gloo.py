@@ -50,7 +50,8 @@ def _worker(rank, world, port_file, q):
     (loss_sum / wsum.float()).backward()
     flat.copy_(_flat_grads(port))
     n = flat.numel()
-    early, late = [(n // 3, n)], [(0, n // 3)]
+    # two slices per bucket, like grad_buckets(): exercises the coalesced launch (one collective per bucket)
+    early, late = [(n // 3, n // 2), (3 * n // 4, n)], [(0, n // 3), (n // 2, 3 * n // 4)]
     sync.launch(early)
     sync.launch(late)
     sync.wait()
