@@ -129,3 +129,52 @@ def dgrad_masked(dy, W, y_prev, bnp_prev, keep=None, keep_scale=1.0):
 def wgrad(dy, a_prev):
     """conv backward-weight: dW = dy^T a_prev."""
     return np.asarray(dy, np.float64).T @ np.asarray(a_prev, np.float64)
+
+
+# ---------------------------------------------------------------------------------------------
+# Conditioning of the train-mode forward under storage rounding (DESIGN.md §4): the same network with weights and the
+# stored tensors (pre-BN outputs y, activations a) rounded to a given number of significand bits, everything else fp64.
+# 8 bits = bf16 (what the CUDA path stores), 11 bits = TF32 (the reference's own cuDNN default), 24 bits = fp32.
+# ---------------------------------------------------------------------------------------------
+def round_to_bits(bits):
+    def f(a):
+        m, e = np.frexp(np.asarray(a, np.float64))
+        return np.ldexp(np.round(m * 2.0 ** bits) / 2.0 ** bits, e)
+    return f
+
+
+def forward_rounded(sd, x, bits, train=True):
+    """pcs.py:98-133 with storage rounding to `bits` significand bits (conv1 runs on fp32 FMA units: its weights are
+    not rounded).  train=True: batch statistics (dropout off); train=False: running statistics."""
+    from . import pointnet_oracle as orc
+    r = round_to_bits(bits)
+    B, N, _ = x.shape
+    a = x.reshape(B * N, -1).astype(np.float64)
+
+    def block(a_in, conv, bn, first=False, extra=None, wcols=None):
+        W = sd[f"{conv}.weight"][:, :, 0].astype(np.float64)
+        if wcols is not None:
+            W = W[:, wcols]
+        if not first:
+            W = r(W)
+        y = a_in @ W.T + sd[f"{conv}.bias"].astype(np.float64)
+        if extra is not None:
+            y = y + extra
+        y = r(y)
+        if train:
+            mean, var = y.mean(0), y.var(0)
+        else:
+            mean, var = sd[f"{bn}.running_mean"].astype(np.float64), sd[f"{bn}.running_var"].astype(np.float64)
+        return (y - mean) / np.sqrt(var + orc.BN_EPS) * sd[f"{bn}.weight"] + sd[f"{bn}.bias"]
+
+    a = r(np.maximum(block(a, "conv1", "bn1", first=True), 0))
+    pf = a = r(np.maximum(block(a, "conv2", "bn2"), 0))
+    for conv, bn in (("conv3", "bn3"), ("conv4", "bn4"), ("conv5", "bn5")):
+        a = r(np.maximum(block(a, conv, bn), 0))
+    g = np.maximum(block(a, "global_feat", "bn_global"), 0).reshape(B, N, -1).max(1)
+    cb = g @ sd["seg_conv1.weight"][:, 64:, 0].astype(np.float64).T
+    a = r(np.maximum(block(pf, "seg_conv1", "bn_seg1", extra=np.repeat(cb, N, axis=0), wcols=slice(0, 64)), 0))
+    a = r(np.maximum(block(a, "seg_conv2", "bn_seg2"), 0))
+    z = np.maximum(block(a, "seg_conv3", "bn_seg3"), 0)
+    W4 = sd["seg_conv4.weight"][:, :, 0].astype(np.float64)
+    return (z @ W4.T + sd["seg_conv4.bias"]).reshape(B, N, -1)
