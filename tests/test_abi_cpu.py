@@ -188,3 +188,38 @@ def test_ragged_plan_invariants(lib):
     small = (ctypes.c_int * 4)()
     assert lib.pcseg_ragged_plan(2, 10, ok, small, 4, None, None) == -1
     assert b"too small" in lib.pcseg_last_error()
+
+
+def test_header_is_plain_c():
+    """the boundary is a C ABI: include/pcseg_b200.h must compile as C99 (and as C++) on its own, and a C host that calls
+    the layout queries must link against the shared library"""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "pcseg_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    src = r'''
+#include <stdio.h>
+#include "pcseg_b200.h"
+int main(void) {
+    int lengths[3] = {1000, 517, 1};
+    long long rows = 0; int strips = 0;
+    long long n = pcseg_ragged_plan(3, 1000, lengths, NULL, 0, &rows, &strips);
+    printf("%lld %lld %lld %d\n", pcseg_param_count(5), pcseg_bn_buffer_count(), rows, strips > 0 && n > 0);
+    return 0;
+}
+'''
+    libdir = os.path.join(ROOT, "point-cloud-cnn-segmentation_b200", "lib")
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "host.c")
+        exe = os.path.join(td, "host")
+        with open(c, "w") as f:
+            f.write(src)
+        subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe, "-L", libdir, "-lpcseg_b200",
+                        "-Wl,-rpath," + libdir], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == "1927621" and out[1] == "6528" and int(out[2]) == 1024 + 640 + 128 and out[3] == "1"
