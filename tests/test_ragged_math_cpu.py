@@ -74,3 +74,34 @@ def test_caller_gradients_on_pad_rows_are_summed_into_the_representative_row():
         if name.endswith(".bias") and name.split(".")[0] in orc.CONV_NAMES[:-1]:
             continue
         np.testing.assert_allclose(got[name], g, rtol=0, atol=1e-9 * max(np.abs(g).max(), 1e-12) + 1e-13, err_msg=name)
+
+
+def test_packed_scheme_against_the_reference_fixture():
+    """the ragged fixture was produced by the UNMODIFIED reference (collate_fn + model.train() + loss.backward(),
+    tests/golden/make_golden.py): the packed scheme reproduces its logits, loss and gradients without computing a pad row
+    more than once"""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "case_ragged_c3.npz"))
+    C, seed = int(gold["C"]), int(gold["seed"])
+    sd = orc.synth_state(C, seed)
+    x, y, cw = gold["x"].astype(np.float64), gold["labels"], gold["class_w"].astype(np.float64)
+    B, N, _ = x.shape
+    lengths = (y != -1).sum(1).tolist()
+    assert min(lengths) < N
+    xp, labp, mult, cloud = rr.pack(x, y, lengths)
+    assert len(xp) < B * N                                             # fewer rows than the padded batch
+    lp, pc = rr.forward_train_packed(sd, xp, mult, cloud, B, N)
+    loss_p, dlp = orc.weighted_ce(lp[None], labp[None], cw)
+    assert abs(loss_p - float(gold["loss"])) < 1e-5
+    r = 0
+    for b, L in enumerate(lengths):
+        np.testing.assert_allclose(lp[r:r + L], gold["train_logits"][b, :L], rtol=0, atol=5e-5)
+        r += L + (1 if L < N else 0)
+    got = rr.backward_packed(pc, dlp[0])
+    for key in gold.files:
+        if key.startswith("g/"):
+            name = key[2:]
+            if name.endswith(".bias") and name.split(".")[0] in orc.CONV_NAMES[:-1]:
+                continue
+            ref = gold[key]
+            np.testing.assert_allclose(got[name], ref, rtol=0, atol=1e-3 * np.abs(ref).max() + 1e-6, err_msg=name)
