@@ -167,3 +167,23 @@ def test_stock_torch_model_matches_reference(path):
     loss = torch.nn.functional.cross_entropy(lt.contiguous().view(-1, C), torch.from_numpy(gold["labels"]).view(-1),
                                              weight=torch.from_numpy(gold["class_w"]), ignore_index=-1)
     assert abs(loss.item() - float(gold["loss"])) < 1e-5
+
+
+def test_oracle_adam_matches_torch_optim():
+    """optimizer.step() of pcs.py:217,255 (torch.optim.Adam, lr 1e-3, weight_decay 1e-4) restated in the oracle"""
+    import torch
+    rng = np.random.default_rng(0)
+    p0 = {"a": rng.normal(size=(7, 5)), "b": rng.normal(size=(11,))}
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p0.items()}
+    opt = torch.optim.Adam(list(tp.values()), lr=1e-3, weight_decay=1e-4)
+    params = {k: v.copy() for k, v in p0.items()}
+    m = {k: np.zeros_like(v) for k, v in p0.items()}
+    v = {k: np.zeros_like(val) for k, val in p0.items()}
+    for step in range(1, 4):
+        grads = {k: rng.normal(size=val.shape) for k, val in p0.items()}
+        for k in tp:
+            tp[k].grad = torch.tensor(grads[k])
+        opt.step()
+        params = orc.adam_step(params, grads, m, v, step)
+        for k in tp:
+            np.testing.assert_allclose(params[k], tp[k].detach().numpy(), rtol=0, atol=1e-12)
