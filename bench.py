@@ -168,7 +168,8 @@ def run_reference(args, B, N, mode):
     cores = os.cpu_count() or 1
     steps = max(1, args.steps)
     warmup = max(0, min(args.warmup, 3))
-    value, ms, sample = time_cpu(mode, B, N, NUM_CLASSES, steps, warmup, budget_s=120.0)
+    # whole run bounded to about two minutes of CPU work (PCSEG_REF_BUDGET_S overrides: the contract test uses a few seconds)
+    value, ms, sample = time_cpu(mode, B, N, NUM_CLASSES, steps, warmup, budget_s=float(os.environ.get("PCSEG_REF_BUDGET_S", "120")))
     line = {
         "impl": "reference", "metric": metric_name(mode), "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
