@@ -2,13 +2,18 @@
 """Benchmark of the point-cloud segmentation hot path (BASELINE.json metric: segmentation points/sec,
 fwd+bwd training step).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2|cfg3_train|cfg2_eval|cfg3_eval]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--no-cpu-baseline]
+                    [--workload cfg2|cfg3_train|cfg4|cfg2_eval|cfg3_eval|cfg5_eval|cfg5_eval_sharded]
 
 One "step" = one full training step (forward with batch statistics and dropout p=0.3, weighted
 cross-entropy, backward of all 38 parameter tensors, NCCL gradient all-reduce when N > 1, Adam) on one
 batch of synthetic clouds.  N = 1 workload: BASELINE.json configs[1] = batch 8 x 16 384 points, C = 5.
 N > 1: every rank runs that batch on its own clouds (weak scaling, data parallel).
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0): value = device-timed throughput with resident inputs, e2e = the same through the public API
+with pinned-host inputs copied every step and the result read back, roofline = the dominant tcgen05 GEMM against the
+measured bf16 peak, cpu_baseline = the torch-CPU port of the reference step on the host cores, torch_eager_same_gpu = the
+reference network with stock torch layers on this GPU (TF32 and IEEE fp32).  The *_eval workloads time inference,
+cfg5_eval_sharded splits one 1M-point scene over the ranks (strong scaling).
 """
 import argparse
 import json
