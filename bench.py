@@ -3,7 +3,7 @@
 fwd+bwd training step).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--no-cpu-baseline]
-                    [--workload cfg2|cfg3_train|cfg4|cfg2_eval|cfg3_eval|cfg5_eval|cfg5_eval_sharded]
+                    [--workload cfg2|cfg3_train|cfg4|cfg1_eval|cfg2_eval|cfg3_eval|cfg5_eval|cfg5_eval_sharded]
 
 One "step" = one full training step (forward with batch statistics and dropout p=0.3, weighted
 cross-entropy, backward of all 38 parameter tensors, NCCL gradient all-reduce when N > 1, Adam) on one
@@ -32,6 +32,7 @@ WORKLOADS = {
     # name: (clouds per rank, points per cloud, mode)
     "cfg2": (8, 16384, "train"),
     "cfg3_train": (16, 131072, "train"),
+    "cfg1_eval": (1, 16384, "eval"),      # configs[0]: one 16k-point cloud, inference (the reference's CPU-runnable case)
     "cfg2_eval": (8, 16384, "eval"),
     "cfg3_eval": (16, 131072, "eval"),
     "cfg4": (8, 65536, "train"),          # configs[3] at 8 GPUs: global 64 x 64k -> 8 clouds x 65 536 per GPU
