@@ -140,10 +140,13 @@ int pcseg_backward(pcseg_ctx* ctx, const float* x, const float* params, const fl
                    const float* logits, const long long* labels, const float* class_w,
                    const double* wsum_total, float* grads, int phase, void* stream);
 
-/* optimizer.step() of torch.optim.Adam(lr, weight_decay) on the flat arena, pcs.py:217,255. */
+/* optimizer.step() of torch.optim.Adam(lr, weight_decay) on the flat arena, pcs.py:217,255.  The gradient is taken as
+ * grads * grad_scale / (*grad_div) (grad_div: device double, may be NULL): data-parallel ranks back-propagate the
+ * un-normalised loss (pcseg_backward with *wsum_total == 1) and divide by the all-reduced sum of class weights here,
+ * which is what the reference's single weighted-mean loss over the gathered logits amounts to (pcs.py:244-251). */
 int pcseg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                     int step, float lr, float beta1, float beta2, float eps, float weight_decay,
-                    float grad_scale, const pcseg_step_state* state, void* stream);
+                    float grad_scale, const pcseg_step_state* state, const double* grad_div, void* stream);
 
 /* state (device): seed += odd constant, step += 1, bias corrections recomputed.  If state is non-NULL in
  * pcseg_adam_step, `step` and `lr` are taken from it instead of from the arguments. */

@@ -176,7 +176,7 @@ def forward_train(sd, x, dropout_masks=None, dtype=np.float64):
         if drop is not None:
             scale = drop.astype(dtype) / (1.0 - DROPOUT_P)
             out = out * scale
-        cache["layers"][conv] = dict(a_in=a_in, W=W, bn=bnc, relu=(z > 0), drop=scale)
+        cache["layers"][conv] = dict(a_in=a_in, W=W, b=b, bn=bnc, relu=(z > 0), drop=scale)
         return out
 
     for conv, bn, _, _ in TRUNK:
@@ -220,9 +220,10 @@ def weighted_ce(logits, labels, class_w, dtype=np.float64):
     return loss, dz.reshape(logits.shape)
 
 
-def backward(cache, dlogits):
+def backward(cache, dlogits, taps=None):
     """Gradients of every parameter for `forward_train` (what autograd computes at
-    pcs.py:254).  Returns dict name -> grad with state_dict shapes."""
+    pcs.py:254).  Returns dict name -> grad with state_dict shapes.  `taps` (optional dict) receives
+    intermediate gradients: 'dg' (wrt the pooled feature) and 'dx:<conv>' (wrt the input of a conv)."""
     B, N = cache["B"], cache["N"]
     P = B * N
     L = cache["layers"]
@@ -232,7 +233,10 @@ def backward(cache, dlogits):
         c = L[conv]
         grads[f"{conv}.weight"] = (dy.T @ c["a_in"])[:, :, None]
         grads[f"{conv}.bias"] = dy.sum(axis=0)
-        return dy @ c["W"] if need_dx else None
+        dx = dy @ c["W"] if need_dx else None
+        if taps is not None and need_dx:
+            taps[f"dx:{conv}"] = dx
+        return dx
 
     def act_bwd(conv, bn, da):
         c = L[conv]
@@ -250,6 +254,8 @@ def backward(cache, dlogits):
         da = conv_bwd(conv, act_bwd(conv, bn, da))
     d_point_feat = da[:, :64]                                           # cat split, pcs.py:120
     dg = da[:, 64:].reshape(B, N, -1).sum(axis=1)                       # repeat bwd, pcs.py:117
+    if taps is not None:
+        taps["dg"] = dg
     da6 = np.zeros((B, N, dg.shape[1]), dtype=da.dtype)                 # max bwd, pcs.py:114
     np.put_along_axis(da6, cache["argmax"][:, None, :], dg[:, None, :], axis=1)
     da = da6.reshape(P, -1)

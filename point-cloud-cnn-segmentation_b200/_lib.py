@@ -52,7 +52,7 @@ def _load():
     lib.pcseg_forward_eval_ragged.argtypes = [vp, vp, C.POINTER(i32), i32, vp, vp, vp]
     lib.pcseg_forward_train_ragged.argtypes = [vp, vp, C.POINTER(i32), i32, vp, vp, u64, f32, vp, vp, vp, vp, vp, vp]
     lib.pcseg_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
-    lib.pcseg_adam_step.argtypes = [vp, vp, vp, vp, ll, i32, f32, f32, f32, f32, f32, f32, vp, vp]
+    lib.pcseg_adam_step.argtypes = [vp, vp, vp, vp, ll, i32, f32, f32, f32, f32, f32, f32, vp, vp, vp]
     lib.pcseg_step_advance.argtypes = [vp, f32, f32, vp]
     lib.pcseg_eval_metrics.argtypes = [vp, vp, ll, i32, vp, vp, vp, vp, vp]
     lib.pcseg_gemm_test.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]

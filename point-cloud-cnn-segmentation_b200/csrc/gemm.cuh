@@ -23,6 +23,14 @@
 //   EPI_DGRAD     : dz = acc * relu'(bn(y)) * dropout; column sum dz, sum dz*yhat     -> bf16 store + fp64 atomics
 //   EPI_WGRAD     : split-K partial tile                                              -> fp32 red.add
 //   EPI_LOGITS    : logits = W4 * relu(acc + bias) + b4  (BN == 128 == all channels)  -> fp32 store
+//   EPI_BN_RELU   : out = relu(scale[n] * acc + shift[n]) with {scale, shift} = bnp[n].xy (train-mode BatchNorm whose batch
+//                   statistics were PREDICTED from the Gram matrix of the layer input, see k_predict_bn)   -> bf16 store
+//   EPI_DGRAD_ACT : EPI_DGRAD with the mask taken from the stored ACTIVATION of the layer below (a > 0 <=> ReLU on and not
+//                   dropped; no BN parameters, no Philox); column sums: sum dz and sum a                 -> bf16 store + fp64 atomics
+// DGRAD / DGRAD_ACT add bias[n] to the accumulator when p.bias != nullptr (constant row of the folded BatchNorm backward).
+//
+// The A operand may be the K-concatenation of two tensors: k-blocks [0, kb_switch) come from tmA, the rest from tmA2
+// (folded BatchNorm backward: [dz | a_prev]).
 //
 // cloud(row): dense batches hold pts_per_cloud consecutive rows per cloud (row / pts_per_cloud; a tile may straddle two
 // clouds); packed ragged batches (pointwise.cuh, k_pack_rows) start every cloud at a multiple of 128 rows and look the
@@ -32,7 +40,8 @@
 
 namespace pcseg {
 
-enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EPI_WGRAD = 4, EPI_LOGITS = 5, EPI_STATS_POOL = 6 };
+enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EPI_WGRAD = 4, EPI_LOGITS = 5, EPI_STATS_POOL = 6,
+              EPI_BN_RELU = 7, EPI_DGRAD_ACT = 8 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -45,6 +54,8 @@ struct GemmParams {
     int M, N, K;                 // logical problem (for MN/wgrad: M = Cout, N = Cin, K = points)
     int num_m_tiles, num_n_tiles;
     int num_splits, kb_per_split;   // split-K (wgrad only; otherwise 1 / K/64)
+    int kb_switch;               // k-blocks [0, kb_switch) of A come from tmA, the rest from tmA2 (0 = everything from tmA)
+    int store_out;               // EPI_STATS_POOL: 0 = statistics / max-pool only, the output tile is not written
     // epilogue operands (all optional depending on EPI)
     const float* bias;           // [N]
     const float* cloud_bias;     // [clouds][N] or nullptr
@@ -76,8 +87,9 @@ struct GemmCfg {
     static constexpr int STAGE_A = GEMM_BM * GEMM_BK * 2;
     static constexpr int STAGE_B = BN * GEMM_BK * 2;
     static constexpr int STAGE = STAGE_A + STAGE_B;
-    static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD);
-    static constexpr bool HAS_Y = (EPI == EPI_DGRAD);
+    static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD ||
+                                     EPI == EPI_BN_RELU || EPI == EPI_DGRAD_ACT);
+    static constexpr bool HAS_Y = (EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
     static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
     static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
     static constexpr int COMB_BYTES = (EPI == EPI_LOGITS) ? (epi_warps_for(EPI) / 4 - 1) * 128 * MAX_CLASSES * 4 + 1024
@@ -157,9 +169,34 @@ __device__ __forceinline__ void dgrad_pass2_rows(uint32_t tile_s, uint32_t ytile
     }
 }
 
+// DGRAD_ACT epilogue, pass 2: the mask is (stored activation > 0); accumulates s1 = sum dz, s2 = sum activation.
+template <int RPT>
+__device__ __forceinline__ void dgrad_act_pass2_rows(uint32_t tile_s, uint32_t atile, int rbase, int chunk, float (&s1)[8],
+                                                     float (&s2)[8]) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
+        const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+        const uint4 dw = lds128(tile_s + off);
+        const uint4 aw = lds128(atile + off);
+        const uint32_t ds[4] = {dw.x, dw.y, dw.z, dw.w};
+        const uint32_t as[4] = {aw.x, aw.y, aw.z, aw.w};
+        float dz[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float av = (e & 1) ? bf16_hi(as[e >> 1]) : bf16_lo(as[e >> 1]);
+            const float da = (e & 1) ? bf16_hi(ds[e >> 1]) : bf16_lo(ds[e >> 1]);
+            dz[e] = (av > 0.f) ? da : 0.f;
+            s1[e] += dz[e];
+            s2[e] += av;
+        }
+        sts128(tile_s + off, make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7])));
+    }
+}
+
 template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(GemmCfg<BN, EPI, MN>::THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmY,
             const GemmParams p) {
     using Cfg = GemmCfg<BN, EPI, MN>;
@@ -192,6 +229,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
+        if (p.kb_switch > 0) tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
         if (Cfg::HAS_OUT) tma_prefetch_desc(&tmOut);
         if (Cfg::HAS_Y) tma_prefetch_desc(&tmY);
@@ -246,7 +284,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     uint8_t* sb = sa + Cfg::STAGE_A;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
                     if (!MN) {
-                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_tile * GEMM_BM);
+                        if (p.kb_switch > 0 && kb >= p.kb_switch)
+                            tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - p.kb_switch) * GEMM_BK, m_tile * GEMM_BM);
+                        else
+                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_tile * GEMM_BM);
                         tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_tile * BN);
                     } else {
 #pragma unroll
@@ -342,11 +383,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             issue_y_load(0);
             issue_y_load(1);
         }
-        constexpr bool COLACC = (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD);
+        constexpr bool COLACC = (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
+        constexpr bool IS_DGRAD = (EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
         if constexpr (COLACC) {
             // per-CTA column accumulators [NH][2][BN]: valid because every tile of this CTA has the same n_tile
             // (the host launches a grid that is a multiple of num_n_tiles)
             for (int i = et; i < NH * 2 * BN; i += EPI_THREADS) comb[i] = 0.f;
+            named_bar_sync(1, EPI_THREADS);
+        }
+        if constexpr (EPI == EPI_BN_RELU) {
+            // {scale, shift} of this CTA's BN columns (n_tile is fixed per CTA): comb[0..BN) = scale, comb[BN..2BN) = shift
+            const int n0_fixed = (blockIdx.x % p.num_n_tiles) * BN;
+            for (int i = et; i < BN; i += EPI_THREADS) {
+                const float4 bp = __ldg(p.bnp + n0_fixed + i);
+                comb[i] = bp.x;
+                comb[BN + i] = bp.y;
+            }
             named_bar_sync(1, EPI_THREADS);
         }
 
@@ -494,6 +546,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     atomicMax(p.colmax + static_cast<size_t>(cloud) * p.N + c0 + i, __float_as_uint(o[i]));
                             }
                         }
+                    } else if constexpr (EPI == EPI_BN_RELU) {
+                        // rows beyond M are clipped by the TMA store
+                        const float* scs = comb + sub * 64 + cq * CW;
+#pragma unroll
+                        for (int i = 0; i < CW / 2; ++i)
+                            packed[i] = pack_bf16x2(fmaxf(fmaf(scs[2 * i], __uint_as_float(v[2 * i]), scs[BN + 2 * i]), 0.f),
+                                                    fmaxf(fmaf(scs[2 * i + 1], __uint_as_float(v[2 * i + 1]), scs[BN + 2 * i + 1]), 0.f));
                     } else if constexpr (EPI == EPI_STATS || EPI == EPI_STATS_POOL) {
                         // pass 1 (row-mapped): accumulator (+ per-cloud term) -> bf16 -> staging tile.
                         // Rows beyond M have exactly-zero accumulators (TMA zero fill), so they add nothing to the sums.
@@ -511,8 +570,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
 #pragma unroll
                         for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                    } else if constexpr (EPI == EPI_DGRAD) {
-                        // pass 1 (row-mapped): dA * 1/(1-p) -> bf16 -> staging tile (masking happens column-mapped in pass 2)
+                    } else if constexpr (IS_DGRAD) {
+                        // pass 1 (row-mapped): (dA + constant row) * 1/(1-p) -> bf16 -> staging tile (masking happens
+                        // column-mapped in pass 2)
+                        if (p.bias != nullptr && valid) {      // (rows beyond M keep their exactly-zero accumulators)
+#pragma unroll
+                            for (int i = 0; i < CW; i += 4) {
+                                const float4 b4v = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+                                v[i] = __float_as_uint(__uint_as_float(v[i]) + b4v.x);
+                                v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + b4v.y);
+                                v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + b4v.z);
+                                v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + b4v.w);
+                            }
+                        }
                         if (p.drop_thr16 != 0u) {
 #pragma unroll
                             for (int i = 0; i < CW / 2; ++i)
@@ -559,7 +629,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         float s1[8], s2[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-                        if constexpr (EPI == EPI_DGRAD) {
+                        if constexpr (EPI == EPI_DGRAD_ACT) {
+                            dgrad_act_pass2_rows<RPT>(tile_s, y_s + buf * 16384, rbase, chunk, s1, s2);
+                        } else if constexpr (EPI == EPI_DGRAD) {
                             const uint32_t ytile = y_s + buf * 16384;
                             if (p.drop_thr16 != 0u)
                                 dgrad_pass2_rows<true, RPT>(tile_s, ytile, rbase, chunk, p2a, p2b, s1, s2, seed_eff, p.drop_thr16, m0, p.N, colbase);
@@ -668,15 +740,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 sts_f32(ca, lds_f32(ca) + t[0]);      // unique owner: no race
                             }
                         }
-                        if constexpr (EPI == EPI_DGRAD) {
+                        if constexpr (IS_DGRAD) {
                             fence_proxy_async_smem();
                             named_bar_sync(2, EPI_THREADS);     // staging tile was modified in place
                         }
                     }
                     if constexpr (Cfg::HAS_OUT) {
                         if (elected) {
-                            tma_store_2d(&tmOut, out_stage + buf * 16384, n0 + sub * 64, m0);
-                            tma_store_commit();
+                            if (EPI != EPI_STATS_POOL || p.store_out) {
+                                tma_store_2d(&tmOut, out_stage + buf * 16384, n0 + sub * 64, m0);
+                                tma_store_commit();
+                            }
                             if constexpr (Cfg::HAS_Y) issue_y_load(sub_it + 2);
                         }
                     }

@@ -195,7 +195,7 @@ int num_sms() {
 // GEMM launcher
 // ------------------------------------------------------------------------------------------------
 struct GemmOp {
-    CUtensorMap tmA, tmB, tmOut, tmY;
+    CUtensorMap tmA, tmA2, tmB, tmOut, tmY;
     GemmParams p;
     int bn, epi;
     bool mn;
@@ -216,7 +216,7 @@ int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
     const int tiles = op.p.num_m_tiles * op.p.num_n_tiles * op.p.num_splits;
     int grid = tiles < num_sms() ? tiles : num_sms();
     if (!MN) grid = (grid / op.p.num_n_tiles) * op.p.num_n_tiles;   // every CTA keeps one n_tile (per-CTA column accumulators)
-    pdl_launch(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, op.tmA, op.tmB, op.tmOut, op.tmY, op.p);
+    pdl_launch(kern, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, op.tmA, op.tmA2, op.tmB, op.tmOut, op.tmY, op.p);
     LAUNCH_OK("gemm_kernel");
     return 0;
 }
@@ -231,6 +231,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t s) {
     CASE(64, EPI_STATS, false) CASE(128, EPI_STATS, false) CASE(256, EPI_STATS, false)
     CASE(256, EPI_STATS_POOL, false)
     CASE(64, EPI_DGRAD, false) CASE(128, EPI_DGRAD, false) CASE(256, EPI_DGRAD, false)
+    CASE(256, EPI_BN_RELU, false) CASE(256, EPI_DGRAD_ACT, false)
     CASE(64, EPI_WGRAD, true) CASE(128, EPI_WGRAD, true) CASE(256, EPI_WGRAD, true)
 #undef CASE
     return fail("internal: no GEMM instantiation for BN=%d EPI=%d MN=%d", op.bn, op.epi, (int)op.mn);
@@ -250,6 +251,7 @@ int setup_gemm_kmajor(GemmOp* op, int epi, const void* A, int lda, const void* B
     op->epi = epi;
     op->mn = false;
     TRY(make_tmap(&op->tmA, A, K, M, lda, 64, 128));
+    op->tmA2 = op->tmA;
     TRY(make_tmap(&op->tmB, B, K, N, ldb, 64, op->bn));
     if (out) TRY(make_tmap(&op->tmOut, out, N, M, ldo, 64, 128)); else op->tmOut = op->tmA;
     if (ymask) TRY(make_tmap(&op->tmY, ymask, N, M, ldy, 64, 128)); else op->tmY = op->tmA;
@@ -261,7 +263,21 @@ int setup_gemm_kmajor(GemmOp* op, int epi, const void* A, int lda, const void* B
     op->p.num_splits = 1;
     op->p.kb_per_split = K / 64;
     op->p.keep_scale = 1.f;
+    op->p.store_out = 1;
     op->ready = true;
+    return 0;
+}
+
+// Same with the A operand given as the K-concatenation [A1 (K1 columns) | A2 (K2 columns)] of two tensors.
+int setup_gemm_kmajor_cat(GemmOp* op, int epi, const void* A1, int lda1, int K1, const void* A2, int lda2, int K2, const void* B,
+                          int ldb, long long M, int N, void* out, int ldo, const void* ymask, int ldy) {
+    if (K1 % 64 != 0 || K2 % 64 != 0) return fail("GEMM K1=%d / K2=%d must be multiples of 64", K1, K2);
+    TRY(setup_gemm_kmajor(op, epi, A1, lda1, B, ldb, M, N, K1, out, ldo, ymask, ldy));
+    TRY(make_tmap(&op->tmA2, A2, K2, M, lda2, 64, 128));
+    TRY(make_tmap(&op->tmB, B, K1 + K2, N, ldb, 64, op->bn));
+    op->p.K = K1 + K2;
+    op->p.kb_per_split = (K1 + K2) / 64;
+    op->p.kb_switch = K1 / 64;
     return 0;
 }
 
@@ -275,6 +291,7 @@ int setup_gemm_wgrad(GemmOp* op, const void* A, int lda, int Mc, const void* B, 
     op->mn = true;
     TRY(make_tmap(&op->tmA, A, Mc, P, lda, 64, 64));
     TRY(make_tmap(&op->tmB, B, Nc, P, ldb, 64, 64));
+    op->tmA2 = op->tmA;
     op->tmOut = op->tmA;
     op->tmY = op->tmA;
     op->p.M = Mc;
@@ -299,6 +316,8 @@ int setup_gemm_wgrad(GemmOp* op, const void* A, int lda, int Mc, const void* B, 
 // workspace carving
 // ------------------------------------------------------------------------------------------------
 constexpr int RAG_MAX_STRIPS = 1024;
+// folded conv5 scratch that is zeroed once per backward: Q (1024 x 128) | S32 (128 x 128) | const (128) | tile tickets (64)
+constexpr size_t FOLD4_ZERO_FLOATS = 1024 * 128 + 128 * 128 + 128 + 64;
 
 struct Carver {
     uint8_t* base;
@@ -382,6 +401,18 @@ struct pcseg_ctx {
     int* argidx = nullptr;
     float* dcb = nullptr;
     float* dzv = nullptr;
+    // ---- Gram-predicted BatchNorm + folded BatchNorm backward (dense batches).  Index = conv index of the
+    // layer whose y / dy are never materialised (4 = conv5); gram / colsum describe its INPUT activation.
+    bool folded = true;
+    float* gramf[NUM_BN] = {};    // [Ci][Ci] fp32  a_prev^T a_prev
+    double* colsum[NUM_BN] = {};  // [Ci] fp64      sum_p a_prev   (directly behind gramf: one memset)
+    float* qraw[NUM_BN] = {};     // [Co][Ci] fp32  dz^T a_prev
+    bf16* bwf[NUM_BN] = {};       // [Ci][Co + Ci]  data-gradient weights [diag(A) W ; S]^T
+    float* cstf[NUM_BN] = {};     // [Ci]           constant row of the data gradient
+    float* s32f[NUM_BN] = {};     // [Ci][Ci] fp32 accumulator of S; qraw | s32f | cstf | ticket are contiguous (one memset)
+    int* foldticket[NUM_BN] = {};
+    float* gcf[NUM_BN] = {};      // [Ci][Ci] centred Gram matrix
+    GemmOp gram_op[NUM_BN];
     unsigned long long seed = 0;
     const unsigned long long* seed_ptr = nullptr;
     unsigned int thr16 = 0;
@@ -441,6 +472,16 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
             c->wt[i] = k.take<bf16>(static_cast<size_t>(cv[i].cout) * cin);
         }
         c->wcat = k.take<bf16>(64 * 576);
+        {   // folded conv5: Ci = 128, Co = 1024
+            c->gramf[4] = k.take<float>(128 * 128 + 2 * 128);      // + colsum (fp64) right behind
+            c->colsum[4] = reinterpret_cast<double*>(c->gramf[4] ? c->gramf[4] + 128 * 128 : nullptr);
+            c->qraw[4] = k.take<float>(FOLD4_ZERO_FLOATS);
+            c->s32f[4] = c->qraw[4] ? c->qraw[4] + 1024 * 128 : nullptr;
+            c->cstf[4] = c->qraw[4] ? c->s32f[4] + 128 * 128 : nullptr;
+            c->foldticket[4] = c->qraw[4] ? reinterpret_cast<int*>(c->cstf[4] + 128) : nullptr;
+            c->gcf[4] = k.take<float>(128 * 128);
+            c->bwf[4] = k.take<bf16>(128 * (1024 + 128));
+        }
     }
     // ---- shape-dependent buffers
     c->gmax = k.take<float>(static_cast<size_t>(B) * 1024);
@@ -500,6 +541,10 @@ extern "C" int pcseg_create(pcseg_ctx** out, int num_classes) {
     pcseg_ctx* c = new pcseg_ctx();
     c->C = num_classes;
     c->L = make_layout(num_classes);
+    {
+        const char* e = getenv("PCSEG_FOLDED");       // 0: legacy training step (y / dy of every layer materialised)
+        c->folded = !(e && e[0] == '0');
+    }
     *out = c;
     return 0;
 }
@@ -628,6 +673,22 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         TRY(wgrad(3, c->dy[3], 128, c->act[2], 64, 64));
         TRY(wgrad(2, c->dycat, 576, c->act[1], 64, 64));
         TRY(wgrad(1, c->dy[1], 64, c->act[0], 64, 64));
+        if (c->folded && !rag) {
+            // conv5 with Gram-predicted statistics: G = a3^T a3, BN + ReLU in the GEMM epilogue, y4 never stored
+            TRY(setup_gemm_wgrad(&c->gram_op[4], c->act[3], 128, 128, c->act[3], 128, 128, P, c->gramf[4], 128));
+            TRY(setup_gemm_kmajor(&O.fw[4], EPI_BN_RELU, c->act[3], 128, c->wk[4], 128, P, 1024, 128, c->act[4], 1024, nullptr, 0));
+            O.fw[4].p.bnp = c->bnp[4];
+            // global_feat data gradient masked by the stored activation a4 (column sums: sum dz4, sum a4)
+            TRY(setup_gemm_kmajor(&O.dg[5], EPI_DGRAD_ACT, c->dy[5], 1024, c->wt[5], 1024, P, 1024, 1024, c->dz[4], 1024, c->act[4], 1024));
+            O.dg[5].p.stats = c->stats_b + c->stat_off[4];
+            // folded BN backward of conv5: Q = dz4^T a3 (raw), then dz3 = mask3 . ([dz4 | a3] [diag(A) W ; S] + const)
+            TRY(setup_gemm_wgrad(&O.wg_op[4], c->dz[4], 1024, 1024, c->act[3], 128, 128, P, c->qraw[4], 128));
+            TRY(setup_gemm_kmajor_cat(&O.dg[4], EPI_DGRAD, c->dz[4], 1024, 1024, c->act[3], 128, 128, c->bwf[4], 1024 + 128, P, 128, c->dz[3], 128,
+                                      c->y[3], 128));
+            O.dg[4].p.stats = c->stats_b + c->stat_off[3];
+            O.dg[4].p.bnp = c->bnp[3];
+            O.dg[4].p.bias = c->cstf[4];
+        }
     }
     }   // op sets
     c->bound = true;
@@ -979,6 +1040,8 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
     CUDA_OK(cudaMemsetAsync(c->stats_f, 0, c->stat_total * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(c->keys, 0, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long), s));
     if (ce) CUDA_OK(cudaMemsetAsync(ce, 0, sizeof(pcseg_ce_accum), s));
+    const bool folded = c->folded && !rag;
+    if (folded) CUDA_OK(cudaMemsetAsync(c->gramf[4], 0, 128 * 128 * sizeof(float) + 128 * sizeof(double), s));
 
     auto fin_args = [&](int i) {
         BnFinalizeArgs f;
@@ -996,9 +1059,9 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         return f;
     };
     // BN finalize of layer i is folded into this kernel (block 0 publishes bnp + running statistics)
-    auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks) -> int {
+    auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks, double* colsum = nullptr) -> int {
         const int co = cv[i].cout;
-        pdl_launch(k_bn_relu, strip_grid(P, co), 256, 0, s, c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks);
+        pdl_launch(k_bn_relu, strip_grid(P, co), 256, 0, s, c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks, colsum);
         LAUNCH_OK("k_bn_relu");
         return 0;
     };
@@ -1027,11 +1090,19 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
             GemmOp op = O.fw[5];
             op.p.gamma = params + L.off[20 + 2 * 5];
             TRY(timed_gemm(c, op, 5, s));
+        } else if (i == 4 && folded) {
+            // conv5: batch statistics predicted from the Gram matrix of a3, BN + ReLU applied in the GEMM epilogue
+            TRY(timed_gemm(c, c->gram_op[4], 48 + 4, s));
+            pdl_launch(k_predict_bn<4>, 1024 / 16, 512, 0, s, static_cast<const float*>(c->gramf[4]), static_cast<const double*>(c->colsum[4]),
+                       static_cast<const bf16*>(c->wk[4]), fin_args(4), c->stats_f + c->stat_off[4]);
+            LAUNCH_OK("k_predict_bn");
+            TRY(timed_gemm(c, O.fw[4], 4, s));
+            continue;
         } else {
             TRY(timed_gemm(c, O.fw[i], i, s));
         }
         TRY(stats_fix(i));
-        if (i < 5) TRY(bn_relu(i, 0, 0, 1.f));
+        if (i < 5) TRY(bn_relu(i, 0, 0, 1.f, (i == 3 && folded) ? c->colsum[4] : nullptr));
     }
     {   // global max-pool of relu(bn(y6)) with arg-index
         const int total = c->B * 1024;
@@ -1262,9 +1333,44 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     }   // phase != 2
     if (phase == 1) return 0;
     // conv5
-    TRY(apply(4, c->dy[4], 1024, nullptr));
-    TRY(wgrad(4, grads + L.off[8], 128));
-    TRY(dgrad(4, 0, 0, 1.f));
+    if (c->folded && !rag) {
+        // folded BatchNorm backward: neither y4 nor dy4 exist.  Q = dz4^T a3, per-channel coefficients, dW / S / const on
+        // CUDA cores (K = 128), then ONE data-gradient GEMM over [dz4 | a3]
+        CUDA_OK(cudaMemsetAsync(c->qraw[4], 0, FOLD4_ZERO_FLOATS * sizeof(float), s));
+        TRY(timed_gemm(c, O.wg_op[4], 32 + 4, s));
+        FoldArgs f;
+        f.Q = c->qraw[4];
+        f.W = c->wk[4];
+        f.Wt = c->wt[4];
+        f.G = c->gramf[4];
+        f.s = c->colsum[4];
+        f.sum_dz = c->stats_b + c->stat_off[4];
+        f.bnp = c->bnp[4];
+        f.coef = c->coef[4];
+        f.dgamma = grads + L.off[20 + 2 * 4];
+        f.dbeta = grads + L.off[21 + 2 * 4];
+        f.dbias = grads + L.off[2 * 4 + 1];
+        f.dW = grads + L.off[8];
+        f.ld_dw = 128;
+        f.Bw = c->bwf[4];
+        f.ld_bw = 1024 + 128;
+        f.cst = c->cstf[4];
+        f.S32 = c->s32f[4];
+        f.ticket = c->foldticket[4];
+        f.Gc = c->gcf[4];
+        f.n = static_cast<double>(c->P);
+        f.Co = 1024;
+        f.Ci = 128;
+        pdl_launch(k_fold_coef, fold_coef_blocks(f.Co, f.Ci), 256, 0, s, f);
+        LAUNCH_OK("k_fold_coef");
+        pdl_launch(k_fold_bwd, fold_bwd_blocks(f.Co, f.Ci), 256, 0, s, f);
+        LAUNCH_OK("k_fold_bwd");
+        TRY(timed_gemm(c, O.dg[4], 16 + 4, s));
+    } else {
+        TRY(apply(4, c->dy[4], 1024, nullptr));
+        TRY(wgrad(4, grads + L.off[8], 128));
+        TRY(dgrad(4, 0, 0, 1.f));
+    }
     // conv4
     TRY(apply(3, c->dy[3], 128, nullptr));
     TRY(wgrad(3, grads + L.off[6], 64));
@@ -1289,7 +1395,8 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
 }
 
 extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, float* v, long long n, int step, float lr, float b1,
-                               float b2, float eps, float wd, float grad_scale, const pcseg_step_state* state, void* stream) {
+                               float b2, float eps, float wd, float grad_scale, const pcseg_step_state* state, const double* grad_div,
+                               void* stream) {
     g_pdl_call = !stream_is_capturing(stream);
     if (!params || !grads || !m || !v || n <= 0 || (step < 1 && !state)) return fail("pcseg_adam_step: bad arguments");
     if (step < 1) step = 1;
@@ -1297,7 +1404,7 @@ extern "C" int pcseg_adam_step(float* params, const float* grads, float* m, floa
     const float bc1 = 1.f - powf(b1, static_cast<float>(step));
     const float bc2 = 1.f - powf(b2, static_cast<float>(step));
     pdl_launch(k_adam, ew_grid(n), 256, 0, s, params, grads, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale,
-                                      reinterpret_cast<const StepState*>(state));
+                                      reinterpret_cast<const StepState*>(state), grad_div);
     LAUNCH_OK("k_adam");
     return 0;
 }
@@ -1363,7 +1470,7 @@ extern "C" int pcseg_gemm_test(int layout, int M, int N, int K, const void* A, i
 extern "C" int pcseg_debug_copy(pcseg_ctx* c, int kind, int layer, void* dst, long long dst_bytes, long long* rows, long long* cols,
                                 int* elem_bytes, void* stream) {
     if (!c || !c->bound || !c->train) return fail("pcseg_debug_copy: context not bound in train mode");
-    if (kind <= 7 && (layer < 0 || layer >= NUM_BN)) return fail("pcseg_debug_copy: bad layer %d", layer);
+    if ((kind <= 7 || kind >= 14) && (layer < 0 || layer >= NUM_BN)) return fail("pcseg_debug_copy: bad layer %d", layer);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const ConvDef* cv = c->L.conv;
     const long long P = c->P, B = c->B;
@@ -1390,6 +1497,12 @@ extern "C" int pcseg_debug_copy(pcseg_ctx* c, int kind, int layer, void* dst, lo
         case 11: src = c->cb; r = B; cc = 512; eb = 4; break;
         case 12: src = c->dcb; r = B; cc = 512; eb = 4; break;
         case 13: src = c->dzv; r = B; cc = 1024; eb = 4; break;
+        // folded layers (layer = conv index of the layer whose y / dy are not materialised)
+        case 14: src = c->gramf[layer]; r = cv[layer].cin; cc = cv[layer].cin; eb = 4; break;
+        case 15: src = c->colsum[layer]; r = 1; cc = cv[layer].cin; eb = 8; break;
+        case 16: src = c->qraw[layer]; r = cv[layer].cout; cc = cv[layer].cin; eb = 4; break;
+        case 17: src = c->bwf[layer]; r = cv[layer].cin; cc = cv[layer].cout + cv[layer].cin; eb = 2; break;
+        case 18: src = c->cstf[layer]; r = 1; cc = cv[layer].cin; eb = 4; break;
         default: return fail("pcseg_debug_copy: unknown kind %d", kind);
     }
     if (!src) return fail("pcseg_debug_copy: tensor kind %d layer %d is not materialised", kind, layer);

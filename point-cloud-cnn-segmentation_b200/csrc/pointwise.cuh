@@ -204,12 +204,18 @@ __device__ __forceinline__ void bn_publish(const BnFinalizeArgs& f, bool first_b
 
 // a = relu(scale*y + shift) (* dropout keep / (1-p)).  Each thread owns 8 fixed channels (scale/shift live in
 // registers) and walks down the rows of its block's strip; 4 independent 16-byte loads in flight per thread.
+// colsum (optional, [C] fp64, zeroed by the caller): column sums of the STORED (bf16-rounded) activation, the `s` of the
+// Gram-predicted statistics of the next layer (k_predict_bn).
 __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
                                                  int ld_a, long P, int C, const BnFinalizeArgs fin,
                                                  unsigned long long seed_arg, const unsigned long long* __restrict__ seed_ptr,
-                                                 unsigned int thr16, float keep_scale) {
+                                                 unsigned int thr16, float keep_scale, double* __restrict__ colsum) {
     pdl_launch_dependents();
     pdl_wait();
+    __shared__ float red[256 * 8];
+    float csum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) csum[e] = 0.f;
     bn_publish(fin, blockIdx.x == 0);
     const unsigned long long seed = seed_arg + (seed_ptr != nullptr ? *seed_ptr : 0ull);
     const int tpr = C >> 3;                       // threads per row (C <= 2048)
@@ -247,9 +253,100 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
                 const float t = fmaf(sc[e], yv, sh[e]);
                 o[e] = (t > 0.f && ((keep >> e) & 1u)) ? t * keep_scale : 0.f;
             }
-            *reinterpret_cast<uint4*>(a + rr * ld_a + c0) =
-                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            const uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            *reinterpret_cast<uint4*>(a + rr * ld_a + c0) = pk;
+            if (colsum != nullptr) {
+                const uint32_t ps[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) csum[e] += (e & 1) ? bf16_hi(ps[e >> 1]) : bf16_lo(ps[e >> 1]);
+            }
         }
+    }
+    if (colsum != nullptr) {          // red[row slot][C]: combine the row slots, then one fp64 atomic per column per block
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[rslot * C + c0 + e] = csum[e];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            float sum = 0.f;
+            for (int sl = 0; sl < rpp; ++sl) sum += red[sl * C + c];
+            atomicAdd(colsum + c, static_cast<double>(sum));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram-predicted train-mode BatchNorm (oracle/folded_bn_ref.py identity (1)).
+// The batch statistics of y = a W^T over n rows follow from s = sum_p a and G = a^T a (an MN-major tcgen05 GEMM with
+// A = B = a):   mean[c] = W[c,:] m,   var[c] = W[c,:] (G/n - m m^T) W[c,:]^T,   m = s/n.
+// Knowing them BEFORE the GEMM runs lets its epilogue apply BN + ReLU directly (EPI_BN_RELU): y is never stored.
+// W is the bf16 copy the GEMM multiplies with, so the statistics describe the fp32 accumulators exactly.
+// One warp per output channel, fp64 throughout (K x K is small).  Also updates the running statistics (momentum,
+// unbiased variance, conv bias re-added to the mean) and writes {sum y, sum y^2} for inspection.
+// ---------------------------------------------------------------------------------------------
+template <int KQ>      // K = 32 * KQ input channels; 16 warps = 16 output channels per block
+__global__ void __launch_bounds__(512) k_predict_bn(const float* __restrict__ G, const double* __restrict__ colsum,
+                                                    const __nv_bfloat16* __restrict__ W, const BnFinalizeArgs fin,
+                                                    double* __restrict__ stats_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int K = 32 * KQ;
+    __shared__ float g_s[32][K];          // 32 rows of G at a time (all warps of the block share them)
+    __shared__ double m_s[K];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 16 + warp;
+    const double inv_n = 1.0 / fin.n;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) m_s[k] = colsum[k] * inv_n;
+    const bool live = c < fin.C;
+    const __nv_bfloat16* wr = W + static_cast<size_t>(live ? c : 0) * K;
+    float wf[KQ];
+    double t[KQ], mk[KQ];
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+        t[q] = 0.0;
+        wf[q] = __bfloat162float(wr[lane + 32 * q]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) mk[q] = m_s[lane + 32 * q];
+#pragma unroll 1
+    for (int jc = 0; jc < KQ; ++jc) {          // rows j = 32 jc .. 32 jc + 31
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) g_s[i / K][i % K] = G[static_cast<size_t>(32 * jc) * K + i];
+        __syncthreads();
+#pragma unroll 8
+        for (int jj = 0; jj < 32; ++jj) {
+            const double wj = static_cast<double>(__shfl_sync(0xffffffffu, wf[jc], jj));
+            const double mj = m_s[32 * jc + jj];
+#pragma unroll
+            for (int q = 0; q < KQ; ++q)      // G is symmetric: row j read conflict-free
+                t[q] = fma(fma(static_cast<double>(g_s[jj][lane + 32 * q]), inv_n, -mj * mk[q]), wj, t[q]);
+        }
+    }
+    double var = 0.0, mean = 0.0;
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+        var = fma(static_cast<double>(wf[q]), t[q], var);
+        mean = fma(static_cast<double>(wf[q]), mk[q], mean);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        var += __shfl_xor_sync(0xffffffffu, var, o);
+        mean += __shfl_xor_sync(0xffffffffu, mean, o);
+    }
+    if (lane != 0 || !live) return;
+    if (var < 0.0) var = 0.0;
+    const float invstd = rsqrtf(static_cast<float>(var) + fin.eps);
+    const float meanf = static_cast<float>(mean);
+    const float sc = fin.gamma[c] * invstd;
+    fin.bnp[c] = make_float4(sc, fmaf(-meanf, sc, fin.beta[c]), invstd, -meanf * invstd);
+    if (fin.rmean != nullptr) {
+        const double unb = fin.n > 1.0 ? var * fin.n / (fin.n - 1.0) : var;
+        fin.rmean[c] = static_cast<float>((1.0 - fin.momentum) * fin.rmean[c] + fin.momentum * (mean + fin.conv_bias[c]));
+        fin.rvar[c] = static_cast<float>((1.0 - fin.momentum) * fin.rvar[c] + fin.momentum * unb);
+    }
+    if (stats_out != nullptr) {
+        stats_out[c] = mean * fin.n;
+        stats_out[fin.C + c] = (var + mean * mean) * fin.n;
     }
 }
 
@@ -859,6 +956,152 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// Folded BatchNorm backward (oracle/folded_bn_ref.py identities (2) and (3)) for a layer whose pre-BN
+// output y = a_prev W^T is never stored.  Inputs: Q = dz^T a_prev (the raw weight-gradient GEMM), sum_dz, the Gram matrix
+// G and column sums s of a_prev, the forward normalisation bnp.  With yc = y - mean:
+//     dy = A dz + Bc yc + D,      A = scale,  Bc = -A invstd dgamma / n,  D = -A sum_dz / n,
+//     dgamma = sum dz*yhat = invstd * rowdot(Q, W) + (-mean invstd) * sum_dz
+//     dW = diag(A) Q + diag(Bc) W Gc + D s^T,            Gc = G - s s^T / n   (centred: no cancellation against D s^T)
+//     dy W = [dz | a_prev] [diag(A) W ; S]  + const,     S = W^T diag(Bc) W,  const = (D - Bc mean)^T W
+// k_fold_coef: one warp per output channel.  k_fold_bwd: block roles (dW | scaled transposed weights | S | const).
+// ---------------------------------------------------------------------------------------------
+struct FoldArgs {
+    const float* Q;               // [Co][Ci]
+    const __nv_bfloat16* W;       // [Co][Ci] bf16 forward weights
+    const __nv_bfloat16* Wt;      // [Ci][Co] bf16 transposed weights
+    const float* G;               // [Ci][Ci]
+    const double* s;              // [Ci]
+    const double* sum_dz;         // [Co]
+    const float4* bnp;            // [Co]
+    float4* coef;                 // [Co] {A, Bc, D - Bc*mean, D}
+    float* dgamma;                // parameter gradients
+    float* dbeta;
+    float* dbias;                 // conv bias ahead of a train-mode BN: zero
+    float* dW;                    // [Co][ld_dw]
+    int ld_dw;
+    __nv_bfloat16* Bw;            // [Ci][ld_bw]: columns [0, Co) = A_c W[c][j], columns [Co, Co + Ci) = S[i][j]
+    int ld_bw;
+    float* cst;                   // [Ci]   (zeroed by the caller)
+    float* S32;                   // [Ci][Ci] fp32 accumulator of S (zeroed by the caller)
+    float* Gc;                    // [Ci][Ci] centred Gram matrix (written by k_fold_coef)
+    int* ticket;                  // [Ci*Ci/256] completion counters of the S tiles (zeroed by the caller)
+    double n;
+    int Co, Ci;
+};
+
+// blocks [0, Co/8): per-channel coefficients (one warp per channel); the remaining blocks centre the Gram matrix
+__global__ void __launch_bounds__(256) k_fold_coef(const FoldArgs f) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nco = (f.Co + 7) / 8;
+    if (static_cast<int>(blockIdx.x) >= nco) {
+        const int idx = (blockIdx.x - nco) * 256 + threadIdx.x;
+        if (idx >= f.Ci * f.Ci) return;
+        const int i = idx / f.Ci, j = idx - i * f.Ci;
+        f.Gc[idx] = static_cast<float>(static_cast<double>(f.G[idx]) - f.s[i] * f.s[j] / f.n);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= f.Co) return;
+    const float* q = f.Q + static_cast<size_t>(c) * f.Ci;
+    const __nv_bfloat16* w = f.W + static_cast<size_t>(c) * f.Ci;
+    double dot = 0.0;
+    for (int k = lane; k < f.Ci; k += 32) dot = fma(static_cast<double>(q[k]), static_cast<double>(__bfloat162float(w[k])), dot);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane != 0) return;
+    const float4 bp = f.bnp[c];
+    const double s1 = f.sum_dz[c];
+    const double dgamma = static_cast<double>(bp.z) * dot + static_cast<double>(bp.w) * s1;
+    const double A = bp.x;
+    const double Bc = -A * static_cast<double>(bp.z) * dgamma / f.n;
+    const double D = -A * s1 / f.n;
+    const double mean = -static_cast<double>(bp.w) / static_cast<double>(bp.z);
+    f.coef[c] = make_float4(static_cast<float>(A), static_cast<float>(Bc), static_cast<float>(D - Bc * mean), static_cast<float>(D));
+    f.dgamma[c] = static_cast<float>(dgamma);
+    f.dbeta[c] = static_cast<float>(s1);
+    f.dbias[c] = 0.f;
+}
+__host__ __device__ inline int fold_coef_blocks(int Co, int Ci) { return (Co + 7) / 8 + (Ci * Ci + 255) / 256; }
+
+// Block roles of k_fold_bwd (1-D grid, see fold_bwd_blocks): dW | scaled transposed weights | S (reduction over the output
+// channels split into chunks of FOLD_CHUNK, fp32 atomics into S32; the chunk block that finishes a tile last converts it
+// to bf16 into Bw) | const (same split).  S32, cst and the tickets are zeroed by the caller before the launch.
+constexpr int FOLD_CHUNK = 64;
+__host__ __device__ inline int fold_bwd_blocks(int Co, int Ci) {
+    const int nA = (Co * Ci + 255) / 256, nS = (Ci * Ci + 255) / 256, ch = (Co + FOLD_CHUNK - 1) / FOLD_CHUNK;
+    return 2 * nA + nS * ch + ch;
+}
+__global__ void __launch_bounds__(256) k_fold_bwd(const FoldArgs f) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Co = f.Co, Ci = f.Ci;
+    const int nA = (Co * Ci + 255) / 256, nB1 = nA, nS = (Ci * Ci + 255) / 256, ch = (Co + FOLD_CHUNK - 1) / FOLD_CHUNK;
+    int blk = blockIdx.x;
+    if (blk < nA) {                                   // dW[c][k] = A Q + Bc (W Gc) + D s
+        const int idx = blk * 256 + threadIdx.x;
+        if (idx >= Co * Ci) return;
+        const int c = idx / Ci, k = idx - c * Ci;
+        const __nv_bfloat16* w = f.W + static_cast<size_t>(c) * Ci;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < Ci; ++j) acc = fmaf(__bfloat162float(w[j]), f.Gc[static_cast<size_t>(j) * Ci + k], acc);
+        const float4 cf = f.coef[c];
+        f.dW[static_cast<size_t>(c) * f.ld_dw + k] = fmaf(cf.x, f.Q[idx], fmaf(cf.y, acc, cf.w * static_cast<float>(f.s[k])));
+        return;
+    }
+    blk -= nA;
+    if (blk < nB1) {                                  // Bw[j][c] = A_c W[c][j]
+        const int idx = blk * 256 + threadIdx.x;
+        if (idx >= Co * Ci) return;
+        const int j = idx / Co, c = idx - j * Co;
+        f.Bw[static_cast<size_t>(j) * f.ld_bw + c] = __float2bfloat16_rn(f.coef[c].x * __bfloat162float(f.Wt[idx]));
+        return;
+    }
+    blk -= nB1;
+    __shared__ float coef_s[FOLD_CHUNK];
+    __shared__ int last_s;
+    if (blk < nS * ch) {                              // S32[i][j] += sum_{c in chunk} W[c][i] Bc_c W[c][j]
+        const int chunk = blk / nS, tile = blk - chunk * nS;
+        const int c0 = chunk * FOLD_CHUNK, c1 = min(c0 + FOLD_CHUNK, Co);
+        if (static_cast<int>(threadIdx.x) < c1 - c0) coef_s[threadIdx.x] = f.coef[c0 + threadIdx.x].y;
+        __syncthreads();
+        const int idx = tile * 256 + threadIdx.x;
+        const bool ok = idx < Ci * Ci;
+        const int i = ok ? idx / Ci : 0, j = ok ? idx - i * Ci : 0;
+        if (ok) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int c = c0; c < c1; ++c) {
+                const __nv_bfloat16* w = f.W + static_cast<size_t>(c) * Ci;
+                acc = fmaf(__bfloat162float(w[i]) * coef_s[c - c0], __bfloat162float(w[j]), acc);
+            }
+            atomicAdd(f.S32 + idx, acc);
+        }
+        // the chunk block that finishes this tile last converts it: Bw[j][Co + i] = bf16(S[i][j])
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last_s = (atomicAdd(f.ticket + tile, 1) == ch - 1);
+        __syncthreads();
+        if (!last_s) return;
+        __threadfence();
+        if (ok) f.Bw[static_cast<size_t>(j) * f.ld_bw + Co + i] = __float2bfloat16_rn(__ldcg(f.S32 + idx));
+    } else {                                          // cst[j] += sum_{c in chunk} (D_c - Bc_c mean_c) W[c][j]
+        const int chunk = blk - nS * ch;
+        const int c0 = chunk * FOLD_CHUNK, c1 = min(c0 + FOLD_CHUNK, Co);
+        if (static_cast<int>(threadIdx.x) < c1 - c0) coef_s[threadIdx.x] = f.coef[c0 + threadIdx.x].z;
+        __syncthreads();
+        for (int j = threadIdx.x; j < Ci; j += 256) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int c = c0; c < c1; ++c) acc = fmaf(coef_s[c - c0], __bfloat162float(f.W[static_cast<size_t>(c) * Ci + j]), acc);
+            atomicAdd(f.cst + j, acc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Backward of the per-cloud seg_conv1 branch and of the max-pool.
 //   dg[b][j]   = sum_n dcb[b][n] * Wg[n][j]                 (repeat/cat backward folded per cloud)
 //   dWg[n][j] += sum_b dcb[b][n] * g[b][j]
@@ -954,7 +1197,9 @@ __global__ void __launch_bounds__(256) k_ingest_bwd(const __nv_bfloat16* __restr
 
 // ---------------------------------------------------------------------------------------------
 // Fused Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias correction).
-// grad_scale lets data-parallel ranks fold an averaging factor in (1.0 when grads are already summed).
+// grad_scale lets data-parallel ranks fold an averaging factor in (1.0 when grads are already summed); grad_div (device,
+// optional) divides the gradient as well: data-parallel ranks back-propagate the UN-normalised loss and divide by the
+// all-reduced sum of class weights here, which takes that all-reduce off the critical path (backward is linear in the loss).
 // ---------------------------------------------------------------------------------------------
 struct StepState {                 // == pcseg_step_state
     unsigned long long seed;
@@ -972,9 +1217,11 @@ __global__ void k_step_advance(StepState* st, float b1, float b2) {
 }
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
-                                              float bc1, float bc2_sqrt, float grad_scale, const StepState* __restrict__ st) {
+                                              float bc1, float bc2_sqrt, float grad_scale, const StepState* __restrict__ st,
+                                              const double* __restrict__ grad_div) {
     pdl_launch_dependents();
     pdl_wait();
+    if (grad_div != nullptr) grad_scale = static_cast<float>(static_cast<double>(grad_scale) / *grad_div);
     if (st != nullptr) {
         lr = st->lr;
         bc1 = st->bias_corr1;

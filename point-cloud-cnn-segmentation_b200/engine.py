@@ -193,10 +193,10 @@ class Engine:
             check(lib.pcseg_backward(b.handle, ptr(x), ptr(flat_params), ptr(dlogits), ptr(logits), ptr(labels), ptr(class_w),
                                      ptr(wsum), ptr(flat_grads), phase, self._stream()), "pcseg_backward")
 
-    def adam(self, flat_params, flat_grads, m, v, step, lr, betas, eps, weight_decay, grad_scale=1.0, state=None):
+    def adam(self, flat_params, flat_grads, m, v, step, lr, betas, eps, weight_decay, grad_scale=1.0, state=None, grad_div=None):
         with torch.cuda.device(self.device):
             check(lib.pcseg_adam_step(ptr(flat_params), ptr(flat_grads), ptr(m), ptr(v), flat_params.numel(), step, lr, betas[0],
-                                      betas[1], eps, weight_decay, grad_scale, ptr(state), self._stream()), "pcseg_adam_step")
+                                      betas[1], eps, weight_decay, grad_scale, ptr(state), ptr(grad_div), self._stream()), "pcseg_adam_step")
 
     def eval_metrics(self, logits, labels, class_w=None, want_pred=False):
         """Weighted CE sums, accuracy counters and confusion matrix of eval-mode logits (one kernel, no host sync)."""
@@ -215,7 +215,7 @@ class Engine:
 
 
 DEBUG_KINDS = {"y": 0, "act": 1, "dz": 2, "dy": 3, "bnp": 4, "coef": 5, "stats_f": 6, "stats_b": 7, "g": 8, "ystar": 9,
-               "argidx": 10, "cb": 11, "dcb": 12, "dzv": 13}
+               "argidx": 10, "cb": 11, "dcb": 12, "dzv": 13, "gram": 14, "colsum": 15, "qraw": 16, "bwf": 17, "cstf": 18}
 
 
 def debug_tensor(engine, B, N, kind, layer=0):
@@ -242,7 +242,7 @@ def profile_read(engine, B, N):
     """{tag: (total_ms, launches)} for the GEMMs of the training step (tags: conv index + 0/16/32 = fwd/dgrad/wgrad)."""
     b = engine.binding(B, N, True)
     out = {}
-    for base in (0, 16, 32):
+    for base in (0, 16, 32, 48):          # forward / data gradient / weight gradient / Gram matrix
         for i in range(1, 9):
             ms, n = C.c_double(), C.c_longlong()
             check(lib.pcseg_profile_read(b.handle, base + i, C.byref(ms), C.byref(n)))

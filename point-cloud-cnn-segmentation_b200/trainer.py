@@ -4,8 +4,10 @@ nn.DataParallel, pcs.py:209-211, and the loop body pcs.py:241-255).
 
 Data-parallel semantics follow the reference's single-process DataParallel: one global weighted-mean
 loss over all points of the global batch (so every rank divides by the ALL-REDUCED sum of class weights
-and gradients are SUMMED), per-replica BatchNorm batch statistics (no SyncBN), rank 0's running
-statistics are the ones that survive (broadcast on demand with `sync_bn_buffers`).
+and gradients are SUMMED), per-replica BatchNorm batch statistics (no SyncBN), per-replica dropout masks,
+replicas that start from rank 0's parameters (DataParallel re-broadcasts them every step; here they are
+broadcast once at construction and stay identical because every rank applies the same summed gradient),
+rank 0's running statistics are the ones that survive (broadcast on demand with `sync_bn_buffers`).
 """
 import torch
 import torch.distributed as dist
@@ -34,7 +36,15 @@ class FusedTrainer:
         self.sync = GradSync(self.flat["grads"], process_group)
         self.world = self.sync.world
         self.distributed = self.world > 1
+        self.rank = dist.get_rank(process_group) if self.distributed else 0
         self.overlap = overlap
+        if self.distributed:
+            # replicas = rank 0's model (nn.DataParallel replicates module 0, pcs.py:211): do not rely on identical seeding
+            dist.broadcast(self.flat["params"], src=0, group=self.pg)
+            dist.broadcast(self.flat["bn"], src=0, group=self.pg)
+            for name in _BNS:
+                dist.broadcast(getattr(self.model, name).num_batches_tracked, src=0, group=self.pg)
+            self.model._manual_version += 1
         # 32-byte CE accumulator {loss_num f64, w_sum f64, correct u64, valid u64}
         self.ce_raw = torch.zeros(32, dtype=torch.uint8, device=self.device)
         self.ce_f64 = self.ce_raw.view(torch.float64)
@@ -44,8 +54,13 @@ class FusedTrainer:
         self.loss_num, self.wsum = self.lw[0:1], self.lw[1:2]
         # device-resident step state (pcseg_step_state): dropout seed, Adam step / bias corrections, learning rate
         self.state = torch.zeros(32, dtype=torch.uint8, device=self.device)
-        seed0 = int(torch.empty((), dtype=torch.int64).random_().item())
+        seed_t = torch.empty((), dtype=torch.int64).random_().to(self.device)
+        if self.distributed:
+            dist.broadcast(seed_t, src=0, group=self.pg)
+        # one base seed, a different stream per rank: DataParallel replicas draw independent dropout masks
+        seed0 = (int(seed_t.item()) + self.rank * 0x632BE59BD9B4E019) & (2 ** 63 - 1)
         self.state.view(torch.int64)[0] = seed0
+        self.one = torch.ones(1, dtype=torch.float64, device=self.device)
         self.state.view(torch.float32)[4] = lr
         # static outputs of a step
         self.out_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -68,8 +83,15 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------ one step = 4 capturable segments + collectives
     # Collectives are never captured (they run eagerly between the graph segments), so the same code serves one GPU and
-    # data-parallel ranks:  [forward] -> all-reduce(loss num, sum w) -> [backward phase 1] -> async all-reduce(bucket 1)
-    #                       -> [backward phase 2] -> all-reduce(bucket 2), wait -> [Adam + outputs]
+    # data-parallel ranks:  [forward] -> async all-reduce(loss num, sum w) -> [backward phase 1] -> async all-reduce(bucket 1)
+    #                       -> [backward phase 2] -> async all-reduce(bucket 2), wait for all three -> [Adam + outputs]
+    # Data-parallel ranks back-propagate the UN-normalised loss (wsum = 1) and Adam divides by the all-reduced sum of class
+    # weights, so no collective sits between forward and backward (`deferred`); a single GPU normalises in backward as
+    # before and keeps true gradients in the arena.
+    @property
+    def deferred(self):
+        return self.distributed and self.overlap
+
     def _seg_forward(self, x, labels):
         self.engine.step_advance(self.state, self.betas)
         self.last_logits = self.model._run_train_forward(x, labels=labels, class_w=self.class_w, ce=self.ce_raw, state=self.state,
@@ -79,12 +101,12 @@ class FusedTrainer:
     def _seg_backward(self, x, labels, phase):
         f = self.flat
         self.engine.backward(x, f["params"], f["grads"], phase=phase, logits=self.last_logits, labels=labels, class_w=self.class_w,
-                             wsum=self.wsum)
+                             wsum=self.one if self.deferred else self.wsum)
 
     def _seg_tail(self, x, labels):
         f = self.flat
         self.engine.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, 1, self.lr, self.betas, self.eps, self.weight_decay,
-                         state=self.state)
+                         state=self.state, grad_div=self.wsum if self.deferred else None)
         torch.div(self.loss_num, self.wsum, out=self.out_loss)
         self.out_counts.copy_(self.ce_i64[2:4])
 
@@ -98,7 +120,10 @@ class FusedTrainer:
         f = self.flat
         self.sync.g = f["grads"]
         if i == 0:
-            self.sync.reduce_normaliser(self.lw)
+            if self.deferred:
+                self.sync.launch_tensor(self.lw)            # joined by the wait() ahead of Adam
+            else:
+                self.sync.reduce_normaliser(self.lw)
         elif i == 1:
             if self.distributed and self.overlap:
                 self.sync.launch(self.early)                # NCCL runs on its own stream while phase 2 computes
@@ -223,11 +248,48 @@ class FusedTrainer:
             for n in _BNS:
                 dist.broadcast(getattr(self.model, n).num_batches_tracked, src=src, group=self.pg)
 
+    def optimizer_state_dict(self):
+        """`torch.optim.Adam(model.parameters(), lr, weight_decay).state_dict()` of the fused optimizer (what pcs.py:376
+        saves): per-parameter `step` / `exp_avg` / `exp_avg_sq` keyed by the position in `model.parameters()` (= the
+        arena order) and one param group.  Tensors are clones."""
+        ps = self.model._param_list()
+        state = {}
+        if self.step_count > 0:
+            for i, (p, (o, n)) in enumerate(zip(ps, self.flat["offs"])):
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(ps)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state(self, sd):
+        """Restore the optimizer from `optimizer_state_dict()` or from a `torch.optim.Adam.state_dict()` of the reference
+        loop (pcs.py:217, 376): moments, step count (host and device copies) and the hyper-parameters of the group."""
+        group = sd["param_groups"][0]
+        self.betas, self.eps, self.weight_decay = tuple(group["betas"]), group["eps"], group["weight_decay"]
+        self.set_lr(group["lr"])
+        ps = self.model._param_list()
+        if len(group["params"]) != len(ps):
+            raise ValueError(f"optimizer state has {len(group['params'])} parameters, the model has {len(ps)}")
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        step = 0
+        for i, (p, (o, n)) in enumerate(zip(ps, self.flat["offs"])):
+            st = sd["state"].get(group["params"][i])
+            if st is None:
+                continue
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, int(float(st["step"])))
+        self.step_count = step
+        self.state.view(torch.int64)[1] = step
+        self._graph, self._graph_key = None, None          # hyper-parameters may be baked into a captured step
+
     def checkpoint_dict(self, epoch=0, **extra):
-        """Same dict layout as the reference writes to best_model.pth (pcs.py:373-382)."""
-        d = {"epoch": epoch, "model_state_dict": self.model.state_dict(),
-             "optimizer_state_dict": {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count,
-                                      "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay},
-             "num_classes": self.model.num_classes}
+        """Same dict as the reference writes to best_model.pth (pcs.py:373-382): `optimizer_state_dict` has the
+        torch.optim.Adam layout (loadable by the reference's optimizer and by `load_optimizer_state`)."""
+        d = {"epoch": epoch, "model_state_dict": {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+             "optimizer_state_dict": self.optimizer_state_dict(), "num_classes": self.model.num_classes}
         d.update(extra)
         return d

@@ -17,10 +17,13 @@ def grad_buckets(offs, total):
 class GradSync:
     """Collective protocol of the data-parallel step (backend-agnostic: NCCL on GPUs, gloo in the CPU tests).
 
-    * `reduce_normaliser`: SUM all-reduce of the sum of class weights (and, in the same tiny tensor, the loss numerator,
-      both known after the forward), BEFORE backward, so that every rank scales its dlogits by 1 / (global sum) -- the
-      reference computes ONE weighted-mean loss over the gathered logits of all replicas (pcs.py:244-251 under
-      nn.DataParallel).
+    * The reference computes ONE weighted-mean loss over the gathered logits of all replicas (pcs.py:244-251 under
+      nn.DataParallel): every gradient is divided by the GLOBAL sum of class weights.  Backward is linear in the loss
+      scale, so the ranks back-propagate the un-normalised loss and the division happens in the optimizer:
+      `launch_tensor(lw)` starts the asynchronous SUM all-reduce of {loss numerator, sum of class weights} right after the
+      forward and nobody waits for it before the optimizer step (no collective on the critical path ahead of backward).
+      `reduce_normaliser` is the blocking form (normalise before backward) kept for callers that want true gradients in
+      the arena.
     * `launch(ranges)` / `wait()`: asynchronous SUM all-reduce of slices of the flat gradient arena (summing
       equals DataParallel's reduce-add of replica gradients); launched per bucket so that the first bucket's
       transfer overlaps the rest of backward.
@@ -44,6 +47,11 @@ class GradSync:
         if self.active:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
         return t
+
+    def launch_tensor(self, t):
+        """asynchronous SUM all-reduce of a small tensor (joined by `wait`)"""
+        if self.active:
+            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
     def launch(self, ranges):
         """one asynchronous SUM all-reduce of the given slices of the arena (the slices of a bucket are coalesced into one

@@ -1,5 +1,6 @@
 """Host-side data-parallel protocol on CPU (gloo, world_size 2): the collectives FusedTrainer issues
-(normaliser all-reduce before backward, bucketed SUM all-reduce of the flat gradient arena) reproduce the
+(asynchronous all-reduce of the loss normaliser, un-normalised backward, bucketed SUM all-reduce of the flat gradient
+arena, division by the global normaliser in the optimizer; and the blocking normalise-before-backward form) reproduce the
 reference's single-process nn.DataParallel step (pcs.py:209-211, 244-254): one weighted-mean loss over the whole
 global batch, per-replica BatchNorm statistics, summed replica gradients.  Compute is done by the CPU port in
 oracle/ (tests may use the oracle; the product path needs a GPU)."""
@@ -19,7 +20,7 @@ def _flat_grads(port):
     return torch.cat([port.p[k].grad.reshape(-1) for k in port.params])
 
 
-def _worker(rank, world, port_file, q):
+def _worker(rank, world, port_file, q, deferred=True):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = port_file
@@ -45,9 +46,13 @@ def _worker(rank, world, port_file, q):
     wsum = cw[lab[valid]].sum().double().reshape(1)
     flat = torch.zeros(sum(port.p[k].numel() for k in port.params))
     sync = proto.GradSync(flat)
-    sync.reduce_normaliser(wsum)                                      # global normaliser BEFORE backward
     loss_sum = F.cross_entropy(logits.view(-1, C), lab, weight=cw, ignore_index=-1, reduction="sum")
-    (loss_sum / wsum.float()).backward()
+    if deferred:
+        sync.launch_tensor(wsum)                                      # in flight while backward runs; joined by wait()
+        loss_sum.backward()                                           # un-normalised loss (pcseg_backward with wsum = 1)
+    else:
+        sync.reduce_normaliser(wsum)                                  # global normaliser BEFORE backward
+        (loss_sum / wsum.float()).backward()
     flat.copy_(_flat_grads(port))
     n = flat.numel()
     # two slices per bucket, like grad_buckets(): exercises the coalesced launch (one collective per bucket)
@@ -55,6 +60,8 @@ def _worker(rank, world, port_file, q):
     sync.launch(early)
     sync.launch(late)
     sync.wait()
+    if deferred:
+        flat /= wsum.float()                                          # k_adam's grad_div
     if rank == 0:
         q.put(flat.numpy())
     dist.barrier()
@@ -62,7 +69,8 @@ def _worker(rank, world, port_file, q):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_protocol_equals_dataparallel_semantics(tmp_path):
+@pytest.mark.parametrize("deferred", [True, False])
+def test_two_rank_protocol_equals_dataparallel_semantics(tmp_path, deferred):
     sys.path.insert(0, ROOT)
     from oracle.torch_port import TorchCpuPort
     import torch.nn.functional as F
@@ -70,8 +78,8 @@ def test_two_rank_protocol_equals_dataparallel_semantics(tmp_path):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port_no = str(29500 + (os.getpid() % 2000))
-    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q)) for r in range(world)]
+    port_no = str(29500 + (os.getpid() % 2000) + (2000 if deferred else 0))
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q, deferred)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=240)

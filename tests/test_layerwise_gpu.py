@@ -29,6 +29,14 @@ def _close_bf16(got, ref, what):
     assert bad.mean() < 1e-4, (what, float(bad.mean()), float(np.abs(got - ref).max()), float(rms))
 
 
+def _close_rms(got, ref, what, rel):
+    """two differently-rounded evaluations of the same quantity: relative RMS difference"""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    rms = np.sqrt((ref * ref).mean()) + 1e-30
+    err = np.sqrt(((got - ref) ** 2).mean())
+    assert err <= rel * rms, (what, float(err), float(rms))
+
+
 def _close_red(got, ref, what, rel=2e-4):
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     scale = np.abs(ref).max() + 1e-30
@@ -47,10 +55,19 @@ def _diverse_clouds(B, N, rng):
     return np.stack(xs).astype(np.float32)
 
 
-@pytest.mark.parametrize("B,N,C,p_drop", [(3, 500, 5, 0.0), (4, 1024, 3, 0.3), (2, 200, 8, 0.0), (2, 384, 12, 0.3), (2, 200, 32, 0.0)])
-def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop):
+@pytest.mark.parametrize("B,N,C,p_drop,folded", [(3, 500, 5, 0.0, True), (4, 1024, 3, 0.3, True), (2, 200, 8, 0.0, True),
+                                                 (2, 384, 12, 0.3, True), (2, 200, 32, 0.0, True),
+                                                 (3, 500, 5, 0.0, False), (4, 1024, 3, 0.3, False)])
+def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, monkeypatch):
+    """folded=True: conv5 runs with Gram-predicted BatchNorm statistics and the folded BatchNorm backward (its y / dy are
+    never materialised, oracle/folded_bn_ref.py); folded=False: the legacy step that materialises them (also the path
+    of ragged batches)."""
     import pcseg_b200
     from pcseg_b200.engine import debug_tensor
+    from oracle import folded_bn_ref as fb
+
+    monkeypatch.setenv("PCSEG_FOLDED", "1" if folded else "0")      # read when a context is created
+    FOLDED = {4} if folded else set()
 
     P = B * N
     sd = orc.synth_state(C, 1000 + N)
@@ -90,8 +107,30 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop):
     xin = x.reshape(P, 4).astype(np.float64)
     keeps = {}
     for i in range(9):
-        y[i] = T("y", i)
         bnp[i] = T("bnp", i)
+        if i in FOLDED:
+            # ---- Gram-predicted statistics (pcs.py:110): G and s of the input activation, {sum y, sum y^2} predicted from
+            # them, BN + ReLU applied straight to the fp32 accumulators; y itself is never stored
+            Ci = act[i - 1].shape[1]
+            _close_red(T("gram", i), act[i - 1].T @ act[i - 1], f"gram[{CONVS[i]}]", rel=1e-5)
+            _close_red(T("colsum", i)[0], act[i - 1].sum(0), f"colsum[{CONVS[i]}]", rel=1e-5)
+            yref = lw.conv_pre_bn(act[i - 1], W[CONVS[i]])                                  # fp64, bf16 weights
+            st = lw.bn_batch_stats(yref)
+            _close_red(T("stats_f", i), st, f"predicted stats_f[{BNS[i]}]", rel=1e-4)
+            st = T("stats_f", i)
+            _close_red(bnp[i], lw.bn_params(st, P, sd[f"{BNS[i]}.weight"], sd[f"{BNS[i]}.bias"]), f"bnp[{BNS[i]}]", rel=1e-4)
+            rm, rv = lw.running_stats(st, P, sd[f"{CONVS[i]}.bias"].astype(np.float64), sd[f"{BNS[i]}.running_mean"].astype(np.float64),
+                                      sd[f"{BNS[i]}.running_var"].astype(np.float64))
+            bn_mod = getattr(m, BNS[i])
+            _close_red(_np(bn_mod.running_mean), rm, f"{BNS[i]}.running_mean", rel=1e-5)
+            _close_red(_np(bn_mod.running_var), rv, f"{BNS[i]}.running_var", rel=1e-5)
+            assert int(bn_mod.num_batches_tracked.item()) == int(sd[f"{BNS[i]}.num_batches_tracked"]) + 1
+            act[i] = T("act", i)
+            relu_out, _ = lw.bn_relu(yref, bnp[i])
+            _close_bf16(act[i], relu_out, f"act[{CONVS[i]}] (BN + ReLU in the GEMM epilogue)")
+            y[i] = yref
+            continue
+        y[i] = T("y", i)
         if i == 0:
             ref = lw.conv_pre_bn(xin, W["conv1"], weights_bf16=False)                      # pcs.py:106
         elif i == 6:
@@ -191,8 +230,50 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop):
     bn_backward(5, sparse=dz6.reshape(P, 1024))
     _close_red(grads["global_feat.weight"][:, :, 0], lw.wgrad(dy[5], act[4]), "dW global_feat", rel=3e-4)
     dz[4] = T("dz", 4)
-    _close_bf16(dz[4], lw.dgrad_masked(dy[5], W["global_feat"], y[4], bnp[4]), "dz[conv5]")
+    if 4 in FOLDED:
+        _close_bf16(dz[4], (dy[5] @ lw.bf16_round(W["global_feat"])) * (act[4] > 0), "dz[conv5] (mask from the stored activation)")
+    else:
+        _close_bf16(dz[4], lw.dgrad_masked(dy[5], W["global_feat"], y[4], bnp[4]), "dz[conv5]")
+
+    def folded_backward(i, prev):
+        """conv i without y / dy (oracle/folded_bn_ref.py identities (2), (3)), every quantity from the CUDA tensors"""
+        sb = T("stats_b", i)
+        _close_red(sb[0], dz[i].sum(0), f"sum dz[{CONVS[i]}]", rel=3e-4)
+        _close_red(sb[1], act[i].sum(0), f"sum act[{CONVS[i]}]", rel=3e-4)
+        Q = T("qraw", i)
+        _close_red(Q, dz[i].T @ act[prev], f"Q[{CONVS[i]}]", rel=3e-4)
+        Wb = lw.bf16_round(W[CONVS[i]])
+        s, G = T("colsum", i)[0], T("gram", i)
+        gamma = sd[f"{BNS[i]}.weight"].astype(np.float64)
+        mean, invstd = -bnp[i][:, 3] / bnp[i][:, 2], bnp[i][:, 2]
+        fr = fb.folded_layer_backward(Wb, np.zeros(Wb.shape[0]), s, G, P, gamma, mean, invstd, Q, sb[0])
+        _close_red(grads[f"{BNS[i]}.weight"], fr["dgamma"], f"dgamma {BNS[i]}", rel=1e-4)
+        _close_red(grads[f"{BNS[i]}.bias"], fr["dbeta"], f"dbeta {BNS[i]}", rel=1e-5)
+        # dgamma must also be what the un-folded definition gives: sum dz * yhat with yhat from the fp64 y
+        _close_red(grads[f"{BNS[i]}.weight"], (dz[i] * (y[i] * bnp[i][:, 2] + bnp[i][:, 3])).sum(0), f"dgamma {BNS[i]} (definition)", rel=2e-3)
+        _close_red(grads[f"{CONVS[i]}.weight"][:, :, 0], fr["dW"], f"dW {CONVS[i]}", rel=3e-4)
+        assert np.abs(grads[f"{CONVS[i]}.bias"]).max() == 0.0
+        # and the un-folded definition: dW = dy^T a_prev with dy = A dz + Bc y + Cc
+        coef_ref = lw.bn_bwd_coef(np.stack([sb[0], grads[f"{BNS[i]}.weight"]]), P, bnp[i])
+        dy_ref = lw.bn_bwd_apply(dz[i], y[i], coef_ref)
+        _close_red(grads[f"{CONVS[i]}.weight"][:, :, 0], lw.wgrad(dy_ref, act[prev]), f"dW {CONVS[i]} (definition)", rel=2e-3)
+        Bw = T("bwf", i)
+        Co = Wb.shape[0]
+        _close_bf16(Bw[:, :Co], fr["W_dz"].T, f"Bw[{CONVS[i]}] scaled weights")
+        _close_bf16(Bw[:, Co:], fr["S"].T, f"Bw[{CONVS[i]}] S")
+        cst = T("cstf", i)[0]
+        _close_red(cst, fr["const"], f"const[{CONVS[i]}]", rel=1e-4)
+        dz[prev] = T("dz", prev)
+        da = np.concatenate([dz[i], act[prev]], axis=1) @ Bw.T + cst
+        t = np.float32(bnp[prev][:, 0]) * y[prev].astype(np.float32) + np.float32(bnp[prev][:, 1])
+        _close_bf16(dz[prev], da * (t > 0), f"dz[{CONVS[prev]}] (folded data gradient)")
+        # the un-folded definition rounds dy to bf16 where the folded GEMM rounds S: same value, different roundings
+        _close_rms(dz[prev], (dy_ref @ Wb) * (t > 0), f"dz[{CONVS[prev]}] (definition)", rel=2e-2)
+
     for i, prev in ((4, 3), (3, 2)):
+        if i in FOLDED:
+            folded_backward(i, prev)
+            continue
         bn_backward(i)
         _close_red(grads[f"{CONVS[i]}.weight"][:, :, 0], lw.wgrad(dy[i], act[prev]), f"dW {CONVS[i]}", rel=3e-4)
         dz[prev] = T("dz", prev)
