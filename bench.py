@@ -47,10 +47,28 @@ DROPOUT_P = 0.3
 FWD_FLOP_PER_PT = 2 * (1392896 + 128 * NUM_CLASSES)
 TRAIN_FLOP_PER_PT = 3 * FWD_FLOP_PER_PT - 512
 GFEAT_FLOP_PER_PT = 2 * 1024 * 1024          # one global_feat GEMM (forward, dgrad or wgrad), per point
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the three global_feat GEMMs at 8 x 16 384 points, from the
-# committed `ncu --set full` capture profiles/r01_ncu_full_gemm_cfg2_train.txt (MB): fwd 270.7+224.7, dgrad 539.1+243.1,
-# wgrad 541.1+5.2.  Algorithmic minimum: fwd a5 268 + y6 268; dgrad dy6 268 + y5 268 + dz5 268; wgrad dy6 268 + a5 268.
-NCU_TRAFFIC_MB_CFG2 = {5: 495.4, 21: 782.2, 37: 546.3}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) of the global_feat GEMMs at 8 x 16 384 points, from the
+# committed `ncu --set full` capture named in NCU_TRAFFIC_SOURCE (refreshed whenever those kernels change).  Tags: 5 forward
+# (statistics + max-pool epilogue, nothing stored), 21 data gradient (a5 S + side rows, masked by a5), 53 Gram matrix a5^T a5
+# (upper-triangle tiles), 69 inference forward (max-pool epilogue).  Algorithmic minimum: 268 MB per read or written
+# 1024-channel bf16 tensor.
+NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_full_gemm_cfg2_train.txt"
+NCU_TRAFFIC_MB_CFG2 = {}
+
+
+def load_ncu_traffic():
+    """{tag: MB} parsed from the committed capture summary (lines '# traffic tag=<t> MB=<x>'); empty when absent."""
+    path = os.path.join(ROOT, NCU_TRAFFIC_SOURCE)
+    out = {}
+    if os.path.exists(path):
+        for ln in open(path):
+            if ln.startswith("# traffic tag="):
+                try:
+                    t, mb = ln.split()[2:4]
+                    out[int(t.split("=")[1])] = float(mb.split("=")[1])
+                except (ValueError, IndexError):
+                    pass
+    return out
 
 
 def measured_peaks():
@@ -125,36 +143,47 @@ def synth_batch(B, N, C, seed):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU leg: the numpy oracle (port of the reference algorithm) on the host cores
+# CPU leg: the reference's own implementation on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_step_fn(mode, C):
+    """The UNMODIFIED reference module (baseline/_ref/point_cloud_segmentation.py, staged by build(); kind "reference")
+    running its own step (pcs.py:241-258 / 450-452) on all host threads; the torch-CPU port of oracle/ (kind "port") only
+    if that copy is missing."""
     import torch
-    from oracle.torch_port import TorchCpuPort
-    port = TorchCpuPort(C, seed=1234, threads=os.cpu_count())
+    from oracle import reference_module as refmod
+    if refmod.available():
+        runner, kind = refmod.ReferenceCpuStep(C, seed=1234, threads=os.cpu_count()), "reference"
+    else:
+        from oracle.torch_port import TorchCpuPort
+        runner, kind = TorchCpuPort(C, seed=1234, threads=os.cpu_count()), "port"
     cw = torch.ones(C)
 
     def train_step(x, labels):
-        return port.train_step(torch.from_numpy(x), torch.from_numpy(labels), cw, DROPOUT_P)
+        return runner.train_step(torch.from_numpy(x), torch.from_numpy(labels), cw, DROPOUT_P)
 
     def eval_step(x, labels):
-        return port.eval_step(torch.from_numpy(x))
+        return runner.eval_step(torch.from_numpy(x))
 
-    return train_step if mode == "train" else eval_step
+    return (train_step if mode == "train" else eval_step), kind
 
 
 def time_cpu(mode, B, N, C, steps, warmup, budget_s):
-    """Times the oracle port on a bounded sample of the workload (whole clouds of the same size when they fit
-    the budget, otherwise shorter clouds); returns points/s and a description of the sample."""
-    step = cpu_step_fn(mode, C)
+    """Times the reference step on the stated B x N batch when (steps + warmup) of it fit the budget, otherwise on a bounded
+    sample (fewer whole clouds, or one shorter cloud).  Returns a dict: value (points/s), ms, b, n, same_config, kind, sample."""
+    step, kind = cpu_step_fn(mode, C)
     xs, ls = synth_batch(1, 2048, C, 99)
+    for _ in range(2):                               # warm the probe: the first calls pay thread-pool / allocator start-up
+        step(xs, ls)
     t0 = time.perf_counter()
     step(xs, ls)
     step(xs, ls)
     per_pt = (time.perf_counter() - t0) / 2 / 2048
     total_steps = steps + warmup
     pts_budget = max(2048, int(budget_s / max(per_pt, 1e-9) / max(total_steps, 1)))
-    if pts_budget >= N:
-        b, n = max(1, min(B, pts_budget // N)), N
+    if pts_budget >= B * N:
+        b, n = B, N
+    elif pts_budget >= N:
+        b, n = max(1, pts_budget // N), N
     else:
         b, n = 1, max(2048, (pts_budget // 1024) * 1024)
     x, lab = synth_batch(b, n, C, 5)
@@ -164,7 +193,10 @@ def time_cpu(mode, B, N, C, steps, warmup, budget_s):
     for _ in range(steps):
         step(x, lab)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return b * n / dt, dt * 1e3, f"{b} cloud(s) x {n} points per step ({steps} timed steps, torch-CPU fp32 port of the reference step, all host threads, {mode})"
+    what = ("the unmodified reference module (baseline/_ref), CPU fp32" if kind == "reference"
+            else "torch-CPU fp32 port of the reference step (oracle/torch_port.py)")
+    sample = f"{b} cloud(s) x {n} points per step ({steps} timed steps, {what}, all host threads, {mode})"
+    return dict(value=b * n / dt, ms=dt * 1e3, b=b, n=n, same_config=(b == B and n == N), kind=kind, sample=sample)
 
 
 def run_reference(args, B, N, mode):
@@ -174,14 +206,19 @@ def run_reference(args, B, N, mode):
     cores = os.cpu_count() or 1
     steps = max(1, args.steps)
     warmup = max(0, min(args.warmup, 3))
-    # whole run bounded to about two minutes of CPU work (PCSEG_REF_BUDGET_S overrides: the contract test uses a few seconds)
-    value, ms, sample = time_cpu(mode, B, N, NUM_CLASSES, steps, warmup, budget_s=float(os.environ.get("PCSEG_REF_BUDGET_S", "120")))
+    # the stated batch when the whole run fits about two minutes of CPU work, otherwise a bounded sample of it, SAID in
+    # config.workload (PCSEG_REF_BUDGET_S overrides the budget: the contract test uses a few seconds)
+    r = time_cpu(mode, B, N, NUM_CLASSES, steps, warmup, budget_s=float(os.environ.get("PCSEG_REF_BUDGET_S", "150")))
+    workload = workload_desc(args.workload, B, N, mode)
+    if not r["same_config"]:
+        workload += f" -- CPU arm timed on a bounded sample: {r['b']} x {r['n']} points"
     line = {
-        "impl": "reference", "metric": metric_name(mode), "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_desc(args.workload, B, N, mode), "num_classes": NUM_CLASSES},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": metric_name(mode), "value": r["value"], "unit": "points/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload, "num_classes": NUM_CLASSES, "same_config": r["same_config"],
+                                        "sample_batch": [r["b"], r["n"]]},
+        "cpu_baseline": {"value": r["value"], "unit": "points/s", "cores": cores, "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
@@ -197,6 +234,74 @@ def workload_desc(name, B, N, mode):
 # ------------------------------------------------------------------------------------------------
 # GPU leg
 # ------------------------------------------------------------------------------------------------
+def measure_inference(model, eng, x_dev, x_host, B, N, steps, barrier, dev, world):
+    """Inference (pcs.py:448-452) on the workload's batch: device-timed with resident inputs, end to end through
+    PredictStream (pinned host points in, argmax labels out, every step), and the dominant kernel's roofline."""
+    import torch
+    import torch.distributed as dist
+    import pcseg_b200
+    from pcseg_b200.engine import profile_enable, profile_read
+    model.eval()
+    with torch.no_grad():
+        for _ in range(3):
+            model(x_dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = pcseg_b200.launch_count()
+        e0.record()
+        for _ in range(steps):
+            model(x_dev)
+        e1.record()
+        barrier()
+        launches = pcseg_b200.launch_count() - c0
+        ms = e0.elapsed_time(e1) / steps
+        profile_enable(eng, B, N, True, train=False)
+        for _ in range(steps):
+            model(x_dev)
+        torch.cuda.synchronize()
+        prof = profile_read(eng, B, N, train=False)
+        profile_enable(eng, B, N, False, train=False)
+    ps = pcseg_b200.PredictStream(model)
+    prev = None
+    for _ in range(3):
+        t = ps.submit(x_host)
+        if prev is not None:
+            ps.result(prev)
+        prev = t
+    barrier()
+    e2e_steps = max(steps, 50)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        t = ps.submit(x_host)
+        ps.result(prev)
+        prev = t
+    ps.result(prev)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tt[0].item()), float(tt[1].item())
+    peaks = measured_peaks()
+    pts = B * N * world
+    out = {"metric": metric_name("eval"), "value": pts / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "steps": steps,
+           "gpu_launches": launches,
+           "e2e": {"value": pts / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                   "d2h_bytes_per_step": B * N * 8, "ms_per_step": e2e_ms, "timed_steps": e2e_steps},
+           "step_tflops_per_gpu": FWD_FLOP_PER_PT * B * N / (ms * 1e-3) / 1e12}
+    out["step_frac_of_bf16_burst"] = out["step_tflops_per_gpu"] / peaks["bf16_burst"]
+    if 69 in prof:
+        kms = prof[69][0] / prof[69][1]
+        achieved = GFEAT_FLOP_PER_PT * B * N / (kms * 1e-3) / 1e12
+        traffic = load_ncu_traffic()
+        out["roofline"] = {"bound": "tensor", "kernel": "global_feat inference GEMM (1024x1024, bias + ReLU + max-pool epilogue, nothing stored)",
+                           "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+                           "frac_of_sustained": achieved / peaks["bf16_sustained"], "ms_per_launch": kms,
+                           "traffic": (traffic[69] * 1e6 if (B, N) == (8, 16384) and 69 in traffic else None),
+                           "traffic_source": NCU_TRAFFIC_SOURCE, "share_of_step": kms / ms}
+    return out
+
+
 def run_ours(args, B, N, mode):
     import torch
     import torch.distributed as dist
@@ -333,6 +438,12 @@ def run_ours(args, B, N, mode):
         profile_enable(eng, B, N, False)
         trainer.profiling = False
 
+    # the other half of the metric ("points/sec (fwd, fwd+bwd)"): inference on the same batch, same model, same process
+    fwd = None
+    if mode == "train" and not args.no_fwd:
+        fwd = measure_inference(model, eng, x_dev, x_host, B, N, steps, barrier, dev, world)
+        model.train()
+
     # end-to-end: pinned host inputs copied every step, result read back every step
     for _ in range(3):
         step_e2e()
@@ -364,17 +475,26 @@ def run_ours(args, B, N, mode):
     roof = None
     kernels = {}
     if prof:
-        names = {5: "global_feat fwd GEMM (1024x1024, stats epilogue)", 21: "global_feat dgrad GEMM (mask+stats epilogue)",
-                 37: "global_feat wgrad GEMM (MN-major, split-K)"}
+        # the 1024 x 1024 layer: forward, data gradient, and (folded BatchNorm backward) the Gram matrix of its input that
+        # replaces the weight-gradient GEMM; legacy step (PCSEG_FOLDED=0): tag 37 is the weight gradient
+        names = {5: "global_feat fwd GEMM (1024x1024, BN statistics + max-pool epilogue)",
+                 21: "global_feat data-gradient GEMM (mask + column-sum epilogue)",
+                 37: "global_feat weight-gradient GEMM (MN-major, split-K)",
+                 53: "Gram matrix a5^T a5 (MN-major, split-K, upper-triangle tiles = 62.5 % of 2*1024*1024 FLOP/point)"}
+        flop = {5: GFEAT_FLOP_PER_PT, 21: GFEAT_FLOP_PER_PT, 37: GFEAT_FLOP_PER_PT, 53: GFEAT_FLOP_PER_PT * 20 // 32}
         for tag, (ms, n) in prof.items():
             kernels[str(tag)] = {"ms_per_launch": ms / n, "launches": n}
-        tag = max((5, 21, 37), key=lambda tg: prof.get(tg, (0, 1))[0])
+        tag = max((tg for tg in (5, 21, 37, 53) if tg in prof), key=lambda tg: prof[tg][0] / prof[tg][1])
         ms, n = prof[tag]
-        achieved = GFEAT_FLOP_PER_PT * B * N / (ms / n * 1e-3) / 1e12
-        share = sum(prof.get(tg, (0, 1))[0] for tg in (5, 21, 37)) / ms_prof_total
-        roof = {"bound": "tensor", "kernel": names[tag], "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"],
-                "traffic": (NCU_TRAFFIC_MB_CFG2[tag] * 1e6 if (B, N) == (8, 16384) else None), "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": peaks["source"] + " bf16 sustained",
+        achieved = flop[tag] * B * N / (ms / n * 1e-3) / 1e12
+        share = sum(prof.get(tg, (0, 1))[0] for tg in (5, 21, 37, 53)) / ms_prof_total
+        traffic = load_ncu_traffic()
+        roof = {"bound": "tensor", "kernel": names[tag], "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_burst"], "frac_of_sustained": achieved / peaks["bf16_sustained"],
+                "peak_sustained": peaks["bf16_sustained"],
+                "traffic": (traffic[tag] * 1e6 if (B, N) == (8, 16384) and tag in traffic else None),
+                "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": NCU_TRAFFIC_SOURCE,
+                "peak_source": peaks["source"] + " bf16 burst (kernel event-timed on its own inside a short region at boost clock)",
                 "ms_per_launch": ms / n, "global_feat_gemms_share_of_step": share,
                 "measured": "CUDA events around each GEMM launch during a second pass of the same K steps (eager launches); "
                             "the headline value is from the first pass (CUDA-graph replay, no per-kernel events)"}
@@ -382,8 +502,8 @@ def run_ours(args, B, N, mode):
 
     cores = os.cpu_count() or 1
     if args.gpus == 1 and not args.no_cpu_baseline:
-        cpu_value, _, cpu_sample = time_cpu(mode, B, N, C, steps=2, warmup=1, budget_s=8.0)
-        cpu = {"value": cpu_value, "unit": "points/s", "cores": cores, "kind": "port", "sample": cpu_sample}
+        r = time_cpu(mode, B, N, C, steps=2, warmup=1, budget_s=12.0)
+        cpu = {"value": r["value"], "unit": "points/s", "cores": cores, "kind": r["kind"], "sample": r["sample"]}
         # the reference network through stock torch eager (cuDNN / cuBLAS fp32) on this same B200,
         # on a bounded sample of the workload (whole clouds; the reference keeps ~37 KB of saved tensors per point)
         from oracle.torch_port import time_stock_torch_on_gpu
@@ -409,9 +529,13 @@ def run_ours(args, B, N, mode):
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_total / steps, "timed_steps": e2e_steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "torch_eager_same_gpu": torch_eager,
-        "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
+        "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_burst": step_tflops / peaks["bf16_burst"],
+        "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
         "gemm_kernels": kernels,
     }
+    if fwd is not None:
+        line["fwd"] = fwd
+        line["metric"] = "segmentation points/sec (fwd+bwd train step; fwd inference under key 'fwd')"
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -425,6 +549,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fwd", action="store_true", help="train workloads: skip the inference half of the metric")
     args = ap.parse_args()
     B, N, mode = WORKLOADS[args.workload]
     if args.impl == "reference":

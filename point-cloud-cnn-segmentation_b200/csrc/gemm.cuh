@@ -29,6 +29,13 @@
 //                   dropped; no BN parameters, no Philox); column sums: sum dz and sum a                 -> bf16 store + fp64 atomics
 // DGRAD / DGRAD_ACT add bias[n] to the accumulator when p.bias != nullptr (constant row of the folded BatchNorm backward).
 //
+//   EPI_BIAS_RELU_X3: EPI_BIAS_RELU whose fp32 result is stored as a bf16 PAIR: hi = bf16(out) in columns [n, n + 64) and
+//                   lo = bf16(out - hi) in columns [x3_lo_col + n, ...) of the output tensor (split-bf16 inference)
+//
+// Split-bf16 ("bf16x3") inference, p.x3_kb > 0: operands are stored as [hi | lo] column halves (x3_kb k-blocks each) and
+// every logical k-block j is issued three times, (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi): the fp32 accumulator then holds
+// the product of the ~16-bit-significand operands (the dropped lo*lo term is 2^-16 smaller than the sum).
+//
 // The A operand may be the K-concatenation of two tensors: k-blocks [0, kb_switch) come from tmA, the rest from tmA2
 // (folded BatchNorm backward: [dz | a_prev]).
 //
@@ -41,7 +48,7 @@
 namespace pcseg {
 
 enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EPI_WGRAD = 4, EPI_LOGITS = 5, EPI_STATS_POOL = 6,
-              EPI_BN_RELU = 7, EPI_DGRAD_ACT = 8 };
+              EPI_BN_RELU = 7, EPI_DGRAD_ACT = 8, EPI_BIAS_RELU_X3 = 9 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -56,6 +63,21 @@ struct GemmParams {
     int num_splits, kb_per_split;   // split-K (wgrad only; otherwise 1 / K/64)
     int kb_switch;               // k-blocks [0, kb_switch) of A come from tmA, the rest from tmA2 (0 = everything from tmA)
     int store_out;               // EPI_STATS_POOL: 0 = statistics / max-pool only, the output tile is not written
+    int x3_kb;                   // > 0: split-bf16 k-schedule, = logical K / 64 (K in this struct then counts 3 * logical K)
+    int x3_lo_col;               // EPI_BIAS_RELU_X3: first column of the lo halves in the output tensor
+    int sym_tiles;               // EPI_WGRAD with A == B (Gram matrix): > 0 = number of (m, n) tiles that touch the upper
+                                 // triangle; only those are computed (tile order: n-tile major, m-tiles 0 .. (n+1)*BN/128-1)
+    int wg_mode;                 // EPI_WGRAD: 0 = fp32 red.add into out_f32 (split-K), 1 = bf16 store into out_bf16 (one split),
+                                 // 2 = folded weight gradient out_f32 = cA*wq + cB*acc + cD*ws[col] with {cA, cB, -, cD} = wcoef[row]
+                                 // 3 = every split stores its partial tile to out_f32 + split*M*ldc (summed in a fixed order
+                                 //     by k_gram_reduce: deterministic, unlike the atomics of mode 0)
+    __nv_bfloat16* out_bf16;     // wg_mode 1
+    const float* wq;             // wg_mode 2: Q = dz^T a_prev [M][ldc]
+    const float4* wcoef;         // wg_mode 2: per output row
+    const double* ws;            // wg_mode 2: column sums of a_prev [N]
+    const int* rowslot;          // DGRAD / DGRAD_ACT: per-row index into `side` (>= side_rows: none), or nullptr
+    const float* side;           // [side_rows][N] fp32 rows added to the accumulator before masking (max-pool gradient rows)
+    int side_rows;
     // epilogue operands (all optional depending on EPI)
     const float* bias;           // [N]
     const float* cloud_bias;     // [clouds][N] or nullptr
@@ -88,7 +110,7 @@ struct GemmCfg {
     static constexpr int STAGE_B = BN * GEMM_BK * 2;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD ||
-                                     EPI == EPI_BN_RELU || EPI == EPI_DGRAD_ACT);
+                                     EPI == EPI_BN_RELU || EPI == EPI_DGRAD_ACT || EPI == EPI_BIAS_RELU_X3);
     static constexpr bool HAS_Y = (EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
     static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
     static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
@@ -225,7 +247,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int warp_idx = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
 
-    const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits;
+    const int total_tiles = ((EPI == EPI_WGRAD && p.sym_tiles > 0) ? p.sym_tiles : p.num_m_tiles * p.num_n_tiles) * p.num_splits;
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -263,6 +285,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     auto tile_coords = [&](int tile, int& m_tile, int& n_tile, int& split) {
         split = tile % p.num_splits;
         int t = tile / p.num_splits;
+        if (EPI == EPI_WGRAD && p.sym_tiles > 0) {
+            n_tile = 0;
+            for (;;) {
+                const int cnt = min((n_tile + 1) * (BN / GEMM_BM), p.num_m_tiles);
+                if (t < cnt) break;
+                t -= cnt;
+                ++n_tile;
+            }
+            m_tile = t;
+            return;
+        }
         n_tile = t % p.num_n_tiles;
         m_tile = t / p.num_n_tiles;
     };
@@ -284,11 +317,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     uint8_t* sb = sa + Cfg::STAGE_A;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
                     if (!MN) {
+                        int ka = kb, kbb = kb;                  // k-block columns of A and B
+                        if (p.x3_kb > 0) {
+                            const int j = kb / 3, t = kb - 3 * j;
+                            ka = j + (t == 2 ? p.x3_kb : 0);
+                            kbb = j + (t == 1 ? p.x3_kb : 0);
+                        }
                         if (p.kb_switch > 0 && kb >= p.kb_switch)
                             tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - p.kb_switch) * GEMM_BK, m_tile * GEMM_BM);
                         else
-                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_tile * GEMM_BM);
-                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_tile * BN);
+                            tma_load_2d(sa, &tmA, &full_bar[stage], ka * GEMM_BK, m_tile * GEMM_BM);
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kbb * GEMM_BK, n_tile * BN);
                     } else {
 #pragma unroll
                         for (int j = 0; j < GEMM_BM / 64; ++j)
@@ -425,7 +464,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     uint32_t v[CW];
                     tmem_ld_cols<CW>(t_acc + c * CW, v);
                     tmem_ld_wait();
-                    if (valid && nonempty) {
+                    if (p.wg_mode == 1) {
+                        // single split: the tile is final -> bf16 (the B operand of a later GEMM)
+                        if (valid) {
+                            __nv_bfloat16* drow = p.out_bf16 + static_cast<size_t>(grow) * p.ldc + n0 + c * CW;
+#pragma unroll
+                            for (int j = 0; j < CW / 8; ++j)
+                                *reinterpret_cast<uint4*>(drow + j * 8) =
+                                    make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                               pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                               pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                               pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                        }
+                    } else if (p.wg_mode == 2) {
+                        // folded BatchNorm backward: dW = A Q + Bc (W Gc) + D s^T, acc = (W Gc)[row][col]
+                        if (valid) {
+                            const float4 cf = __ldg(p.wcoef + grow);
+                            const float* qrow = p.wq + static_cast<size_t>(grow) * p.ldc + n0 + c * CW;
+#pragma unroll
+                            for (int j = 0; j < CW / 4; ++j) {
+                                const float4 q4 = *reinterpret_cast<const float4*>(qrow + j * 4);
+                                const int col = n0 + c * CW + j * 4;
+                                float4 o;
+                                o.x = fmaf(cf.x, q4.x, fmaf(cf.y, __uint_as_float(v[4 * j]), cf.w * static_cast<float>(p.ws[col])));
+                                o.y = fmaf(cf.x, q4.y, fmaf(cf.y, __uint_as_float(v[4 * j + 1]), cf.w * static_cast<float>(p.ws[col + 1])));
+                                o.z = fmaf(cf.x, q4.z, fmaf(cf.y, __uint_as_float(v[4 * j + 2]), cf.w * static_cast<float>(p.ws[col + 2])));
+                                o.w = fmaf(cf.x, q4.w, fmaf(cf.y, __uint_as_float(v[4 * j + 3]), cf.w * static_cast<float>(p.ws[col + 3])));
+                                *reinterpret_cast<float4*>(dst_row + c * CW + j * 4) = o;
+                            }
+                        }
+                    } else if (p.wg_mode == 3) {
+                        if (valid) {
+                            float* prow = dst_row + static_cast<size_t>(split) * p.M * p.ldc + c * CW;
+#pragma unroll
+                            for (int j = 0; j < CW / 4; ++j)
+                                *reinterpret_cast<float4*>(prow + j * 4) =
+                                    nonempty ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    } else if (valid && nonempty) {
 #pragma unroll
                         for (int j = 0; j < CW / 4; ++j) {
                             const int col = n0 + c * CW + j * 4;
@@ -496,6 +574,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     row0_in_cloud = m0 - tile_cl * p.pts_per_cloud;
                     uniform_cloud = row0_in_cloud + (min(m0 + GEMM_BM, p.M) - m0) <= p.pts_per_cloud;
                 }
+                int side_slot = 0x7fffffff;
+                if constexpr (IS_DGRAD) {
+                    if (p.rowslot != nullptr && valid) side_slot = __ldg(p.rowslot + grow);
+                }
                 const int cloud = uniform_cloud ? tile_cl : (valid ? grow / p.pts_per_cloud : 0);
                 const float* cb_row = (p.cloud_bias != nullptr) ? p.cloud_bias + static_cast<size_t>(cloud) * p.N : nullptr;
                 const bool pool_uniform = uniform_cloud;
@@ -506,6 +588,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float* comb_b = comb + buf * (4 * 64);        // COLMAX only: [buf][row group][64]
                     if constexpr (Cfg::HAS_Y) mbar_wait(&y_full[buf], (sub_it >> 1) & 1);
                     uint32_t packed[CW / 2];
+                    uint32_t packed_lo[(EPI == EPI_BIAS_RELU_X3) ? CW / 2 : 1];
+                    (void)packed_lo;
+                    if constexpr (EPI == EPI_BIAS_RELU_X3) {       // hi -> staging buffer 0, lo -> buffer 1: both must be free
+                        if (elected) tma_store_wait_read<0>();
+                        named_bar_sync(3, EPI_THREADS);
+                    }
                     uint32_t v[CW];
                     tmem_ld_cols<CW>(t_acc + sub * 64 + cq * CW, v);
                     tmem_ld_wait();
@@ -513,7 +601,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tc_fence_before();
                         mbar_arrive(&tmem_empty[acc]);
                     }
-                    if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX) {
+                    if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX || EPI == EPI_BIAS_RELU_X3) {
                         float o[CW];
 #pragma unroll
                         for (int i = 0; i < CW; i += 4) {
@@ -534,6 +622,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             // rows beyond M are clipped by the TMA store: no masking needed
 #pragma unroll
                             for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(fmaxf(o[2 * i], 0.f), fmaxf(o[2 * i + 1], 0.f));
+                        } else if constexpr (EPI == EPI_BIAS_RELU_X3) {
+#pragma unroll
+                            for (int i = 0; i < CW / 2; ++i) {
+                                const float a0 = fmaxf(o[2 * i], 0.f), a1 = fmaxf(o[2 * i + 1], 0.f);
+                                packed[i] = pack_bf16x2(a0, a1);
+                                packed_lo[i] = pack_bf16x2(a0 - bf16_lo(packed[i]), a1 - bf16_hi(packed[i]));
+                            }
                         } else {
 #pragma unroll
                             for (int i = 0; i < CW; ++i) o[i] = valid ? fmaxf(o[i], 0.f) : 0.f;
@@ -583,6 +678,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + b4v.w);
                             }
                         }
+                        if (side_slot < p.side_rows) {       // rare: this row receives max-pool gradient rows
+                            const float* e = p.side + static_cast<size_t>(side_slot) * p.N + c0;
+#pragma unroll
+                            for (int i = 0; i < CW; i += 4) {
+                                const float4 e4 = *reinterpret_cast<const float4*>(e + i);
+                                v[i] = __float_as_uint(__uint_as_float(v[i]) + e4.x);
+                                v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + e4.y);
+                                v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + e4.z);
+                                v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + e4.w);
+                            }
+                        }
                         if (p.drop_thr16 != 0u) {
 #pragma unroll
                             for (int i = 0; i < CW / 2; ++i)
@@ -592,7 +698,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
                         }
                     }
-                    if constexpr (Cfg::HAS_OUT) {
+                    if constexpr (EPI == EPI_BIAS_RELU_X3) {
+                        const uint32_t orow = out_s + row * 128;
+#pragma unroll
+                        for (int j = 0; j < CW / 8; ++j) {
+                            const uint32_t off = ((cq * (CW / 8) + j) ^ (row & 7)) << 4;
+                            sts128(orow + off, make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]));
+                            sts128(orow + 16384 + off, make_uint4(packed_lo[4 * j], packed_lo[4 * j + 1], packed_lo[4 * j + 2], packed_lo[4 * j + 3]));
+                        }
+                        fence_proxy_async_smem();
+                    } else if constexpr (Cfg::HAS_OUT) {
                         const uint32_t orow = out_s + buf * 16384 + row * 128;
 #pragma unroll
                         for (int j = 0; j < CW / 8; ++j)
@@ -745,7 +860,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             named_bar_sync(2, EPI_THREADS);     // staging tile was modified in place
                         }
                     }
-                    if constexpr (Cfg::HAS_OUT) {
+                    if constexpr (EPI == EPI_BIAS_RELU_X3) {
+                        if (elected) {
+                            tma_store_2d(&tmOut, out_stage, n0 + sub * 64, m0);
+                            tma_store_2d(&tmOut, out_stage + 16384, p.x3_lo_col + n0 + sub * 64, m0);
+                            tma_store_commit();
+                        }
+                    } else if constexpr (Cfg::HAS_OUT) {
                         if (elected) {
                             if (EPI != EPI_STATS_POOL || p.store_out) {
                                 tma_store_2d(&tmOut, out_stage + buf * 16384, n0 + sub * 64, m0);

@@ -232,6 +232,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t s) {
     CASE(256, EPI_STATS_POOL, false)
     CASE(64, EPI_DGRAD, false) CASE(128, EPI_DGRAD, false) CASE(256, EPI_DGRAD, false)
     CASE(256, EPI_BN_RELU, false) CASE(256, EPI_DGRAD_ACT, false)
+    CASE(64, EPI_BIAS_RELU_X3, false) CASE(128, EPI_BIAS_RELU_X3, false) CASE(256, EPI_BIAS_RELU_X3, false)
     CASE(64, EPI_WGRAD, true) CASE(128, EPI_WGRAD, true) CASE(256, EPI_WGRAD, true)
 #undef CASE
     return fail("internal: no GEMM instantiation for BN=%d EPI=%d MN=%d", op.bn, op.epi, (int)op.mn);
@@ -281,6 +282,17 @@ int setup_gemm_kmajor_cat(GemmOp* op, int epi, const void* A1, int lda1, int K1,
     return 0;
 }
 
+// Split-bf16 GEMM: A [M][2K] and B [N][2K] hold [hi | lo] column halves; out (optional) [M][2N] likewise.
+int setup_gemm_x3(GemmOp* op, int epi, const void* A, const void* B, long long M, int N, int K, void* out) {
+    TRY(setup_gemm_kmajor(op, epi, A, 2 * K, B, 2 * K, M, N, 2 * K, nullptr, 0, nullptr, 0));
+    if (out) TRY(make_tmap(&op->tmOut, out, 2 * N, M, 2 * N, 64, 128));
+    op->p.K = 3 * K;
+    op->p.kb_per_split = 3 * K / 64;
+    op->p.x3_kb = K / 64;
+    op->p.x3_lo_col = N;
+    return 0;
+}
+
 // Weight-gradient GEMM  D[Mc,Nc] += A[P,Mc]^T * B[P,Nc]  (both operands point-major, K = points), fp32 atomics.
 int setup_gemm_wgrad(GemmOp* op, const void* A, int lda, int Mc, const void* B, int ldb, int Nc, long long P, float* out, int ldc) {
     memset(&op->p, 0, sizeof(op->p));
@@ -316,6 +328,7 @@ int setup_gemm_wgrad(GemmOp* op, const void* A, int lda, int Mc, const void* B, 
 // workspace carving
 // ------------------------------------------------------------------------------------------------
 constexpr int RAG_MAX_STRIPS = 1024;
+constexpr int GRAM_MAX_SPLITS = 160;         // >= SM count: one partial tile per CTA of the forward Gram GEMM
 // folded conv5 scratch that is zeroed once per backward: Q (1024 x 128) | S32 (128 x 128) | const (128) | tile tickets (64)
 constexpr size_t FOLD4_ZERO_FLOATS = 1024 * 128 + 128 * 128 + 128 + 64;
 
@@ -345,6 +358,7 @@ struct pcseg_ctx {
     int B = 0, N = 0;
     long long P = 0;
     bool bound = false, train = false, eval_ready = false;
+    bool x3 = false;              // inference with split-bf16 ("bf16x3") operands: fp32-grade logits (bind mode 2)
 
     // ---- shared small buffers
     float* zeros1024 = nullptr;
@@ -412,6 +426,15 @@ struct pcseg_ctx {
     float* s32f[NUM_BN] = {};     // [Ci][Ci] fp32 accumulator of S; qraw | s32f | cstf | ticket are contiguous (one memset)
     int* foldticket[NUM_BN] = {};
     float* gcf[NUM_BN] = {};      // [Ci][Ci] centred Gram matrix
+    float* grampart4 = nullptr;   // [GRAM_MAX_SPLITS][128][128] per-split partial tiles of a3^T a3 (summed by k_gram_reduce)
+    // folded global_feat (index 5): gramf[5] = a4^T a4 (upper triangle), qraw[5] | cstf[5] contiguous (one memset)
+    bf16* wb5 = nullptr;          // [1024][1024] diag(Bc) W5
+    bf16* s5b = nullptr;          // [1024][1024] S5 = W5^T diag(Bc) W5 (symmetric; B operand of the data-gradient GEMM)
+    bf16* gc5b = nullptr;         // [1024][1024] centred Gram matrix of a4
+    float* side5 = nullptr;       // [B*1024][1024] rows of dz5 diag(A) W5 (max-pool gradient rows)
+    int* rowslot5 = nullptr;      // [cap_rows] side-buffer slot of every point (>= B*1024: none)
+    bool store_y5 = false;        // PCSEG_STORE_Y5=1: keep writing global_feat's pre-BN output (tests)
+    GemmOp s5_op, t5_op;
     GemmOp gram_op[NUM_BN];
     unsigned long long seed = 0;
     const unsigned long long* seed_ptr = nullptr;
@@ -437,6 +460,7 @@ static int timed_gemm(pcseg_ctx* c, const GemmOp& op, int tag, cudaStream_t s) {
 }
 
 static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes_out) {
+    const size_t x3f = (c->x3 && !train) ? 2 : 1;      // split-bf16 inference stores [hi | lo] halves
     // Shape-independent buffers (weights, per-channel vectors) come first so that their addresses do not depend on
     // (B, N): bindings of different batch shapes can then share one caller-owned workspace and keep prepared weights.
     Carver k(ws);
@@ -455,7 +479,7 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
     }
     for (int i = 1; i < NUM_BN; ++i) {
         const int cin = (i == 6) ? 64 : cv[i].cin;
-        c->wk[i] = k.take<bf16>(static_cast<size_t>(cv[i].cout) * cin);
+        c->wk[i] = k.take<bf16>(static_cast<size_t>(cv[i].cout) * cin * x3f);
     }
     if (train) {
         size_t so = 0;
@@ -480,7 +504,16 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
             c->cstf[4] = c->qraw[4] ? c->s32f[4] + 128 * 128 : nullptr;
             c->foldticket[4] = c->qraw[4] ? reinterpret_cast<int*>(c->cstf[4] + 128) : nullptr;
             c->gcf[4] = k.take<float>(128 * 128);
+            c->grampart4 = k.take<float>(static_cast<size_t>(GRAM_MAX_SPLITS) * 128 * 128);
             c->bwf[4] = k.take<bf16>(128 * (1024 + 128));
+        }
+        {   // folded global_feat: Ci = Co = 1024
+            c->gramf[5] = k.take<float>(1024 * 1024);
+            c->qraw[5] = k.take<float>(1024 * 1024 + 1024);
+            c->cstf[5] = c->qraw[5] ? c->qraw[5] + 1024 * 1024 : nullptr;
+            c->wb5 = k.take<bf16>(1024 * 1024);
+            c->s5b = k.take<bf16>(1024 * 1024);
+            c->gc5b = k.take<bf16>(1024 * 1024);
         }
     }
     // ---- shape-dependent buffers
@@ -498,7 +531,7 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
         // a1..a5, a_s1, a_s2 (global_feat output is reduced in-kernel; seg_conv3 output feeds the fused logits epilogue)
         for (int i = 0; i < NUM_BN; ++i) {
             if (i == 5 || (i == 8 && c->C <= MAX_CLASSES)) continue;      // (wide head: seg_conv3's output is materialised)
-            c->act[i] = k.take<bf16>(P * cv[i].cout);
+            c->act[i] = k.take<bf16>(P * cv[i].cout * x3f);
         }
     } else {
         c->keys = k.take<unsigned long long>(static_cast<size_t>(B) * 1024);
@@ -506,6 +539,8 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
         c->argidx = k.take<int>(static_cast<size_t>(B) * 1024);
         c->dcb = k.take<float>(static_cast<size_t>(B) * 512);
         c->dzv = k.take<float>(static_cast<size_t>(B) * 1024);
+        c->side5 = k.take<float>(static_cast<size_t>(B) * 1024 * 1024);
+        c->rowslot5 = k.take<int>(P);
         c->dycat = k.take<bf16>(P * 576);
         for (int i = 0; i < NUM_BN; ++i) {
             c->y[i] = k.take<bf16>(P * cv[i].cout);
@@ -531,7 +566,8 @@ extern "C" long long pcseg_workspace_bytes(int B, int N, int C, int train) {
     tmp.C = C;
     tmp.L = make_layout(C);
     size_t bytes = 0;
-    carve(&tmp, nullptr, B, N, train != 0, &bytes);
+    tmp.x3 = train == 2;
+    carve(&tmp, nullptr, B, N, train == 1, &bytes);
     return static_cast<long long>(bytes);
 }
 
@@ -544,6 +580,8 @@ extern "C" int pcseg_create(pcseg_ctx** out, int num_classes) {
     {
         const char* e = getenv("PCSEG_FOLDED");       // 0: legacy training step (y / dy of every layer materialised)
         c->folded = !(e && e[0] == '0');
+        const char* y5 = getenv("PCSEG_STORE_Y5");
+        c->store_y5 = y5 && y5[0] == '1';
     }
     *out = c;
     return 0;
@@ -561,7 +599,10 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) return fail("pcseg_bind: workspace must be non-null and 1024-byte aligned");
     size_t need = 0;
     c->B = B; c->N = N; c->P = static_cast<long long>(B) * N;
-    c->train = train != 0;
+    if (train < 0 || train > 2) return fail("pcseg_bind: mode must be 0 (inference), 1 (training) or 2 (split-bf16 inference)");
+    c->train = train == 1;
+    c->x3 = train == 2;
+    if (c->x3 && c->C > MAX_CLASSES) return fail("pcseg_bind: split-bf16 inference supports up to %d classes", MAX_CLASSES);
     carve(c, ws, B, N, c->train, &need);
     if (static_cast<long long>(need) > ws_bytes) return fail("pcseg_bind: workspace too small (%lld < %zu)", ws_bytes, need);
     const ConvDef* cv = c->L.conv;
@@ -574,7 +615,31 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
     const long long P = rag ? c->cap_rows : c->P;       // rows spanned by the tensor maps (ragged: patched per call)
     const int* tile_cloud = rag ? c->meta + 2 * B + 1 : nullptr;
     const int* cloud_off = rag ? c->meta + B : nullptr;
-    if (!c->train) {
+    if (!c->train && c->x3) {
+        // split-bf16 inference (dense batches only): every GEMM runs the three-product k-schedule on [hi | lo] operands
+        if (rag) continue;
+        for (int i = 1; i <= 4; ++i) {
+            TRY(setup_gemm_x3(&O.ev[i], EPI_BIAS_RELU_X3, c->act[i - 1], c->wk[i], P, cv[i].cout, cv[i].cin, c->act[i]));
+            O.ev[i].p.bias = c->delta[i];
+        }
+        TRY(setup_gemm_x3(&O.ev[5], EPI_COLMAX, c->act[4], c->wk[5], P, 1024, 1024, nullptr));
+        O.ev[5].bn = 256;
+        O.ev[5].p.bias = c->delta[5];
+        O.ev[5].p.colmax = reinterpret_cast<unsigned int*>(c->gmax);
+        O.ev[5].p.pts_per_cloud = N;
+        TRY(setup_gemm_x3(&O.ev[6], EPI_BIAS_RELU_X3, c->act[1], c->wk[6], P, 512, 64, c->act[6]));
+        O.ev[6].p.bias = c->zeros1024;
+        O.ev[6].p.cloud_bias = c->cb;
+        O.ev[6].p.pts_per_cloud = N;
+        TRY(setup_gemm_x3(&O.ev[7], EPI_BIAS_RELU_X3, c->act[6], c->wk[7], P, 256, 512, c->act[7]));
+        O.ev[7].p.bias = c->delta[7];
+        TRY(setup_gemm_x3(&O.ev[8], EPI_LOGITS, c->act[7], c->wk[8], P, 128, 256, nullptr));
+        O.ev[8].p.bias = c->delta[8];
+        O.ev[8].p.w4 = c->w4;
+        O.ev[8].p.b4 = c->b4;
+        O.ev[8].p.num_classes = c->C;
+        c->use_head_chain = false;
+    } else if (!c->train) {
         // conv2..conv5
         for (int i = 1; i <= 4; ++i) {
             TRY(setup_gemm_kmajor(&O.ev[i], EPI_BIAS_RELU, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
@@ -675,12 +740,51 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         TRY(wgrad(1, c->dy[1], 64, c->act[0], 64, 64));
         if (c->folded && !rag) {
             // conv5 with Gram-predicted statistics: G = a3^T a3, BN + ReLU in the GEMM epilogue, y4 never stored
-            TRY(setup_gemm_wgrad(&c->gram_op[4], c->act[3], 128, 128, c->act[3], 128, 128, P, c->gramf[4], 128));
+            TRY(setup_gemm_wgrad(&c->gram_op[4], c->act[3], 128, 128, c->act[3], 128, 128, P, c->grampart4, 128));
+            c->gram_op[4].p.wg_mode = 3;        // per-split partial tiles, summed in a fixed order: reproducible statistics
+            if (c->gram_op[4].p.num_splits > GRAM_MAX_SPLITS) return fail("internal: %d Gram splits", c->gram_op[4].p.num_splits);
             TRY(setup_gemm_kmajor(&O.fw[4], EPI_BN_RELU, c->act[3], 128, c->wk[4], 128, P, 1024, 128, c->act[4], 1024, nullptr, 0));
             O.fw[4].p.bnp = c->bnp[4];
-            // global_feat data gradient masked by the stored activation a4 (column sums: sum dz4, sum a4)
-            TRY(setup_gemm_kmajor(&O.dg[5], EPI_DGRAD_ACT, c->dy[5], 1024, c->wt[5], 1024, P, 1024, 1024, c->dz[4], 1024, c->act[4], 1024));
+            // global_feat: statistics + max-pool only (its pre-BN output is not needed by the folded backward)
+            O.fw[5].p.store_out = c->store_y5 ? 1 : 0;
+            // folded BN backward of global_feat.  S5 = (diag(Bc) W5)^T W5 on the tensor cores, bf16 result in one split
+            TRY(setup_gemm_wgrad(&c->s5_op, c->wb5, 1024, 1024, c->wk[5], 1024, 1024, 1024, nullptr, 1024));
+            c->s5_op.p.num_splits = 1;
+            c->s5_op.p.kb_per_split = 1024 / 64;
+            c->s5_op.p.wg_mode = 1;
+            c->s5_op.p.out_bf16 = c->s5b;
+            // data gradient: dz4 = [a4 > 0] . (a4 S5 + const + max-pool gradient rows), column sums: sum dz4, sum a4
+            TRY(setup_gemm_kmajor(&O.dg[5], EPI_DGRAD_ACT, c->act[4], 1024, c->s5b, 1024, P, 1024, 1024, c->dz[4], 1024, c->act[4], 1024));
             O.dg[5].p.stats = c->stats_b + c->stat_off[4];
+            O.dg[5].p.bias = c->cstf[5];
+            O.dg[5].p.rowslot = c->rowslot5;
+            O.dg[5].p.side = c->side5;
+            O.dg[5].p.side_rows = B * 1024;
+            // weight gradient: G4 = a4^T a4 (upper-triangle tiles only), then dW5 = A Q5 + Bc (W5 Gc4) + D s4^T in the
+            // epilogue of the W5 Gc4 GEMM
+            TRY(setup_gemm_wgrad(&c->gram_op[5], c->act[4], 1024, 1024, c->act[4], 1024, 1024, P, c->gramf[5], 1024));
+            {
+                GemmParams& gp = c->gram_op[5].p;
+                int tiles = 0;
+                for (int nt = 0; nt < gp.num_n_tiles; ++nt) {
+                    const int cnt = (nt + 1) * (c->gram_op[5].bn / 128);
+                    tiles += cnt < gp.num_m_tiles ? cnt : gp.num_m_tiles;
+                }
+                gp.sym_tiles = tiles;
+                const int total_kb = static_cast<int>((P + 63) / 64);
+                int splits = num_sms() / tiles;
+                if (splits < 1) splits = 1;
+                if (splits > total_kb) splits = total_kb;
+                gp.kb_per_split = (total_kb + splits - 1) / splits;
+                gp.num_splits = (total_kb + gp.kb_per_split - 1) / gp.kb_per_split;
+            }
+            TRY(setup_gemm_wgrad(&c->t5_op, c->wt[5], 1024, 1024, c->gc5b, 1024, 1024, 1024, nullptr, 1024));
+            c->t5_op.p.num_splits = 1;
+            c->t5_op.p.kb_per_split = 1024 / 64;
+            c->t5_op.p.wg_mode = 2;
+            c->t5_op.p.wq = c->qraw[5];
+            c->t5_op.p.wcoef = c->coef[5];
+            c->t5_op.p.ws = c->stats_b + c->stat_off[4] + 1024;
             // folded BN backward of conv5: Q = dz4^T a3 (raw), then dz3 = mask3 . ([dz4 | a3] [diag(A) W ; S] + const)
             TRY(setup_gemm_wgrad(&O.wg_op[4], c->dz[4], 1024, 1024, c->act[3], 128, 128, P, c->qraw[4], 128));
             TRY(setup_gemm_kmajor_cat(&O.dg[4], EPI_DGRAD, c->dz[4], 1024, 1024, c->act[3], 128, 128, c->bwf[4], 1024 + 128, P, 128, c->dz[3], 128,
@@ -698,9 +802,10 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
 // ------------------------------------------------------------------------------------------------
 // weight preparation
 // ------------------------------------------------------------------------------------------------
-static int convert_rows(const float* src, int ld_src, bf16* dst, int ld_dst, int rows, int cols, const float* alpha, cudaStream_t s) {
+static int convert_rows(const float* src, int ld_src, bf16* dst, int ld_dst, int rows, int cols, const float* alpha, cudaStream_t s,
+                        bf16* dst_lo = nullptr) {
     const int n = rows * cols;
-    pdl_launch(k_convert_rows, (n + 255) / 256, 256, 0, s, src, ld_src, dst, ld_dst, rows, cols, alpha);
+    pdl_launch(k_convert_rows, (n + 255) / 256, 256, 0, s, src, ld_src, dst, ld_dst, rows, cols, alpha, dst_lo);
     LAUNCH_OK("k_convert_rows");
     return 0;
 }
@@ -727,12 +832,14 @@ extern "C" int pcseg_prepare_eval(pcseg_ctx* c, const float* params, const float
     CUDA_OK(cudaMemcpyAsync(c->w4, params + L.off[18], static_cast<size_t>(c->C) * 128 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(c->b4, params + L.off[19], static_cast<size_t>(c->C) * sizeof(float), cudaMemcpyDeviceToDevice, s));
     for (int i = 1; i < NUM_BN; ++i) {
+        const int xf = c->x3 ? 2 : 1;          // split-bf16: rows of [hi | lo] halves
         if (i == 6) {
-            TRY(convert_rows(params + L.off[12], 1088, c->wk[6], 64, 512, 64, c->alpha[6], s));
+            TRY(convert_rows(params + L.off[12], 1088, c->wk[6], 64 * xf, 512, 64, c->alpha[6], s, c->x3 ? c->wk[6] + 64 : nullptr));
             CUDA_OK(cudaMemcpy2DAsync(c->wg, 1024 * sizeof(float), params + L.off[12] + 64, 1088 * sizeof(float), 1024 * sizeof(float), 512,
                                       cudaMemcpyDeviceToDevice, s));
         } else {
-            TRY(convert_rows(params + L.off[2 * i], L.conv[i].cin, c->wk[i], L.conv[i].cin, L.conv[i].cout, L.conv[i].cin, c->alpha[i], s));
+            const int ci = L.conv[i].cin;
+            TRY(convert_rows(params + L.off[2 * i], ci, c->wk[i], ci * xf, L.conv[i].cout, ci, c->alpha[i], s, c->x3 ? c->wk[i] + ci : nullptr));
         }
     }
     c->eval_ready = true;
@@ -875,10 +982,10 @@ static int forward_eval_trunk(pcseg_ctx* c, pcseg_ctx::OpSet& O, long long rows,
         int grid = static_cast<int>((rows + 31) / 32);
         if (grid > num_sms() * 8) grid = num_sms() * 8;
         pdl_launch(k_ingest<false>, grid, 256, 0, s, reinterpret_cast<const float4*>(x), static_cast<int>(rows), c->w1, c->alpha[0], c->delta[0],
-                                            c->act[0], nullptr);
+                                            c->act[0], nullptr, c->x3 ? 1 : 0);
         LAUNCH_OK("k_ingest");
     }
-    for (int i = 1; i <= 5; ++i) TRY(launch_gemm(O.ev[i], s));
+    for (int i = 1; i <= 5; ++i) TRY(timed_gemm(c, O.ev[i], 64 + i, s));      // (event-timed only while profiling)
     return 0;
 }
 // part 2: per-cloud seg_conv1 term from the pooled feature, segmentation head, logits
@@ -976,6 +1083,7 @@ extern "C" int pcseg_forward_eval_ragged(pcseg_ctx* c, const float* x, const int
     if (!c || !c->bound || c->train) return fail("pcseg_forward_eval_ragged: context not bound in eval mode");
     if (!c->eval_ready) return fail("pcseg_forward_eval_ragged: call pcseg_prepare_eval first");
     if (!x || !logits || !lengths) return fail("pcseg_forward_eval_ragged: null argument");
+    if (c->x3) return fail("pcseg_forward_eval_ragged: split-bf16 inference runs dense batches only");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TRY(rag_plan(c, lengths, nmax, s));
     TRY(rag_pack(c, x, nullptr, false, s));
@@ -1041,7 +1149,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
     CUDA_OK(cudaMemsetAsync(c->keys, 0, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long), s));
     if (ce) CUDA_OK(cudaMemsetAsync(ce, 0, sizeof(pcseg_ce_accum), s));
     const bool folded = c->folded && !rag;
-    if (folded) CUDA_OK(cudaMemsetAsync(c->gramf[4], 0, 128 * 128 * sizeof(float) + 128 * sizeof(double), s));
+    if (folded) CUDA_OK(cudaMemsetAsync(c->colsum[4], 0, 128 * sizeof(double), s));
 
     auto fin_args = [&](int i) {
         BnFinalizeArgs f;
@@ -1080,7 +1188,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         int grid = static_cast<int>((P + 31) / 32);
         if (grid > num_sms() * 2) grid = num_sms() * 2;     // every block ends with 128 fp64 atomics on the same addresses
         pdl_launch(k_ingest<true>, grid, 256, 0, s, reinterpret_cast<const float4*>(x), static_cast<int>(P), params + L.off[0], nullptr, nullptr,
-                                           c->y[0], c->stats_f + c->stat_off[0]);
+                                           c->y[0], c->stats_f + c->stat_off[0], 0);
         LAUNCH_OK("k_ingest");
         TRY(stats_fix(0));
         TRY(bn_relu(0, 0, 0, 1.f));
@@ -1093,6 +1201,9 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         } else if (i == 4 && folded) {
             // conv5: batch statistics predicted from the Gram matrix of a3, BN + ReLU applied in the GEMM epilogue
             TRY(timed_gemm(c, c->gram_op[4], 48 + 4, s));
+            pdl_launch(k_gram_reduce, 128 * 128 * 4 / 256, 256, 0, s, static_cast<const float*>(c->grampart4), c->gram_op[4].p.num_splits,
+                       128 * 128, c->gramf[4]);
+            LAUNCH_OK("k_gram_reduce");
             pdl_launch(k_predict_bn<4>, 1024 / 16, 512, 0, s, static_cast<const float*>(c->gramf[4]), static_cast<const double*>(c->colsum[4]),
                        static_cast<const bf16*>(c->wk[4]), fin_args(4), c->stats_f + c->stat_off[4]);
             LAUNCH_OK("k_predict_bn");
@@ -1316,8 +1427,47 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         pdl_launch(k_cloud_bwd_dw, grid_dw, 256, 0, s, c->dcb, c->gmax, B, 512, 1024, grads + L.off[12] + 64, 1088);
         LAUNCH_OK("k_cloud_bwd_dw");
     }
-    // global_feat (sparse max-pool gradient folded into the BN backward)
-    {
+    // global_feat
+    if (c->folded && !rag) {
+        // folded BatchNorm backward (neither y5 nor dy5 exist): coefficients from {sum dzv, sum dzv*yhat}, S5 on the tensor
+        // cores, the max-pool gradient rows through the side buffer, ONE data-gradient GEMM over a4; then the Gram matrix of
+        // a4 and the weight gradient in the epilogue of the W5 Gc4 GEMM
+        CUDA_OK(cudaMemsetAsync(c->qraw[5], 0, (1024 * 1024 + 1024) * sizeof(float), s));
+        CUDA_OK(cudaMemsetAsync(c->side5, 0, static_cast<size_t>(B) * 1024 * 1024 * sizeof(float), s));
+        CUDA_OK(cudaMemsetAsync(c->rowslot5, 0x7f, static_cast<size_t>(c->P) * sizeof(int), s));
+        CUDA_OK(cudaMemsetAsync(c->gramf[5], 0, 1024 * 1024 * sizeof(float), s));
+        Fold5Args f5;
+        f5.stats_b = c->stats_b + c->stat_off[5];
+        f5.bnp = c->bnp[5];
+        f5.coef = c->coef[5];
+        f5.dgamma = grads + L.off[20 + 2 * 5];
+        f5.dbeta = grads + L.off[21 + 2 * 5];
+        f5.dbias = grads + L.off[2 * 5 + 1];
+        f5.W = c->wk[5];
+        f5.WB = c->wb5;
+        f5.cst = c->cstf[5];
+        f5.n = static_cast<double>(c->P);
+        f5.Co = 1024;
+        f5.Ci = 1024;
+        pdl_launch(k_fold5_prep, 1024 / 8, 256, 0, s, f5);
+        LAUNCH_OK("k_fold5_prep");
+        TRY(timed_gemm(c, c->s5_op, 48 + 6, s));
+        pdl_launch(k_pool_claim, (B * 1024 + 255) / 256, 256, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), B * 1024,
+                   1024, N, c->rowslot5);
+        LAUNCH_OK("k_pool_claim");
+        pdl_launch(k_pool_rows, B * 1024, 128, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), 1024, N,
+                   static_cast<const int*>(c->rowslot5), static_cast<const float4*>(c->coef[5]), static_cast<const bf16*>(c->wk[5]),
+                   static_cast<const bf16*>(c->act[4]), c->side5, c->qraw[5]);
+        LAUNCH_OK("k_pool_rows");
+        TRY(dgrad(5, 0, 0, 1.f));
+        TRY(timed_gemm(c, c->gram_op[5], 48 + 5, s));
+        pdl_launch(k_gram_center, 1024 * 1024 / 256, 256, 0, s, static_cast<const float*>(c->gramf[5]),
+                   static_cast<const double*>(c->stats_b + c->stat_off[4] + 1024), static_cast<double>(c->P), 1024, c->gc5b);
+        LAUNCH_OK("k_gram_center");
+        GemmOp t5 = c->t5_op;
+        t5.p.out_f32 = grads + L.off[10];
+        TRY(timed_gemm(c, t5, 32 + 5, s));
+    } else {
         const int rps = apply_rows_per_strip(N, B, 1024);
         dim3 grid((N + rps - 1) / rps, B);
         if (rag)
@@ -1327,9 +1477,9 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
             pdl_launch(k_bn_bwd_apply<true, false>, grid, 256, 0, s, nullptr, 0, c->y[5], 1024, c->dy[5], 1024, N, 1024, rps, bwd_args(5),
                        grads + L.off[11], nullptr, c->argidx, c->dzv, nullptr, nullptr);
         LAUNCH_OK("k_bn_bwd_apply<sparse>");
+        TRY(wgrad(5, grads + L.off[10], 1024));
+        TRY(dgrad(5, 0, 0, 1.f));
     }
-    TRY(wgrad(5, grads + L.off[10], 1024));
-    TRY(dgrad(5, 0, 0, 1.f));
     }   // phase != 2
     if (phase == 1) return 0;
     // conv5
@@ -1503,6 +1653,10 @@ extern "C" int pcseg_debug_copy(pcseg_ctx* c, int kind, int layer, void* dst, lo
         case 16: src = c->qraw[layer]; r = cv[layer].cout; cc = cv[layer].cin; eb = 4; break;
         case 17: src = c->bwf[layer]; r = cv[layer].cin; cc = cv[layer].cout + cv[layer].cin; eb = 2; break;
         case 18: src = c->cstf[layer]; r = 1; cc = cv[layer].cin; eb = 4; break;
+        case 19: src = c->s5b; r = 1024; cc = 1024; eb = 2; break;
+        case 20: src = c->gc5b; r = 1024; cc = 1024; eb = 2; break;
+        case 21: src = c->side5; r = B * 1024; cc = 1024; eb = 4; break;
+        case 22: src = c->rowslot5; r = 1; cc = P; eb = 4; break;
         default: return fail("pcseg_debug_copy: unknown kind %d", kind);
     }
     if (!src) return fail("pcseg_debug_copy: tensor kind %d layer %d is not materialised", kind, layer);

@@ -16,8 +16,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Weight preparation
 // ---------------------------------------------------------------------------------------------
 // dst[r][c] (bf16, pitch ld_dst) = alpha[r] * src[r][c] (fp32, pitch ld_src); alpha may be null.
+// dst_lo (optional, same pitch): the bf16 remainder v - float(bf16(v)) (split-bf16 inference operands [hi | lo]).
 __global__ void k_convert_rows(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
-                               int rows, int cols, const float* __restrict__ alpha) {
+                               int rows, int cols, const float* __restrict__ alpha, __nv_bfloat16* __restrict__ dst_lo) {
     pdl_launch_dependents();
     pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -25,7 +26,9 @@ __global__ void k_convert_rows(const float* __restrict__ src, int ld_src, __nv_b
     const int r = idx / cols, c = idx % cols;
     float v = src[static_cast<size_t>(r) * ld_src + c];
     if (alpha) v *= alpha[r];
-    dst[static_cast<size_t>(r) * ld_dst + c] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    dst[static_cast<size_t>(r) * ld_dst + c] = hi;
+    if (dst_lo) dst_lo[static_cast<size_t>(r) * ld_dst + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 // dst[c][r] (bf16, pitch ld_dst) = src[r][c]: transposed copy used as the dgrad B operand.
 __global__ void k_convert_transpose(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
@@ -108,10 +111,11 @@ __global__ void k_fold_bn(const float* __restrict__ conv_bias, const float* __re
 //   EVAL : a1 = relu(Wf x + bf) with BN folded                     (writes bf16)
 //   TRAIN: y1 = W x (bias dropped: train-mode BN cancels it), column sum / sum-of-squares in fp64
 // ---------------------------------------------------------------------------------------------
+//   EVAL, x3 != 0 (split-bf16 inference): the fp32 result is stored as a bf16 pair, row = [hi (64) | lo (64)]
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) k_ingest(const float4* __restrict__ x, int P, const float* __restrict__ W /*[64][4]*/,
                                                 const float* __restrict__ alpha, const float* __restrict__ delta,
-                                                __nv_bfloat16* __restrict__ out, double* __restrict__ stats) {
+                                                __nv_bfloat16* __restrict__ out, double* __restrict__ stats, int x3) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[2][32][64];   // per point-slot partial sums (TRAIN only)
@@ -131,16 +135,24 @@ __global__ void __launch_bounds__(256) k_ingest(const float4* __restrict__ x, in
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     for (int pnt = blockIdx.x * 32 + slot; pnt < P; pnt += gridDim.x * 32) {
         const float4 xv = __ldg(x + pnt);
-        float o[8];
+        float o[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float v = fmaf(w[j][0], xv.x, fmaf(w[j][1], xv.y, fmaf(w[j][2], xv.z, fmaf(w[j][3], xv.w, bsh[j]))));
             if (!TRAIN) v = fmaxf(v, 0.f);
+            const float full = v;
             v = round_bf16(v);
             o[j] = v;
+            lo[j] = full - v;
             if (TRAIN) { s1[j] += v; s2[j] = fmaf(v, v, s2[j]); }
         }
         uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        if (!TRAIN && x3) {
+            *reinterpret_cast<uint4*>(out + static_cast<size_t>(pnt) * 128 + cg * 8) = pk;
+            *reinterpret_cast<uint4*>(out + static_cast<size_t>(pnt) * 128 + 64 + cg * 8) =
+                make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+            continue;
+        }
         *reinterpret_cast<uint4*>(out + static_cast<size_t>(pnt) * 64 + cg * 8) = pk;
     }
     if (TRAIN) {
@@ -283,6 +295,23 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
 // One warp per output channel, fp64 throughout (K x K is small).  Also updates the running statistics (momentum,
 // unbiased variance, conv bias re-added to the mean) and writes {sum y, sum y^2} for inspection.
 // ---------------------------------------------------------------------------------------------
+// Sum of the per-split partial tiles of a Gram GEMM (EPI_WGRAD, wg_mode 3) in a FIXED order, fp64 accumulation: the
+// batch statistics predicted from it are then reproducible from run to run.  4 lanes per element.
+__global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ part, int splits, int n_elem, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t >> 2, q = t & 3;
+    double acc = 0.0;
+    if (i < n_elem) {
+#pragma unroll 8
+        for (int s = q; s < splits; s += 4) acc += static_cast<double>(part[static_cast<size_t>(s) * n_elem + i]);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0 && i < n_elem) out[i] = static_cast<float>(acc);
+}
+
 template <int KQ>      // K = 32 * KQ input channels; 16 warps = 16 output channels per block
 __global__ void __launch_bounds__(512) k_predict_bn(const float* __restrict__ G, const double* __restrict__ colsum,
                                                     const __nv_bfloat16* __restrict__ W, const BnFinalizeArgs fin,
@@ -1099,6 +1128,121 @@ __global__ void __launch_bounds__(256) k_fold_bwd(const FoldArgs f) {
             atomicAdd(f.cst + j, acc);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Folded BatchNorm backward of global_feat (Ci = Co = 1024), whose dz is the max-pool gradient: one non-zero per (cloud,
+// channel) at the arg-max row (pcs.py:114).  sum dz and sum dz*yhat come from k_cloud_bwd_dg, so the coefficients need no Q.
+//   k_fold5_prep : coefficients {A, Bc, D - Bc mean, D}, dgamma / dbeta / dbias, WB = diag(Bc) W (bf16, the A operand of the
+//                  tcgen05 GEMM S = WB^T W) and const = (D - Bc mean)^T W.   8 channels per block.
+//   k_pool_claim : every arg-max row gets ONE slot of the side buffer (lowest (cloud, channel) index that routes to it).
+//   k_pool_rows  : side[slot] += A_c dzv[b][c] W[c][:]  (the rows of dz diag(A) W, added to the data-gradient accumulator by
+//                  the GEMM epilogue) and Q[c][:] += dzv[b][c] a_prev[row][:]  (= dz^T a_prev).
+//   k_gram_center: Gc = G - s s^T / n from the upper triangle of the Gram GEMM, bf16 (B operand of the W Gc GEMM).
+// ---------------------------------------------------------------------------------------------
+struct Fold5Args {
+    const double* stats_b;        // [2][Co] {sum dz, sum dz*yhat}
+    const float4* bnp;            // [Co]
+    float4* coef;                 // [Co]
+    float* dgamma;
+    float* dbeta;
+    float* dbias;
+    const __nv_bfloat16* W;       // [Co][Ci]
+    __nv_bfloat16* WB;            // [Co][Ci] = Bc_c W[c][:]
+    float* cst;                   // [Ci] (zeroed by the caller)
+    double n;
+    int Co, Ci;                   // Ci == 1024 (4 columns per thread)
+};
+__global__ void __launch_bounds__(256) k_fold5_prep(const Fold5Args f) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float bc_s[8], cz_s[8];
+    const int c0 = blockIdx.x * 8;
+    if (threadIdx.x < 8 && c0 + static_cast<int>(threadIdx.x) < f.Co) {
+        const int c = c0 + threadIdx.x;
+        const float4 bp = f.bnp[c];
+        const double s1 = f.stats_b[c], dgamma = f.stats_b[f.Co + c];
+        const double A = bp.x;
+        const double Bc = -A * static_cast<double>(bp.z) * dgamma / f.n;
+        const double D = -A * s1 / f.n;
+        const double mean = -static_cast<double>(bp.w) / static_cast<double>(bp.z);
+        f.coef[c] = make_float4(static_cast<float>(A), static_cast<float>(Bc), static_cast<float>(D - Bc * mean), static_cast<float>(D));
+        f.dgamma[c] = static_cast<float>(dgamma);
+        f.dbeta[c] = static_cast<float>(s1);
+        f.dbias[c] = 0.f;
+        bc_s[threadIdx.x] = static_cast<float>(Bc);
+        cz_s[threadIdx.x] = static_cast<float>(D - Bc * mean);
+    }
+    __syncthreads();
+    const int j = threadIdx.x * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        const int c = c0 + ch;
+        if (c >= f.Co) break;
+        const uint2 w = *reinterpret_cast<const uint2*>(f.W + static_cast<size_t>(c) * f.Ci + j);
+        const float w0 = bf16_lo(w.x), w1 = bf16_hi(w.x), w2 = bf16_lo(w.y), w3 = bf16_hi(w.y);
+        const float bc = bc_s[ch], cz = cz_s[ch];
+        *reinterpret_cast<uint2*>(f.WB + static_cast<size_t>(c) * f.Ci + j) = make_uint2(pack_bf16x2(bc * w0, bc * w1), pack_bf16x2(bc * w2, bc * w3));
+        acc[0] = fmaf(cz, w0, acc[0]);
+        acc[1] = fmaf(cz, w1, acc[1]);
+        acc[2] = fmaf(cz, w2, acc[2]);
+        acc[3] = fmaf(cz, w3, acc[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) atomicAdd(f.cst + j + e, acc[e]);
+}
+
+__global__ void __launch_bounds__(256) k_pool_claim(const float* __restrict__ dzv, const int* __restrict__ argidx, int total, int C,
+                                                    int N, int* __restrict__ rowslot) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total || dzv[idx] == 0.f) return;
+    const int b = idx / C;
+    atomicMin(rowslot + static_cast<size_t>(b) * N + argidx[idx], idx);
+}
+
+// one block (128 threads x 8 columns) per (cloud, channel); C == Ci == 1024
+__global__ void __launch_bounds__(128) k_pool_rows(const float* __restrict__ dzv, const int* __restrict__ argidx, int C, int N,
+                                                   const int* __restrict__ rowslot, const float4* __restrict__ coef,
+                                                   const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ a_prev,
+                                                   float* __restrict__ side, float* __restrict__ Q) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int idx = blockIdx.x;
+    const float v = dzv[idx];
+    if (v == 0.f) return;
+    const int b = idx / C, c = idx - b * C;
+    const size_t row = static_cast<size_t>(b) * N + argidx[idx];
+    const int slot = rowslot[row];
+    const float alpha = coef[c].x * v;
+    const int j = threadIdx.x * 8;
+    const uint4 w = *reinterpret_cast<const uint4*>(W + static_cast<size_t>(c) * C + j);
+    const uint4 a = *reinterpret_cast<const uint4*>(a_prev + row * C + j);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w}, as[4] = {a.x, a.y, a.z, a.w};
+    float* e = side + static_cast<size_t>(slot) * C + j;
+    float* q = Q + static_cast<size_t>(c) * C + j;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e + 4 * h), "f"(alpha * bf16_lo(ws[2 * h])),
+                     "f"(alpha * bf16_hi(ws[2 * h])), "f"(alpha * bf16_lo(ws[2 * h + 1])), "f"(alpha * bf16_hi(ws[2 * h + 1]))
+                     : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 4 * h), "f"(v * bf16_lo(as[2 * h])),
+                     "f"(v * bf16_hi(as[2 * h])), "f"(v * bf16_lo(as[2 * h + 1])), "f"(v * bf16_hi(as[2 * h + 1]))
+                     : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gram_center(const float* __restrict__ G, const double* __restrict__ s, double n, int K,
+                                                     __nv_bfloat16* __restrict__ Gc) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * K) return;
+    const int i = idx / K, j = idx - i * K;
+    const int lo = min(i, j), hi = max(i, j);                 // only the upper triangle of G is computed
+    Gc[idx] = __float2bfloat16_rn(static_cast<float>(static_cast<double>(G[static_cast<size_t>(lo) * K + hi]) - s[i] * s[j] / n));
 }
 
 // ---------------------------------------------------------------------------------------------

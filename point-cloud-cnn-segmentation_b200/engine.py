@@ -28,19 +28,20 @@ class _Binding:
     """One C context bound to one batch shape.  The device workspace is owned by the Engine and SHARED by all bindings of
     the same mode (activations only have to live from a forward to its backward)."""
 
-    def __init__(self, num_classes, B, N, train):
+    def __init__(self, num_classes, B, N, mode):
+        """mode: 0 inference (bf16), 1 training, 2 inference with split-bf16 operands (fp32-grade logits)"""
         self.handle = C.c_void_p()
         check(lib.pcseg_create(C.byref(self.handle), num_classes), "pcseg_create")
-        self.shape = (B, N, bool(train))
-        self.nbytes = int(lib.pcseg_workspace_bytes(B, N, num_classes, int(train)))
+        self.shape = (B, N, int(mode))
+        self.nbytes = int(lib.pcseg_workspace_bytes(B, N, num_classes, int(mode)))
         if self.nbytes <= 0:
             raise ValueError(f"unsupported shape B={B} N={N} C={num_classes}")
         self.ws_ptr = None
         self.eval_key = None
 
     def bind(self, ws_ptr, ws_bytes):
-        B, N, train = self.shape
-        check(lib.pcseg_bind(self.handle, B, N, C.c_void_p(ws_ptr), ws_bytes, int(train)), "pcseg_bind")
+        B, N, mode = self.shape
+        check(lib.pcseg_bind(self.handle, B, N, C.c_void_p(ws_ptr), ws_bytes, mode), "pcseg_bind")
         self.ws_ptr = ws_ptr
         self.eval_key = None
 
@@ -96,7 +97,7 @@ class Engine:
         ws = self._ws[train]
         if ws is None or ws[2] < need:
             # grow-only; all bindings of this mode point into the old block and are dropped
-            for key in [k for k in self.bindings if k[2] == train]:
+            for key in [k for k in self.bindings if (k[2] == 1) == train]:
                 del self.bindings[key]
             self._ws[train] = None
             del ws
@@ -106,12 +107,13 @@ class Engine:
             self._ws[train] = (storage, ptr_aligned, need)
         return self._ws[train]
 
-    def binding(self, B, N, train):
+    def binding(self, B, N, train, x3=False):
         train = bool(train)
-        key = (B, N, train)
+        mode = 1 if train else (2 if x3 else 0)
+        key = (B, N, mode)
         b = self.bindings.get(key)
         if b is None:
-            b = _Binding(self.C, B, N, train)
+            b = _Binding(self.C, B, N, mode)
         _, ws_ptr, ws_bytes = self._workspace(train, b.nbytes)
         if key not in self.bindings:                 # (the workspace may just have dropped every cached binding)
             self.bindings[key] = b
@@ -128,10 +130,12 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- eval
-    def forward_eval(self, x, flat_params, flat_bn, weights_key, want_labels=False, lengths=None):
+    def forward_eval(self, x, flat_params, flat_bn, weights_key, want_labels=False, lengths=None, x3=False):
         B, N, _ = x.shape
         lengths = host_lengths(lengths, B, N)
-        b = self.binding(B, N if lengths is None else ragged_capacity(N), False)
+        if x3 and lengths is not None:
+            raise ValueError("precision 'bf16x3' runs dense batches only (no ragged execution)")
+        b = self.binding(B, N if lengths is None else ragged_capacity(N), False, x3=x3)
         with torch.cuda.device(self.device):
             if b.eval_key != weights_key:
                 check(lib.pcseg_prepare_eval(b.handle, ptr(flat_params), ptr(flat_bn), self._stream()), "pcseg_prepare_eval")
@@ -145,11 +149,11 @@ class Engine:
                 check(lib.pcseg_forward_eval(b.handle, ptr(x), ptr(logits), ptr(labels), self._stream()), "pcseg_forward_eval")
         return (logits, labels) if want_labels else logits
 
-    def forward_eval_sharded(self, x, flat_params, flat_bn, weights_key, reduce_max, want_labels=False):
+    def forward_eval_sharded(self, x, flat_params, flat_bn, weights_key, reduce_max, want_labels=False, x3=False):
         """Inference on this rank's slice of the points of B clouds: trunk, `reduce_max(pooled)` (the caller's MAX
         all-reduce over the ranks that hold the other slices, in place on a (B, 1024) fp32 tensor), head."""
         B, N, _ = x.shape
-        b = self.binding(B, N, False)
+        b = self.binding(B, N, False, x3=x3)
         with torch.cuda.device(self.device):
             if b.eval_key != weights_key:
                 check(lib.pcseg_prepare_eval(b.handle, ptr(flat_params), ptr(flat_bn), self._stream()), "pcseg_prepare_eval")
@@ -215,7 +219,8 @@ class Engine:
 
 
 DEBUG_KINDS = {"y": 0, "act": 1, "dz": 2, "dy": 3, "bnp": 4, "coef": 5, "stats_f": 6, "stats_b": 7, "g": 8, "ystar": 9,
-               "argidx": 10, "cb": 11, "dcb": 12, "dzv": 13, "gram": 14, "colsum": 15, "qraw": 16, "bwf": 17, "cstf": 18}
+               "argidx": 10, "cb": 11, "dcb": 12, "dzv": 13, "gram": 14, "colsum": 15, "qraw": 16, "bwf": 17, "cstf": 18,
+               "s5b": 19, "gc5b": 20, "side": 21, "rowslot": 22}
 
 
 def debug_tensor(engine, B, N, kind, layer=0):
@@ -224,7 +229,7 @@ def debug_tensor(engine, B, N, kind, layer=0):
     rows, cols, eb = C.c_longlong(), C.c_longlong(), C.c_int()
     k = DEBUG_KINDS[kind]
     check(lib.pcseg_debug_copy(b.handle, k, layer, None, 0, C.byref(rows), C.byref(cols), C.byref(eb), None), "pcseg_debug_copy")
-    dt = {2: torch.bfloat16, 8: torch.float64, 4: torch.int32 if kind == "argidx" else torch.float32}[eb.value]
+    dt = {2: torch.bfloat16, 8: torch.float64, 4: torch.int32 if kind in ("argidx", "rowslot") else torch.float32}[eb.value]
     out = torch.empty((rows.value, cols.value), dtype=dt, device=engine.device)
     with torch.cuda.device(engine.device):
         check(lib.pcseg_debug_copy(b.handle, k, layer, ptr(out), out.numel() * out.element_size(), None, None, None,
@@ -232,17 +237,18 @@ def debug_tensor(engine, B, N, kind, layer=0):
     return out
 
 
-def profile_enable(engine, B, N, on=True):
-    b = engine.binding(B, N, True)
+def profile_enable(engine, B, N, on=True, train=True):
+    b = engine.binding(B, N, train)
     check(lib.pcseg_profile_reset(b.handle))
     check(lib.pcseg_profile_enable(b.handle, int(on)))
 
 
-def profile_read(engine, B, N):
-    """{tag: (total_ms, launches)} for the GEMMs of the training step (tags: conv index + 0/16/32 = fwd/dgrad/wgrad)."""
-    b = engine.binding(B, N, True)
+def profile_read(engine, B, N, train=True):
+    """{tag: (total_ms, launches)} for the tcgen05 GEMMs (tags: conv index + 0 / 16 / 32 / 48 / 64 = training forward / data
+    gradient / weight gradient / Gram and fold GEMMs / inference trunk)."""
+    b = engine.binding(B, N, train)
     out = {}
-    for base in (0, 16, 32, 48):          # forward / data gradient / weight gradient / Gram matrix
+    for base in (0, 16, 32, 48, 64):
         for i in range(1, 9):
             ms, n = C.c_double(), C.c_longlong()
             check(lib.pcseg_profile_read(b.handle, base + i, C.byref(ms), C.byref(n)))

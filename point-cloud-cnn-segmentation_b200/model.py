@@ -63,6 +63,10 @@ class PointNetSegmentation(nn.Module):
         self.dropout = nn.Dropout(0.3)
 
         self.num_classes = num_classes
+        # arithmetic of the INFERENCE path: "bf16" (bf16 tensor-core operands, fp32 accumulation: logits within ~3e-3 of
+        # max|logit|) or "bf16x3" (split-bf16: every operand is a bf16 pair hi + lo and every GEMM accumulates the three
+        # products hi*hi + hi*lo + lo*hi in fp32: fp32-grade logits, <= 1e-3 relative, at about 3x the tensor-core work)
+        self.precision = "bf16"
         self._engine = None
         self._flat = None          # dict(params, grads, bn) of flat arenas
         self._fwd_token = 0
@@ -195,6 +199,13 @@ class PointNetSegmentation(nn.Module):
         eng.backward(x, f["params"], f["grads"], dlogits=dlogits)
         return [g.clone() for g in self.grad_views()]
 
+    def set_precision(self, precision):
+        """Inference arithmetic: "bf16" (default) or "bf16x3" (fp32-grade, see __init__).  Training always runs bf16."""
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        self.precision = precision
+        return self
+
     def forward(self, x, lengths=None):
         """`lengths` (optional, B ints: real points per cloud of a zero-padded batch, pcs.py:44-63) selects ragged
         execution: pad rows cost nothing and the result is the one of the padded batch (see include/pcseg_b200.h)."""
@@ -206,7 +217,7 @@ class PointNetSegmentation(nn.Module):
             return self._run_train_forward(x, lengths=lengths)
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
-        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), lengths=lengths)
+        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), lengths=lengths, x3=self.precision == "bf16x3")
 
     @torch.no_grad()
     def predict(self, x, lengths=None):
@@ -216,7 +227,8 @@ class PointNetSegmentation(nn.Module):
             raise RuntimeError("predict() is an eval-mode call; use model.eval() first")
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
-        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), want_labels=True, lengths=lengths)
+        return eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), want_labels=True, lengths=lengths,
+                                x3=self.precision == "bf16x3")
 
 
     @torch.no_grad()
@@ -236,7 +248,8 @@ class PointNetSegmentation(nn.Module):
             def reduce_max(pooled):
                 if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
                     dist.all_reduce(pooled, op=dist.ReduceOp.MAX, group=group)
-        return eng.forward_eval_sharded(x, f["params"], f["bn"], self._weights_key(), reduce_max, want_labels=True)
+        return eng.forward_eval_sharded(x, f["params"], f["bn"], self._weights_key(), reduce_max, want_labels=True,
+                                        x3=self.precision == "bf16x3")
 
     @torch.no_grad()
     def evaluate(self, x, labels, class_weights=None, lengths=None):
@@ -248,7 +261,7 @@ class PointNetSegmentation(nn.Module):
             raise RuntimeError("evaluate() is an eval-mode call; use model.eval() first")
         f = self._ensure_flat(x.device)
         eng = self._get_engine(x.device)
-        logits = eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), lengths=lengths)
+        logits = eng.forward_eval(x, f["params"], f["bn"], self._weights_key(), lengths=lengths, x3=self.precision == "bf16x3")
         cw = None if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float32, device=x.device).contiguous()
         ce, conf, _ = eng.eval_metrics(logits, labels.contiguous(), cw)
         f64, i64 = ce.view(torch.float64), ce.view(torch.int64)

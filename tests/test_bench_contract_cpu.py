@@ -23,7 +23,10 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["unit"] == "points/s" and d["higher_is_better"] is True
     assert d["metric"] == "segmentation points/sec (fwd+bwd train step)" and d["value"] > 0 and d["steps"] == 1
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # a bounded sample (3 s budget here) must be SAID in the workload string, never labelled as the full batch
+    assert d["config"]["same_config"] is False and "bounded sample" in d["config"]["workload"]
+    assert d["config"]["sample_batch"][0] * d["config"]["sample_batch"][1] < 8 * 16384
     assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

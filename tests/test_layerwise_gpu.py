@@ -67,7 +67,8 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
     from oracle import folded_bn_ref as fb
 
     monkeypatch.setenv("PCSEG_FOLDED", "1" if folded else "0")      # read when a context is created
-    FOLDED = {4} if folded else set()
+    monkeypatch.setenv("PCSEG_STORE_Y5", "1")      # keep global_feat's pre-BN output so that the fused max-pool can be checked bit-exactly
+    FOLDED = {4, 5} if folded else set()
 
     P = B * N
     sd = orc.synth_state(C, 1000 + N)
@@ -108,7 +109,7 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
     keeps = {}
     for i in range(9):
         bnp[i] = T("bnp", i)
-        if i in FOLDED:
+        if i in FOLDED and i != 5:
             # ---- Gram-predicted statistics (pcs.py:110): G and s of the input activation, {sum y, sum y^2} predicted from
             # them, BN + ReLU applied straight to the fp32 accumulators; y itself is never stored
             Ci = act[i - 1].shape[1]
@@ -117,6 +118,8 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
             yref = lw.conv_pre_bn(act[i - 1], W[CONVS[i]])                                  # fp64, bf16 weights
             st = lw.bn_batch_stats(yref)
             _close_red(T("stats_f", i), st, f"predicted stats_f[{BNS[i]}]", rel=1e-4)
+            exact = lw.bn_params(st, P, sd[f"{BNS[i]}.weight"], sd[f"{BNS[i]}.bias"])
+            assert np.abs(bnp[i][:, 2] / exact[:, 2] - 1).max() < 2e-4, "predicted 1/std vs the fp64 batch statistics, per channel"
             st = T("stats_f", i)
             _close_red(bnp[i], lw.bn_params(st, P, sd[f"{BNS[i]}.weight"], sd[f"{BNS[i]}.bias"]), f"bnp[{BNS[i]}]", rel=1e-4)
             rm, rv = lw.running_stats(st, P, sd[f"{CONVS[i]}.bias"].astype(np.float64), sd[f"{BNS[i]}.running_mean"].astype(np.float64),
@@ -227,13 +230,64 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
     arg = T("argidx")
     dz6 = np.zeros((B, N, 1024))
     np.put_along_axis(dz6, arg[:, None, :].astype(np.int64), dzv[:, None, :], axis=1)
-    bn_backward(5, sparse=dz6.reshape(P, 1024))
-    _close_red(grads["global_feat.weight"][:, :, 0], lw.wgrad(dy[5], act[4]), "dW global_feat", rel=3e-4)
     dz[4] = T("dz", 4)
-    if 4 in FOLDED:
-        _close_bf16(dz[4], (dy[5] @ lw.bf16_round(W["global_feat"])) * (act[4] > 0), "dz[conv5] (mask from the stored activation)")
+    if 5 in FOLDED:
+        # ---- folded BatchNorm backward of global_feat: no y5 / dy5 (oracle/folded_bn_ref.py), max-pool gradient rows through
+        # the side buffer, S5 / W5 Gc4 on the tensor cores
+        dz5 = dz6.reshape(P, 1024)
+        sb5 = T("stats_b", 5)
+        _close_red(sb5, lw.bn_bwd_stats(dz5, y[5], bnp[5]), "stats_b[bn_global]", rel=3e-4)
+        A5 = bnp[5][:, 0]
+        Bc5 = -A5 * bnp[5][:, 2] * sb5[1] / P
+        D5 = -A5 * sb5[0] / P
+        mean5 = -bnp[5][:, 3] / bnp[5][:, 2]
+        coef5 = T("coef", 5)
+        _close_red(coef5, np.stack([A5, Bc5, D5 - Bc5 * mean5, D5], axis=1), "coef[bn_global]", rel=1e-4)
+        _close_red(grads["bn_global.weight"], sb5[1], "dgamma bn_global", rel=1e-5)
+        _close_red(grads["bn_global.bias"], sb5[0], "dbeta bn_global", rel=1e-5)
+        assert np.abs(grads["global_feat.bias"]).max() == 0.0
+        Wb5 = lw.bf16_round(W["global_feat"])
+        S5b = T("s5b")
+        _close_bf16(S5b, lw.bf16_round(coef5[:, 1:2] * Wb5).T @ Wb5, "S5 = W5^T diag(Bc) W5")
+        cst5 = T("cstf", 5)[0]
+        _close_red(cst5, coef5[:, 2] @ Wb5, "const[global_feat]", rel=1e-4)
+        # side buffer: one slot per arg-max row (the lowest routing (cloud, channel) index), bit-exact
+        rowflat = (arg.astype(np.int64) + (np.arange(B) * N)[:, None]).reshape(-1)
+        active = dzv.reshape(-1) != 0
+        slot_ref = np.full(P, 0x7F7F7F7F, np.int64)
+        np.minimum.at(slot_ref, rowflat[active], np.arange(B * 1024)[active])
+        assert np.array_equal(debug_tensor(eng, B, N, "rowslot").cpu().numpy()[0].astype(np.int64), slot_ref), "side-buffer slots"
+        ch = np.tile(np.arange(1024), B)
+        E_ref = np.zeros((B * 1024, 1024))
+        np.add.at(E_ref, slot_ref[rowflat[active]], (coef5[ch[active], 0] * dzv.reshape(-1)[active])[:, None] * Wb5[ch[active]])
+        side = T("side")
+        _close_red(side, E_ref, "max-pool gradient rows", rel=1e-4)
+        Q5 = T("qraw", 5)
+        _close_red(Q5, dz5.T @ act[4], "Q[global_feat]", rel=3e-4)
+        da4 = act[4] @ S5b.T + cst5
+        has = slot_ref < B * 1024
+        da4[has] += side[slot_ref[has]]
+        _close_bf16(dz[4], da4 * (act[4] > 0), "dz[conv5] (folded data gradient)")
+        coef5_ref = lw.bn_bwd_coef(sb5, P, bnp[5])
+        dy5_ref = lw.bn_bwd_apply(dz5, y[5], coef5_ref)
+        _close_rms(dz[4], (dy5_ref @ Wb5) * (act[4] > 0), "dz[conv5] (definition)", rel=2e-2)
+        s4 = T("stats_b", 4)[1]
+        _close_red(s4, act[4].sum(0), "sum act[conv5]", rel=3e-4)
+        G4 = np.triu(T("gram", 5))
+        _close_red(G4, np.triu(act[4].T @ act[4]), "gram[global_feat] (upper triangle)", rel=1e-5)
+        G4 = G4 + np.triu(G4, 1).T
+        Gc5b = T("gc5b")
+        _close_bf16(Gc5b, G4 - np.outer(s4, s4) / P, "centred Gram matrix")
+        dW5 = grads["global_feat.weight"][:, :, 0]
+        _close_red(dW5, coef5[:, 0:1] * Q5 + coef5[:, 1:2] * (Wb5 @ Gc5b) + np.outer(coef5[:, 3], s4), "dW global_feat", rel=3e-4)
+        _close_red(dW5, lw.wgrad(dy5_ref, act[4]), "dW global_feat (definition)", rel=3e-3)
     else:
-        _close_bf16(dz[4], lw.dgrad_masked(dy[5], W["global_feat"], y[4], bnp[4]), "dz[conv5]")
+        bn_backward(5, sparse=dz6.reshape(P, 1024))
+        _close_red(grads["global_feat.weight"][:, :, 0], lw.wgrad(dy[5], act[4]), "dW global_feat", rel=3e-4)
+        if 4 in FOLDED:
+            _close_bf16(dz[4], (dy[5] @ lw.bf16_round(W["global_feat"])) * (act[4] > 0), "dz[conv5] (mask from the stored activation)")
+        else:
+            _close_bf16(dz[4], lw.dgrad_masked(dy[5], W["global_feat"], y[4], bnp[4]), "dz[conv5]")
 
     def folded_backward(i, prev):
         """conv i without y / dy (oracle/folded_bn_ref.py identities (2), (3)), every quantity from the CUDA tensors"""

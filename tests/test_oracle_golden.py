@@ -124,9 +124,18 @@ def test_backward_finite_difference():
         assert abs(fd - grads[name][idx]) < 1e-6 + 1e-4 * abs(fd), (name, fd, grads[name][idx])
 
 
-@pytest.mark.parametrize("path", CASES[:1], ids=["torch_port"])
+def _grad_digest(g):
+    """the fingerprint tests/golden/make_golden.py stores for every gradient: sum, abs-sum, 64 strided samples"""
+    flat = np.asarray(g, np.float64).reshape(-1)
+    idx = np.linspace(0, flat.size - 1, num=min(flat.size, 64)).astype(np.int64)
+    return np.concatenate([[flat.sum(), np.abs(flat).sum()], flat[idx]])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_torch_cpu_port_matches_reference(path):
-    """The timed CPU baseline port (oracle/torch_port.py) reproduces the reference's logits, loss and gradients."""
+    """The torch-CPU port (oracle/torch_port.py: the fallback CPU arm of bench.py and the oracle of the BASELINE-size GPU
+    parity tests) reproduces the reference on EVERY fixture, the ragged one included: logits, loss, the gradient of every
+    parameter (full tensors where the fixture holds them, digests otherwise) and the updated BatchNorm buffers."""
     import torch
     from oracle.torch_port import TorchCpuPort
     gold = np.load(path)
@@ -140,11 +149,26 @@ def test_torch_cpu_port_matches_reference(path):
                                              weight=torch.from_numpy(gold["class_w"]), ignore_index=-1)
     assert abs(loss.item() - float(gold["loss"])) < 1e-5
     loss.backward()
-    for name in ("seg_conv4.weight", "bn_seg1.weight", "conv1.weight"):
+    checked = 0
+    for name in port.params:
         g = port.p[name].grad.numpy()
-        ref = gold["g/" + name] if ("g/" + name) in gold.files else None
-        if ref is not None:
-            np.testing.assert_allclose(g, ref, atol=1e-3 * np.abs(ref).max() + 1e-6)
+        dig = gold["gd/" + name]
+        # (fp32 accumulation order differs between the port's point-major GEMMs and the reference's Conv1d: digests of the
+        #  mathematically-zero conv biases ahead of a BatchNorm are compared on an absolute scale)
+        if name.endswith(".bias") and name.split(".")[0] in orc.CONV_NAMES[:-1]:
+            assert np.abs(g).max() < 1e-4 and np.abs(dig[2:]).max() < 1e-4, name      # zero up to fp32 summation noise
+            checked += 1
+            continue
+        scale = max(np.abs(dig[1]) / max(g.size, 1), 1e-7)
+        np.testing.assert_allclose(_grad_digest(g)[2:], dig[2:], rtol=2e-3, atol=2e-2 * scale + 1e-6, err_msg=name)
+        if ("g/" + name) in gold.files:
+            ref = gold["g/" + name]
+            np.testing.assert_allclose(g, ref, rtol=0, atol=1e-3 * np.abs(ref).max() + 5e-6, err_msg=name)   # (B = 1: global-branch gradients are zero up to noise)
+        checked += 1
+    assert checked == 38
+    for key in gold.files:
+        if key.startswith("buf/") and not key.endswith("num_batches_tracked"):
+            np.testing.assert_allclose(port.p[key[4:]].detach().numpy(), gold[key], rtol=1e-4, atol=1e-5, err_msg=key)
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])

