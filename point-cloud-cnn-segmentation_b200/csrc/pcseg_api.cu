@@ -459,6 +459,26 @@ static int timed_gemm(pcseg_ctx* c, const GemmOp& op, int tag, cudaStream_t s) {
     return r;
 }
 
+// event stamps around arbitrary launches while profiling (tags >= 80: CUDA-core kernels, see engine.profile_read)
+struct StampScope {
+    pcseg_ctx* c;
+    cudaStream_t s;
+    pcseg_ctx::Stamp st;
+    bool on;
+    StampScope(pcseg_ctx* c_, int tag, cudaStream_t s_) : c(c_), s(s_), on(c_->profiling) {
+        if (!on) return;
+        st.tag = tag;
+        cudaEventCreate(&st.a);
+        cudaEventCreate(&st.b);
+        cudaEventRecord(st.a, s);
+    }
+    ~StampScope() {
+        if (!on) return;
+        cudaEventRecord(st.b, s);
+        c->stamps.push_back(st);
+    }
+};
+
 static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes_out) {
     const size_t x3f = (c->x3 && !train) ? 2 : 1;      // split-bf16 inference stores [hi | lo] halves
     // Shape-independent buffers (weights, per-channel vectors) come first so that their addresses do not depend on
@@ -1142,7 +1162,8 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
             }
         }
         jobs.count = nj;
-        pdl_launch(k_convert_multi, dim3(64, nj), 256, 0, s, jobs);
+        StampScope ts(c, 88, s);
+        pdl_launch(k_convert_multi, dim3(256, nj), 256, 0, s, jobs);
         LAUNCH_OK("k_convert_multi");
     }
     CUDA_OK(cudaMemsetAsync(c->stats_f, 0, c->stat_total * sizeof(double), s));
@@ -1169,6 +1190,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
     // BN finalize of layer i is folded into this kernel (block 0 publishes bnp + running statistics)
     auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks, double* colsum = nullptr) -> int {
         const int co = cv[i].cout;
+        StampScope ts(c, 89, s);
         pdl_launch(k_bn_relu, strip_grid(P, co), 256, 0, s, c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks, colsum);
         LAUNCH_OK("k_bn_relu");
         return 0;
@@ -1201,12 +1223,18 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         } else if (i == 4 && folded) {
             // conv5: batch statistics predicted from the Gram matrix of a3, BN + ReLU applied in the GEMM epilogue
             TRY(timed_gemm(c, c->gram_op[4], 48 + 4, s));
-            pdl_launch(k_gram_reduce, 128 * 128 * 4 / 256, 256, 0, s, static_cast<const float*>(c->grampart4), c->gram_op[4].p.num_splits,
-                       128 * 128, c->gramf[4]);
-            LAUNCH_OK("k_gram_reduce");
-            pdl_launch(k_predict_bn<4>, 1024 / 16, 512, 0, s, static_cast<const float*>(c->gramf[4]), static_cast<const double*>(c->colsum[4]),
-                       static_cast<const bf16*>(c->wk[4]), fin_args(4), c->stats_f + c->stat_off[4]);
-            LAUNCH_OK("k_predict_bn");
+            {
+                StampScope ts(c, 80, s);
+                pdl_launch(k_gram_reduce, 128 * 128 * 4 / 256, 256, 0, s, static_cast<const float*>(c->grampart4), c->gram_op[4].p.num_splits,
+                           128 * 128, c->gramf[4]);
+                LAUNCH_OK("k_gram_reduce");
+            }
+            {
+                StampScope ts(c, 81, s);
+                pdl_launch(k_predict_bn<4>, 1024 / 16, 512, 0, s, static_cast<const float*>(c->gramf[4]), static_cast<const double*>(c->colsum[4]),
+                           static_cast<const bf16*>(c->wk[4]), fin_args(4), c->stats_f + c->stat_off[4]);
+                LAUNCH_OK("k_predict_bn");
+            }
             TRY(timed_gemm(c, O.fw[4], 4, s));
             continue;
         } else {
@@ -1239,6 +1267,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         pdl_launch(k_head_fwd<NC_, true>, grid, 256, 0, s, c->y[8], P, fin_args(8), params + L.off[18], params + L.off[19], c->C, logits, \
                    labels, class_w, reinterpret_cast<CeAccum*>(ce));                                                          \
         break;
+        StampScope ts(c, 91, s);
         switch (c->C <= MAX_CLASSES ? c->C : (c->C <= 16 ? 16 : 32)) {       // class slots of the kernel
             HEAD_FWD(1) HEAD_FWD(2) HEAD_FWD(3) HEAD_FWD(4) HEAD_FWD(5) HEAD_FWD(6) HEAD_FWD(7) HEAD_FWD(8) HEAD_FWD(16) HEAD_FWD(32)
             default: return fail("pcseg_forward_train: unsupported num_classes %d", c->C);
@@ -1349,6 +1378,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     // (BN-backward coefficients are evaluated inside k_bn_bwd_apply: no launch of their own)
     auto apply = [&](int i, bf16* dy_out, int ld_dy, float* dcb) -> int {
         const int co = cv[i].cout;
+        StampScope ts(c, 90, s);
         const int rps = apply_rows_per_strip(N, B, co);
         dim3 grid((N + rps - 1) / rps, B);
         if (rag)
@@ -1400,6 +1430,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         pdl_launch(k_head_bwd<NC_>, grid, 256, 0, s, c->y[8], P, c->bnp[8], params + L.off[18], dlogits, logits, labels, class_w, wsum_total, \
                                              c->dz[8], grads + L.off[18], grads + L.off[19], c->stats_b + c->stat_off[8]);  \
         break;
+        StampScope ts(c, 92, s);
         switch (c->C) {
             HEAD_BWD(1) HEAD_BWD(2) HEAD_BWD(3) HEAD_BWD(4) HEAD_BWD(5) HEAD_BWD(6) HEAD_BWD(7) HEAD_BWD(8)
             default: return fail("pcseg_backward: unsupported num_classes %d", c->C);
@@ -1432,10 +1463,13 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         // folded BatchNorm backward (neither y5 nor dy5 exist): coefficients from {sum dzv, sum dzv*yhat}, S5 on the tensor
         // cores, the max-pool gradient rows through the side buffer, ONE data-gradient GEMM over a4; then the Gram matrix of
         // a4 and the weight gradient in the epilogue of the W5 Gc4 GEMM
-        CUDA_OK(cudaMemsetAsync(c->qraw[5], 0, (1024 * 1024 + 1024) * sizeof(float), s));
-        CUDA_OK(cudaMemsetAsync(c->side5, 0, static_cast<size_t>(B) * 1024 * 1024 * sizeof(float), s));
-        CUDA_OK(cudaMemsetAsync(c->rowslot5, 0x7f, static_cast<size_t>(c->P) * sizeof(int), s));
-        CUDA_OK(cudaMemsetAsync(c->gramf[5], 0, 1024 * 1024 * sizeof(float), s));
+        {
+            StampScope ts(c, 93, s);
+            CUDA_OK(cudaMemsetAsync(c->qraw[5], 0, (1024 * 1024 + 1024) * sizeof(float), s));
+            CUDA_OK(cudaMemsetAsync(c->side5, 0, static_cast<size_t>(B) * 1024 * 1024 * sizeof(float), s));
+            CUDA_OK(cudaMemsetAsync(c->rowslot5, 0x7f, static_cast<size_t>(c->P) * sizeof(int), s));
+            CUDA_OK(cudaMemsetAsync(c->gramf[5], 0, 1024 * 1024 * sizeof(float), s));
+        }
         Fold5Args f5;
         f5.stats_b = c->stats_b + c->stat_off[5];
         f5.bnp = c->bnp[5];
@@ -1449,21 +1483,33 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         f5.n = static_cast<double>(c->P);
         f5.Co = 1024;
         f5.Ci = 1024;
-        pdl_launch(k_fold5_prep, 1024 / 8, 256, 0, s, f5);
-        LAUNCH_OK("k_fold5_prep");
+        {
+            StampScope ts(c, 82, s);
+            pdl_launch(k_fold5_prep, 1024 / 8, 256, 0, s, f5);
+            LAUNCH_OK("k_fold5_prep");
+        }
         TRY(timed_gemm(c, c->s5_op, 48 + 6, s));
-        pdl_launch(k_pool_claim, (B * 1024 + 255) / 256, 256, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), B * 1024,
-                   1024, N, c->rowslot5);
-        LAUNCH_OK("k_pool_claim");
-        pdl_launch(k_pool_rows, B * 1024, 128, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), 1024, N,
-                   static_cast<const int*>(c->rowslot5), static_cast<const float4*>(c->coef[5]), static_cast<const bf16*>(c->wk[5]),
-                   static_cast<const bf16*>(c->act[4]), c->side5, c->qraw[5]);
-        LAUNCH_OK("k_pool_rows");
+        {
+            StampScope ts(c, 83, s);
+            pdl_launch(k_pool_claim, (B * 1024 + 255) / 256, 256, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), B * 1024,
+                       1024, N, c->rowslot5);
+            LAUNCH_OK("k_pool_claim");
+        }
+        {
+            StampScope ts(c, 84, s);
+            pdl_launch(k_pool_rows, B * 1024, 128, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), 1024, N,
+                       static_cast<const int*>(c->rowslot5), static_cast<const float4*>(c->coef[5]), static_cast<const bf16*>(c->wk[5]),
+                       static_cast<const bf16*>(c->act[4]), c->side5, c->qraw[5]);
+            LAUNCH_OK("k_pool_rows");
+        }
         TRY(dgrad(5, 0, 0, 1.f));
         TRY(timed_gemm(c, c->gram_op[5], 48 + 5, s));
-        pdl_launch(k_gram_center, 1024 * 1024 / 256, 256, 0, s, static_cast<const float*>(c->gramf[5]),
-                   static_cast<const double*>(c->stats_b + c->stat_off[4] + 1024), static_cast<double>(c->P), 1024, c->gc5b);
-        LAUNCH_OK("k_gram_center");
+        {
+            StampScope ts(c, 85, s);
+            pdl_launch(k_gram_center, 1024 * 1024 / 256, 256, 0, s, static_cast<const float*>(c->gramf[5]),
+                       static_cast<const double*>(c->stats_b + c->stat_off[4] + 1024), static_cast<double>(c->P), 1024, c->gc5b);
+            LAUNCH_OK("k_gram_center");
+        }
         GemmOp t5 = c->t5_op;
         t5.p.out_f32 = grads + L.off[10];
         TRY(timed_gemm(c, t5, 32 + 5, s));
@@ -1511,10 +1557,16 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         f.n = static_cast<double>(c->P);
         f.Co = 1024;
         f.Ci = 128;
-        pdl_launch(k_fold_coef, fold_coef_blocks(f.Co, f.Ci), 256, 0, s, f);
-        LAUNCH_OK("k_fold_coef");
-        pdl_launch(k_fold_bwd, fold_bwd_blocks(f.Co, f.Ci), 256, 0, s, f);
-        LAUNCH_OK("k_fold_bwd");
+        {
+            StampScope ts(c, 86, s);
+            pdl_launch(k_fold_coef, fold_coef_blocks(f.Co, f.Ci), 256, 0, s, f);
+            LAUNCH_OK("k_fold_coef");
+        }
+        {
+            StampScope ts(c, 87, s);
+            pdl_launch(k_fold_bwd, fold_bwd_blocks(f.Co, f.Ci), 256, 0, s, f);
+            LAUNCH_OK("k_fold_bwd");
+        }
         TRY(timed_gemm(c, O.dg[4], 16 + 4, s));
     } else {
         TRY(apply(4, c->dy[4], 1024, nullptr));

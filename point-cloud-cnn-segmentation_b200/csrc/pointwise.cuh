@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(512) k_predict_bn(const float* __restrict__ G,
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < KQ; ++q) mk[q] = m_s[lane + 32 * q];
-#pragma unroll 1
-    for (int jc = 0; jc < KQ; ++jc) {          // rows j = 32 jc .. 32 jc + 31
+#pragma unroll
+    for (int jc = 0; jc < KQ; ++jc) {          // rows j = 32 jc .. 32 jc + 31 (unrolled: wf[jc] must stay in registers)
         __syncthreads();
         for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) g_s[i / K][i % K] = G[static_cast<size_t>(32 * jc) * K + i];
         __syncthreads();

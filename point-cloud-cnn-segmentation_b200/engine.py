@@ -248,13 +248,18 @@ def profile_read(engine, B, N, train=True):
     gradient / weight gradient / Gram and fold GEMMs / inference trunk)."""
     b = engine.binding(B, N, train)
     out = {}
-    for base in (0, 16, 32, 48, 64):
-        for i in range(1, 9):
-            ms, n = C.c_double(), C.c_longlong()
-            check(lib.pcseg_profile_read(b.handle, base + i, C.byref(ms), C.byref(n)))
-            if n.value:
-                out[base + i] = (ms.value, n.value)
+    for tag in [base + i for base in (0, 16, 32, 48, 64) for i in range(1, 9)] + list(range(80, 96)):
+        ms, n = C.c_double(), C.c_longlong()
+        check(lib.pcseg_profile_read(b.handle, tag, C.byref(ms), C.byref(n)))
+        if n.value:
+            out[tag] = (ms.value, n.value)
     return out
+
+
+# tags >= 80: CUDA-core kernels of the training step (event-timed while profiling; several launches per step share a tag)
+KERNEL_TAGS = {80: "k_gram_reduce", 81: "k_predict_bn", 82: "k_fold5_prep", 83: "k_pool_claim", 84: "k_pool_rows", 85: "k_gram_center",
+               86: "k_fold_coef", 87: "k_fold_bwd", 88: "k_convert_multi", 89: "k_bn_relu (all layers)", 90: "k_bn_bwd_apply (all layers)",
+               91: "k_head_fwd", 92: "k_head_bwd", 93: "memsets of the folded global_feat backward"}
 
 
 def launch_count():

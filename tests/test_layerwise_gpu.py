@@ -57,6 +57,9 @@ def _diverse_clouds(B, N, rng):
 
 @pytest.mark.parametrize("B,N,C,p_drop,folded", [(3, 500, 5, 0.0, True), (4, 1024, 3, 0.3, True), (2, 200, 8, 0.0, True),
                                                  (2, 384, 12, 0.3, True), (2, 200, 32, 0.0, True),
+                                                 # 256 row tiles: every persistent CTA walks several tiles (TMEM double buffering, per-CTA
+                                                 # column accumulators, split-K over many k-blocks)
+                                                 (2, 16384, 5, 0.3, True),
                                                  (3, 500, 5, 0.0, False), (4, 1024, 3, 0.3, False)])
 def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, monkeypatch):
     """folded=True: conv5 runs with Gram-predicted BatchNorm statistics and the folded BatchNorm backward (its y / dy are

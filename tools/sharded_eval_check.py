@@ -41,4 +41,7 @@ dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(f"sharded over {world} GPUs: bit-identical to the un-sharded forward on rank 0's slice: {ok}; {t.item():.3f} ms per scene "
           f"= {N / t.item() / 1e3:.1f} M points/s")
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
