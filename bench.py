@@ -345,7 +345,8 @@ def run_ours(args, B, N, mode):
 
     if mode == "train":
         model.train()
-        trainer = pcseg_b200.FusedTrainer(model, class_weights=cw, lr=1e-3, weight_decay=1e-4, device=dev)
+        trainer = pcseg_b200.FusedTrainer(model, class_weights=cw, lr=1e-3, weight_decay=1e-4, device=dev,
+                                          overlap=os.environ.get("PCSEG_DDP_OVERLAP", "1") != "0")
 
         def step_resident():
             return trainer.step(x_dev, lab_dev)["loss"]
@@ -365,6 +366,7 @@ def run_ours(args, B, N, mode):
         flop_per_pt = TRAIN_FLOP_PER_PT
     else:
         model.eval()
+        model.set_precision(args.precision)
 
         def step_resident():
             with torch.no_grad():
@@ -531,7 +533,8 @@ def run_ours(args, B, N, mode):
 
     line = {
         "metric": metric_name(mode), "value": value, "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (sharded or strong) else "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (sharded or strong) else "weak", "vs_baseline": None,
+        "dtype": args.precision if mode == "eval" else "bf16",
         "data": "synthetic",
         "config": {"workload": workload_desc(args.workload, B, N, mode), "num_classes": C, "l2_policy": "working set (GBs of activations) >> 126 MB L2, no flush needed",
                    "optimizer": "Adam lr 1e-3 wd 1e-4 (inside the timed step)" if mode == "train" else None,
@@ -563,6 +566,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fwd", action="store_true", help="train workloads: skip the inference half of the metric")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"],
+                    help="inference arithmetic of the *_eval workloads: bf16x3 = split-bf16, fp32-grade logits (DESIGN.md §3.6)")
     args = ap.parse_args()
     B, N, mode = WORKLOADS[args.workload]
     if args.impl == "reference":

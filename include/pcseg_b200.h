@@ -188,6 +188,11 @@ int pcseg_profile_reset(pcseg_ctx* ctx);
 /* Number of kernels launched by this library since load (for the bench's gpu_launches claim). */
 long long pcseg_launch_count(void);
 
+/* Persistent kernels size their grids by the SM count.  n > 0 caps that count (process-wide) so that concurrently running
+ * collectives (the NCCL gradient all-reduce that overlaps backward, replacing DataParallel's reduce-add of pcs.py:209-211)
+ * find free SMs instead of delaying a full wave of a persistent GEMM; n <= 0 removes the cap. */
+int pcseg_set_sm_limit(int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,7 @@ EXPORTS = [
     "pcseg_param_numel", "pcseg_bn_buffer_count", "pcseg_bn_buffer_offset", "pcseg_workspace_bytes", "pcseg_bind",
     "pcseg_prepare_eval", "pcseg_forward_eval", "pcseg_forward_eval_ragged", "pcseg_ragged_plan", "pcseg_forward_eval_part", "pcseg_pooled_feature", "pcseg_forward_train",
     "pcseg_forward_train_ragged", "pcseg_backward", "pcseg_adam_step",
-    "pcseg_gemm_test", "pcseg_launch_count", "pcseg_debug_copy", "pcseg_step_advance", "pcseg_eval_metrics", "pcseg_profile_enable", "pcseg_profile_read", "pcseg_profile_reset",
+    "pcseg_gemm_test", "pcseg_launch_count", "pcseg_set_sm_limit", "pcseg_debug_copy", "pcseg_step_advance", "pcseg_eval_metrics", "pcseg_profile_enable", "pcseg_profile_read", "pcseg_profile_reset",
 ]
 
 
@@ -57,6 +57,7 @@ def _load():
     lib.pcseg_eval_metrics.argtypes = [vp, vp, ll, i32, vp, vp, vp, vp, vp]
     lib.pcseg_gemm_test.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
     lib.pcseg_launch_count.restype = ll
+    lib.pcseg_set_sm_limit.argtypes = [i32]
     lib.pcseg_profile_enable.argtypes = [vp, i32]
     lib.pcseg_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(ll)]
     lib.pcseg_profile_reset.argtypes = [vp]

@@ -58,6 +58,7 @@ extern "C" const char* pcseg_last_error(void) { return g_err.c_str(); }
 extern "C" const char* pcseg_version(void) { return "pcseg_b200 0.1 (sm_100a, tcgen05/TMA)"; }
 extern "C" long long pcseg_launch_count(void) { return g_launches; }
 
+
 // ------------------------------------------------------------------------------------------------
 // kernel launch with optional programmatic dependent launch (PDL): the next kernel of the stream may start its prologue
 // while this one drains; every kernel calls griddepcontrol.wait before touching data (ptx.cuh).
@@ -180,6 +181,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long inner, long long outer,
 }
 
 int g_num_sms[64] = {};
+int g_sm_limit = 0;          // pcseg_set_sm_limit: persistent grids leave SMs free for concurrent collectives
 int num_sms() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -188,7 +190,7 @@ int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -589,6 +591,11 @@ extern "C" long long pcseg_workspace_bytes(int B, int N, int C, int train) {
     tmp.x3 = train == 2;
     carve(&tmp, nullptr, B, N, train == 1, &bytes);
     return static_cast<long long>(bytes);
+}
+
+extern "C" int pcseg_set_sm_limit(int n) {
+    g_sm_limit = n > 0 ? n : 0;
+    return 0;
 }
 
 extern "C" int pcseg_create(pcseg_ctx** out, int num_classes) {
@@ -1231,7 +1238,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
             }
             {
                 StampScope ts(c, 81, s);
-                pdl_launch(k_predict_bn<4>, 1024 / 16, 512, 0, s, static_cast<const float*>(c->gramf[4]), static_cast<const double*>(c->colsum[4]),
+                pdl_launch(k_predict_bn<4>, 1024 / 8, 256, 0, s, static_cast<const float*>(c->gramf[4]), static_cast<const double*>(c->colsum[4]),
                            static_cast<const bf16*>(c->wk[4]), fin_args(4), c->stats_f + c->stat_off[4]);
                 LAUNCH_OK("k_predict_bn");
             }
@@ -1465,8 +1472,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         // a4 and the weight gradient in the epilogue of the W5 Gc4 GEMM
         {
             StampScope ts(c, 93, s);
-            CUDA_OK(cudaMemsetAsync(c->qraw[5], 0, (1024 * 1024 + 1024) * sizeof(float), s));
-            CUDA_OK(cudaMemsetAsync(c->side5, 0, static_cast<size_t>(B) * 1024 * 1024 * sizeof(float), s));
+            CUDA_OK(cudaMemsetAsync(c->cstf[5], 0, 1024 * sizeof(float), s));       // (Q5 and the side rows are written, not accumulated)
             CUDA_OK(cudaMemsetAsync(c->rowslot5, 0x7f, static_cast<size_t>(c->P) * sizeof(int), s));
             CUDA_OK(cudaMemsetAsync(c->gramf[5], 0, 1024 * 1024 * sizeof(float), s));
         }
@@ -1497,10 +1503,14 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         }
         {
             StampScope ts(c, 84, s);
-            pdl_launch(k_pool_rows, B * 1024, 128, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), 1024, N,
+            pdl_launch(k_pool_rows_own, 1024, 128, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), B, 1024, N,
                        static_cast<const int*>(c->rowslot5), static_cast<const float4*>(c->coef[5]), static_cast<const bf16*>(c->wk[5]),
                        static_cast<const bf16*>(c->act[4]), c->side5, c->qraw[5]);
-            LAUNCH_OK("k_pool_rows");
+            LAUNCH_OK("k_pool_rows_own");
+            pdl_launch(k_pool_rows_add, B * 1024, 128, 0, s, static_cast<const float*>(c->dzv), static_cast<const int*>(c->argidx), 1024, N,
+                       static_cast<const int*>(c->rowslot5), static_cast<const float4*>(c->coef[5]), static_cast<const bf16*>(c->wk[5]),
+                       c->side5);
+            LAUNCH_OK("k_pool_rows_add");
         }
         TRY(dgrad(5, 0, 0, 1.f));
         TRY(timed_gemm(c, c->gram_op[5], 48 + 5, s));

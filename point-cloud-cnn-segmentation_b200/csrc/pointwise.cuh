@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ p
     if (q == 0 && i < n_elem) out[i] = static_cast<float>(acc);
 }
 
-template <int KQ>      // K = 32 * KQ input channels; 16 warps = 16 output channels per block
-__global__ void __launch_bounds__(512) k_predict_bn(const float* __restrict__ G, const double* __restrict__ colsum,
+template <int KQ>      // K = 32 * KQ input channels; 8 warps = 8 output channels per block
+__global__ void __launch_bounds__(256) k_predict_bn(const float* __restrict__ G, const double* __restrict__ colsum,
                                                     const __nv_bfloat16* __restrict__ W, const BnFinalizeArgs fin,
                                                     double* __restrict__ stats_out) {
     pdl_launch_dependents();
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(512) k_predict_bn(const float* __restrict__ G,
     __shared__ float g_s[32][K];          // 32 rows of G at a time (all warps of the block share them)
     __shared__ double m_s[K];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 16 + warp;
+    const int c = blockIdx.x * 8 + warp;
     const double inv_n = 1.0 / fin.n;
     for (int k = threadIdx.x; k < K; k += blockDim.x) m_s[k] = colsum[k] * inv_n;
     const bool live = c < fin.C;
@@ -1136,8 +1136,8 @@ __global__ void __launch_bounds__(256) k_fold_bwd(const FoldArgs f) {
 //   k_fold5_prep : coefficients {A, Bc, D - Bc mean, D}, dgamma / dbeta / dbias, WB = diag(Bc) W (bf16, the A operand of the
 //                  tcgen05 GEMM S = WB^T W) and const = (D - Bc mean)^T W.   8 channels per block.
 //   k_pool_claim : every arg-max row gets ONE slot of the side buffer (lowest (cloud, channel) index that routes to it).
-//   k_pool_rows  : side[slot] += A_c dzv[b][c] W[c][:]  (the rows of dz diag(A) W, added to the data-gradient accumulator by
-//                  the GEMM epilogue) and Q[c][:] += dzv[b][c] a_prev[row][:]  (= dz^T a_prev).
+//   k_pool_rows_*: side[slot] = sum_{c -> row} A_c dzv[b][c] W[c][:]  (the rows of dz diag(A) W, added to the data-gradient
+//                  accumulator by the GEMM epilogue) and Q[c][:] = sum_b dzv[b][c] a_prev[row][:]  (= dz^T a_prev).
 //   k_gram_center: Gc = G - s s^T / n from the upper triangle of the Gram GEMM, bf16 (B operand of the W Gc GEMM).
 // ---------------------------------------------------------------------------------------------
 struct Fold5Args {
@@ -1203,35 +1203,70 @@ __global__ void __launch_bounds__(256) k_pool_claim(const float* __restrict__ dz
     atomicMin(rowslot + static_cast<size_t>(b) * N + argidx[idx], idx);
 }
 
-// one block (128 threads x 8 columns) per (cloud, channel); C == Ci == 1024
-__global__ void __launch_bounds__(128) k_pool_rows(const float* __restrict__ dzv, const int* __restrict__ argidx, int C, int N,
-                                                   const int* __restrict__ rowslot, const float4* __restrict__ coef,
-                                                   const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ a_prev,
-                                                   float* __restrict__ side, float* __restrict__ Q) {
+// Max-pool gradient rows, two launches (no zero-fill of the side buffer, no atomics on Q):
+//   k_pool_rows_own  : one block (128 threads x 8 columns) per CHANNEL c, looping over the clouds: Q[c][:] = sum_b dzv[b][c]
+//                      a_prev[row(b,c)][:] (plain store), and for every (b, c) that owns the slot of its row the slot is
+//                      INITIALISED with its own contribution side[slot] = A_c dzv[b][c] W[c][:] (plain store).
+//   k_pool_rows_add  : one block per (cloud, channel) that routes to a row owned by another channel: vector red.add.
+// A slot that nobody owns is never read (rowslot says so), so stale contents are harmless.  C == Ci == 1024.
+__global__ void __launch_bounds__(128) k_pool_rows_own(const float* __restrict__ dzv, const int* __restrict__ argidx, int clouds, int C,
+                                                       int N, const int* __restrict__ rowslot, const float4* __restrict__ coef,
+                                                       const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ a_prev,
+                                                       float* __restrict__ side, float* __restrict__ Q) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int c = blockIdx.x;
+    const int j = threadIdx.x * 8;
+    const uint4 w = *reinterpret_cast<const uint4*>(W + static_cast<size_t>(c) * C + j);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    const float Ac = coef[c].x;
+    float q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = 0.f;
+    for (int b = 0; b < clouds; ++b) {
+        const int idx = b * C + c;
+        const float v = dzv[idx];
+        if (v == 0.f) continue;                                   // (block-uniform)
+        const size_t row = static_cast<size_t>(b) * N + argidx[idx];
+        const uint4 a = *reinterpret_cast<const uint4*>(a_prev + row * C + j);
+        const uint32_t as[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            q[2 * e] = fmaf(v, bf16_lo(as[e]), q[2 * e]);
+            q[2 * e + 1] = fmaf(v, bf16_hi(as[e]), q[2 * e + 1]);
+        }
+        if (rowslot[row] == idx) {
+            const float alpha = Ac * v;
+            float4* e4 = reinterpret_cast<float4*>(side + static_cast<size_t>(idx) * C + j);
+            e4[0] = make_float4(alpha * bf16_lo(ws[0]), alpha * bf16_hi(ws[0]), alpha * bf16_lo(ws[1]), alpha * bf16_hi(ws[1]));
+            e4[1] = make_float4(alpha * bf16_lo(ws[2]), alpha * bf16_hi(ws[2]), alpha * bf16_lo(ws[3]), alpha * bf16_hi(ws[3]));
+        }
+    }
+    float4* q4 = reinterpret_cast<float4*>(Q + static_cast<size_t>(c) * C + j);
+    q4[0] = make_float4(q[0], q[1], q[2], q[3]);
+    q4[1] = make_float4(q[4], q[5], q[6], q[7]);
+}
+__global__ void __launch_bounds__(128) k_pool_rows_add(const float* __restrict__ dzv, const int* __restrict__ argidx, int C, int N,
+                                                       const int* __restrict__ rowslot, const float4* __restrict__ coef,
+                                                       const __nv_bfloat16* __restrict__ W, float* __restrict__ side) {
     pdl_launch_dependents();
     pdl_wait();
     const int idx = blockIdx.x;
     const float v = dzv[idx];
     if (v == 0.f) return;
     const int b = idx / C, c = idx - b * C;
-    const size_t row = static_cast<size_t>(b) * N + argidx[idx];
-    const int slot = rowslot[row];
+    const int slot = rowslot[static_cast<size_t>(b) * N + argidx[idx]];
+    if (slot == idx) return;                                      // owner: written by k_pool_rows_own
     const float alpha = coef[c].x * v;
     const int j = threadIdx.x * 8;
     const uint4 w = *reinterpret_cast<const uint4*>(W + static_cast<size_t>(c) * C + j);
-    const uint4 a = *reinterpret_cast<const uint4*>(a_prev + row * C + j);
-    const uint32_t ws[4] = {w.x, w.y, w.z, w.w}, as[4] = {a.x, a.y, a.z, a.w};
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
     float* e = side + static_cast<size_t>(slot) * C + j;
-    float* q = Q + static_cast<size_t>(c) * C + j;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2; ++h)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e + 4 * h), "f"(alpha * bf16_lo(ws[2 * h])),
                      "f"(alpha * bf16_hi(ws[2 * h])), "f"(alpha * bf16_lo(ws[2 * h + 1])), "f"(alpha * bf16_hi(ws[2 * h + 1]))
                      : "memory");
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 4 * h), "f"(v * bf16_lo(as[2 * h])),
-                     "f"(v * bf16_hi(as[2 * h])), "f"(v * bf16_lo(as[2 * h + 1])), "f"(v * bf16_hi(as[2 * h + 1]))
-                     : "memory");
-    }
 }
 
 __global__ void __launch_bounds__(256) k_gram_center(const float* __restrict__ G, const double* __restrict__ s, double n, int K,

@@ -264,7 +264,9 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
         E_ref = np.zeros((B * 1024, 1024))
         np.add.at(E_ref, slot_ref[rowflat[active]], (coef5[ch[active], 0] * dzv.reshape(-1)[active])[:, None] * Wb5[ch[active]])
         side = T("side")
-        _close_red(side, E_ref, "max-pool gradient rows", rel=1e-4)
+        owned = np.unique(slot_ref[rowflat[active]])              # slots nobody owns are never initialised nor read
+        _close_red(side[owned], E_ref[owned], "max-pool gradient rows", rel=1e-4)
+        side = np.where(np.isin(np.arange(B * 1024), owned)[:, None], side, 0.0)
         Q5 = T("qraw", 5)
         _close_red(Q5, dz5.T @ act[4], "Q[global_feat]", rel=3e-4)
         da4 = act[4] @ S5b.T + cst5
@@ -277,7 +279,7 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
         s4 = T("stats_b", 4)[1]
         _close_red(s4, act[4].sum(0), "sum act[conv5]", rel=3e-4)
         G4 = np.triu(T("gram", 5))
-        _close_red(G4, np.triu(act[4].T @ act[4]), "gram[global_feat] (upper triangle)", rel=1e-5)
+        _close_red(G4, np.triu(act[4].T @ act[4]), "gram[global_feat] (upper triangle)", rel=1e-4)      # fp32 split-K atomics
         G4 = G4 + np.triu(G4, 1).T
         Gc5b = T("gc5b")
         _close_bf16(Gc5b, G4 - np.outer(s4, s4) / P, "centred Gram matrix")
