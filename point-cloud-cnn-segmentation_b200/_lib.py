@@ -11,7 +11,8 @@ EXPORTS = [
     "pcseg_param_numel", "pcseg_bn_buffer_count", "pcseg_bn_buffer_offset", "pcseg_workspace_bytes", "pcseg_bind",
     "pcseg_prepare_eval", "pcseg_forward_eval", "pcseg_forward_eval_ragged", "pcseg_ragged_plan", "pcseg_forward_eval_part", "pcseg_pooled_feature", "pcseg_forward_train",
     "pcseg_forward_train_ragged", "pcseg_backward", "pcseg_adam_step",
-    "pcseg_gemm_test", "pcseg_launch_count", "pcseg_set_sm_limit", "pcseg_debug_copy", "pcseg_step_advance", "pcseg_eval_metrics", "pcseg_profile_enable", "pcseg_profile_read", "pcseg_profile_reset",
+    "pcseg_gemm_test", "pcseg_launch_count", "pcseg_set_sm_limit", "pcseg_ipc_export", "pcseg_peer_ar_signal_bytes", "pcseg_peer_ar_create",
+    "pcseg_peer_ar_open", "pcseg_peer_ar_run", "pcseg_peer_ar_destroy", "pcseg_debug_copy", "pcseg_step_advance", "pcseg_eval_metrics", "pcseg_profile_enable", "pcseg_profile_read", "pcseg_profile_reset",
 ]
 
 
@@ -58,6 +59,12 @@ def _load():
     lib.pcseg_gemm_test.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
     lib.pcseg_launch_count.restype = ll
     lib.pcseg_set_sm_limit.argtypes = [i32]
+    lib.pcseg_ipc_export.argtypes = [vp, C.c_char_p, C.POINTER(ll)]
+    lib.pcseg_peer_ar_signal_bytes.restype = ll
+    lib.pcseg_peer_ar_create.argtypes = [C.POINTER(vp), i32, i32, vp, ll, vp, vp, vp, vp]
+    lib.pcseg_peer_ar_open.argtypes = [vp, i32, C.c_char_p, ll, C.c_char_p, ll]
+    lib.pcseg_peer_ar_run.argtypes = [vp, vp]
+    lib.pcseg_peer_ar_destroy.argtypes = [vp]
     lib.pcseg_profile_enable.argtypes = [vp, i32]
     lib.pcseg_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(ll)]
     lib.pcseg_profile_reset.argtypes = [vp]

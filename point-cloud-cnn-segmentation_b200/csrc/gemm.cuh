@@ -25,6 +25,8 @@
 //   EPI_LOGITS    : logits = W4 * relu(acc + bias) + b4  (BN == 128 == all channels)  -> fp32 store
 //   EPI_BN_RELU   : out = relu(scale[n] * acc + shift[n]) with {scale, shift} = bnp[n].xy (train-mode BatchNorm whose batch
 //                   statistics were PREDICTED from the Gram matrix of the layer input, see k_predict_bn)   -> bf16 store
+//   EPI_BN_RELU_DROP: EPI_BN_RELU with the per-cloud term added before the normalisation and Philox dropout after the ReLU
+//                   (seg_conv1, pcs.py:117-124); a separate instantiation so that conv5's epilogue stays lean
 //   EPI_DGRAD_ACT : EPI_DGRAD with the mask taken from the stored ACTIVATION of the layer below (a > 0 <=> ReLU on and not
 //                   dropped; no BN parameters, no Philox); column sums: sum dz and sum a                 -> bf16 store + fp64 atomics
 // DGRAD / DGRAD_ACT add bias[n] to the accumulator when p.bias != nullptr (constant row of the folded BatchNorm backward).
@@ -48,7 +50,7 @@
 namespace pcseg {
 
 enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EPI_WGRAD = 4, EPI_LOGITS = 5, EPI_STATS_POOL = 6,
-              EPI_BN_RELU = 7, EPI_DGRAD_ACT = 8, EPI_BIAS_RELU_X3 = 9 };
+              EPI_BN_RELU = 7, EPI_DGRAD_ACT = 8, EPI_BIAS_RELU_X3 = 9, EPI_BN_RELU_DROP = 10 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -63,6 +65,11 @@ struct GemmParams {
     int num_splits, kb_per_split;   // split-K (wgrad only; otherwise 1 / K/64)
     int kb_switch;               // k-blocks [0, kb_switch) of A come from tmA, the rest from tmA2 (0 = everything from tmA)
     int store_out;               // EPI_STATS_POOL: 0 = statistics / max-pool only, the output tile is not written
+    int kb_group, splits_per_group;   // EPI_WGRAD, kb_group > 0: the k-blocks (points) form groups of kb_group (= one cloud) and every
+                                 // group is split on its own: split s covers group s / splits_per_group (per-cloud Gram
+                                 // matrices; with wg_mode 3 the partial tiles of a group are consecutive)
+    float* cloud_sums;           // EPI_DGRAD_ACT: [clouds][N] per-cloud column sums of dz (fp32 atomics; tiles must not straddle
+                                 // clouds), in addition to the batch sums in stats
     int x3_kb;                   // > 0: split-bf16 k-schedule, = logical K / 64 (K in this struct then counts 3 * logical K)
     int x3_lo_col;               // EPI_BIAS_RELU_X3: first column of the lo halves in the output tensor
     int sym_tiles;               // EPI_WGRAD with A == B (Gram matrix): > 0 = number of (m, n) tiles that touch the upper
@@ -110,7 +117,7 @@ struct GemmCfg {
     static constexpr int STAGE_B = BN * GEMM_BK * 2;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD ||
-                                     EPI == EPI_BN_RELU || EPI == EPI_DGRAD_ACT || EPI == EPI_BIAS_RELU_X3);
+                                     EPI == EPI_BN_RELU || EPI == EPI_DGRAD_ACT || EPI == EPI_BIAS_RELU_X3 || EPI == EPI_BN_RELU_DROP);
     static constexpr bool HAS_Y = (EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
     static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
     static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
@@ -300,6 +307,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         m_tile = t / p.num_n_tiles;
     };
 
+    auto kb_range = [&](int split, int& kb0, int& kb1) {
+        const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+        if (EPI == EPI_WGRAD && p.kb_group > 0) {
+            const int g = split / p.splits_per_group, l = split - g * p.splits_per_group;
+            kb0 = g * p.kb_group + l * p.kb_per_split;
+            kb1 = min(min(kb0 + p.kb_per_split, (g + 1) * p.kb_group), total_kb);
+        } else {
+            kb0 = split * p.kb_per_split;
+            kb1 = min(kb0 + p.kb_per_split, total_kb);
+        }
+    };
+
     if (warp_idx == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
@@ -308,9 +327,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int m_tile, n_tile, split;
                 tile_coords(tile, m_tile, n_tile, split);
-                const int kb0 = split * p.kb_per_split;
-                const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-                const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+                int kb0, kb1;
+                kb_range(split, kb0, kb1);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = stage_base + stage * Cfg::STAGE;
@@ -349,9 +367,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             int m_tile, n_tile, split;
             tile_coords(tile, m_tile, n_tile, split);
-            const int kb0 = split * p.kb_per_split;
-            const int total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-            const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+            int kb0, kb1;
+            kb_range(split, kb0, kb1);
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -430,7 +447,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int i = et; i < NH * 2 * BN; i += EPI_THREADS) comb[i] = 0.f;
             named_bar_sync(1, EPI_THREADS);
         }
-        if constexpr (EPI == EPI_BN_RELU) {
+        if constexpr (EPI == EPI_BN_RELU || EPI == EPI_BN_RELU_DROP) {
             // {scale, shift} of this CTA's BN columns (n_tile is fixed per CTA): comb[0..BN) = scale, comb[BN..2BN) = shift
             const int n0_fixed = (blockIdx.x % p.num_n_tiles) * BN;
             for (int i = et; i < BN; i += EPI_THREADS) {
@@ -440,6 +457,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             named_bar_sync(1, EPI_THREADS);
         }
+
+        // EPI_DGRAD_ACT with per-cloud sums: the per-CTA accumulators of sum dz are flushed whenever the CTA's tile sequence
+        // (increasing rows) enters another cloud
+        int cur_cl = -1;
+        auto flush_cloud = [&](int cl) {
+            named_bar_sync(1, EPI_THREADS);
+            const int n0f = (blockIdx.x % p.num_n_tiles) * BN;
+            for (int c = et; c < BN; c += EPI_THREADS) {
+                float a0 = 0.f;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    a0 += comb[(h * 2) * BN + c];
+                    comb[(h * 2) * BN + c] = 0.f;
+                }
+                atomicAdd(p.cloud_sums + static_cast<size_t>(cl) * p.N + n0f + c, a0);
+                atomicAdd(p.stats + n0f + c, static_cast<double>(a0));
+            }
+            named_bar_sync(1, EPI_THREADS);
+        };
+        (void)cur_cl;
+        (void)flush_cloud;
 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             int m_tile, n_tile, split;
@@ -457,8 +495,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if constexpr (EPI == EPI_WGRAD) {
                 // fp32 split-K partials straight from registers: row = output channel, CW consecutive input channels
                 float* dst_row = p.out_f32 + static_cast<size_t>(grow) * p.ldc + n0;
-                const int kb0 = split * p.kb_per_split;
-                const bool nonempty = kb0 < (p.K + GEMM_BK - 1) / GEMM_BK;
+                int kb0, kb1;
+                kb_range(split, kb0, kb1);
+                const bool nonempty = kb0 < kb1;
 #pragma unroll 1
                 for (int c = cq; c < BN / CW; c += NQ) {
                     uint32_t v[CW];
@@ -581,6 +620,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int cloud = uniform_cloud ? tile_cl : (valid ? grow / p.pts_per_cloud : 0);
                 const float* cb_row = (p.cloud_bias != nullptr) ? p.cloud_bias + static_cast<size_t>(cloud) * p.N : nullptr;
                 const bool pool_uniform = uniform_cloud;
+                if constexpr (EPI == EPI_DGRAD_ACT) {
+                    if (p.cloud_sums != nullptr && tile_cl != cur_cl) {
+                        if (cur_cl >= 0) flush_cloud(cur_cl);
+                        cur_cl = tile_cl;
+                    }
+                }
 #pragma unroll 1
                 for (int sub = 0; sub < SUBS; ++sub, ++sub_it) {
                     const int buf = sub_it & 1;
@@ -648,6 +693,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int i = 0; i < CW / 2; ++i)
                             packed[i] = pack_bf16x2(fmaxf(fmaf(scs[2 * i], __uint_as_float(v[2 * i]), scs[BN + 2 * i]), 0.f),
                                                     fmaxf(fmaf(scs[2 * i + 1], __uint_as_float(v[2 * i + 1]), scs[BN + 2 * i + 1]), 0.f));
+                    } else if constexpr (EPI == EPI_BN_RELU_DROP) {
+                        const float* scs = comb + sub * 64 + cq * CW;
+                        if (cb_row != nullptr) {       // per-cloud term of seg_conv1 (pcs.py:117-123), added before the normalisation
+#pragma unroll
+                            for (int i = 0; i < CW; i += 4) {
+                                const float4 c4v = __ldg(reinterpret_cast<const float4*>(cb_row + c0 + i));
+                                v[i] = __float_as_uint(__uint_as_float(v[i]) + c4v.x);
+                                v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + c4v.y);
+                                v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + c4v.z);
+                                v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + c4v.w);
+                            }
+                        }
+                        if (p.drop_thr16 != 0u) {      // dropout (pcs.py:124): Philox keep mask per 8 consecutive channels of the row
+#pragma unroll
+                            for (int j = 0; j < CW / 8; ++j) {
+                                const unsigned long long e0 = static_cast<unsigned long long>(grow) * p.N + c0 + 8 * j;
+                                const uint32_t keep = dropout_keep8(seed_eff, e0 >> 3, p.drop_thr16);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const int i = 8 * j + e;
+                                    const float t = fmaxf(fmaf(scs[i], __uint_as_float(v[i]), scs[BN + i]), 0.f) * p.keep_scale;
+                                    v[i] = __float_as_uint(((keep >> e) & 1u) ? t : 0.f);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < CW / 2; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CW / 2; ++i)
+                                packed[i] = pack_bf16x2(fmaxf(fmaf(scs[2 * i], __uint_as_float(v[2 * i]), scs[BN + 2 * i]), 0.f),
+                                                        fmaxf(fmaf(scs[2 * i + 1], __uint_as_float(v[2 * i + 1]), scs[BN + 2 * i + 1]), 0.f));
+                        }
                     } else if constexpr (EPI == EPI_STATS || EPI == EPI_STATS_POOL) {
                         // pass 1 (row-mapped): accumulator (+ per-cloud term) -> bf16 -> staging tile.
                         // Rows beyond M have exactly-zero accumulators (TMA zero fill), so they add nothing to the sums.
@@ -676,6 +753,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + b4v.y);
                                 v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + b4v.z);
                                 v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + b4v.w);
+                            }
+                        }
+                        if (cb_row != nullptr && valid) {    // per-cloud constant row of the folded seg_conv1 backward
+#pragma unroll
+                            for (int i = 0; i < CW; i += 4) {
+                                const float4 c4v = __ldg(reinterpret_cast<const float4*>(cb_row + c0 + i));
+                                v[i] = __float_as_uint(__uint_as_float(v[i]) + c4v.x);
+                                v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + c4v.y);
+                                v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + c4v.z);
+                                v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + c4v.w);
                             }
                         }
                         if (side_slot < p.side_rows) {       // rare: this row receives max-pool gradient rows
@@ -885,6 +972,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
             }
+        }
+        if constexpr (EPI == EPI_DGRAD_ACT) {
+            if (p.cloud_sums != nullptr && cur_cl >= 0) flush_cloud(cur_cl);
         }
         if constexpr (COLACC) {
             named_bar_sync(1, EPI_THREADS);

@@ -11,6 +11,7 @@
 
 #include "gemm.cuh"
 #include "head_chain.cuh"
+#include "peer_allreduce.cuh"
 #include "pointwise.cuh"
 
 using namespace pcseg;
@@ -233,7 +234,7 @@ int launch_gemm(const GemmOp& op, cudaStream_t s) {
     CASE(64, EPI_STATS, false) CASE(128, EPI_STATS, false) CASE(256, EPI_STATS, false)
     CASE(256, EPI_STATS_POOL, false)
     CASE(64, EPI_DGRAD, false) CASE(128, EPI_DGRAD, false) CASE(256, EPI_DGRAD, false)
-    CASE(256, EPI_BN_RELU, false) CASE(256, EPI_DGRAD_ACT, false)
+    CASE(256, EPI_BN_RELU, false) CASE(256, EPI_DGRAD_ACT, false) CASE(256, EPI_BN_RELU_DROP, false)
     CASE(64, EPI_BIAS_RELU_X3, false) CASE(128, EPI_BIAS_RELU_X3, false) CASE(256, EPI_BIAS_RELU_X3, false)
     CASE(64, EPI_WGRAD, true) CASE(128, EPI_WGRAD, true) CASE(256, EPI_WGRAD, true)
 #undef CASE
@@ -331,8 +332,8 @@ int setup_gemm_wgrad(GemmOp* op, const void* A, int lda, int Mc, const void* B, 
 // ------------------------------------------------------------------------------------------------
 constexpr int RAG_MAX_STRIPS = 1024;
 constexpr int GRAM_MAX_SPLITS = 160;         // >= SM count: one partial tile per CTA of the forward Gram GEMM
-// folded conv5 scratch that is zeroed once per backward: Q (1024 x 128) | S32 (128 x 128) | const (128) | tile tickets (64)
-constexpr size_t FOLD4_ZERO_FLOATS = 1024 * 128 + 128 * 128 + 128 + 64;
+// folded conv5 scratch that is zeroed once per backward: Q (1024 x 128, accumulated by the split-K weight-gradient GEMM)
+constexpr size_t FOLD4_ZERO_FLOATS = 1024 * 128;
 
 struct Carver {
     uint8_t* base;
@@ -425,8 +426,6 @@ struct pcseg_ctx {
     float* qraw[NUM_BN] = {};     // [Co][Ci] fp32  dz^T a_prev
     bf16* bwf[NUM_BN] = {};       // [Ci][Co + Ci]  data-gradient weights [diag(A) W ; S]^T
     float* cstf[NUM_BN] = {};     // [Ci]           constant row of the data gradient
-    float* s32f[NUM_BN] = {};     // [Ci][Ci] fp32 accumulator of S; qraw | s32f | cstf | ticket are contiguous (one memset)
-    int* foldticket[NUM_BN] = {};
     float* gcf[NUM_BN] = {};      // [Ci][Ci] centred Gram matrix
     float* grampart4 = nullptr;   // [GRAM_MAX_SPLITS][128][128] per-split partial tiles of a3^T a3 (summed by k_gram_reduce)
     // folded global_feat (index 5): gramf[5] = a4^T a4 (upper triangle), qraw[5] | cstf[5] contiguous (one memset)
@@ -437,6 +436,16 @@ struct pcseg_ctx {
     int* rowslot5 = nullptr;      // [cap_rows] side-buffer slot of every point (>= B*1024: none)
     bool store_y5 = false;        // PCSEG_STORE_Y5=1: keep writing global_feat's pre-BN output (tests)
     GemmOp s5_op, t5_op;
+    // folded seg_conv1 (index 6; needs N % 128 == 0 so that tiles never straddle clouds): per-cloud Gram matrices of a1
+    bool fold6 = false;
+    float* grampart6 = nullptr;   // [splits][64][64] partial tiles (splits of one cloud are consecutive)
+    float* cloudsum6 = nullptr;   // [B][512] per-cloud sums of dz6; cloudsum6 | qraw[6] contiguous (one memset)
+    float* gsum6 = nullptr;       // [64][64] sum_b G_b
+    double* ssum6 = nullptr;      // [64]     sum_b s_b
+    float* cst6 = nullptr;        // [B][64]  per-cloud constant rows of the data gradient into point_feat
+    bf16* wcat6 = nullptr;        // [64][640] = [W3^T | diag(A) Wpf^T | S6]
+    double* part6 = nullptr;      // [B][512][2] {lin, quad} of every (cloud, channel) (k_predict_bn_cloud)
+    int* ticket6 = nullptr;       // [64] completion counters of the channel groups (zero between launches)
     GemmOp gram_op[NUM_BN];
     unsigned long long seed = 0;
     const unsigned long long* seed_ptr = nullptr;
@@ -522,9 +531,7 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
             c->gramf[4] = k.take<float>(128 * 128 + 2 * 128);      // + colsum (fp64) right behind
             c->colsum[4] = reinterpret_cast<double*>(c->gramf[4] ? c->gramf[4] + 128 * 128 : nullptr);
             c->qraw[4] = k.take<float>(FOLD4_ZERO_FLOATS);
-            c->s32f[4] = c->qraw[4] ? c->qraw[4] + 1024 * 128 : nullptr;
-            c->cstf[4] = c->qraw[4] ? c->s32f[4] + 128 * 128 : nullptr;
-            c->foldticket[4] = c->qraw[4] ? reinterpret_cast<int*>(c->cstf[4] + 128) : nullptr;
+            c->cstf[4] = k.take<float>(128);
             c->gcf[4] = k.take<float>(128 * 128);
             c->grampart4 = k.take<float>(static_cast<size_t>(GRAM_MAX_SPLITS) * 128 * 128);
             c->bwf[4] = k.take<bf16>(128 * (1024 + 128));
@@ -563,6 +570,19 @@ static int carve(pcseg_ctx* c, void* ws, int B, int N, bool train, size_t* bytes
         c->dzv = k.take<float>(static_cast<size_t>(B) * 1024);
         c->side5 = k.take<float>(static_cast<size_t>(B) * 1024 * 1024);
         c->rowslot5 = k.take<int>(P);
+        {   // folded seg_conv1: Ci = 64, Co = 512
+            c->gramf[6] = k.take<float>(static_cast<size_t>(B) * 64 * 64);
+            c->colsum[6] = k.take<double>(static_cast<size_t>(B) * 64);
+            c->grampart6 = k.take<float>((static_cast<size_t>(B) + GRAM_MAX_SPLITS) * 64 * 64);
+            c->cloudsum6 = k.take<float>(static_cast<size_t>(B) * 512 + 512 * 64);
+            c->qraw[6] = c->cloudsum6 ? c->cloudsum6 + static_cast<size_t>(B) * 512 : nullptr;
+            c->gsum6 = k.take<float>(64 * 64);
+            c->ssum6 = k.take<double>(64);
+            c->cst6 = k.take<float>(static_cast<size_t>(B) * 64);
+            c->wcat6 = k.take<bf16>(64 * 640);
+            c->part6 = k.take<double>(static_cast<size_t>(B) * 512 * 2);
+            c->ticket6 = k.take<int>(64);
+        }
         c->dycat = k.take<bf16>(P * 576);
         for (int i = 0; i < NUM_BN; ++i) {
             c->y[i] = k.take<bf16>(P * cv[i].cout);
@@ -636,6 +656,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
     c->bound = false;
     c->eval_ready = false;
     c->rag_active = false;
+    c->fold6 = false;
     for (int set = 0; set < 2; ++set) {
     pcseg_ctx::OpSet& O = c->ops[set];
     const bool rag = set == 1;
@@ -804,6 +825,39 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
                 if (splits > total_kb) splits = total_kb;
                 gp.kb_per_split = (total_kb + splits - 1) / splits;
                 gp.num_splits = (total_kb + gp.kb_per_split - 1) / gp.kb_per_split;
+            }
+            c->fold6 = (N % 128 == 0) && !(getenv("PCSEG_FOLD6") && getenv("PCSEG_FOLD6")[0] == '0');
+            if (c->fold6) {
+                CUDA_OK(cudaMemset(c->ticket6, 0, 64 * sizeof(int)));
+                // seg_conv1: per-cloud Gram matrices of a1 (point_feat), every cloud split on its own
+                TRY(setup_gemm_wgrad(&c->gram_op[6], c->act[1], 64, 64, c->act[1], 64, 64, P, c->grampart6, 64));
+                GemmParams& gp = c->gram_op[6].p;
+                gp.kb_group = N / 64;
+                int spg = num_sms() / B;
+                if (spg < 1) spg = 1;
+                if (spg > gp.kb_group) spg = gp.kb_group;
+                gp.kb_per_split = (gp.kb_group + spg - 1) / spg;
+                gp.splits_per_group = (gp.kb_group + gp.kb_per_split - 1) / gp.kb_per_split;
+                gp.num_splits = B * gp.splits_per_group;
+                gp.wg_mode = 3;
+                if (gp.num_splits > B + GRAM_MAX_SPLITS) return fail("internal: %d per-cloud Gram splits", gp.num_splits);
+                // forward: BN + ReLU + dropout in the epilogue, per-cloud term added before the normalisation
+                TRY(setup_gemm_kmajor(&O.fw[6], EPI_BN_RELU_DROP, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->act[6], 512, nullptr, 0));
+                O.fw[6].p.bnp = c->bnp[6];
+                O.fw[6].p.cloud_bias = c->cb;
+                O.fw[6].p.pts_per_cloud = N;
+                // seg_conv2 data gradient: dz6 (straight into dycat[:, 64:576]) masked by the stored activation a6, per-cloud sums
+                TRY(setup_gemm_kmajor(&O.dg[7], EPI_DGRAD_ACT, c->dy[7], 256, c->wt[7], 256, P, 512, 256, c->dycat + 64, 576, c->act[6], 512));
+                O.dg[7].p.stats = c->stats_b + c->stat_off[6];
+                O.dg[7].p.cloud_sums = c->cloudsum6;
+                O.dg[7].p.pts_per_cloud = N;
+                // Q6 = dz6^T a1 (raw), then the skip join: dz1 = mask1 . ([dy2 | dz6 | a1] [W3 ; diag(A) Wpf ; S6] + const_b)
+                TRY(setup_gemm_wgrad(&O.wg_op[6], c->dycat + 64, 576, 512, c->act[1], 64, 64, P, c->qraw[6], 64));
+                TRY(setup_gemm_kmajor_cat(&O.dg[2], EPI_DGRAD, c->dycat, 576, 576, c->act[1], 64, 64, c->wcat6, 640, P, 64, c->dz[1], 64, c->y[1], 64));
+                O.dg[2].p.stats = c->stats_b + c->stat_off[1];
+                O.dg[2].p.bnp = c->bnp[1];
+                O.dg[2].p.cloud_bias = c->cst6;
+                O.dg[2].p.pts_per_cloud = N;
             }
             TRY(setup_gemm_wgrad(&c->t5_op, c->wt[5], 1024, 1024, c->gc5b, 1024, 1024, 1024, nullptr, 1024));
             c->t5_op.p.num_splits = 1;
@@ -1164,7 +1218,10 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
                 add(params + L.off[12], 1088, c->wcat + 64, 576, 512, 64, 1);
             } else {
                 add(params + L.off[2 * i], cv[i].cin, c->wk[i], cv[i].cin, cv[i].cout, cv[i].cin, 0);
-                if (i == 2) add(params + L.off[4], 64, c->wcat, 576, 64, 64, 1);
+                if (i == 2) {
+                    add(params + L.off[4], 64, c->wcat, 576, 64, 64, 1);
+                    if (c->folded && !rag && c->fold6) add(params + L.off[4], 64, c->wcat6, 640, 64, 64, 1);
+                }
                 else add(params + L.off[2 * i], cv[i].cin, c->wt[i], cv[i].cout, cv[i].cout, cv[i].cin, 1);
             }
         }
@@ -1177,7 +1234,9 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
     CUDA_OK(cudaMemsetAsync(c->keys, 0, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long), s));
     if (ce) CUDA_OK(cudaMemsetAsync(ce, 0, sizeof(pcseg_ce_accum), s));
     const bool folded = c->folded && !rag;
+    const bool fold6 = folded && c->fold6;
     if (folded) CUDA_OK(cudaMemsetAsync(c->colsum[4], 0, 128 * sizeof(double), s));
+    if (fold6) CUDA_OK(cudaMemsetAsync(c->colsum[6], 0, static_cast<size_t>(c->B) * 64 * sizeof(double), s));
 
     auto fin_args = [&](int i) {
         BnFinalizeArgs f;
@@ -1195,10 +1254,17 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         return f;
     };
     // BN finalize of layer i is folded into this kernel (block 0 publishes bnp + running statistics)
-    auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks, double* colsum = nullptr) -> int {
+    auto bn_relu = [&](int i, unsigned long long sd, unsigned int thr, float ks, double* colsum = nullptr, int rows_per_cloud = 0) -> int {
         const int co = cv[i].cout;
         StampScope ts(c, 89, s);
-        pdl_launch(k_bn_relu, strip_grid(P, co), 256, 0, s, c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks, colsum);
+        int grid = strip_grid(P, co);
+        if (rows_per_cloud > 0) {          // (clouds x blocks per cloud): strips never straddle clouds, colsum is per cloud
+            const int clouds = static_cast<int>(P / rows_per_cloud);
+            int bpc = grid / clouds;
+            if (bpc < 1) bpc = 1;
+            grid = clouds * bpc;
+        }
+        pdl_launch(k_bn_relu, grid, 256, 0, s, c->y[i], co, c->act[i], co, P, co, fin_args(i), sd, c->seed_ptr, thr, ks, colsum, rows_per_cloud);
         LAUNCH_OK("k_bn_relu");
         return 0;
     };
@@ -1248,7 +1314,8 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
             TRY(timed_gemm(c, O.fw[i], i, s));
         }
         TRY(stats_fix(i));
-        if (i < 5) TRY(bn_relu(i, 0, 0, 1.f, (i == 3 && folded) ? c->colsum[4] : nullptr));
+        if (i == 1 && fold6) TRY(bn_relu(1, 0, 0, 1.f, c->colsum[6], c->N));      // per-cloud column sums of point_feat
+        else if (i < 5) TRY(bn_relu(i, 0, 0, 1.f, (i == 3 && folded) ? c->colsum[4] : nullptr));
     }
     {   // global max-pool of relu(bn(y6)) with arg-index
         const int total = c->B * 1024;
@@ -1258,9 +1325,33 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         pdl_launch(k_cloud_bias, (warps * 32 + 255) / 256, 256, 0, s, params + L.off[12] + 64, 1088, c->gmax, c->B, 512, 1024, nullptr, nullptr, c->cb);
         LAUNCH_OK("k_cloud_bias");
     }
-    TRY(timed_gemm(c, O.fw[6], 6, s));
-    TRY(stats_fix(6));
-    TRY(bn_relu(6, seed + 1, c->thr16, c->keep_scale));
+    if (fold6) {
+        // seg_conv1 with predicted statistics: per-cloud Gram matrices of point_feat, BN + ReLU + dropout in the GEMM epilogue
+        TRY(timed_gemm(c, c->gram_op[6], 48 + 7, s));
+        {
+            StampScope ts(c, 80, s);
+            pdl_launch(k_gram_reduce, dim3(64 * 64 * 4 / 256, c->B), 256, 0, s, static_cast<const float*>(c->grampart6),
+                       c->gram_op[6].p.splits_per_group, 64 * 64, c->gramf[6]);
+            LAUNCH_OK("k_gram_reduce");
+        }
+        {
+            StampScope ts(c, 81, s);
+            pdl_launch(k_predict_bn_cloud, dim3(512 / 8, c->B), 256, 0, s, static_cast<const float*>(c->gramf[6]),
+                       static_cast<const double*>(c->colsum[6]), static_cast<const bf16*>(c->wk[6]), static_cast<const float*>(c->cb), c->B, c->N,
+                       fin_args(6), c->stats_f + c->stat_off[6], c->part6, c->ticket6);
+            LAUNCH_OK("k_predict_bn_cloud");
+        }
+        GemmOp op = O.fw[6];
+        op.p.seed = seed + 1;
+        op.p.seed_ptr = c->seed_ptr;
+        op.p.drop_thr16 = c->thr16;
+        op.p.keep_scale = c->keep_scale;
+        TRY(timed_gemm(c, op, 6, s));
+    } else {
+        TRY(timed_gemm(c, O.fw[6], 6, s));
+        TRY(stats_fix(6));
+        TRY(bn_relu(6, seed + 1, c->thr16, c->keep_scale));
+    }
     TRY(timed_gemm(c, O.fw[7], 7, s));
     TRY(stats_fix(7));
     TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
@@ -1369,6 +1460,8 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         CUDA_OK(cudaMemsetAsync(grads, 0, static_cast<size_t>(L.total) * sizeof(float), s));
         CUDA_OK(cudaMemsetAsync(c->stats_b, 0, c->stat_total * sizeof(double), s));
         CUDA_OK(cudaMemsetAsync(c->dcb, 0, static_cast<size_t>(B) * 512 * sizeof(float), s));
+        if (c->folded && !rag && c->fold6)
+            CUDA_OK(cudaMemsetAsync(c->cloudsum6, 0, (static_cast<size_t>(B) * 512 + 512 * 64) * sizeof(float), s));
     }
 
     auto bwd_args = [&](int i) {
@@ -1454,8 +1547,50 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     TRY(wgrad(7, grads + L.off[14], 512));
     TRY(dgrad(7, c->seed + 1, c->thr16, c->keep_scale));
     // seg_conv1: point-feature columns by GEMM, global columns per cloud
-    TRY(apply(6, c->dycat + 64, 576, c->dcb));
-    TRY(wgrad(6, grads + L.off[12], 1088));
+    if (c->folded && !rag && c->fold6) {
+        // folded: Q6 = dz6^T a1, coefficients (incl. the per-cloud gradient dcb of the pooled branch), dW / data-gradient
+        // weights / per-cloud constant rows; dz6 itself already sits in dycat[:, 64:576]
+        TRY(timed_gemm(c, O.wg_op[6], 32 + 6, s));
+        Fold6Args f6;
+        f6.Q = c->qraw[6];
+        f6.W = c->wk[6];
+        f6.G = c->gramf[6];
+        f6.s = c->colsum[6];
+        f6.cb = c->cb;
+        f6.S1 = c->cloudsum6;
+        f6.bnp = c->bnp[6];
+        f6.coef = c->coef[6];
+        f6.dgamma = grads + L.off[20 + 2 * 6];
+        f6.dbeta = grads + L.off[21 + 2 * 6];
+        f6.dbias = grads + L.off[2 * 6 + 1];
+        f6.dcb = c->dcb;
+        f6.gsum = c->gsum6;
+        f6.ssum = c->ssum6;
+        f6.dW = grads + L.off[12];
+        f6.ld_dw = 1088;
+        f6.wcat = c->wcat6;
+        f6.ld_wcat = 640;
+        f6.col0 = 64;
+        f6.cst = c->cst6;
+        f6.n = static_cast<double>(c->P);
+        f6.N = c->N;
+        f6.clouds = B;
+        f6.Co = 512;
+        f6.Ci = 64;
+        {
+            StampScope ts(c, 86, s);
+            pdl_launch(k_fold6_coef, fold6_coef_blocks(512, 64), 256, 0, s, f6);
+            LAUNCH_OK("k_fold6_coef");
+        }
+        {
+            StampScope ts(c, 87, s);
+            pdl_launch(k_fold6_bwd, fold6_bwd_blocks(512, 64, B), 256, 0, s, f6);
+            LAUNCH_OK("k_fold6_bwd");
+        }
+    } else {
+        TRY(apply(6, c->dycat + 64, 576, c->dcb));
+        TRY(wgrad(6, grads + L.off[12], 1088));
+    }
     {
         dim3 grid_dg(1024 / 32, B);
         pdl_launch(k_cloud_bwd_dg, grid_dg, 256, 0, s, c->dcb, params + L.off[12] + 64, 1088, B, 512, 1024, c->gmax, c->ystar, c->bnp[5], c->dzv,
@@ -1561,8 +1696,6 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         f.Bw = c->bwf[4];
         f.ld_bw = 1024 + 128;
         f.cst = c->cstf[4];
-        f.S32 = c->s32f[4];
-        f.ticket = c->foldticket[4];
         f.Gc = c->gcf[4];
         f.n = static_cast<double>(c->P);
         f.Co = 1024;
@@ -1647,6 +1780,105 @@ extern "C" int pcseg_step_advance(pcseg_step_state* state, float b1, float b2, v
 }
 
 // ------------------------------------------------------------------------------------------------
+// gradient all-reduce over NVLink peer memory (peer_allreduce.cuh)
+// ------------------------------------------------------------------------------------------------
+struct pcseg_peer_ar {
+    PeerArArgs a;
+    uint32_t* local = nullptr;       // {arrive counter, generation, epoch, -} in local device memory
+    void* opened[2 * AR_MAX_RANKS] = {};
+    int num_opened = 0;
+};
+
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+
+extern "C" int pcseg_ipc_export(const void* ptr, unsigned char* handle_out /* 64 bytes */, long long* offset_out) {
+    if (!ptr || !handle_out || !offset_out) return fail("pcseg_ipc_export: null argument");
+    static GetAddressRangeFn get_range = nullptr;
+    if (!get_range) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return fail("pcseg_ipc_export: cuMemGetAddressRange unavailable");
+        get_range = reinterpret_cast<GetAddressRangeFn>(fn);
+    }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return fail("pcseg_ipc_export: cuMemGetAddressRange failed");
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(handle_out, &h, 64);
+    *offset_out = static_cast<long long>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+    return 0;
+}
+
+extern "C" long long pcseg_peer_ar_signal_bytes(void) { return static_cast<long long>(sizeof(PeerSignals)); }
+
+extern "C" int pcseg_peer_ar_create(pcseg_peer_ar** out, int rank, int world, float* arena, long long n_floats, void* signals,
+                                    void* counters /* 4 x uint32, zeroed */, const double* lw_in, double* lw_out) {
+    if (!out || !arena || !signals || !counters) return fail("pcseg_peer_ar_create: null argument");
+    if (world < 2 || world > AR_MAX_RANKS || (world != 2 && world != 4 && world != 8)) return fail("pcseg_peer_ar_create: world size %d unsupported (2, 4, 8)", world);
+    if (rank < 0 || rank >= world) return fail("pcseg_peer_ar_create: bad rank");
+    if (n_floats % 4 != 0 || (reinterpret_cast<uintptr_t>(arena) & 15)) return fail("pcseg_peer_ar_create: the arena must be 16-byte aligned and a multiple of 4 floats long");
+    pcseg_peer_ar* h = new pcseg_peer_ar();
+    memset(&h->a, 0, sizeof(h->a));
+    h->a.rank = rank;
+    h->a.world = world;
+    h->a.n = n_floats;
+    h->a.arena[rank] = arena;
+    h->a.sig[rank] = static_cast<PeerSignals*>(signals);
+    h->local = static_cast<uint32_t*>(counters);
+    h->a.epoch = h->local + 2;
+    h->a.lw_in = lw_in;
+    h->a.lw_out = lw_out;
+    *out = h;
+    return 0;
+}
+
+extern "C" int pcseg_peer_ar_open(pcseg_peer_ar* h, int peer, const unsigned char* arena_handle, long long arena_offset,
+                                  const unsigned char* sig_handle, long long sig_offset) {
+    if (!h || peer < 0 || peer >= h->a.world || peer == h->a.rank) return fail("pcseg_peer_ar_open: bad peer");
+    cudaIpcMemHandle_t ha, hs;
+    memcpy(&ha, arena_handle, 64);
+    memcpy(&hs, sig_handle, 64);
+    void* pa = nullptr;
+    void* ps = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&pa, ha, cudaIpcMemLazyEnablePeerAccess));
+    h->opened[h->num_opened++] = pa;
+    if (memcmp(&ha, &hs, 64) == 0) {
+        ps = pa;                       // same allocation block (caching allocator): one mapping
+    } else {
+        CUDA_OK(cudaIpcOpenMemHandle(&ps, hs, cudaIpcMemLazyEnablePeerAccess));
+        h->opened[h->num_opened++] = ps;
+    }
+    h->a.arena[peer] = reinterpret_cast<float*>(static_cast<char*>(pa) + arena_offset);
+    h->a.sig[peer] = reinterpret_cast<PeerSignals*>(static_cast<char*>(ps) + sig_offset);
+    return 0;
+}
+
+extern "C" int pcseg_peer_ar_run(pcseg_peer_ar* h, void* stream) {
+    if (!h) return fail("pcseg_peer_ar_run: null handle");
+    for (int p = 0; p < h->a.world; ++p)
+        if (!h->a.arena[p] || !h->a.sig[p]) return fail("pcseg_peer_ar_run: peer %d not opened", p);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = 64;               // constant: the intra-rank barrier counts arrivals per launch
+    switch (h->a.world) {
+        case 2: k_peer_allreduce<2><<<grid, 512, 0, s>>>(h->a, h->local); break;
+        case 4: k_peer_allreduce<4><<<grid, 512, 0, s>>>(h->a, h->local); break;
+        default: k_peer_allreduce<8><<<grid, 512, 0, s>>>(h->a, h->local); break;
+    }
+    LAUNCH_OK("k_peer_allreduce");
+    return 0;
+}
+
+extern "C" int pcseg_peer_ar_destroy(pcseg_peer_ar* h) {
+    if (!h) return 0;
+    for (int i = 0; i < h->num_opened; ++i) cudaIpcCloseMemHandle(h->opened[i]);
+    delete h;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // stand-alone GEMM for unit tests
 // ------------------------------------------------------------------------------------------------
 extern "C" int pcseg_gemm_test(int layout, int M, int N, int K, const void* A, int lda, const void* Bm, int ldb, void* D, int ldc,
@@ -1712,13 +1944,18 @@ extern "C" int pcseg_debug_copy(pcseg_ctx* c, int kind, int layer, void* dst, lo
         // folded layers (layer = conv index of the layer whose y / dy are not materialised)
         case 14: src = c->gramf[layer]; r = cv[layer].cin; cc = cv[layer].cin; eb = 4; break;
         case 15: src = c->colsum[layer]; r = 1; cc = cv[layer].cin; eb = 8; break;
-        case 16: src = c->qraw[layer]; r = cv[layer].cout; cc = cv[layer].cin; eb = 4; break;
+        case 16: src = c->qraw[layer]; r = cv[layer].cout; cc = (layer == 6) ? 64 : cv[layer].cin; eb = 4; break;
         case 17: src = c->bwf[layer]; r = cv[layer].cin; cc = cv[layer].cout + cv[layer].cin; eb = 2; break;
         case 18: src = c->cstf[layer]; r = 1; cc = cv[layer].cin; eb = 4; break;
         case 19: src = c->s5b; r = 1024; cc = 1024; eb = 2; break;
         case 20: src = c->gc5b; r = 1024; cc = 1024; eb = 2; break;
         case 21: src = c->side5; r = B * 1024; cc = 1024; eb = 4; break;
         case 22: src = c->rowslot5; r = 1; cc = P; eb = 4; break;
+        case 23: src = c->cloudsum6; r = B; cc = 512; eb = 4; break;
+        case 24: src = c->cst6; r = B; cc = 64; eb = 4; break;
+        case 25: src = c->wcat6; r = 64; cc = 640; eb = 2; break;
+        case 26: src = c->fold6 ? c->gramf[6] : nullptr; r = B * 64; cc = 64; eb = 4; break;
+        case 27: src = c->fold6 ? c->colsum[6] : nullptr; r = B; cc = 64; eb = 8; break;
         default: return fail("pcseg_debug_copy: unknown kind %d", kind);
     }
     if (!src) return fail("pcseg_debug_copy: tensor kind %d layer %d is not materialised", kind, layer);

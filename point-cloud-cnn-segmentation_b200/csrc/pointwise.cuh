@@ -54,7 +54,7 @@ struct ConvertJob {
     __nv_bfloat16* dst;
     int ld_src, ld_dst, rows, cols, transpose;
 };
-constexpr int MAX_CONVERT_JOBS = 16;
+constexpr int MAX_CONVERT_JOBS = 20;
 struct ConvertJobs {
     ConvertJob job[MAX_CONVERT_JOBS];
     int count;
@@ -221,7 +221,8 @@ __device__ __forceinline__ void bn_publish(const BnFinalizeArgs& f, bool first_b
 __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict__ y, int ld_y, __nv_bfloat16* __restrict__ a,
                                                  int ld_a, long P, int C, const BnFinalizeArgs fin,
                                                  unsigned long long seed_arg, const unsigned long long* __restrict__ seed_ptr,
-                                                 unsigned int thr16, float keep_scale, double* __restrict__ colsum) {
+                                                 unsigned int thr16, float keep_scale, double* __restrict__ colsum,
+                                                 int rows_per_cloud) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[256 * 8];
@@ -241,9 +242,22 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
         sc[e] = bp.x;
         sh[e] = bp.y;
     }
-    const long rows_per_block = (P + gridDim.x - 1) / gridDim.x;
-    const long r_begin = blockIdx.x * rows_per_block;
-    const long r_end = min(P, r_begin + rows_per_block);
+    // rows_per_cloud > 0: the grid is (clouds x blocks per cloud), strips never straddle clouds and colsum is [clouds][C]
+    long r_begin, r_end;
+    if (rows_per_cloud > 0) {
+        const int clouds = static_cast<int>(P / rows_per_cloud);
+        const int bpc = gridDim.x / clouds;
+        const int cloud = blockIdx.x / bpc, within = blockIdx.x - cloud * bpc;
+        const long rpb = (rows_per_cloud + bpc - 1) / bpc;
+        r_begin = static_cast<long>(cloud) * rows_per_cloud + within * rpb;
+        r_end = min(static_cast<long>(cloud + 1) * rows_per_cloud, r_begin + rpb);
+        if (cloud >= clouds) r_end = r_begin;
+        if (colsum != nullptr) colsum += static_cast<size_t>(cloud < clouds ? cloud : 0) * C;
+    } else {
+        const long rows_per_block = (P + gridDim.x - 1) / gridDim.x;
+        r_begin = blockIdx.x * rows_per_block;
+        r_end = min(P, r_begin + rows_per_block);
+    }
     for (long r = r_begin + rslot; r < r_end; r += 4L * rpp) {
         uint4 yw[4];
 #pragma unroll
@@ -297,9 +311,12 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
 // ---------------------------------------------------------------------------------------------
 // Sum of the per-split partial tiles of a Gram GEMM (EPI_WGRAD, wg_mode 3) in a FIXED order, fp64 accumulation: the
 // batch statistics predicted from it are then reproducible from run to run.  4 lanes per element.
+// blockIdx.y = group (cloud): out[g][i] = sum over the `splits` consecutive partial tiles of group g.
 __global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ part, int splits, int n_elem, float* __restrict__ out) {
     pdl_launch_dependents();
     pdl_wait();
+    part += static_cast<size_t>(blockIdx.y) * splits * n_elem;
+    out += static_cast<size_t>(blockIdx.y) * n_elem;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t >> 2, q = t & 3;
     double acc = 0.0;
@@ -1010,10 +1027,8 @@ struct FoldArgs {
     int ld_dw;
     __nv_bfloat16* Bw;            // [Ci][ld_bw]: columns [0, Co) = A_c W[c][j], columns [Co, Co + Ci) = S[i][j]
     int ld_bw;
-    float* cst;                   // [Ci]   (zeroed by the caller)
-    float* S32;                   // [Ci][Ci] fp32 accumulator of S (zeroed by the caller)
+    float* cst;                   // [Ci]
     float* Gc;                    // [Ci][Ci] centred Gram matrix (written by k_fold_coef)
-    int* ticket;                  // [Ci*Ci/256] completion counters of the S tiles (zeroed by the caller)
     double n;
     int Co, Ci;
 };
@@ -1054,19 +1069,36 @@ __global__ void __launch_bounds__(256) k_fold_coef(const FoldArgs f) {
 }
 __host__ __device__ inline int fold_coef_blocks(int Co, int Ci) { return (Co + 7) / 8 + (Ci * Ci + 255) / 256; }
 
-// Block roles of k_fold_bwd (1-D grid, see fold_bwd_blocks): dW | scaled transposed weights | S (reduction over the output
-// channels split into chunks of FOLD_CHUNK, fp32 atomics into S32; the chunk block that finishes a tile last converts it
-// to bf16 into Bw) | const (same split).  S32, cst and the tickets are zeroed by the caller before the launch.
-constexpr int FOLD_CHUNK = 64;
-__host__ __device__ inline int fold_bwd_blocks(int Co, int Ci) {
-    const int nA = (Co * Ci + 255) / 256, nS = (Ci * Ci + 255) / 256, ch = (Co + FOLD_CHUNK - 1) / FOLD_CHUNK;
-    return 2 * nA + nS * ch + ch;
+// out[j0 + lane] = sum_c scale(c) * W[c][j0 + lane] for one block of 256 threads: the 8 warps split the Co rows of W, lane = one
+// of 32 consecutive columns (coalesced row reads, scale(c) broadcast); the partial sums meet in shared memory.  The result is
+// returned to the lanes of warp 0 (other warps return 0).
+template <typename ScaleFn>
+__device__ __forceinline__ float block_weighted_colsum32(const __nv_bfloat16* __restrict__ W, int Ci, int Co, int j0, ScaleFn scale) {
+    __shared__ float part_s[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (Co + 7) / 8;
+    const int c0 = warp * per, c1 = min(c0 + per, Co);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) acc = fmaf(scale(c), __bfloat162float(W[static_cast<size_t>(c) * Ci + j0 + lane]), acc);
+    part_s[warp][lane] = acc;
+    __syncthreads();
+    float r = 0.f;
+    if (warp == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += part_s[w][lane];
+    }
+    return r;
 }
+
+// Block roles of k_fold_bwd (1-D grid, see fold_bwd_blocks): dW (thread per element) | scaled transposed weights (thread per
+// element) | S: one block per (i, 32 columns j) | constant row: one block per 32 columns.  No atomics.  Ci % 32 == 0.
+__host__ __device__ inline int fold_bwd_blocks(int Co, int Ci) { return 2 * ((Co * Ci + 255) / 256) + Ci * (Ci / 32) + Ci / 32; }
 __global__ void __launch_bounds__(256) k_fold_bwd(const FoldArgs f) {
     pdl_launch_dependents();
     pdl_wait();
     const int Co = f.Co, Ci = f.Ci;
-    const int nA = (Co * Ci + 255) / 256, nB1 = nA, nS = (Ci * Ci + 255) / 256, ch = (Co + FOLD_CHUNK - 1) / FOLD_CHUNK;
+    const int nA = (Co * Ci + 255) / 256;
     int blk = blockIdx.x;
     if (blk < nA) {                                   // dW[c][k] = A Q + Bc (W Gc) + D s
         const int idx = blk * 256 + threadIdx.x;
@@ -1081,52 +1113,266 @@ __global__ void __launch_bounds__(256) k_fold_bwd(const FoldArgs f) {
         return;
     }
     blk -= nA;
-    if (blk < nB1) {                                  // Bw[j][c] = A_c W[c][j]
+    if (blk < nA) {                                   // Bw[j][c] = A_c W[c][j]
         const int idx = blk * 256 + threadIdx.x;
         if (idx >= Co * Ci) return;
         const int j = idx / Co, c = idx - j * Co;
         f.Bw[static_cast<size_t>(j) * f.ld_bw + c] = __float2bfloat16_rn(f.coef[c].x * __bfloat162float(f.Wt[idx]));
         return;
     }
-    blk -= nB1;
-    __shared__ float coef_s[FOLD_CHUNK];
+    blk -= nA;
+    const int lane = threadIdx.x & 31;
+    const int jb = Ci / 32;
+    if (blk < Ci * jb) {                              // S[i][j] = sum_c W[c][i] Bc_c W[c][j]  ->  Bw[j][Co + i]
+        const int i = blk / jb, j0 = (blk - i * jb) * 32;
+        const float r = block_weighted_colsum32(f.W, Ci, Co, j0, [&](int c) { return __bfloat162float(f.W[static_cast<size_t>(c) * Ci + i]) * f.coef[c].y; });
+        if (threadIdx.x < 32) f.Bw[static_cast<size_t>(j0 + lane) * f.ld_bw + Co + i] = __float2bfloat16_rn(r);
+    } else {                                          // const[j] = sum_c (D_c - Bc_c mean_c) W[c][j]
+        const int j0 = (blk - Ci * jb) * 32;
+        const float r = block_weighted_colsum32(f.W, Ci, Co, j0, [&](int c) { return f.coef[c].z; });
+        if (threadIdx.x < 32) f.cst[j0 + lane] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// seg_conv1 (Ci = 64 point features + the per-cloud term cb[b][c] of the pooled feature, pcs.py:117-123; Co = 512) with
+// predicted statistics and folded backward.  y[p][c] = W[c,:] a[p,:] + cb[b(p)][c]; per cloud b: s_b = sum a, G_b = a^T a.
+//   k_predict_bn_cloud : lin_b = W s_b, quad_b = W G_b W^T;  mean = sum_b (lin_b + N cb_b) / n,
+//                        n var = sum_b [ (quad_b - lin_b^2 / N) + N (lin_b / N + cb_b - mean)^2 ]   (centred: no cancellation
+//                        against the large per-cloud term).  One warp per channel, fp64.
+//   k_fold6_coef       : sum dz*y = rowdot(Q, W) + sum_b cb_b S1_b  (S1_b = per-cloud sum of dz from the GEMM epilogue),
+//                        coefficients {A, Bc, D - Bc mean, D}, dgamma / dbeta / dbias, the per-cloud gradient of the pooled
+//                        branch dcb[b][c] = sum_{p in b} dy = A S1_b + Bc (lin_b + N cb_b - N mean) + N D, and gsum = sum_b G_b,
+//                        ssum = sum_b s_b.
+//   k_fold6_bwd        : dW[c][k] = A Q + Bc ((W gsum)[c][k] + sum_b cb_b[c] s_b[k] - mean_c ssum[k]) + D ssum[k];
+//                        data-gradient weights wcat[j][Co0 + c] = A_c W[c][j], wcat[j][Co0 + Co + i] = S[i][j] = sum_c W[c][i]
+//                        Bc_c W[c][j]; per-cloud constant rows cst[b][j] = sum_c (Bc_c (cb_b[c] - mean_c) + D_c) W[c][j].
+// ---------------------------------------------------------------------------------------------
+struct Fold6Args {
+    const float* Q;               // [Co][Ci]
+    const __nv_bfloat16* W;       // [Co][Ci]
+    const float* G;               // [clouds][Ci][Ci]
+    const double* s;              // [clouds][Ci]
+    const float* cb;              // [clouds][Co]
+    const float* S1;              // [clouds][Co] per-cloud sums of dz
+    const float4* bnp;            // [Co]
+    float4* coef;                 // [Co]
+    float* dgamma;
+    float* dbeta;
+    float* dbias;
+    float* dcb;                   // [clouds][Co]
+    float* gsum;                  // [Ci][Ci]
+    double* ssum;                 // [Ci]
+    float* dW;                    // [Co][ld_dw]
+    int ld_dw;
+    __nv_bfloat16* wcat;          // [Ci][ld_wcat]
+    int ld_wcat, col0;            // first column of the scaled weights inside wcat
+    float* cst;                   // [clouds][Ci]
+    double n;                     // all rows
+    int N;                        // rows per cloud
+    int clouds, Co, Ci;           // Ci == 64
+};
+
+// grid (C / 8, clouds), 8 warps = 8 channels of one cloud per block: {lin, quad} of every (cloud, channel) into `part`
+// ([clouds][C][2] fp64); the block that finishes a channel group last (ticket[blockIdx.x], zeroed by the caller) combines the
+// clouds and publishes the normalisation.
+__global__ void __launch_bounds__(256) k_predict_bn_cloud(const float* __restrict__ G, const double* __restrict__ s,
+                                                          const __nv_bfloat16* __restrict__ W, const float* __restrict__ cb, int clouds,
+                                                          int N, const BnFinalizeArgs fin, double* __restrict__ stats_out,
+                                                          double* __restrict__ part, int* __restrict__ ticket) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int K = 64;
+    __shared__ float g_s[K][K];
     __shared__ int last_s;
-    if (blk < nS * ch) {                              // S32[i][j] += sum_{c in chunk} W[c][i] Bc_c W[c][j]
-        const int chunk = blk / nS, tile = blk - chunk * nS;
-        const int c0 = chunk * FOLD_CHUNK, c1 = min(c0 + FOLD_CHUNK, Co);
-        if (static_cast<int>(threadIdx.x) < c1 - c0) coef_s[threadIdx.x] = f.coef[c0 + threadIdx.x].y;
-        __syncthreads();
-        const int idx = tile * 256 + threadIdx.x;
-        const bool ok = idx < Ci * Ci;
-        const int i = ok ? idx / Ci : 0, j = ok ? idx - i * Ci : 0;
-        if (ok) {
-            float acc = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 8 + warp;
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) g_s[i / K][i % K] = G[static_cast<size_t>(b) * K * K + i];
+    __syncthreads();
+    if (c < fin.C) {
+        const float wf0 = __bfloat162float(W[static_cast<size_t>(c) * K + lane]), wf1 = __bfloat162float(W[static_cast<size_t>(c) * K + 32 + lane]);
+        double t0 = 0.0, t1 = 0.0;
 #pragma unroll 8
-            for (int c = c0; c < c1; ++c) {
-                const __nv_bfloat16* w = f.W + static_cast<size_t>(c) * Ci;
-                acc = fmaf(__bfloat162float(w[i]) * coef_s[c - c0], __bfloat162float(w[j]), acc);
-            }
-            atomicAdd(f.S32 + idx, acc);
+        for (int j = 0; j < K; ++j) {
+            const double wj = static_cast<double>(__shfl_sync(0xffffffffu, j < 32 ? wf0 : wf1, j & 31));
+            t0 = fma(static_cast<double>(g_s[j][lane]), wj, t0);
+            t1 = fma(static_cast<double>(g_s[j][32 + lane]), wj, t1);
         }
-        // the chunk block that finishes this tile last converts it: Bw[j][Co + i] = bf16(S[i][j])
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) last_s = (atomicAdd(f.ticket + tile, 1) == ch - 1);
-        __syncthreads();
-        if (!last_s) return;
-        __threadfence();
-        if (ok) f.Bw[static_cast<size_t>(j) * f.ld_bw + Co + i] = __float2bfloat16_rn(__ldcg(f.S32 + idx));
-    } else {                                          // cst[j] += sum_{c in chunk} (D_c - Bc_c mean_c) W[c][j]
-        const int chunk = blk - nS * ch;
-        const int c0 = chunk * FOLD_CHUNK, c1 = min(c0 + FOLD_CHUNK, Co);
-        if (static_cast<int>(threadIdx.x) < c1 - c0) coef_s[threadIdx.x] = f.coef[c0 + threadIdx.x].z;
-        __syncthreads();
-        for (int j = threadIdx.x; j < Ci; j += 256) {
-            float acc = 0.f;
+        const double* sb = s + static_cast<size_t>(b) * K;
+        double quad = wf0 * t0 + wf1 * t1, lin = wf0 * sb[lane] + wf1 * sb[32 + lane];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            quad += __shfl_xor_sync(0xffffffffu, quad, o);
+            lin += __shfl_xor_sync(0xffffffffu, lin, o);
+        }
+        if (lane == 0) {
+            part[(static_cast<size_t>(b) * fin.C + c) * 2] = lin;
+            part[(static_cast<size_t>(b) * fin.C + c) * 2 + 1] = quad;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_s = (atomicAdd(ticket + blockIdx.x, 1) == clouds - 1);
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    if (threadIdx.x == 0) ticket[blockIdx.x] = 0;                    // ready for the next step
+    if (threadIdx.x >= 8) return;
+    const int cc = blockIdx.x * 8 + threadIdx.x;                     // one thread per channel of the group
+    if (cc >= fin.C) return;
+    double sum_y = 0.0, within = 0.0;
+    for (int bb = 0; bb < clouds; ++bb) {
+        const double lin = __ldcg(part + (static_cast<size_t>(bb) * fin.C + cc) * 2), quad = __ldcg(part + (static_cast<size_t>(bb) * fin.C + cc) * 2 + 1);
+        sum_y += lin + N * static_cast<double>(cb[static_cast<size_t>(bb) * fin.C + cc]);
+        within += quad - lin * lin / N;
+    }
+    const double mean = sum_y / fin.n;
+    double between = 0.0;
+    for (int bb = 0; bb < clouds; ++bb) {
+        const double mu = __ldcg(part + (static_cast<size_t>(bb) * fin.C + cc) * 2) / N + static_cast<double>(cb[static_cast<size_t>(bb) * fin.C + cc]);
+        between += N * (mu - mean) * (mu - mean);
+    }
+    double var = (within + between) / fin.n;
+    if (var < 0.0) var = 0.0;
+    const float invstd = rsqrtf(static_cast<float>(var) + fin.eps);
+    const float meanf = static_cast<float>(mean);
+    const float sc = fin.gamma[cc] * invstd;
+    fin.bnp[cc] = make_float4(sc, fmaf(-meanf, sc, fin.beta[cc]), invstd, -meanf * invstd);
+    if (fin.rmean != nullptr) {
+        const double unb = fin.n > 1.0 ? var * fin.n / (fin.n - 1.0) : var;
+        fin.rmean[cc] = static_cast<float>((1.0 - fin.momentum) * fin.rmean[cc] + fin.momentum * (mean + fin.conv_bias[cc]));
+        fin.rvar[cc] = static_cast<float>((1.0 - fin.momentum) * fin.rvar[cc] + fin.momentum * unb);
+    }
+    if (stats_out != nullptr) {
+        stats_out[cc] = sum_y;
+        stats_out[fin.C + cc] = (var + mean * mean) * fin.n;
+    }
+}
+
+// blocks [0, Co/8): one warp per channel; the remaining blocks sum G_b / s_b over the clouds
+__global__ void __launch_bounds__(256) k_fold6_coef(const Fold6Args f) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int K = f.Ci;
+    const int nco = (f.Co + 7) / 8;
+    if (static_cast<int>(blockIdx.x) >= nco) {
+        const int idx = (blockIdx.x - nco) * 256 + threadIdx.x;
+        if (idx < K * K) {
+            float g = 0.f;
+            for (int b = 0; b < f.clouds; ++b) g += f.G[static_cast<size_t>(b) * K * K + idx];
+            f.gsum[idx] = g;
+        }
+        if (idx < K) {
+            double sv = 0.0;
+            for (int b = 0; b < f.clouds; ++b) sv += f.s[static_cast<size_t>(b) * K + idx];
+            f.ssum[idx] = sv;
+        }
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= f.Co) return;
+    const float* q = f.Q + static_cast<size_t>(c) * K;
+    const __nv_bfloat16* w = f.W + static_cast<size_t>(c) * K;
+    const double w0 = __bfloat162float(w[lane]), w1 = __bfloat162float(w[32 + lane]);
+    double dot = static_cast<double>(q[lane]) * w0 + static_cast<double>(q[32 + lane]) * w1;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float4 bp = f.bnp[c];
+    const double mean = -static_cast<double>(bp.w) / static_cast<double>(bp.z);
+    // per cloud (lane b handles cloud b, b + 32, ...): S1_b, lin_b
+    double s1 = 0.0, dzy = 0.0;
+    for (int b0 = 0; b0 < f.clouds; b0 += 32) {
+        const int b = b0 + lane;
+        double S1b = 0.0, cbv = 0.0;
+        if (b < f.clouds) {
+            S1b = f.S1[static_cast<size_t>(b) * f.Co + c];
+            cbv = f.cb[static_cast<size_t>(b) * f.Co + c];
+        }
+        s1 += S1b;
+        dzy += cbv * S1b;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        dzy += __shfl_xor_sync(0xffffffffu, dzy, o);
+    }
+    const double dgamma = static_cast<double>(bp.z) * (dot + dzy - mean * s1);
+    const double A = bp.x;
+    const double Bc = -A * static_cast<double>(bp.z) * dgamma / f.n;
+    const double D = -A * s1 / f.n;
+    // per-cloud gradient of the pooled branch: dcb[b][c] = A S1_b + Bc (lin_b + N cb_b - N mean) + N D
+    for (int b = 0; b < f.clouds; ++b) {
+        const double* sb = f.s + static_cast<size_t>(b) * K;
+        double lin = w0 * sb[lane] + w1 * sb[32 + lane];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) lin += __shfl_xor_sync(0xffffffffu, lin, o);
+        if (lane == 0) {
+            const double cbv = f.cb[static_cast<size_t>(b) * f.Co + c];
+            f.dcb[static_cast<size_t>(b) * f.Co + c] =
+                static_cast<float>(A * f.S1[static_cast<size_t>(b) * f.Co + c] + Bc * (lin + f.N * (cbv - mean)) + f.N * D);
+        }
+    }
+    if (lane != 0) return;
+    f.coef[c] = make_float4(static_cast<float>(A), static_cast<float>(Bc), static_cast<float>(D - Bc * mean), static_cast<float>(D));
+    f.dgamma[c] = static_cast<float>(dgamma);
+    f.dbeta[c] = static_cast<float>(s1);
+    f.dbias[c] = 0.f;
+}
+__host__ __device__ inline int fold6_coef_blocks(int Co, int Ci) { return (Co + 7) / 8 + (Ci * Ci + 255) / 256; }
+
+// block roles: dW (thread per element) | scaled transposed weights (thread per element) | S: one block per (i, 32 columns) |
+// per-cloud constant rows: one block per (cloud, 32 columns)
+__host__ __device__ inline int fold6_bwd_blocks(int Co, int Ci, int clouds) { return 2 * ((Co * Ci + 255) / 256) + (Ci + clouds) * (Ci / 32); }
+__global__ void __launch_bounds__(256) k_fold6_bwd(const Fold6Args f) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Co = f.Co, Ci = f.Ci;
+    const int nA = (Co * Ci + 255) / 256;
+    int blk = blockIdx.x;
+    if (blk < nA) {                                   // dW[c][k]
+        const int idx = blk * 256 + threadIdx.x;
+        if (idx >= Co * Ci) return;
+        const int c = idx / Ci, k = idx - c * Ci;
+        const __nv_bfloat16* w = f.W + static_cast<size_t>(c) * Ci;
+        float wg = 0.f;
 #pragma unroll 8
-            for (int c = c0; c < c1; ++c) acc = fmaf(coef_s[c - c0], __bfloat162float(f.W[static_cast<size_t>(c) * Ci + j]), acc);
-            atomicAdd(f.cst + j, acc);
-        }
+        for (int j = 0; j < Ci; ++j) wg = fmaf(__bfloat162float(w[j]), f.gsum[j * Ci + k], wg);
+        float cbs = 0.f;
+        for (int b = 0; b < f.clouds; ++b) cbs = fmaf(f.cb[static_cast<size_t>(b) * Co + c], static_cast<float>(f.s[static_cast<size_t>(b) * Ci + k]), cbs);
+        const float4 cf = f.coef[c];
+        const float4 bp = f.bnp[c];
+        const float mean = -bp.w / bp.z;
+        const float sk = static_cast<float>(f.ssum[k]);
+        const float yca = wg + cbs - mean * sk;                                       // sum_p (y - mean)[p][c] a[p][k]
+        f.dW[static_cast<size_t>(c) * f.ld_dw + k] = fmaf(cf.x, f.Q[idx], fmaf(cf.y, yca, cf.w * sk));
+        return;
+    }
+    blk -= nA;
+    if (blk < nA) {                                   // wcat[j][col0 + c] = A_c W[c][j]
+        const int idx = blk * 256 + threadIdx.x;
+        if (idx >= Co * Ci) return;
+        const int j = idx / Co, c = idx - j * Co;
+        f.wcat[static_cast<size_t>(j) * f.ld_wcat + f.col0 + c] = __float2bfloat16_rn(f.coef[c].x * __bfloat162float(f.W[static_cast<size_t>(c) * Ci + j]));
+        return;
+    }
+    blk -= nA;
+    const int lane = threadIdx.x & 31;
+    const int jb = Ci / 32;
+    if (blk < Ci * jb) {                              // wcat[j][col0 + Co + i] = S[i][j]
+        const int i = blk / jb, j0 = (blk - i * jb) * 32;
+        const float r = block_weighted_colsum32(f.W, Ci, Co, j0, [&](int c) { return __bfloat162float(f.W[static_cast<size_t>(c) * Ci + i]) * f.coef[c].y; });
+        if (threadIdx.x < 32) f.wcat[static_cast<size_t>(j0 + lane) * f.ld_wcat + f.col0 + Co + i] = __float2bfloat16_rn(r);
+    } else {                                          // cst[b][j] = sum_c (Bc_c (cb_b[c] - mean_c) + D_c) W[c][j]
+        const int o = blk - Ci * jb;
+        const int b = o / jb, j0 = (o - b * jb) * 32;
+        const float r = block_weighted_colsum32(f.W, Ci, Co, j0, [&](int c) {
+            const float4 cf = f.coef[c];
+            const float4 bp = f.bnp[c];
+            return fmaf(cf.y, f.cb[static_cast<size_t>(b) * Co + c] + bp.w / bp.z, cf.w);
+        });
+        if (threadIdx.x < 32) f.cst[static_cast<size_t>(b) * Ci + j0 + lane] = r;
     }
 }
 

@@ -53,10 +53,20 @@ class _Binding:
             pass
 
 
-def host_lengths(lengths, B, N):
+def train_ragged_min_pad():
+    """Smallest pad fraction of a TRAINING batch for which the packed (ragged) step is used.  The dense step runs the
+    folded-BatchNorm kernels inside CUDA graphs, the packed step the materialising kernels launched eagerly: measured on
+    8 x 16 384 points the packed step wins below ~77 % valid points.  The padded batch IS the reference computation, so
+    routing a mostly-full batch to the dense path changes nothing but speed.  PCSEG_RAGGED_MIN_PAD overrides."""
+    import os
+    return float(os.environ.get("PCSEG_RAGGED_MIN_PAD", "0.25"))
+
+
+def host_lengths(lengths, B, N, min_pad_fraction=0.0):
     """Per-cloud point counts of a zero-padded batch as a ctypes int array (None stays None).  Accepts a list, a numpy
     array or a tensor (a CUDA tensor costs one device->host read); the reference's collate_fn (pcs.py:44-63) knows
-    them on the host: `masks.sum(1)`."""
+    them on the host: `masks.sum(1)`.  Returns None (dense execution of the padded batch) when less than
+    `min_pad_fraction` of the rows are padding."""
     if lengths is None:
         return None
     vals = lengths.detach().cpu().tolist() if torch.is_tensor(lengths) else [int(v) for v in lengths]
@@ -67,6 +77,8 @@ def host_lengths(lengths, B, N):
         raise ValueError(f"lengths must be within 0..{N}")
     if all(v == N for v in vals):
         return None                      # nothing is padded: the dense path is the same computation without the packing
+    if 1.0 - sum(vals) / float(B * N) < min_pad_fraction:
+        return None                      # mostly full: the padded batch on the dense path is faster
     return (C.c_int * B)(*vals)
 
 
@@ -173,7 +185,7 @@ class Engine:
     # ---- train
     def forward_train(self, x, flat_params, flat_bn, seed, dropout_p, labels=None, class_w=None, ce=None, state=None, lengths=None):
         B, N, _ = x.shape
-        lengths = host_lengths(lengths, B, N)
+        lengths = host_lengths(lengths, B, N, train_ragged_min_pad())
         b = self.binding(B, N if lengths is None else ragged_capacity(N), True)
         self._train_binding = b              # backward runs on the binding of the latest training forward
         logits = torch.empty((B, N, self.C), dtype=torch.float32, device=self.device)
@@ -220,7 +232,7 @@ class Engine:
 
 DEBUG_KINDS = {"y": 0, "act": 1, "dz": 2, "dy": 3, "bnp": 4, "coef": 5, "stats_f": 6, "stats_b": 7, "g": 8, "ystar": 9,
                "argidx": 10, "cb": 11, "dcb": 12, "dzv": 13, "gram": 14, "colsum": 15, "qraw": 16, "bwf": 17, "cstf": 18,
-               "s5b": 19, "gc5b": 20, "side": 21, "rowslot": 22}
+               "s5b": 19, "gc5b": 20, "side": 21, "rowslot": 22, "cloudsum6": 23, "cst6": 24, "wcat6": 25, "gram6": 26, "colsum6": 27}
 
 
 def debug_tensor(engine, B, N, kind, layer=0):

@@ -144,7 +144,8 @@ class PointNetSegmentation(nn.Module):
             m.running_var = flat_bn[ov:ov + c]
             if m.num_batches_tracked.device != device:
                 m.num_batches_tracked = m.num_batches_tracked.to(device)
-        flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        # (storage padded to a multiple of 4 floats: the NVLink peer all-reduce moves float4s, peer_allreduce.cuh)
+        flat_g = torch.zeros((total + 3) // 4 * 4, dtype=torch.float32, device=device)[:total]
         self._flat = dict(params=flat_p, grads=flat_g, bn=flat_bn, offs=offs)
         self._manual_version += 1
         return self._flat

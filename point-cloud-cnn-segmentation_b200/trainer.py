@@ -85,6 +85,19 @@ class FusedTrainer:
         self._static_x = None
         self._static_labels = None
         self._lengths = None            # per-cloud point counts of the current batch (ragged execution) or None
+        import os as _os
+        self.one_graph = self.distributed and _os.environ.get("PCSEG_DDP_ONE_GRAPH", "0") == "1"
+        # Gradient exchange: "peer" = one NVLink peer-memory kernel on the compute stream (the whole step is ONE CUDA graph,
+        # csrc/peer_allreduce.cuh); "nccl" = bucketed NCCL all-reduce between graph segments.  PCSEG_COMM overrides.
+        self.comm = _os.environ.get("PCSEG_COMM", "peer") if self.distributed else "none"
+        self.peer = None
+        if self.comm == "peer":
+            if self.world not in (2, 4, 8):
+                self.comm = "nccl"
+            else:
+                from .peer_ar import PeerAllReduce
+                self.lw_global = torch.zeros(2, dtype=torch.float64, device=self.device)
+                self.peer = PeerAllReduce(self.flat["grads"], self.lw, self.lw_global, group=self.pg)
 
     def set_lr(self, lr):
         self.lr = lr
@@ -99,7 +112,7 @@ class FusedTrainer:
     # before and keeps true gradients in the arena.
     @property
     def deferred(self):
-        return self.distributed and self.overlap
+        return self.distributed and (self.overlap or self.peer is not None)
 
     def _seg_forward(self, x, labels):
         self.engine.step_advance(self.state, self.betas)
@@ -119,13 +132,34 @@ class FusedTrainer:
         torch.div(self.loss_num, self.wsum, out=self.out_loss)
         self.out_counts.copy_(self.ce_i64[2:4])
 
+    @property
+    def global_wsum(self):
+        """sum of class weights over the valid points of the GLOBAL batch of the latest step (device, fp64)"""
+        return self.lw_global[1:2] if self.peer is not None else self.wsum
+
+    def _seg_peer_step(self, x, labels):
+        """data-parallel step with the peer-memory all-reduce: forward, un-normalised backward, ONE all-reduce kernel (gradient
+        arena + {loss numerator, sum w}), Adam dividing by the global sum of class weights -- all on the compute stream"""
+        self._seg_forward(x, labels)
+        self._seg_backward(x, labels, 0)
+        self.peer.run()
+        f = self.flat
+        self.engine.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, 1, self.lr, self.betas, self.eps, self.weight_decay,
+                         state=self.state, grad_div=self.lw_global[1:2])
+        torch.div(self.lw_global[0:1], self.lw_global[1:2], out=self.out_loss)
+        self.out_counts.copy_(self.ce_i64[2:4])
+
     def _segments(self):
+        if self.peer is not None:
+            return [self._seg_peer_step, None, None, None]
         if self.distributed and self.overlap:
             return [self._seg_forward, lambda x, l: self._seg_backward(x, l, 1), lambda x, l: self._seg_backward(x, l, 2), self._seg_tail]
         return [self._seg_forward, lambda x, l: self._seg_backward(x, l, 0), None, self._seg_tail]
 
     def _collective_after(self, i):
         """eager collectives that follow segment i"""
+        if self.peer is not None:
+            return
         f = self.flat
         self.sync.g = f["grads"]
         if i == 0:
@@ -145,6 +179,9 @@ class FusedTrainer:
                 self.sync.wait()
 
     def _run_step(self, x, labels, graphs=None):
+        if graphs is not None and len(graphs) == 1:      # the whole step, collectives included, is ONE graph
+            graphs[0].replay()
+            return
         for i, seg in enumerate(self._segments()):
             if seg is not None:
                 if graphs is not None:
@@ -159,6 +196,13 @@ class FusedTrainer:
             self._static_x = x.clone()
             self._static_labels = labels.clone()
             torch.cuda.synchronize(self.device)
+            if self.one_graph:
+                # compute segments AND the NCCL collectives between them in a single graph: no host launches, no idle gaps
+                # between segments (the collectives' side-stream events become graph edges)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_step(self._static_x, self._static_labels)
+                return [g]
             graphs, pool = [], None
             for seg in self._segments():
                 if seg is None:
@@ -189,8 +233,10 @@ class FusedTrainer:
         labels = labels.contiguous()
         if not m._flat_quick_ok(self.device):
             self.flat = m._ensure_flat(self.device)
-        if lengths is not None and all(int(v) == x.shape[1] for v in (lengths.tolist() if torch.is_tensor(lengths) else lengths)):
-            lengths = None                                      # nothing padded: dense (CUDA-graph) path
+        if lengths is not None:
+            from .engine import host_lengths, train_ragged_min_pad
+            if host_lengths(lengths, x.shape[0], x.shape[1], train_ragged_min_pad()) is None:
+                lengths = None                                  # nothing / little padded: dense (CUDA-graph) path
         self._lengths = lengths
         if lengths is not None:
             # packed step: launched eagerly on a capacity-bucketed binding (engine.ragged_capacity); graphs are left alone

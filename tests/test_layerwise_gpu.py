@@ -72,6 +72,8 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
     monkeypatch.setenv("PCSEG_FOLDED", "1" if folded else "0")      # read when a context is created
     monkeypatch.setenv("PCSEG_STORE_Y5", "1")      # keep global_feat's pre-BN output so that the fused max-pool can be checked bit-exactly
     FOLDED = {4, 5} if folded else set()
+    if folded and N % 128 == 0:
+        FOLDED.add(6)            # seg_conv1: per-cloud Gram matrices; needs row tiles that never straddle clouds
 
     P = B * N
     sd = orc.synth_state(C, 1000 + N)
@@ -112,6 +114,35 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
     keeps = {}
     for i in range(9):
         bnp[i] = T("bnp", i)
+        if i == 6 and 6 in FOLDED:
+            # ---- seg_conv1 with predicted statistics: per-cloud Gram matrices / column sums of point_feat, per-cloud term cb
+            cb = T("cb")
+            a1c = act[1].reshape(B, N, 64)
+            _close_red(T("gram6").reshape(B, 64, 64), np.einsum("bnk,bnj->bkj", a1c, a1c), "per-cloud gram[seg_conv1]", rel=1e-5)
+            _close_red(T("colsum6"), a1c.sum(1), "per-cloud colsum[seg_conv1]", rel=1e-5)
+            yref = lw.conv_pre_bn(act[1], W["seg_conv1"][:, :64], cloud_bias=cb, pts_per_cloud=N)
+            st = lw.bn_batch_stats(yref)
+            _close_red(T("stats_f", i), st, "predicted stats_f[bn_seg1]", rel=1e-4)
+            exact = lw.bn_params(st, P, sd["bn_seg1.weight"], sd["bn_seg1.bias"])
+            assert np.abs(bnp[i][:, 2] / exact[:, 2] - 1).max() < 2e-4, "predicted 1/std of bn_seg1 vs the fp64 batch statistics"
+            st = T("stats_f", i)
+            rm, rv = lw.running_stats(st, P, sd["seg_conv1.bias"].astype(np.float64), sd["bn_seg1.running_mean"].astype(np.float64),
+                                      sd["bn_seg1.running_var"].astype(np.float64))
+            _close_red(_np(m.bn_seg1.running_mean), rm, "bn_seg1.running_mean", rel=1e-5)
+            _close_red(_np(m.bn_seg1.running_var), rv, "bn_seg1.running_var", rel=1e-5)
+            assert int(m.bn_seg1.num_batches_tracked.item()) == int(sd["bn_seg1.num_batches_tracked"]) + 1
+            act[i] = T("act", i)
+            relu_out, _ = lw.bn_relu(yref, bnp[i])
+            if p_drop > 0:
+                keep = (act[i] != 0).astype(np.float64)
+                live = relu_out > 1e-3
+                assert abs(1.0 - keep[live].mean() - p_drop) < 0.01, "dropout fraction of seg_conv1"
+                keeps[i] = keep
+                _close_bf16(act[i], relu_out * keep * keep_scale, "act[seg_conv1] (BN + ReLU + dropout in the GEMM epilogue)")
+            else:
+                _close_bf16(act[i], relu_out, "act[seg_conv1] (BN + ReLU in the GEMM epilogue)")
+            y[i] = yref
+            continue
         if i in FOLDED and i != 5:
             # ---- Gram-predicted statistics (pcs.py:110): G and s of the input activation, {sum y, sum y^2} predicted from
             # them, BN + ReLU applied straight to the fp32 accumulators; y itself is never stored
@@ -217,14 +248,44 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
     _close_bf16(dz[7], lw.dgrad_masked(dy[8], W["seg_conv3"], y[7], bnp[7], keeps.get(7), keep_scale), "dz[seg_conv2]")
     bn_backward(7)
     _close_red(grads["seg_conv2.weight"][:, :, 0], lw.wgrad(dy[7], act[6]), "dW seg_conv2", rel=3e-4)
-    dz[6] = T("dz", 6)
-    _close_bf16(dz[6], lw.dgrad_masked(dy[7], W["seg_conv2"], y[6], bnp[6], keeps.get(6), keep_scale), "dz[seg_conv1]")
-    # seg_conv1: point-feature columns + per-cloud global columns (cat / repeat / max backward, pcs.py:114-120)
-    bn_backward(6)
     dW1 = grads["seg_conv1.weight"][:, :, 0]
-    _close_red(dW1[:, :64], lw.wgrad(dy[6], act[1]), "dW seg_conv1[:, :64]", rel=3e-4)
-    dcb_ref = dy[6].reshape(B, N, -1).sum(1)
-    _close_red(T("dcb"), dcb_ref, "dcb", rel=1e-3)
+    if 6 in FOLDED:
+        # ---- folded seg_conv1: dz6 is written straight into the skip-join operand, masked by the stored activation
+        dz[6] = T("dy", 6)
+        da6 = dy[7] @ lw.bf16_round(W["seg_conv2"])
+        _close_bf16(dz[6], lw.bf16_round(da6 * keep_scale) * (act[6] > 0), "dz[seg_conv1] (mask from the stored activation)")
+        _close_red(T("stats_b", 6)[0], dz[6].sum(0), "sum dz[seg_conv1]", rel=3e-4)
+        S1 = T("cloudsum6")
+        _close_red(S1, dz[6].reshape(B, N, -1).sum(1), "per-cloud sum dz[seg_conv1]", rel=3e-4)
+        Q6 = T("qraw", 6)
+        _close_red(Q6, dz[6].T @ act[1], "Q[seg_conv1]", rel=3e-4)
+        yhat6 = y[6] * bnp[6][:, 2] + bnp[6][:, 3]
+        sb6 = np.stack([dz[6].sum(0), (dz[6] * yhat6).sum(0)])
+        _close_red(grads["bn_seg1.weight"], sb6[1], "dgamma bn_seg1", rel=1e-3)
+        _close_red(grads["bn_seg1.bias"], sb6[0], "dbeta bn_seg1", rel=3e-4)
+        assert np.abs(grads["seg_conv1.bias"]).max() == 0.0
+        coef6_ref = lw.bn_bwd_coef(sb6, P, bnp[6])
+        _close_red(T("coef", 6)[:, :2], coef6_ref[:, :2], "coef[bn_seg1] A, Bc", rel=1e-3)
+        dy[6] = lw.bn_bwd_apply(dz[6], y[6], coef6_ref)                      # never materialised by the CUDA path
+        _close_red(dW1[:, :64], lw.wgrad(dy[6], act[1]), "dW seg_conv1[:, :64] (definition)", rel=2e-3)
+        dcb_ref = dy[6].reshape(B, N, -1).sum(1)
+        _close_red(T("dcb"), dcb_ref, "dcb (definition)", rel=2e-3)
+        coef6 = T("coef", 6)
+        Wpf = lw.bf16_round(W["seg_conv1"][:, :64])
+        wcat6 = T("wcat6")
+        _close_bf16(wcat6[:, :64], lw.bf16_round(W["conv3"]).T, "wcat6 W3^T")
+        _close_bf16(wcat6[:, 64:576], (coef6[:, 0:1] * Wpf).T, "wcat6 scaled Wpf^T")
+        _close_bf16(wcat6[:, 576:], (Wpf.T @ (coef6[:, 1:2] * Wpf)).T, "wcat6 S6")
+        mean6 = -bnp[6][:, 3] / bnp[6][:, 2]
+        _close_red(T("cst6"), (coef6[:, 1] * (T("cb") - mean6) + coef6[:, 3]) @ Wpf, "per-cloud constant rows", rel=1e-3)
+    else:
+        dz[6] = T("dz", 6)
+        _close_bf16(dz[6], lw.dgrad_masked(dy[7], W["seg_conv2"], y[6], bnp[6], keeps.get(6), keep_scale), "dz[seg_conv1]")
+        # seg_conv1: point-feature columns + per-cloud global columns (cat / repeat / max backward, pcs.py:114-120)
+        bn_backward(6)
+        _close_red(dW1[:, :64], lw.wgrad(dy[6], act[1]), "dW seg_conv1[:, :64]", rel=3e-4)
+        dcb_ref = dy[6].reshape(B, N, -1).sum(1)
+        _close_red(T("dcb"), dcb_ref, "dcb", rel=1e-3)
     dcb = T("dcb")
     _close_red(dW1[:, 64:], dcb.T @ g, "dW seg_conv1[:, 64:]", rel=1e-4)
     dzv_ref = (dcb @ W["seg_conv1"][:, 64:]) * (g > 0)
@@ -343,7 +404,12 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
     dz[1] = T("dz", 1)
     da_join = dy[2] @ lw.bf16_round(W["conv3"]) + dy[6] @ lw.bf16_round(W["seg_conv1"][:, :64])
     t1 = np.float32(bnp[1][:, 0]) * y[1].astype(np.float32) + np.float32(bnp[1][:, 1])
-    _close_bf16(dz[1], da_join * (t1 > 0), "dz[conv2] (skip join)")
+    if 6 in FOLDED:
+        da_f = np.concatenate([dy[2], dz[6], act[1]], axis=1) @ T("wcat6").T + np.repeat(T("cst6"), N, axis=0)
+        _close_bf16(dz[1], da_f * (t1 > 0), "dz[conv2] (skip join, folded seg_conv1)")
+        _close_rms(dz[1], da_join * (t1 > 0), "dz[conv2] (skip join, definition)", rel=2e-2)
+    else:
+        _close_bf16(dz[1], da_join * (t1 > 0), "dz[conv2] (skip join)")
     bn_backward(1)
     _close_red(grads["conv2.weight"][:, :, 0], lw.wgrad(dy[1], act[0]), "dW conv2", rel=3e-4)
     dz[0] = T("dz", 0)

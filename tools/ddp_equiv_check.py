@@ -42,7 +42,7 @@ dist.all_gather(seeds, tr.state.view(torch.int64)[0:1].clone())
 distinct_seeds = len({int(s.item()) for s in seeds}) == world
 params_before = tr.flat["params"].clone()
 out = tr.step(x[rank * per:(rank + 1) * per].contiguous(), y[rank * per:(rank + 1) * per].contiguous())
-wsum_dp = tr.wsum.item()
+wsum_dp = tr.global_wsum.item()
 g_dp = tr.flat["grads"].clone() / (wsum_dp if tr.deferred else 1.0)      # deferred: the arena holds the un-normalised sum
 loss_dp = out["loss"].item()
 p_after = tr.flat["params"].clone()
@@ -77,7 +77,7 @@ if rank == 0:
     step_cos = torch.nn.functional.cosine_similarity(dp_step.double(), ref_step.double(), dim=0).item()
     res = dict(world=world, grad_cosine=cos, grad_rel_diff=rel, loss_dp=loss_dp, loss_emulated=num / wsum.item(), wsum_dp=wsum_dp,
                wsum=wsum.item(), same_init=same_init, distinct_dropout_seeds=distinct_seeds, params_identical_after_step=same_after,
-               adam_step_cosine=step_cos, deferred=bool(tr.deferred))
+               adam_step_cosine=step_cos, deferred=bool(tr.deferred), comm=tr.comm)
     ok = (cos > 0.9995 and rel < 3e-2 and abs(loss_dp - num / wsum.item()) < 1e-5 * abs(loss_dp) and abs(wsum_dp - wsum.item()) < 1e-6 * wsum.item()
           and same_init and distinct_seeds and same_after and step_cos > 0.95)      # (first Adam step ~ lr * sign(g): near-zero gradient elements flip)
     res["ok"] = bool(ok)

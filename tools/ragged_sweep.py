@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+os.environ.setdefault("PCSEG_RAGGED_MIN_PAD", "0")      # measure the packed step itself (the trainer routes mostly-full batches to the dense path)
 import pcseg_b200  # noqa: E402
 
 
