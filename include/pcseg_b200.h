@@ -193,6 +193,28 @@ long long pcseg_launch_count(void);
  * find free SMs instead of delaying a full wave of a persistent GEMM; n <= 0 removes the cap. */
 int pcseg_set_sm_limit(int n);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (one node, 2 / 4 / 8 ranks, one process per GPU) ----
+ * Replaces nn.DataParallel's reduce-add of the replica gradients (pcs.py:209-211, behind loss.backward() at pcs.py:254).
+ * Every rank maps the gradient arenas and signal blocks of its peers (CUDA IPC) and launches ONE kernel per step on its
+ * compute stream (capturable in a CUDA graph): cross-rank barrier, reduce-scatter of the arena with peer loads, barrier,
+ * all-gather, barrier.  {loss numerator, sum of class weights} of the deferred loss normalisation travel along (lw_in ->
+ * lw_out = sums over the ranks; see pcseg_adam_step's grad_div).
+ *   pcseg_ipc_export      : 64-byte IPC handle of the allocation that holds `ptr` + the offset of `ptr` inside it
+ *   pcseg_peer_ar_create  : arena = this rank's gradient arena (16-byte aligned, n_floats a multiple of 4), signals = zeroed,
+ *                           256-byte aligned device block of pcseg_peer_ar_signal_bytes(n_floats, world) bytes (flags + the
+ *                           publish buffer the peers gather the reduced slice from), counters = 4 zeroed uint32
+ *   pcseg_peer_ar_open    : map peer `peer`'s arena / signal block from the handles it exported
+ *   pcseg_peer_ar_run     : enqueue the all-reduce (every rank must call it once per step) */
+typedef struct pcseg_peer_ar pcseg_peer_ar;
+int pcseg_ipc_export(const void* ptr, unsigned char* handle_out, long long* offset_out);
+long long pcseg_peer_ar_signal_bytes(long long n_floats, int world);
+int pcseg_peer_ar_create(pcseg_peer_ar** out, int rank, int world, float* arena, long long n_floats, void* signals,
+                         void* counters, const double* lw_in, double* lw_out);
+int pcseg_peer_ar_open(pcseg_peer_ar* h, int peer, const unsigned char* arena_handle, long long arena_offset,
+                       const unsigned char* sig_handle, long long sig_offset);
+int pcseg_peer_ar_run(pcseg_peer_ar* h, void* stream);
+int pcseg_peer_ar_destroy(pcseg_peer_ar* h);
+
 #ifdef __cplusplus
 }
 #endif

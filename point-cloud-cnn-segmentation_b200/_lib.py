@@ -60,6 +60,7 @@ def _load():
     lib.pcseg_launch_count.restype = ll
     lib.pcseg_set_sm_limit.argtypes = [i32]
     lib.pcseg_ipc_export.argtypes = [vp, C.c_char_p, C.POINTER(ll)]
+    lib.pcseg_peer_ar_signal_bytes.argtypes = [ll, i32]
     lib.pcseg_peer_ar_signal_bytes.restype = ll
     lib.pcseg_peer_ar_create.argtypes = [C.POINTER(vp), i32, i32, vp, ll, vp, vp, vp, vp]
     lib.pcseg_peer_ar_open.argtypes = [vp, i32, C.c_char_p, ll, C.c_char_p, ll]

@@ -1298,8 +1298,8 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
             TRY(timed_gemm(c, c->gram_op[4], 48 + 4, s));
             {
                 StampScope ts(c, 80, s);
-                pdl_launch(k_gram_reduce, 128 * 128 * 4 / 256, 256, 0, s, static_cast<const float*>(c->grampart4), c->gram_op[4].p.num_splits,
-                           128 * 128, c->gramf[4]);
+                pdl_launch(k_gram_reduce, 128 * 128 * 16 / 256, 256, 0, s, static_cast<const float*>(c->grampart4), c->gram_op[4].p.num_splits,
+                           128 * 128, c->gramf[4], static_cast<const double*>(c->colsum[4]), static_cast<double>(c->P), 128);
                 LAUNCH_OK("k_gram_reduce");
             }
             {
@@ -1330,8 +1330,9 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         TRY(timed_gemm(c, c->gram_op[6], 48 + 7, s));
         {
             StampScope ts(c, 80, s);
-            pdl_launch(k_gram_reduce, dim3(64 * 64 * 4 / 256, c->B), 256, 0, s, static_cast<const float*>(c->grampart6),
-                       c->gram_op[6].p.splits_per_group, 64 * 64, c->gramf[6]);
+            pdl_launch(k_gram_reduce, dim3(64 * 64 * 16 / 256, c->B), 256, 0, s, static_cast<const float*>(c->grampart6),
+                       c->gram_op[6].p.splits_per_group, 64 * 64, c->gramf[6], static_cast<const double*>(c->colsum[6]),
+                       static_cast<double>(c->N), 64);
             LAUNCH_OK("k_gram_reduce");
         }
         {
@@ -1556,6 +1557,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         f6.W = c->wk[6];
         f6.G = c->gramf[6];
         f6.s = c->colsum[6];
+        f6.part = c->part6;
         f6.cb = c->cb;
         f6.S1 = c->cloudsum6;
         f6.bnp = c->bnp[6];
@@ -1683,7 +1685,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         f.Q = c->qraw[4];
         f.W = c->wk[4];
         f.Wt = c->wt[4];
-        f.G = c->gramf[4];
+        f.Gc = c->gramf[4];
         f.s = c->colsum[4];
         f.sum_dz = c->stats_b + c->stat_off[4];
         f.bnp = c->bnp[4];
@@ -1696,7 +1698,6 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         f.Bw = c->bwf[4];
         f.ld_bw = 1024 + 128;
         f.cst = c->cstf[4];
-        f.Gc = c->gcf[4];
         f.n = static_cast<double>(c->P);
         f.Co = 1024;
         f.Ci = 128;
@@ -1812,10 +1813,15 @@ extern "C" int pcseg_ipc_export(const void* ptr, unsigned char* handle_out /* 64
     return 0;
 }
 
-extern "C" long long pcseg_peer_ar_signal_bytes(void) { return static_cast<long long>(sizeof(PeerSignals)); }
+// bytes of the IPC-shared block of one rank: signals + publish buffer (one slice of the arena)
+extern "C" long long pcseg_peer_ar_signal_bytes(long long n_floats, int world) {
+    const long long n4 = n_floats / 4, per = (n4 + world - 1) / world;
+    return static_cast<long long>((sizeof(PeerSignals) + 255) & ~size_t(255)) + per * 16 + 256;
+}
 
 extern "C" int pcseg_peer_ar_create(pcseg_peer_ar** out, int rank, int world, float* arena, long long n_floats, void* signals,
                                     void* counters /* 4 x uint32, zeroed */, const double* lw_in, double* lw_out) {
+    // signals = [PeerSignals | publish buffer of ceil(n_floats / 4 / world) float4]
     if (!out || !arena || !signals || !counters) return fail("pcseg_peer_ar_create: null argument");
     if (world < 2 || world > AR_MAX_RANKS || (world != 2 && world != 4 && world != 8)) return fail("pcseg_peer_ar_create: world size %d unsupported (2, 4, 8)", world);
     if (rank < 0 || rank >= world) return fail("pcseg_peer_ar_create: bad rank");
@@ -1827,6 +1833,7 @@ extern "C" int pcseg_peer_ar_create(pcseg_peer_ar** out, int rank, int world, fl
     h->a.n = n_floats;
     h->a.arena[rank] = arena;
     h->a.sig[rank] = static_cast<PeerSignals*>(signals);
+    h->a.pub[rank] = reinterpret_cast<float*>(static_cast<char*>(signals) + ((sizeof(PeerSignals) + 255) & ~size_t(255)));
     h->local = static_cast<uint32_t*>(counters);
     h->a.epoch = h->local + 2;
     h->a.lw_in = lw_in;
@@ -1853,6 +1860,7 @@ extern "C" int pcseg_peer_ar_open(pcseg_peer_ar* h, int peer, const unsigned cha
     }
     h->a.arena[peer] = reinterpret_cast<float*>(static_cast<char*>(pa) + arena_offset);
     h->a.sig[peer] = reinterpret_cast<PeerSignals*>(static_cast<char*>(ps) + sig_offset);
+    h->a.pub[peer] = reinterpret_cast<float*>(static_cast<char*>(ps) + sig_offset + ((sizeof(PeerSignals) + 255) & ~size_t(255)));
     return 0;
 }
 
@@ -1861,7 +1869,7 @@ extern "C" int pcseg_peer_ar_run(pcseg_peer_ar* h, void* stream) {
     for (int p = 0; p < h->a.world; ++p)
         if (!h->a.arena[p] || !h->a.sig[p]) return fail("pcseg_peer_ar_run: peer %d not opened", p);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int grid = 64;               // constant: the intra-rank barrier counts arrivals per launch
+    const int grid = 128;              // constant: the intra-rank barrier counts arrivals per launch (all CTAs must be co-resident)
     switch (h->a.world) {
         case 2: k_peer_allreduce<2><<<grid, 512, 0, s>>>(h->a, h->local); break;
         case 4: k_peer_allreduce<4><<<grid, 512, 0, s>>>(h->a, h->local); break;

@@ -4,10 +4,13 @@
 // Every rank maps the gradient arenas and signal blocks of all ranks (CUDA IPC).  One kernel per step and rank, launched on
 // the compute stream (capturable in the step's CUDA graph: no host involvement, no NCCL launch / stream hand-over latency):
 //   barrier A   every rank's backward has finished (its arena is complete)
-//   phase 1     two-shot reduce-scatter: rank r sums slice r of ALL arenas (peer loads over NVLink) into its own arena
+//   phase 1     two-shot reduce-scatter: rank r sums slice r of ALL arenas (peer loads over NVLink) into its own arena AND
+//               into its publish buffer
 //   barrier B
-//   phase 2     all-gather: rank r copies the reduced slices p != r from their owners
-//   barrier C   nobody still reads a slice that the next step's backward will overwrite
+//   phase 2     all-gather: rank r copies the reduced slices p != r from their owners' publish buffers
+// No third barrier: a publish buffer is rewritten only in the next step's phase 1, i.e. after the next barrier A, which a
+// rank reaches only after it has finished this kernel (its phase-2 reads included); the arenas themselves are read by
+// peers in phase 1 only, and barrier B separates that from anything that follows.
 // The {loss numerator, sum of class weights} pair of the deferred loss normalisation travels in the signal block and is summed
 // after barrier A.  Barriers are flag exchanges in peer memory: rank r writes its epoch counter into slot r of every peer's
 // signal block (st.release.sys) and spins until all slots of its own block carry that epoch (ld.acquire.sys).
@@ -28,6 +31,7 @@ struct PeerSignals {                     // lives in every rank's IPC-shared sig
 
 struct PeerArArgs {
     float* arena[AR_MAX_RANKS];          // gradient arenas of all ranks (arena[rank] is local)
+    float* pub[AR_MAX_RANKS];            // publish buffers (one slice each) of all ranks
     PeerSignals* sig[AR_MAX_RANKS];      // signal blocks of all ranks
     long long n;                         // floats in the arena
     int rank, world;
@@ -54,9 +58,10 @@ __device__ __forceinline__ float4 ld_cg_f4(const float4* p) {
 // `local` = {arrive counter, generation} in local device memory.
 __device__ __forceinline__ void peer_barrier(const PeerArArgs& a, int which, uint32_t epoch, uint32_t* local) {
     __syncthreads();
-    __threadfence_system();                                  // this block's writes (arena slices) are visible system-wide
     if (threadIdx.x == 0) {
-        const uint32_t target = (epoch - 1) * 3 + which + 1; // barriers passed so far (the grid size never changes)
+        // one system-scope fence per block: fences are cumulative, the block's writes were ordered before it by bar.sync
+        __threadfence_system();
+        const uint32_t target = (epoch - 1) * 2 + which + 1; // barriers passed so far (the grid size never changes)
         const uint32_t arrived = atomicAdd(&local[0], 1u) + 1;
         if (arrived == gridDim.x * target) {                 // last block of this rank to arrive: exchange flags with the peers
             for (int p = 0; p < a.world; ++p) st_release_sys(&a.sig[p]->flag[which][a.rank][0], epoch);
@@ -71,9 +76,12 @@ __device__ __forceinline__ void peer_barrier(const PeerArArgs& a, int which, uin
                 }
             }
             __threadfence_system();
-            atomicExch(&local[1], target);
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&local[1]), "r"(target) : "memory");
         } else {
-            while (atomicAdd(&local[1], 0u) < target) {}
+            uint32_t g;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(&local[1]) : "memory");
+            } while (g < target);
         }
         __threadfence_system();
     }
@@ -100,17 +108,32 @@ __global__ void __launch_bounds__(512) k_peer_allreduce(const PeerArArgs a, uint
     {   // phase 1: reduce my slice
         const long long lo = a.rank * per, hi = min(lo + per, n4);
         float4* mine = reinterpret_cast<float4*>(a.arena[a.rank]);
+        float4* pub = reinterpret_cast<float4*>(a.pub[a.rank]) - lo;
         const float4* peer[WORLD];
 #pragma unroll
         for (int q = 1; q < WORLD; ++q) peer[q] = reinterpret_cast<const float4*>(a.arena[(a.rank + q) % WORLD]);   // staggered start
-        for (long long i = lo + tid; i < hi; i += stride) {
-            float4 v[WORLD];
-            v[0] = mine[i];
+        constexpr int U = (WORLD <= 2) ? 4 : (WORLD <= 4 ? 2 : 1);          // elements per thread in flight: U * (WORLD - 1) peer loads
+        for (long long i0 = lo + tid; i0 < hi; i0 += stride * U) {
+            float4 v[U][WORLD];
 #pragma unroll
-            for (int q = 1; q < WORLD; ++q) v[q] = ld_cg_f4(peer[q] + i);        // all peer loads in flight before the first add
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + u * stride;
+                if (i < hi) {
+                    v[u][0] = mine[i];
 #pragma unroll
-            for (int q = 1; q < WORLD; ++q) { v[0].x += v[q].x; v[0].y += v[q].y; v[0].z += v[q].z; v[0].w += v[q].w; }
-            mine[i] = v[0];
+                    for (int q = 1; q < WORLD; ++q) v[u][q] = ld_cg_f4(peer[q] + i);      // all peer loads in flight before the first add
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + u * stride;
+                if (i < hi) {
+#pragma unroll
+                    for (int q = 1; q < WORLD; ++q) { v[u][0].x += v[u][q].x; v[u][0].y += v[u][q].y; v[u][0].z += v[u][q].z; v[u][0].w += v[u][q].w; }
+                    mine[i] = v[u][0];
+                    pub[i] = v[u][0];
+                }
+            }
         }
     }
     peer_barrier(a, 1, epoch, local);
@@ -120,12 +143,23 @@ __global__ void __launch_bounds__(512) k_peer_allreduce(const PeerArArgs a, uint
         for (int q = 1; q < WORLD; ++q) {
             const int p = (a.rank + q) % WORLD;
             const long long lo = p * per, hi = min(lo + per, n4);
-            const float4* src = reinterpret_cast<const float4*>(a.arena[p]);
-            for (long long i = lo + tid; i < hi; i += stride) mine[i] = ld_cg_f4(src + i);
+            const float4* src = reinterpret_cast<const float4*>(a.pub[p]) - lo;
+            for (long long i0 = lo + tid; i0 < hi; i0 += stride * 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * stride < hi) v[u] = ld_cg_f4(src + i0 + u * stride);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * stride < hi) mine[i0 + u * stride] = v[u];
+            }
         }
     }
-    peer_barrier(a, 2, epoch, local);
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.epoch[0] = epoch;
+    // the epoch counter may only advance once every block has read it: count the blocks that are done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&local[3], 1u) + 1 == gridDim.x * epoch) a.epoch[0] = epoch;
+    }
 }
 
 }  // namespace pcseg

@@ -310,76 +310,78 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
 // unbiased variance, conv bias re-added to the mean) and writes {sum y, sum y^2} for inspection.
 // ---------------------------------------------------------------------------------------------
 // Sum of the per-split partial tiles of a Gram GEMM (EPI_WGRAD, wg_mode 3) in a FIXED order, fp64 accumulation: the
-// batch statistics predicted from it are then reproducible from run to run.  4 lanes per element.
-// blockIdx.y = group (cloud): out[g][i] = sum over the `splits` consecutive partial tiles of group g.
-__global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ part, int splits, int n_elem, float* __restrict__ out) {
+// batch statistics predicted from it are then reproducible from run to run.  16 lanes per element.  blockIdx.y = group
+// (cloud): out[g][i] = sum over the `splits` consecutive partial tiles of group g.  With colsum != nullptr the result is the
+// CENTRED Gram matrix  Gc[r][c] = G[r][c] - s[r] s[c] / n_rows  (s = colsum + g * K): the only fp64 arithmetic of the
+// predicted-statistics path happens here, once per matrix element (CUDA-core fp64 is slow on this part).
+__global__ void __launch_bounds__(256) k_gram_reduce(const float* __restrict__ part, int splits, int n_elem, float* __restrict__ out,
+                                                     const double* __restrict__ colsum, double n_rows, int K) {
     pdl_launch_dependents();
     pdl_wait();
     part += static_cast<size_t>(blockIdx.y) * splits * n_elem;
     out += static_cast<size_t>(blockIdx.y) * n_elem;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = t >> 2, q = t & 3;
+    const int i = t >> 4, q = t & 15;
     double acc = 0.0;
     if (i < n_elem) {
-#pragma unroll 8
-        for (int s = q; s < splits; s += 4) acc += static_cast<double>(part[static_cast<size_t>(s) * n_elem + i]);
+#pragma unroll 4
+        for (int s = q; s < splits; s += 16) acc += static_cast<double>(part[static_cast<size_t>(s) * n_elem + i]);
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (q == 0 && i < n_elem) out[i] = static_cast<float>(acc);
+#pragma unroll
+    for (int o = 1; o <= 8; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (q == 0 && i < n_elem) {
+        if (colsum != nullptr) {
+            const double* sg = colsum + static_cast<size_t>(blockIdx.y) * K;
+            acc -= sg[i / K] * sg[i % K] / n_rows;
+        }
+        out[i] = static_cast<float>(acc);
+    }
 }
 
 template <int KQ>      // K = 32 * KQ input channels; 8 warps = 8 output channels per block
-__global__ void __launch_bounds__(256) k_predict_bn(const float* __restrict__ G, const double* __restrict__ colsum,
+__global__ void __launch_bounds__(256) k_predict_bn(const float* __restrict__ Gc /* centred Gram matrix */, const double* __restrict__ colsum,
                                                     const __nv_bfloat16* __restrict__ W, const BnFinalizeArgs fin,
                                                     double* __restrict__ stats_out) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int K = 32 * KQ;
-    __shared__ float g_s[32][K];          // 32 rows of G at a time (all warps of the block share them)
-    __shared__ double m_s[K];
+    __shared__ float g_s[32][K];          // 32 rows of Gc at a time (all warps of the block share them)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 8 + warp;
-    const double inv_n = 1.0 / fin.n;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) m_s[k] = colsum[k] * inv_n;
     const bool live = c < fin.C;
     const __nv_bfloat16* wr = W + static_cast<size_t>(live ? c : 0) * K;
-    float wf[KQ];
-    double t[KQ], mk[KQ];
+    float wf[KQ], t[KQ];
 #pragma unroll
     for (int q = 0; q < KQ; ++q) {
-        t[q] = 0.0;
+        t[q] = 0.f;
         wf[q] = __bfloat162float(wr[lane + 32 * q]);
     }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < KQ; ++q) mk[q] = m_s[lane + 32 * q];
 #pragma unroll
     for (int jc = 0; jc < KQ; ++jc) {          // rows j = 32 jc .. 32 jc + 31 (unrolled: wf[jc] must stay in registers)
         __syncthreads();
-        for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) g_s[i / K][i % K] = G[static_cast<size_t>(32 * jc) * K + i];
+        for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) g_s[i / K][i % K] = Gc[static_cast<size_t>(32 * jc) * K + i];
         __syncthreads();
 #pragma unroll 8
         for (int jj = 0; jj < 32; ++jj) {
-            const double wj = static_cast<double>(__shfl_sync(0xffffffffu, wf[jc], jj));
-            const double mj = m_s[32 * jc + jj];
+            const float wj = __shfl_sync(0xffffffffu, wf[jc], jj);
 #pragma unroll
-            for (int q = 0; q < KQ; ++q)      // G is symmetric: row j read conflict-free
-                t[q] = fma(fma(static_cast<double>(g_s[jj][lane + 32 * q]), inv_n, -mj * mk[q]), wj, t[q]);
+            for (int q = 0; q < KQ; ++q) t[q] = fmaf(g_s[jj][lane + 32 * q], wj, t[q]);      // Gc is symmetric: row j read conflict-free
         }
     }
-    double var = 0.0, mean = 0.0;
+    double nvar = 0.0, sum_y = 0.0;          // n * var = w^T Gc w,  sum y = w . s
 #pragma unroll
     for (int q = 0; q < KQ; ++q) {
-        var = fma(static_cast<double>(wf[q]), t[q], var);
-        mean = fma(static_cast<double>(wf[q]), mk[q], mean);
+        nvar += static_cast<double>(wf[q]) * static_cast<double>(t[q]);
+        sum_y += static_cast<double>(wf[q]) * colsum[lane + 32 * q];
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
-        var += __shfl_xor_sync(0xffffffffu, var, o);
-        mean += __shfl_xor_sync(0xffffffffu, mean, o);
+        nvar += __shfl_xor_sync(0xffffffffu, nvar, o);
+        sum_y += __shfl_xor_sync(0xffffffffu, sum_y, o);
     }
     if (lane != 0 || !live) return;
+    const double mean = sum_y / fin.n;
+    double var = nvar / fin.n;
     if (var < 0.0) var = 0.0;
     const float invstd = rsqrtf(static_cast<float>(var) + fin.eps);
     const float meanf = static_cast<float>(mean);
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(256) k_predict_bn(const float* __restrict__ G,
         fin.rvar[c] = static_cast<float>((1.0 - fin.momentum) * fin.rvar[c] + fin.momentum * unb);
     }
     if (stats_out != nullptr) {
-        stats_out[c] = mean * fin.n;
+        stats_out[c] = sum_y;
         stats_out[fin.C + c] = (var + mean * mean) * fin.n;
     }
 }
@@ -1015,7 +1017,7 @@ struct FoldArgs {
     const float* Q;               // [Co][Ci]
     const __nv_bfloat16* W;       // [Co][Ci] bf16 forward weights
     const __nv_bfloat16* Wt;      // [Ci][Co] bf16 transposed weights
-    const float* G;               // [Ci][Ci]
+    const float* Gc;              // [Ci][Ci] centred Gram matrix of a_prev (k_gram_reduce)
     const double* s;              // [Ci]
     const double* sum_dz;         // [Co]
     const float4* bnp;            // [Co]
@@ -1028,23 +1030,14 @@ struct FoldArgs {
     __nv_bfloat16* Bw;            // [Ci][ld_bw]: columns [0, Co) = A_c W[c][j], columns [Co, Co + Ci) = S[i][j]
     int ld_bw;
     float* cst;                   // [Ci]
-    float* Gc;                    // [Ci][Ci] centred Gram matrix (written by k_fold_coef)
     double n;
     int Co, Ci;
 };
 
-// blocks [0, Co/8): per-channel coefficients (one warp per channel); the remaining blocks centre the Gram matrix
+// per-channel coefficients: one warp per channel
 __global__ void __launch_bounds__(256) k_fold_coef(const FoldArgs f) {
     pdl_launch_dependents();
     pdl_wait();
-    const int nco = (f.Co + 7) / 8;
-    if (static_cast<int>(blockIdx.x) >= nco) {
-        const int idx = (blockIdx.x - nco) * 256 + threadIdx.x;
-        if (idx >= f.Ci * f.Ci) return;
-        const int i = idx / f.Ci, j = idx - i * f.Ci;
-        f.Gc[idx] = static_cast<float>(static_cast<double>(f.G[idx]) - f.s[i] * f.s[j] / f.n);
-        return;
-    }
     const int lane = threadIdx.x & 31;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= f.Co) return;
@@ -1067,7 +1060,7 @@ __global__ void __launch_bounds__(256) k_fold_coef(const FoldArgs f) {
     f.dbeta[c] = static_cast<float>(s1);
     f.dbias[c] = 0.f;
 }
-__host__ __device__ inline int fold_coef_blocks(int Co, int Ci) { return (Co + 7) / 8 + (Ci * Ci + 255) / 256; }
+__host__ __device__ inline int fold_coef_blocks(int Co, int Ci) { return (Co + 7) / 8; }
 
 // out[j0 + lane] = sum_c scale(c) * W[c][j0 + lane] for one block of 256 threads: the 8 warps split the Co rows of W, lane = one
 // of 32 consecutive columns (coalesced row reads, scale(c) broadcast); the partial sums meet in shared memory.  The result is
@@ -1137,22 +1130,24 @@ __global__ void __launch_bounds__(256) k_fold_bwd(const FoldArgs f) {
 // ---------------------------------------------------------------------------------------------
 // seg_conv1 (Ci = 64 point features + the per-cloud term cb[b][c] of the pooled feature, pcs.py:117-123; Co = 512) with
 // predicted statistics and folded backward.  y[p][c] = W[c,:] a[p,:] + cb[b(p)][c]; per cloud b: s_b = sum a, G_b = a^T a.
-//   k_predict_bn_cloud : lin_b = W s_b, quad_b = W G_b W^T;  mean = sum_b (lin_b + N cb_b) / n,
-//                        n var = sum_b [ (quad_b - lin_b^2 / N) + N (lin_b / N + cb_b - mean)^2 ]   (centred: no cancellation
-//                        against the large per-cloud term).  One warp per channel, fp64.
+//   k_predict_bn_cloud : lin_b = W s_b, quad_b = W Gc_b W^T (Gc_b = G_b - s_b s_b^T / N, centred by k_gram_reduce);
+//                        mean = sum_b (lin_b + N cb_b) / n,  n var = sum_b [ quad_b + N (lin_b / N + cb_b - mean)^2 ]   (centred:
+//                        no cancellation against the large per-cloud term).
 //   k_fold6_coef       : sum dz*y = rowdot(Q, W) + sum_b cb_b S1_b  (S1_b = per-cloud sum of dz from the GEMM epilogue),
 //                        coefficients {A, Bc, D - Bc mean, D}, dgamma / dbeta / dbias, the per-cloud gradient of the pooled
 //                        branch dcb[b][c] = sum_{p in b} dy = A S1_b + Bc (lin_b + N cb_b - N mean) + N D, and gsum = sum_b G_b,
 //                        ssum = sum_b s_b.
-//   k_fold6_bwd        : dW[c][k] = A Q + Bc ((W gsum)[c][k] + sum_b cb_b[c] s_b[k] - mean_c ssum[k]) + D ssum[k];
+//   k_fold6_bwd        : dW[c][k] = A Q + Bc ((W gsum)[c][k] + sum_b (lin_b[c] / N + cb_b[c] - mean_c) s_b[k]) + D ssum[k]
+//                        (gsum = sum_b Gc_b, the centred per-cloud Gram matrices);
 //                        data-gradient weights wcat[j][Co0 + c] = A_c W[c][j], wcat[j][Co0 + Co + i] = S[i][j] = sum_c W[c][i]
 //                        Bc_c W[c][j]; per-cloud constant rows cst[b][j] = sum_c (Bc_c (cb_b[c] - mean_c) + D_c) W[c][j].
 // ---------------------------------------------------------------------------------------------
 struct Fold6Args {
     const float* Q;               // [Co][Ci]
     const __nv_bfloat16* W;       // [Co][Ci]
-    const float* G;               // [clouds][Ci][Ci]
+    const float* G;               // [clouds][Ci][Ci] centred per-cloud Gram matrices
     const double* s;              // [clouds][Ci]
+    const double* part;           // [clouds][Co][2] {lin = W s_b, quad} of k_predict_bn_cloud
     const float* cb;              // [clouds][Co]
     const float* S1;              // [clouds][Co] per-cloud sums of dz
     const float4* bnp;            // [Co]
@@ -1192,15 +1187,16 @@ __global__ void __launch_bounds__(256) k_predict_bn_cloud(const float* __restric
     __syncthreads();
     if (c < fin.C) {
         const float wf0 = __bfloat162float(W[static_cast<size_t>(c) * K + lane]), wf1 = __bfloat162float(W[static_cast<size_t>(c) * K + 32 + lane]);
-        double t0 = 0.0, t1 = 0.0;
+        float t0 = 0.f, t1 = 0.f;
 #pragma unroll 8
         for (int j = 0; j < K; ++j) {
-            const double wj = static_cast<double>(__shfl_sync(0xffffffffu, j < 32 ? wf0 : wf1, j & 31));
-            t0 = fma(static_cast<double>(g_s[j][lane]), wj, t0);
-            t1 = fma(static_cast<double>(g_s[j][32 + lane]), wj, t1);
+            const float wj = __shfl_sync(0xffffffffu, j < 32 ? wf0 : wf1, j & 31);
+            t0 = fmaf(g_s[j][lane], wj, t0);
+            t1 = fmaf(g_s[j][32 + lane], wj, t1);
         }
         const double* sb = s + static_cast<size_t>(b) * K;
-        double quad = wf0 * t0 + wf1 * t1, lin = wf0 * sb[lane] + wf1 * sb[32 + lane];
+        // quad = w^T Gc_b w = N * (within-cloud variance of W a);  lin = w . s_b
+        double quad = static_cast<double>(wf0) * t0 + static_cast<double>(wf1) * t1, lin = wf0 * sb[lane] + wf1 * sb[32 + lane];
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             quad += __shfl_xor_sync(0xffffffffu, quad, o);
@@ -1225,7 +1221,7 @@ __global__ void __launch_bounds__(256) k_predict_bn_cloud(const float* __restric
     for (int bb = 0; bb < clouds; ++bb) {
         const double lin = __ldcg(part + (static_cast<size_t>(bb) * fin.C + cc) * 2), quad = __ldcg(part + (static_cast<size_t>(bb) * fin.C + cc) * 2 + 1);
         sum_y += lin + N * static_cast<double>(cb[static_cast<size_t>(bb) * fin.C + cc]);
-        within += quad - lin * lin / N;
+        within += quad;
     }
     const double mean = sum_y / fin.n;
     double between = 0.0;
@@ -1303,16 +1299,11 @@ __global__ void __launch_bounds__(256) k_fold6_coef(const Fold6Args f) {
     const double Bc = -A * static_cast<double>(bp.z) * dgamma / f.n;
     const double D = -A * s1 / f.n;
     // per-cloud gradient of the pooled branch: dcb[b][c] = A S1_b + Bc (lin_b + N cb_b - N mean) + N D
-    for (int b = 0; b < f.clouds; ++b) {
-        const double* sb = f.s + static_cast<size_t>(b) * K;
-        double lin = w0 * sb[lane] + w1 * sb[32 + lane];
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) lin += __shfl_xor_sync(0xffffffffu, lin, o);
-        if (lane == 0) {
-            const double cbv = f.cb[static_cast<size_t>(b) * f.Co + c];
-            f.dcb[static_cast<size_t>(b) * f.Co + c] =
-                static_cast<float>(A * f.S1[static_cast<size_t>(b) * f.Co + c] + Bc * (lin + f.N * (cbv - mean)) + f.N * D);
-        }
+    for (int b = lane; b < f.clouds; b += 32) {
+        const double lin = f.part[(static_cast<size_t>(b) * f.Co + c) * 2];                  // W[c,:] s_b (k_predict_bn_cloud)
+        const double cbv = f.cb[static_cast<size_t>(b) * f.Co + c];
+        f.dcb[static_cast<size_t>(b) * f.Co + c] =
+            static_cast<float>(A * f.S1[static_cast<size_t>(b) * f.Co + c] + Bc * (lin + f.N * (cbv - mean)) + f.N * D);
     }
     if (lane != 0) return;
     f.coef[c] = make_float4(static_cast<float>(A), static_cast<float>(Bc), static_cast<float>(D - Bc * mean), static_cast<float>(D));
@@ -1339,13 +1330,16 @@ __global__ void __launch_bounds__(256) k_fold6_bwd(const Fold6Args f) {
         float wg = 0.f;
 #pragma unroll 8
         for (int j = 0; j < Ci; ++j) wg = fmaf(__bfloat162float(w[j]), f.gsum[j * Ci + k], wg);
-        float cbs = 0.f;
-        for (int b = 0; b < f.clouds; ++b) cbs = fmaf(f.cb[static_cast<size_t>(b) * Co + c], static_cast<float>(f.s[static_cast<size_t>(b) * Ci + k]), cbs);
         const float4 cf = f.coef[c];
         const float4 bp = f.bnp[c];
         const float mean = -bp.w / bp.z;
+        float cbs = 0.f;                 // sum_b (mean of y over cloud b - mean) s_b[k]
+        for (int b = 0; b < f.clouds; ++b) {
+            const float mu = static_cast<float>(f.part[(static_cast<size_t>(b) * Co + c) * 2]) / f.N + f.cb[static_cast<size_t>(b) * Co + c] - mean;
+            cbs = fmaf(mu, static_cast<float>(f.s[static_cast<size_t>(b) * Ci + k]), cbs);
+        }
         const float sk = static_cast<float>(f.ssum[k]);
-        const float yca = wg + cbs - mean * sk;                                       // sum_p (y - mean)[p][c] a[p][k]
+        const float yca = wg + cbs;                                                   // sum_p (y - mean)[p][c] a[p][k]
         f.dW[static_cast<size_t>(c) * f.ld_dw + k] = fmaf(cf.x, f.Q[idx], fmaf(cf.y, yca, cf.w * sk));
         return;
     }

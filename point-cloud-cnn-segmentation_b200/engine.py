@@ -271,7 +271,8 @@ def profile_read(engine, B, N, train=True):
 # tags >= 80: CUDA-core kernels of the training step (event-timed while profiling; several launches per step share a tag)
 KERNEL_TAGS = {80: "k_gram_reduce", 81: "k_predict_bn", 82: "k_fold5_prep", 83: "k_pool_claim", 84: "k_pool_rows", 85: "k_gram_center",
                86: "k_fold_coef", 87: "k_fold_bwd", 88: "k_convert_multi", 89: "k_bn_relu (all layers)", 90: "k_bn_bwd_apply (all layers)",
-               91: "k_head_fwd", 92: "k_head_bwd", 93: "memsets of the folded global_feat backward"}
+               91: "k_head_fwd", 92: "k_head_bwd", 93: "memsets of the folded global_feat backward",
+               94: "k_peer_allreduce (NVLink peer-memory gradient all-reduce, incl. waiting for the slowest rank)"}
 
 
 def launch_count():

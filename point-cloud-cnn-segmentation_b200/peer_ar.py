@@ -28,7 +28,7 @@ class PeerAllReduce:
         n = (arena.numel() + 3) // 4 * 4
         if arena.untyped_storage().nbytes() < arena.storage_offset() * 4 + n * 4:
             raise ValueError("gradient arena storage is not padded to a multiple of 4 floats")
-        self.signals = torch.zeros(int(lib.pcseg_peer_ar_signal_bytes()) // 4 + 4, dtype=torch.int32, device=dev)
+        self.signals = torch.zeros(int(lib.pcseg_peer_ar_signal_bytes(n, self.world)) // 4 + 64, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
         self.keep = (arena, lw_in, lw_out)
         torch.cuda.synchronize(dev)

@@ -91,6 +91,8 @@ class FusedTrainer:
         # csrc/peer_allreduce.cuh); "nccl" = bucketed NCCL all-reduce between graph segments.  PCSEG_COMM overrides.
         self.comm = _os.environ.get("PCSEG_COMM", "peer") if self.distributed else "none"
         self.peer = None
+        self.peer_events = []
+        self._peer_skip = _os.environ.get("PCSEG_PEER_SKIP", "0") == "1"     # experiments only: no gradient exchange at all
         if self.comm == "peer":
             if self.world not in (2, 4, 8):
                 self.comm = "nccl"
@@ -142,7 +144,16 @@ class FusedTrainer:
         arena + {loss numerator, sum w}), Adam dividing by the global sum of class weights -- all on the compute stream"""
         self._seg_forward(x, labels)
         self._seg_backward(x, labels, 0)
-        self.peer.run()
+        if self.profiling:                       # (eager, event-timed pass of the bench: time the exchange kernel as well)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.peer.run()
+            e1.record()
+            self.peer_events.append((e0, e1))
+        elif not self._peer_skip:
+            self.peer.run()
+        else:
+            self.lw_global.copy_(self.lw)
         f = self.flat
         self.engine.adam(f["params"], f["grads"], self.exp_avg, self.exp_avg_sq, 1, self.lr, self.betas, self.eps, self.weight_decay,
                          state=self.state, grad_div=self.lw_global[1:2])

@@ -118,7 +118,9 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
             # ---- seg_conv1 with predicted statistics: per-cloud Gram matrices / column sums of point_feat, per-cloud term cb
             cb = T("cb")
             a1c = act[1].reshape(B, N, 64)
-            _close_red(T("gram6").reshape(B, 64, 64), np.einsum("bnk,bnj->bkj", a1c, a1c), "per-cloud gram[seg_conv1]", rel=1e-5)
+            s1c = a1c.sum(1)
+            _close_red(T("gram6").reshape(B, 64, 64), np.einsum("bnk,bnj->bkj", a1c, a1c) - np.einsum("bk,bj->bkj", s1c, s1c) / N,
+                       "centred per-cloud gram[seg_conv1]", rel=1e-5)
             _close_red(T("colsum6"), a1c.sum(1), "per-cloud colsum[seg_conv1]", rel=1e-5)
             yref = lw.conv_pre_bn(act[1], W["seg_conv1"][:, :64], cloud_bias=cb, pts_per_cloud=N)
             st = lw.bn_batch_stats(yref)
@@ -147,8 +149,9 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
             # ---- Gram-predicted statistics (pcs.py:110): G and s of the input activation, {sum y, sum y^2} predicted from
             # them, BN + ReLU applied straight to the fp32 accumulators; y itself is never stored
             Ci = act[i - 1].shape[1]
-            _close_red(T("gram", i), act[i - 1].T @ act[i - 1], f"gram[{CONVS[i]}]", rel=1e-5)
-            _close_red(T("colsum", i)[0], act[i - 1].sum(0), f"colsum[{CONVS[i]}]", rel=1e-5)
+            s_in = act[i - 1].sum(0)
+            _close_red(T("gram", i), act[i - 1].T @ act[i - 1] - np.outer(s_in, s_in) / P, f"centred gram[{CONVS[i]}]", rel=1e-5)
+            _close_red(T("colsum", i)[0], s_in, f"colsum[{CONVS[i]}]", rel=1e-5)
             yref = lw.conv_pre_bn(act[i - 1], W[CONVS[i]])                                  # fp64, bf16 weights
             st = lw.bn_batch_stats(yref)
             _close_red(T("stats_f", i), st, f"predicted stats_f[{BNS[i]}]", rel=1e-4)
@@ -363,7 +366,8 @@ def test_every_training_kernel_against_its_own_inputs(B, N, C, p_drop, folded, m
         Q = T("qraw", i)
         _close_red(Q, dz[i].T @ act[prev], f"Q[{CONVS[i]}]", rel=3e-4)
         Wb = lw.bf16_round(W[CONVS[i]])
-        s, G = T("colsum", i)[0], T("gram", i)
+        s = T("colsum", i)[0]
+        G = T("gram", i) + np.outer(s, s) / P            # the kernels keep the CENTRED Gram matrix
         gamma = sd[f"{BNS[i]}.weight"].astype(np.float64)
         mean, invstd = -bnp[i][:, 3] / bnp[i][:, 2], bnp[i][:, 2]
         fr = fb.folded_layer_backward(Wb, np.zeros(Wb.shape[0]), s, G, P, gamma, mean, invstd, Q, sb[0])

@@ -156,7 +156,7 @@ def test_torch_cpu_port_matches_reference(path):
         # (fp32 accumulation order differs between the port's point-major GEMMs and the reference's Conv1d: digests of the
         #  mathematically-zero conv biases ahead of a BatchNorm are compared on an absolute scale)
         if name.endswith(".bias") and name.split(".")[0] in orc.CONV_NAMES[:-1]:
-            assert np.abs(g).max() < 1e-4 and np.abs(dig[2:]).max() < 1e-4, name      # zero up to fp32 summation noise
+            assert np.abs(g).max() < 1e-3 and np.abs(dig[2:]).max() < 1e-3, name      # zero up to fp32 summation noise (depends on the thread count)
             checked += 1
             continue
         scale = max(np.abs(dig[1]) / max(g.size, 1), 1e-7)
