@@ -709,12 +709,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                             for (int j = 0; j < CW / 8; ++j) {
                                 const unsigned long long e0 = static_cast<unsigned long long>(grow) * p.N + c0 + 8 * j;
-                                const uint32_t keep = dropout_keep8(seed_eff, e0 >> 3, p.drop_thr16);
+                                const uint4 rb = dropout_bits8_fast(seed_eff, e0 >> 3);
+                                const uint32_t rs[4] = {rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     const int i = 8 * j + e;
+                                    const uint32_t u16 = (e & 1) ? (rs[e >> 1] >> 16) : (rs[e >> 1] & 0xFFFFu);
                                     const float t = fmaxf(fmaf(scs[i], __uint_as_float(v[i]), scs[BN + i]), 0.f) * p.keep_scale;
-                                    v[i] = __float_as_uint(((keep >> e) & 1u) ? t : 0.f);
+                                    v[i] = __float_as_uint(u16 >= p.drop_thr16 ? t : 0.f);
                                 }
                             }
 #pragma unroll

@@ -1248,6 +1248,7 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
         f.rvar = bnbuf + L.bn_off[i][1];
         f.bnp = c->bnp[i];
         f.n = static_cast<double>(rag ? static_cast<long long>(c->B) * c->rag_N : c->P);
+        f.inv_n = 1.0 / f.n;
         f.eps = BN_EPS;
         f.momentum = BN_MOMENTUM;
         f.C = cv[i].cout;
@@ -1473,6 +1474,7 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         b.dgamma = grads + L.off[20 + 2 * i];
         b.dbeta = grads + L.off[21 + 2 * i];
         b.n = static_cast<double>(rag ? static_cast<long long>(c->B) * c->rag_N : c->P);
+        b.inv_n = 1.0 / b.n;
         b.C = cv[i].cout;
         return b;
     };

@@ -67,9 +67,9 @@ __device__ __forceinline__ void peer_barrier(const PeerArArgs& a, int which, uin
             for (int p = 0; p < a.world; ++p) st_release_sys(&a.sig[p]->flag[which][a.rank][0], epoch);
             for (int p = 0; p < a.world; ++p) {
                 const uint32_t* f = &a.sig[a.rank]->flag[which][p][0];
-                unsigned long long spins = 0;
+                const long long t0 = clock64();
                 while (ld_acquire_sys(f) != epoch) {
-                    if (++spins > (1ull << 31)) {            // ~ tens of seconds: a peer died or never launched; abort instead of hanging
+                    if (clock64() - t0 > 20000000000LL) {    // ~10 s of SM clocks: a peer died or never launched; abort instead of hanging
                         printf("pcseg peer all-reduce: rank %d timed out waiting for rank %d (barrier %d, epoch %u)\n", a.rank, p, which, epoch);
                         __trap();
                     }

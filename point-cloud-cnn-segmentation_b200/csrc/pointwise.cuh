@@ -185,12 +185,14 @@ struct BnFinalizeArgs {
     float* rvar;
     float4* bnp;              // [C] output copy for later kernels
     double n;
+    double inv_n;             // 1 / n, computed on the host: CUDA-core fp64 (a division above all) is slow on this part and every
+                              // consumer thread evaluates bn_from_stats
     float eps, momentum;
     int C;
 };
 __device__ __forceinline__ float4 bn_from_stats(const BnFinalizeArgs& f, int c) {
     // only the cancellation-prone part (E[y^2] - mean^2) is done in fp64: this runs in every consumer thread
-    const double inv_n = 1.0 / f.n;              // uniform, hoisted by the compiler
+    const double inv_n = f.inv_n;
     const double mean = f.stats[c] * inv_n;
     double var = fma(-mean, mean, f.stats[f.C + c] * inv_n);
     if (var < 0.0) var = 0.0;
@@ -897,10 +899,11 @@ struct BnBwdArgs {
     float* dgamma;            // parameter gradients written by block (0, 0)
     float* dbeta;
     double n;
+    double inv_n;             // 1 / n (host)
     int C;
 };
 __device__ __forceinline__ float4 bn_bwd_coef(const BnBwdArgs& f, int c) {
-    const double inv_n = 1.0 / f.n;
+    const double inv_n = f.inv_n;
     const float c1 = static_cast<float>(f.stats[c] * inv_n), c2 = static_cast<float>(f.stats[f.C + c] * inv_n);
     const float4 bp = f.bnp[c];
     return make_float4(bp.x, -bp.x * c2 * bp.z, -bp.x * fmaf(c2, bp.w, c1), 0.f);

@@ -321,3 +321,45 @@ def test_predict_stream_matches_predict():
     t = ps.submit(x, lengths=[1500, 400])
     with torch.no_grad():
         assert torch.equal(ps.result(t), m.predict(x.cuda())[1].cpu())
+
+
+def test_optimizer_state_has_the_torch_adam_layout_and_resumes():
+    """FusedTrainer.checkpoint_dict writes what the reference saves at pcs.py:373-382: `optimizer_state_dict` must load into
+    torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4) (pcs.py:217), and load_optimizer_state must resume a
+    run exactly where it stopped (moments, step count, hyper-parameters)."""
+    import pcseg_b200
+    C, B, N = 3, 4, 256
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.random((B, N, 4), dtype=np.float32)).cuda()
+    labels = torch.from_numpy(rng.integers(0, C, (B, N)).astype(np.int64)).cuda()
+    m = _model(C, 13, train=True)
+    m.dropout.p = 0.0
+    tr = pcseg_b200.FusedTrainer(m, class_weights=torch.ones(C), lr=2e-3, weight_decay=1e-4, use_cuda_graph=False)
+    for _ in range(3):
+        tr.step(x, labels)
+    ckpt = tr.checkpoint_dict(epoch=7, train_loss=0.5, val_loss=0.6, f1_class2=0.1, f1_per_class=[0.1, 0.2, 0.3])
+    assert set(ckpt) >= {"epoch", "model_state_dict", "optimizer_state_dict", "train_loss", "val_loss", "f1_class2", "f1_per_class", "num_classes"}
+    osd = ckpt["optimizer_state_dict"]
+    # (1) the reference's optimizer accepts it
+    ref_model = pcseg_b200.PointNetSegmentation(C).cuda()
+    ref_model.load_state_dict(ckpt["model_state_dict"], strict=True)
+    opt = torch.optim.Adam(ref_model.parameters(), lr=0.001, weight_decay=1e-4)
+    opt.load_state_dict(osd)
+    st = opt.state_dict()
+    assert len(st["state"]) == 38 and st["param_groups"][0]["lr"] == 2e-3
+    assert float(st["state"][0]["step"]) == 3.0
+    p0 = next(iter(ref_model.parameters()))
+    assert torch.equal(opt.state[p0]["exp_avg"].cpu(), osd["state"][0]["exp_avg"].cpu())
+    # (2) a fresh trainer resumed from the checkpoint takes the same next step as the original one
+    m2 = _model(C, 13, train=True)
+    m2.dropout.p = 0.0
+    m2.load_state_dict(ckpt["model_state_dict"], strict=True)
+    tr2 = pcseg_b200.FusedTrainer(m2, class_weights=torch.ones(C), use_cuda_graph=False)
+    tr2.load_optimizer_state(osd)
+    assert tr2.step_count == 3 and tr2.lr == 2e-3
+    a = tr.step(x, labels)["loss"].item()
+    b = tr2.step(x, labels)["loss"].item()
+    assert abs(a - b) < 1e-4 * abs(a)
+    # (Adam normalises every element's step to ~lr: compare the parameters with an lr-sized tolerance)
+    assert (tr.flat["params"] - tr2.flat["params"]).abs().max().item() < 2.5 * 2e-3
+    assert int(tr2.state.view(torch.int64)[1].item()) == 4
