@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpcseg_b200.so")
+LIB_PATH = os.path.join(HERE, "lib", "libpcseg_b200%s.so" % os.environ.get("PCSEG_LIB_SUFFIX", ""))   # (suffix: A/B builds)
 
 EXPORTS = [
     "pcseg_last_error", "pcseg_version", "pcseg_create", "pcseg_destroy", "pcseg_param_count", "pcseg_param_offset",

@@ -11,6 +11,16 @@
 //                 column-mapped over that tile (a warp owns 8 columns, per-column parameters in registers) and does the
 //                 masking and the column reductions into per-CTA shared-memory accumulators (n_tile is fixed per CTA).
 //
+//   XF kernels only (forward GEMMs of the training step whose input still needs its train-mode BatchNorm):
+//   warps 12..15: transform stage between TMA and MMA: the landed A tile holds PRE-BatchNorm values y of the layer below;
+//                 these warps turn the batch sums of that layer into scale / shift once per CTA (CTA 0 also publishes them and
+//                 the running statistics), then rewrite every A tile in place as a = relu(scale*y + shift) (* dropout), fence
+//                 the async proxy and release the tile to the MMA warp (xf_bar).  The activation tensor is still needed by
+//                 the backward pass, so
+//   warp 3      : TMA-stores every transformed A tile to the activation tensor (tmA2) and only then lets the producer
+//                 refill the stage (empty_bar counts the MMA commit AND this warp).
+//                 The separate BN-apply kernel (one read of y, one write of a, one launch) disappears.
+//
 // Operand layouts:
 //   MN == false : A is [M x K] row-major (K contiguous), B is [N x K] row-major  (forward, dgrad)
 //   MN == true  : A is [K x M] row-major (M contiguous), B is [K x N] row-major  (wgrad: K = points)
@@ -46,6 +56,7 @@
 // cloud of a tile up in tile_cloud[].  Either way the lookup happens once per tile, outside the column loop.
 #pragma once
 #include "ptx.cuh"
+#include "bn.cuh"
 
 namespace pcseg {
 
@@ -56,7 +67,10 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 // Epilogue warps per kernel variant: 8 everywhere except the train-mode global_feat forward (stats + fused max-pool), whose
 // epilogue is the longest and measurably profits from 16 (282 vs 296 us); 16 everywhere was slower overall.
-constexpr int epi_warps_for(int epi) { return epi == 6 /* EPI_STATS_POOL */ ? 16 : 8; }
+#ifndef PCSEG_DGRAD_ACT_WARPS
+#define PCSEG_DGRAD_ACT_WARPS 8
+#endif
+constexpr int epi_warps_for(int epi) { return epi == 6 /* EPI_STATS_POOL */ ? 16 : epi == 8 /* EPI_DGRAD_ACT */ ? PCSEG_DGRAD_ACT_WARPS : 8; }
 constexpr int MAX_CLASSES = 8;    // compile-time cap on num_classes for the fused head kernels
 
 struct GemmParams {
@@ -106,23 +120,44 @@ struct GemmParams {
     float* logits;               // [M][C]
     const float* gamma;          // [N] BN weight: its sign picks max / min for the fused train-mode max-pool
     unsigned long long* pool_keys;   // [clouds][N] packed (orderable value << 32 | ~row) arg-extremum keys
+    // XF kernels (transform stage, see gemm_kernel): tmA is the PRE-BatchNorm tensor y of the layer below, tmA2 its activation
+    // tensor (written by the kernel); xf_fin = that layer's BatchNorm (batch sums -> scale / shift, running statistics)
+    BnFinalizeArgs xf_fin;
+    unsigned long long xf_seed;  // dropout of the activation (effective seed = xf_seed + *seed_ptr), xf_thr16 == 0: none
+    unsigned int xf_thr16;
+    float xf_keep_scale;
+    double* xf_colsum;           // [clouds][64] per-cloud column sums of the stored activation (K == 64 only), or nullptr
 };
 
-template <int BN, int EPI, bool MN>
+template <int BN, int EPI, bool MN, bool XF = false>
 struct GemmCfg {
     static constexpr int EPI_WARPS = epi_warps_for(EPI);
     static constexpr int EPI_THREADS = EPI_WARPS * 32;
-    static constexpr int THREADS = 128 + EPI_THREADS;
+#ifndef PCSEG_XF_WARPS
+#define PCSEG_XF_WARPS 4
+#endif
+    static constexpr int XF_WARPS = XF ? PCSEG_XF_WARPS : 0;      // transform warps behind the epilogue warps (4 or 8)
+    static constexpr int XF_THREADS = XF_WARPS * 32;
+    static constexpr int THREADS = 128 + EPI_THREADS + XF_THREADS;
+    static_assert(!XF || (EPI == EPI_STATS && !MN && BN <= 256), "transform stage: K-major EPI_STATS kernels only");
     static constexpr int STAGE_A = GEMM_BM * GEMM_BK * 2;
     static constexpr int STAGE_B = BN * GEMM_BK * 2;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD ||
                                      EPI == EPI_BN_RELU || EPI == EPI_DGRAD_ACT || EPI == EPI_BIAS_RELU_X3 || EPI == EPI_BN_RELU_DROP);
     static constexpr bool HAS_Y = (EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
-    static constexpr int OUT_BYTES = HAS_OUT ? 2 * 16384 : 0;
+    // EPI_STATS_POOL (K = 1024, the mainloop is bound by the bytes it can keep in flight): ONE staging tile instead of two
+    // buys a 4th 48 KB pipeline stage; the price is a second barrier per 64-column sub-tile
+#ifndef PCSEG_POOL_SINGLE_STAGING
+#define PCSEG_POOL_SINGLE_STAGING 1
+#endif
+    static constexpr bool SINGLE_OUT = (EPI == EPI_STATS_POOL) && PCSEG_POOL_SINGLE_STAGING != 0;
+    static constexpr int OUT_BYTES = HAS_OUT ? (SINGLE_OUT ? 16384 : 2 * 16384) : 0;
     static constexpr int Y_BYTES = HAS_Y ? 2 * 16384 : 0;
     static constexpr int COMB_BYTES = (EPI == EPI_LOGITS) ? (epi_warps_for(EPI) / 4 - 1) * 128 * MAX_CLASSES * 4 + 1024
-                                                             : 4096;   // column accumulators / colmax exchange / logits partials
+                                      : (EPI == EPI_STATS_POOL) ? 4096 + BN * 4 + (epi_warps_for(EPI) / 8) * BN * 8   // + sign-flip word per
+                                                                  // column + per-CTA arg-extremum keys [row group][column]
+                                                                : 4096;   // column accumulators / colmax exchange / logits partials
     static constexpr int W4_BYTES = (EPI == EPI_LOGITS) ? (MAX_CLASSES * 128 + MAX_CLASSES) * 4 : 0;
     static constexpr int BAR_BYTES = 256;
     static constexpr int FIXED = OUT_BYTES + Y_BYTES + COMB_BYTES + W4_BYTES + BAR_BYTES;
@@ -198,6 +233,25 @@ __device__ __forceinline__ void dgrad_pass2_rows(uint32_t tile_s, uint32_t ytile
     }
 }
 
+// Train-mode max-pool keys of one row x 8 columns of a tile that straddles two clouds (rows per cloud not a multiple of
+// 128; rare): one atomicMax per element.  xw = 8 bf16 values of the row, flip_s = shared-memory address of the 8 sign-flip
+// words of the columns.  (Scalar arguments only: arrays by reference would force the caller's registers to local memory.)
+__device__ __noinline__ void pool_keys_straddle(uint4 xw, uint32_t flip_s, int gr, int pts_per_cloud,
+                                                unsigned long long* keys_col, int ncols) {
+    const int cl = gr / pts_per_cloud;
+    const uint32_t rlow = 0xFFFFFFFFu - static_cast<uint32_t>(gr - cl * pts_per_cloud);
+    const uint32_t xs[4] = {xw.x, xw.y, xw.z, xw.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t bits = (e & 1) ? (xs[e >> 1] & 0xFFFF0000u) : (xs[e >> 1] << 16);
+        uint32_t fl;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(fl) : "r"(flip_s + 4u * e));
+        const uint32_t bb = bits ^ fl;
+        const uint32_t ord = (bb & 0x80000000u) ? ~bb : (bb | 0x80000000u);
+        atomicMax(keys_col + static_cast<size_t>(cl) * ncols + e, (static_cast<unsigned long long>(ord) << 32) | rlow);
+    }
+}
+
 // DGRAD_ACT epilogue, pass 2: the mask is (stored activation > 0); accumulates s1 = sum dz, s2 = sum activation.
 template <int RPT>
 __device__ __forceinline__ void dgrad_act_pass2_rows(uint32_t tile_s, uint32_t atile, int rbase, int chunk, float (&s1)[8],
@@ -223,12 +277,12 @@ __device__ __forceinline__ void dgrad_act_pass2_rows(uint32_t tile_s, uint32_t a
     }
 }
 
-template <int BN, int EPI, bool MN>
-__global__ void __launch_bounds__(GemmCfg<BN, EPI, MN>::THREADS, 1)
+template <int BN, int EPI, bool MN, bool XF = false>
+__global__ void __launch_bounds__(GemmCfg<BN, EPI, MN, XF>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmY,
             const GemmParams p) {
-    using Cfg = GemmCfg<BN, EPI, MN>;
+    using Cfg = GemmCfg<BN, EPI, MN, XF>;
     constexpr int EPI_WARPS = Cfg::EPI_WARPS;
     constexpr int EPI_THREADS = Cfg::EPI_THREADS;
     constexpr int GEMM_THREADS = Cfg::THREADS;
@@ -249,7 +303,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
     uint64_t* y_full = tmem_empty + 2;          // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(y_full + 2);
+    uint64_t* xf_bar = y_full + 2;              // [STAGES] (XF only): A tile transformed
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(xf_bar + (XF ? STAGES : 0));
+    static_assert((2 * STAGES + 6 + (XF ? STAGES : 0)) * 8 + 4 <= Cfg::BAR_BYTES, "barrier block too small");
 
     const int warp_idx = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
@@ -266,7 +322,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp_idx == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], XF ? 2 : 1);      // XF: MMA commit + the warp that stores the transformed tile
+            if (XF) mbar_init(&xf_bar[i], Cfg::XF_WARPS);          // one arrival per transform warp
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -361,6 +418,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp_idx == 1) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+#ifdef PCSEG_PROF_WAIT
+        // diagnostic build: where does the MMA warp wait -- for operands (full_bar) or for a free accumulator (tmem_empty)?
+        long long prof_wait_acc = 0, prof_wait_full = 0;
+        const long long prof_t0 = clock64();
+#endif
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
@@ -371,11 +433,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             kb_range(split, kb0, kb1);
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
+#ifdef PCSEG_PROF_WAIT
+            const long long w0 = clock64();
+#endif
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+#ifdef PCSEG_PROF_WAIT
+            prof_wait_acc += clock64() - w0;
+#endif
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+#ifdef PCSEG_PROF_WAIT
+                const long long w1 = clock64();
+#endif
+                mbar_wait(XF ? &xf_bar[stage] : &full_bar[stage], phase);
+#ifdef PCSEG_PROF_WAIT
+                prof_wait_full += clock64() - w1;
+#endif
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE);
@@ -401,7 +475,142 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (kb1 <= kb0 && lane == 0) umma_commit(&tmem_full[acc]);   // empty split: still release the epilogue
             __syncwarp();
         }
-    } else if (warp_idx >= 4) {
+#ifdef PCSEG_PROF_WAIT
+        if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && p.K >= 1024)
+            printf("PROF gemm<%d,%d,%d> cta %d tiles %d: total %lld cyc, wait accumulator %lld, wait operands %lld\n", BN, EPI, (int)MN,
+                   blockIdx.x, iter, clock64() - prof_t0, prof_wait_acc, prof_wait_full);
+#endif
+    } else if (XF && warp_idx == 3) {
+        // ------------------------------------------------------------ activation store (XF): transformed A tiles -> tmA2
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int m_tile, n_tile, split;
+                tile_coords(tile, m_tile, n_tile, split);
+                int kb0, kb1;
+                kb_range(split, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&xf_bar[stage], phase);
+                    if (n_tile == 0) {      // (every n-tile of a row block transforms the same values; one of them stores)
+                        tma_store_2d(&tmA2, stage_base + stage * Cfg::STAGE, kb * GEMM_BK, m_tile * GEMM_BM);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                    }
+                    mbar_arrive(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+            tma_store_wait_all<0>();
+        }
+    } else if (XF && warp_idx >= 4 + EPI_WARPS) {
+        // ------------------------------------------------------------ transform stage (XF): y tile -> relu(bn(y)) in place
+        // thread = (16-byte chunk = 8 channels, row slot): rows rsub + 16 i.  A warp touches 4 rows x 128 B per access:
+        // conflict-free under the 128-byte swizzle.
+        constexpr int XT = Cfg::XF_THREADS > 0 ? Cfg::XF_THREADS : 128;
+        constexpr int RSTEP = XT / 8, RPX = 128 / RSTEP;      // row step / rows per thread and k-block
+        const int xt = threadIdx.x - (128 + Cfg::EPI_THREADS);      // 0..XF_THREADS-1
+        const uint32_t tab_s = smem_u32(comb) + 2048;               // floats [0,256) scale, [256,512) shift
+        float* tabf = comb + 512;
+        for (int c = xt; c < p.K; c += XT) {
+            const float4 bp = bn_from_stats(p.xf_fin, c);
+            tabf[c] = bp.x;
+            tabf[256 + c] = bp.y;
+        }
+        if (p.xf_colsum != nullptr && xt < 64) tabf[128 + xt] = 0.f;
+        named_bar_sync(4, XT);
+        const int chunk = xt & 7, rsub = xt >> 3;          // rows rsub + RSTEP * i
+        const unsigned long long xseed = p.xf_seed + (p.seed_ptr != nullptr ? *p.seed_ptr : 0ull);
+        float csum[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) csum[e] = 0.f;
+        int cur_cl = -1;
+        auto flush_colsum = [&](int cl) {     // per-cloud column sums of the stored activation (k_predict_bn_cloud's `s`)
+            // lanes sharing a chunk -> shared-memory accumulators (K == 64: floats [128,192) of the table are free) -> one fp64
+            // atomic per column and CTA.  (Measured: fp64 atomics straight from the lanes cost 20 us more per launch.)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                csum[e] += __shfl_xor_sync(0xffffffffu, csum[e], 8);
+                csum[e] += __shfl_xor_sync(0xffffffffu, csum[e], 16);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(tabf + 128 + chunk * 8 + e, csum[e]);
+            }
+            named_bar_sync(4, XT);
+            if (xt < 64) {
+                atomicAdd(p.xf_colsum + static_cast<size_t>(cl) * 64 + xt, static_cast<double>(tabf[128 + xt]));
+                tabf[128 + xt] = 0.f;
+            }
+            named_bar_sync(4, XT);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) csum[e] = 0.f;
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int m_tile, n_tile, split;
+            tile_coords(tile, m_tile, n_tile, split);
+            int kb0, kb1;
+            kb_range(split, kb0, kb1);
+            const int m0 = m_tile * GEMM_BM;
+            if (p.xf_colsum != nullptr) {
+                const int cl = p.pts_per_cloud > 0 ? m0 / p.pts_per_cloud : 0;     // (tiles do not straddle clouds: host check)
+                if (cl != cur_cl) {
+                    if (cur_cl >= 0) flush_colsum(cur_cl);
+                    cur_cl = cl;
+                }
+            }
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE);
+                const int col0 = kb * GEMM_BK + chunk * 8;
+                const uint4 sc0 = lds128(tab_s + 4u * col0), sc1 = lds128(tab_s + 4u * col0 + 16);
+                const uint4 sh0 = lds128(tab_s + 1024u + 4u * col0), sh1 = lds128(tab_s + 1024u + 4u * col0 + 16);
+                const float sc[8] = {__uint_as_float(sc0.x), __uint_as_float(sc0.y), __uint_as_float(sc0.z), __uint_as_float(sc0.w),
+                                     __uint_as_float(sc1.x), __uint_as_float(sc1.y), __uint_as_float(sc1.z), __uint_as_float(sc1.w)};
+                const float sh[8] = {__uint_as_float(sh0.x), __uint_as_float(sh0.y), __uint_as_float(sh0.z), __uint_as_float(sh0.w),
+                                     __uint_as_float(sh1.x), __uint_as_float(sh1.y), __uint_as_float(sh1.z), __uint_as_float(sh1.w)};
+                uint4 yw[RPX];
+#pragma unroll
+                for (int i = 0; i < RPX; ++i) {
+                    const int r = rsub + RSTEP * i;
+                    yw[i] = lds128(sa + r * 128 + ((chunk ^ (r & 7)) << 4));
+                }
+#pragma unroll
+                for (int i = 0; i < RPX; ++i) {
+                    const int r = rsub + RSTEP * i;
+                    const uint32_t ws[4] = {yw[i].x, yw[i].y, yw[i].z, yw[i].w};
+                    uint32_t keep = 0xFFu;
+                    if (p.xf_thr16 != 0u)
+                        keep = dropout_keep8(xseed, (static_cast<unsigned long long>(m0 + r) * p.K + col0) >> 3, p.xf_thr16);
+                    if (m0 + r >= p.M) keep = 0u;      // rows beyond M must stay exactly zero (statistics of the epilogue)
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float yv = (e & 1) ? bf16_hi(ws[e >> 1]) : bf16_lo(ws[e >> 1]);
+                        const float t = fmaf(sc[e], yv, sh[e]);
+                        o[e] = (t > 0.f && ((keep >> e) & 1u)) ? t * p.xf_keep_scale : 0.f;
+                    }
+                    const uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                    sts128(sa + r * 128 + ((chunk ^ (r & 7)) << 4), pk);
+                    if (p.xf_colsum != nullptr) {
+                        const uint32_t ps[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) csum[e] += (e & 1) ? bf16_hi(ps[e >> 1]) : bf16_lo(ps[e >> 1]);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xf_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        if (p.xf_colsum != nullptr && cur_cl >= 0) flush_colsum(cur_cl);
+        // later kernels (and the backward pass) read the published {scale, shift, invstd, -mean*invstd}; CTA 0 writes them
+        // and the running statistics AFTER its tiles so that its fp64 divisions are off the kernel's critical path
+        if (blockIdx.x == 0) bn_publish_by(p.xf_fin, xt, XT);
+    } else if (warp_idx >= 4 && warp_idx < 4 + EPI_WARPS) {
         // ------------------------------------------------------------ epilogue (EPI_WARPS warps)
         // Pass 1 is row-mapped: warp w may only read TMEM lanes 32*(w%4)..+31, so the NQ warps that share a lane
         // quadrant split every 64-column sub-tile into NQ column groups of CW columns.
@@ -441,10 +650,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         constexpr bool COLACC = (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
         constexpr bool IS_DGRAD = (EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT);
+#ifndef PCSEG_TMEM_PREFETCH
+#define PCSEG_TMEM_PREFETCH 1
+#endif
+        // (EPI_DGRAD keeps the simple order: its pass 2 is the register-hungriest and would spill with CW more live registers)
+        constexpr bool PREFETCH = PCSEG_TMEM_PREFETCH != 0 && SUBS > 1 &&
+                                  (EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_BIAS_RELU || EPI == EPI_DGRAD_ACT);
+        // (measured on cfg2: the whole step gains ~10 us with it; conv5 / seg_conv1 forward (EPI_BN_RELU[_DROP], HBM-write
+        //  bound, no second pass to hide the load behind) lose 2.5 us each, so they keep the simple order)
         if constexpr (COLACC) {
             // per-CTA column accumulators [NH][2][BN]: valid because every tile of this CTA has the same n_tile
             // (the host launches a grid that is a multiple of num_n_tiles)
             for (int i = et; i < NH * 2 * BN; i += EPI_THREADS) comb[i] = 0.f;
+            if constexpr (EPI == EPI_STATS_POOL) {
+                // sign of the BN weight per column of this CTA (n_tile is fixed per CTA): the train-mode max-pool takes the
+                // max of gamma >= 0 columns and the min of the others, i.e. the max after flipping the sign bit
+                const int n0_fixed = (blockIdx.x % p.num_n_tiles) * BN;
+                for (int i = et; i < BN; i += EPI_THREADS)
+                    reinterpret_cast<uint32_t*>(comb)[NH * 2 * BN + i] =
+                        (n0_fixed + i < p.N && __ldg(p.gamma + n0_fixed + i) >= 0.f) ? 0u : 0x80000000u;
+                for (int i = et; i < NH * BN * 2; i += EPI_THREADS) reinterpret_cast<uint32_t*>(comb)[NH * 2 * BN + BN + i] = 0u;
+            }
             named_bar_sync(1, EPI_THREADS);
         }
         if constexpr (EPI == EPI_BN_RELU || EPI == EPI_BN_RELU_DROP) {
@@ -478,6 +704,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         };
         (void)cur_cl;
         (void)flush_cloud;
+        // EPI_STATS_POOL: the arg-extremum keys of the CTA's tiles are merged in shared memory (pool_s: [NH][BN] 64-bit keys,
+        // 0 = empty) and go to global memory with ONE atomicMax per column whenever the CTA's tile sequence enters another
+        // cloud -- instead of one per column and sub-tile, whose outstanding atomics every later proxy fence had to wait for
+        const uint32_t pool_s = comb_s + 4u * (NH * 2 * BN + BN);
+        auto flush_pool = [&](int cl) {
+            named_bar_sync(1, EPI_THREADS);
+            const int n0f = (blockIdx.x % p.num_n_tiles) * BN;
+            for (int c = et; c < BN; c += EPI_THREADS) {
+                unsigned long long best = 0ull;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const unsigned long long k = lds_u64(pool_s + 8u * (h * BN + c));
+                    best = k > best ? k : best;
+                    sts_u64(pool_s + 8u * (h * BN + c), 0ull);
+                }
+                if (best != 0ull && n0f + c < p.N) atomicMax(p.pool_keys + static_cast<size_t>(cl) * p.N + n0f + c, best);
+            }
+            named_bar_sync(1, EPI_THREADS);
+        };
+        (void)pool_s;
+        (void)flush_pool;
 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             int m_tile, n_tile, split;
@@ -626,9 +873,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         cur_cl = tile_cl;
                     }
                 }
+                if constexpr (EPI == EPI_STATS_POOL) {
+                    if (uniform_cloud && tile_cl != cur_cl) {
+                        if (cur_cl >= 0) flush_pool(cur_cl);
+                        cur_cl = tile_cl;
+                    }
+                }
+                // Software pipelining of the TMEM reads (PREFETCH): the accumulator columns of sub-tile s + 1 are requested as
+                // soon as pass 1 of sub-tile s has consumed its registers, so that the tcgen05.ld latency hides behind the
+                // barrier and pass 2 instead of heading every sub-tile.
+                uint32_t v[CW];
 #pragma unroll 1
                 for (int sub = 0; sub < SUBS; ++sub, ++sub_it) {
-                    const int buf = sub_it & 1;
+                    const int buf = Cfg::SINGLE_OUT ? 0 : (sub_it & 1);
                     const int c0 = n0 + sub * 64 + cq * CW;       // first global column handled by this thread in pass 1
                     float* comb_b = comb + buf * (4 * 64);        // COLMAX only: [buf][row group][64]
                     if constexpr (Cfg::HAS_Y) mbar_wait(&y_full[buf], (sub_it >> 1) & 1);
@@ -639,9 +896,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         if (elected) tma_store_wait_read<0>();
                         named_bar_sync(3, EPI_THREADS);
                     }
-                    uint32_t v[CW];
-                    tmem_ld_cols<CW>(t_acc + sub * 64 + cq * CW, v);
-                    tmem_ld_wait();
+                    if (!PREFETCH || sub == 0) tmem_ld_cols<CW>(t_acc + sub * 64 + cq * CW, v);
+                    tmem_ld_wait_regs<CW>(v);
                     if (sub == SUBS - 1) {       // all TMEM reads of this accumulator (by this thread) are done
                         tc_fence_before();
                         mbar_arrive(&tmem_empty[acc]);
@@ -802,8 +1058,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < CW / 8; ++j)
                             sts128(orow + (((cq * (CW / 8) + j) ^ (row & 7)) << 4),
                                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]));
-                        fence_proxy_async_smem();
-                        if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
+                        if (EPI != EPI_STATS_POOL || p.store_out) fence_proxy_async_smem();   // (generic-proxy readers only otherwise)
+                        if constexpr (!Cfg::SINGLE_OUT) {
+                            if (elected) tma_store_wait_read<0>();     // stores issued before this iteration have drained
+                        }
+                    }
+                    if constexpr (PREFETCH) {
+                        if (sub + 1 < SUBS) tmem_ld_cols<CW>(t_acc + (sub + 1) * 64 + cq * CW, v);
                     }
                     // per-column parameters of pass 2 are fetched BEFORE the barrier so that their latency hides behind it
                     float p2a[8], p2b[8];
@@ -815,12 +1076,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             p2a[e] = bp.x;
                             p2b[e] = bp.y;
                         }
-                    } else if constexpr (EPI == EPI_STATS_POOL) {
-                        const int colbase_pre = n0 + sub * 64 + ((warp_idx - 4) & 7) * 8;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) p2a[e] = (__ldg(p.gamma + colbase_pre + e) >= 0.f) ? 1.f : -1.f;
                     }
                     named_bar_sync(1, EPI_THREADS);
+                    if constexpr (Cfg::SINGLE_OUT) {
+                        // single staging tile: pass 2 only reads it, so the store can go out now; it must have drained (and
+                        // every reader must be done) before pass 1 of the next sub-tile overwrites the tile
+                        if (elected && p.store_out) {
+                            tma_store_2d(&tmOut, out_stage, n0 + sub * 64, m0);
+                            tma_store_commit();
+                        }
+                    }
                     if constexpr (COLACC) {
                         // pass 2 (column-mapped): warp pw owns 16-byte chunk (pw & 7) = 8 columns of row group (pw >> 3);
                         // lane l handles rows rg*(128/NH) + l + 32 i; per-column parameters live in registers.
@@ -841,78 +1106,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 dgrad_pass2_rows<true, RPT>(tile_s, ytile, rbase, chunk, p2a, p2b, s1, s2, seed_eff, p.drop_thr16, m0, p.N, colbase);
                             else
                                 dgrad_pass2_rows<false, RPT>(tile_s, ytile, rbase, chunk, p2a, p2b, s1, s2, 0ull, 0u, m0, p.N, colbase);
-                        } else {
-                            float bestv[8];
-                            const float (&sg)[8] = p2a;
-                            int besti[8];
-                            if constexpr (EPI == EPI_STATS_POOL) {
+                        } else if constexpr (EPI == EPI_STATS_POOL) {
+                            // statistics as packed fp32 pairs (FADD2 / FFMA2); arg-extremum as ONE signed 32-bit key per
+                            // column: (order-preserving image of +-x, whose low 16 bits are free because x is a bf16) |
+                            // (0xFFFF - row in tile), so that an integer max keeps the first row among equal values
+                            const uint32_t fl_s = comb_s + 4u * (NH * 2 * BN + sub * 64 + chunk * 8);
+                            const uint4 f0 = lds128(fl_s), f1 = lds128(fl_s + 16);
+                            const uint32_t flip[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                            unsigned long long s1p[4], s2p[4];
+                            int kb[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    bestv[e] = -INFINITY;
-                                    besti[e] = 0;
-                                }
-                            }
+                            for (int j = 0; j < 4; ++j) s1p[j] = s2p[j] = 0ull;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) kb[e] = static_cast<int>(0x80000000u);
 #pragma unroll
                             for (int i = 0; i < RPT; ++i) {
                                 const int r = rbase + 32 * i;
                                 const uint4 xw = lds128(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4));
                                 const uint32_t xs[4] = {xw.x, xw.y, xw.z, xw.w};
                                 const bool row_ok = (m0 + r) < p.M;
+                                const uint32_t rc = 0xFFFFu - static_cast<uint32_t>(r);
+                                uint32_t bits[8];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    bits[2 * j] = xs[j] << 16;
+                                    bits[2 * j + 1] = xs[j] & 0xFFFF0000u;
+                                    const unsigned long long xp = pack_f32x2(__uint_as_float(bits[2 * j]), __uint_as_float(bits[2 * j + 1]));
+                                    s1p[j] = add_f32x2(s1p[j], xp);
+                                    s2p[j] = fma_f32x2(xp, xp, s2p[j]);
+                                }
+                                if (pool_uniform) {
+                                    if (row_ok) {
+#pragma unroll
+                                        for (int e = 0; e < 8; ++e) {
+                                            const uint32_t f = bits[e] ^ flip[e];
+                                            const uint32_t k = (f ^ (static_cast<uint32_t>(static_cast<int>(f) >> 31) & 0x7FFF0000u)) | rc;
+                                            kb[e] = max(kb[e], static_cast<int>(k));
+                                        }
+                                    }
+                                } else if (row_ok) {
+                                    pool_keys_straddle(xw, fl_s, m0 + r, p.pts_per_cloud, p.pool_keys + colbase, p.N);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                unpack_f32x2(s1p[j], s1[2 * j], s1[2 * j + 1]);
+                                unpack_f32x2(s2p[j], s2[2 * j], s2[2 * j + 1]);
+                            }
+                            if (pool_uniform) {
+                                // 8 keys x 32 lanes -> lanes with (lane & 3) == 0 hold the warp-wide max of one column
+#pragma unroll
+                                for (int offk = 16, cnt = 4; offk >= 4; offk >>= 1, cnt >>= 1) {
+                                    const bool up = (lane & offk) != 0;
+#pragma unroll
+                                    for (int e = 0; e < cnt; ++e) {
+                                        const int send = up ? kb[e] : kb[e + cnt];
+                                        const int keepk = up ? kb[e + cnt] : kb[e];
+                                        kb[e] = max(keepk, __shfl_xor_sync(0xffffffffu, send, offk));
+                                    }
+                                }
+                                kb[0] = max(kb[0], __shfl_xor_sync(0xffffffffu, kb[0], 2));
+                                kb[0] = max(kb[0], __shfl_xor_sync(0xffffffffu, kb[0], 1));
+                                if ((lane & 3) == 0 && kb[0] != static_cast<int>(0x80000000u)) {
+                                    const int colk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                                    const uint32_t kk = static_cast<uint32_t>(kb[0]);
+                                    const uint32_t sord = kk & 0xFFFF0000u;
+                                    const uint32_t rwin = 0xFFFFu - (kk & 0xFFFFu);
+                                    // back to the unsigned orderable form k_maxpool_finish decodes (float_orderable)
+                                    const uint32_t ord = (sord ^ 0x80000000u) | ((sord & 0x80000000u) ? 0xFFFFu : 0u);
+                                    const unsigned long long key = (static_cast<unsigned long long>(ord) << 32) |
+                                                                   (0xFFFFFFFFu - static_cast<uint32_t>(row0_in_cloud) - rwin);
+                                    // per-CTA running best of (row group, column): this lane is its only writer
+                                    const uint32_t ka = pool_s + 8u * (rg * BN + sub * 64 + chunk * 8 + colk);
+                                    if (key > lds_u64(ka)) sts_u64(ka, key);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < RPT; ++i) {
+                                const int r = rbase + 32 * i;
+                                const uint4 xw = lds128(tile_s + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                const uint32_t xs[4] = {xw.x, xw.y, xw.z, xw.w};
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     const float x = (e & 1) ? bf16_hi(xs[e >> 1]) : bf16_lo(xs[e >> 1]);
                                     s1[e] += x;
                                     s2[e] = fmaf(x, x, s2[e]);
-                                    if constexpr (EPI == EPI_STATS_POOL) {
-                                        const float sx = sg[e] * x;
-                                        if (pool_uniform) {
-                                            // rows are visited in increasing order: strict '>' keeps the first maximum
-                                            const bool better = row_ok && (sx > bestv[e]);
-                                            bestv[e] = better ? sx : bestv[e];
-                                            besti[e] = better ? r : besti[e];
-                                        } else if (row_ok) {
-                                            const int gr = m0 + r;
-                                            const uint32_t bb = __float_as_uint(sx);
-                                            const uint32_t ord = (bb & 0x80000000u) ? ~bb : (bb | 0x80000000u);
-                                            const unsigned long long key = (static_cast<unsigned long long>(ord) << 32) |
-                                                                           (0xFFFFFFFFu - static_cast<uint32_t>(gr % p.pts_per_cloud));
-                                            atomicMax(p.pool_keys + static_cast<size_t>(gr / p.pts_per_cloud) * p.N + colbase + e, key);
-                                        }
-                                    }
-                                }
-                            }
-                            if constexpr (EPI == EPI_STATS_POOL) {
-                                if (pool_uniform) {
-                                    unsigned long long best[8];
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) {
-                                        const uint32_t bb = __float_as_uint(bestv[e]);
-                                        const uint32_t ord = (bb & 0x80000000u) ? ~bb : (bb | 0x80000000u);
-                                        best[e] = (bestv[e] == -INFINITY) ? 0ull
-                                                  : ((static_cast<unsigned long long>(ord) << 32) |
-                                                     (0xFFFFFFFFu - static_cast<uint32_t>(row0_in_cloud + besti[e])));
-                                    }
-                                    // 8 keys x 32 lanes -> lanes with (lane & 3) == 0 hold the warp-wide max of one column
-#pragma unroll
-                                    for (int offk = 16, cnt = 4; offk >= 4; offk >>= 1, cnt >>= 1) {
-                                        const bool up = (lane & offk) != 0;
-#pragma unroll
-                                        for (int e = 0; e < cnt; ++e) {
-                                            const unsigned long long send = up ? best[e] : best[e + cnt];
-                                            const unsigned long long keepk = up ? best[e + cnt] : best[e];
-                                            const unsigned long long got = __shfl_xor_sync(0xffffffffu, send, offk);
-                                            best[e] = keepk > got ? keepk : got;
-                                        }
-                                    }
-#pragma unroll
-                                    for (int offk = 2; offk >= 1; offk >>= 1) {
-                                        const unsigned long long got = __shfl_xor_sync(0xffffffffu, best[0], offk);
-                                        best[0] = best[0] > got ? best[0] : got;
-                                    }
-                                    if ((lane & 3) == 0 && best[0] != 0ull) {
-                                        const int colk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                                        atomicMax(p.pool_keys + static_cast<size_t>(tile_cl) * p.N + colbase + colk, best[0]);
-                                    }
                                 }
                             }
                         }
@@ -948,6 +1227,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             fence_proxy_async_smem();
                             named_bar_sync(2, EPI_THREADS);     // staging tile was modified in place
                         }
+                        if constexpr (Cfg::SINGLE_OUT) {
+                            if (elected && p.store_out) tma_store_wait_read<0>();
+                            named_bar_sync(2, EPI_THREADS);
+                        }
                     }
                     if constexpr (EPI == EPI_BIAS_RELU_X3) {
                         if (elected) {
@@ -955,7 +1238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             tma_store_2d(&tmOut, out_stage + 16384, p.x3_lo_col + n0 + sub * 64, m0);
                             tma_store_commit();
                         }
-                    } else if constexpr (Cfg::HAS_OUT) {
+                    } else if constexpr (Cfg::HAS_OUT && !Cfg::SINGLE_OUT) {
                         if (elected) {
                             if (EPI != EPI_STATS_POOL || p.store_out) {
                                 tma_store_2d(&tmOut, out_stage + buf * 16384, n0 + sub * 64, m0);
@@ -977,6 +1260,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if constexpr (EPI == EPI_DGRAD_ACT) {
             if (p.cloud_sums != nullptr && cur_cl >= 0) flush_cloud(cur_cl);
+        }
+        if constexpr (EPI == EPI_STATS_POOL) {
+            if (cur_cl >= 0) flush_pool(cur_cl);
         }
         if constexpr (COLACC) {
             named_bar_sync(1, EPI_THREADS);

@@ -202,14 +202,15 @@ struct GemmOp {
     GemmParams p;
     int bn, epi;
     bool mn;
+    bool xf = false;       // transform-stage variant (tmA = pre-BN input, tmA2 = its activation tensor, written by the kernel)
     bool ready = false;
 };
 
-template <int BN, int EPI, bool MN>
+template <int BN, int EPI, bool MN, bool XF = false>
 int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
-    using Cfg = GemmCfg<BN, EPI, MN>;
+    using Cfg = GemmCfg<BN, EPI, MN, XF>;
     static unsigned long long attr_set_mask = 0;       // per device: the attribute is a per-device function property
-    auto kern = gemm_kernel<BN, EPI, MN>;
+    auto kern = gemm_kernel<BN, EPI, MN, XF>;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(attr_set_mask & (1ull << (dev & 63)))) {
@@ -226,6 +227,11 @@ int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
 
 int launch_gemm(const GemmOp& op, cudaStream_t s) {
     if (!op.ready) return fail("internal: GEMM op not initialised");
+    if (op.xf) {
+        if (op.bn == 64 && op.epi == EPI_STATS && !op.mn) return launch_gemm_t<64, EPI_STATS, false, true>(op, s);
+        if (op.bn == 128 && op.epi == EPI_STATS && !op.mn) return launch_gemm_t<128, EPI_STATS, false, true>(op, s);
+        return fail("internal: no transform-stage GEMM instantiation for BN=%d EPI=%d", op.bn, op.epi);
+    }
 #define CASE(BN_, EPI_, MN_) \
     if (op.bn == BN_ && op.epi == EPI_ && op.mn == MN_) return launch_gemm_t<BN_, EPI_, MN_>(op, s);
     CASE(64, EPI_BIAS_RELU, false) CASE(128, EPI_BIAS_RELU, false) CASE(256, EPI_BIAS_RELU, false)
@@ -383,6 +389,7 @@ struct pcseg_ctx {
         CUtensorMap hcA1;             // fused inference head (head_chain_kernel): point_feat operand
         HeadChainParams hcp;
         GemmOp fw[NUM_BN], dg[NUM_BN], wg_op[NUM_BN];   // training
+        GemmOp fwx[NUM_BN];           // training forward with the BN-apply of the layer below fused in (transform stage, XF)
     };
     OpSet ops[2];
     CUtensorMap hcB1, hcB2, hcB3;
@@ -435,6 +442,12 @@ struct pcseg_ctx {
     float* side5 = nullptr;       // [B*1024][1024] rows of dz5 diag(A) W5 (max-pool gradient rows)
     int* rowslot5 = nullptr;      // [cap_rows] side-buffer slot of every point (>= B*1024: none)
     bool store_y5 = false;        // PCSEG_STORE_Y5=1: keep writing global_feat's pre-BN output (tests)
+    bool xf_seg3 = false;         // PCSEG_XF_SEG3=1: seg_conv3 too (measured slower: 4 transform warps per SM generate the Philox
+                                  // dropout mask of 256 channels more slowly than k_bn_relu does with the whole machine)
+    bool xf = false;              // PCSEG_XF=1, dense training forward: conv2 / conv3 / conv4 apply the BatchNorm + ReLU of their input
+                                  // inside the GEMM (gemm_kernel XF) instead of a k_bn_relu launch.  OFF by default: measured on
+                                  // cfg2, the three GEMMs grow by 9 + 17 + 4 us (4 transform warps per SM in front of the MMA of a
+                                  // latency-bound 7-tiles-per-CTA kernel) while three 12-13 us launches disappear: 1.869 vs 1.867 ms
     GemmOp s5_op, t5_op;
     // folded seg_conv1 (index 6; needs N % 128 == 0 so that tiles never straddle clouds): per-cloud Gram matrices of a1
     bool fold6 = false;
@@ -657,6 +670,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
     c->eval_ready = false;
     c->rag_active = false;
     c->fold6 = false;
+    c->xf = false;
     for (int set = 0; set < 2; ++set) {
     pcseg_ctx::OpSet& O = c->ops[set];
     const bool rag = set == 1;
@@ -758,6 +772,25 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
             TRY(setup_gemm_kmajor(&O.fw[i], EPI_STATS, c->act[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
                                   c->y[i], cv[i].cout, nullptr, 0));
             O.fw[i].p.stats = c->stats_f + c->stat_off[i];
+        }
+        // ---- the same forward GEMMs reading the PRE-BatchNorm output of the layer below (transform stage): conv2, conv3, conv4,
+        //      seg_conv3.  (conv5 / seg_conv1 need their input activation earlier, for the Gram matrices; seg_conv2's input is
+        //      written by seg_conv1's epilogue.)  Tiles must not straddle clouds (per-cloud column sums of point_feat).
+        if (!rag) {
+            c->xf = (N % 128 == 0) && getenv("PCSEG_XF") && getenv("PCSEG_XF")[0] == '1';
+            c->xf_seg3 = getenv("PCSEG_XF_SEG3") && getenv("PCSEG_XF_SEG3")[0] == '1';
+            const int xl[4] = {1, 2, 3, 8};
+            for (int j = 0; j < 4; ++j) {
+                const int i = xl[j];
+                TRY(setup_gemm_kmajor(&O.fwx[i], EPI_STATS, c->y[i - 1], cv[i].cin, c->wk[i], cv[i].cin, P, cv[i].cout, cv[i].cin,
+                                      c->y[i], cv[i].cout, nullptr, 0));
+                TRY(make_tmap(&O.fwx[i].tmA2, c->act[i - 1], cv[i].cin, P, cv[i].cin, 64, 128));
+                O.fwx[i].p.stats = c->stats_f + c->stat_off[i];
+                O.fwx[i].p.pts_per_cloud = N;
+                O.fwx[i].p.xf_keep_scale = 1.f;
+                O.fwx[i].xf = true;
+                if (cv[i].cin > 256) return fail("internal: transform stage supports K <= 256");
+            }
         }
         // ---- backward data gradients: dz_{i-1} = (dy_i W_i) masked by layer i-1
         auto dgrad = [&](int i, const bf16* dyA, int lda, int K, const bf16* Bw, int prev) -> int {
@@ -1226,17 +1259,22 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
             }
         }
         jobs.count = nj;
+        // the accumulators of the forward pass are cleared by extra slices of the same launch
+        int nf = 0;
+        auto zero = [&](void* ptr, size_t bytes) { jobs.fill[nf++] = FillJob{ptr, bytes, 0u}; };
+        zero(c->stats_f, c->stat_total * sizeof(double));
+        zero(c->keys, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long));
+        if (ce) zero(ce, sizeof(pcseg_ce_accum));
+        if (c->folded && !rag) zero(c->colsum[4], 128 * sizeof(double));
+        if (c->folded && !rag && c->fold6) zero(c->colsum[6], static_cast<size_t>(c->B) * 64 * sizeof(double));
+        jobs.fill_count = nf;
         StampScope ts(c, 88, s);
-        pdl_launch(k_convert_multi, dim3(256, nj), 256, 0, s, jobs);
+        pdl_launch(k_convert_multi, dim3(256, nj + nf), 256, 0, s, jobs);
         LAUNCH_OK("k_convert_multi");
     }
-    CUDA_OK(cudaMemsetAsync(c->stats_f, 0, c->stat_total * sizeof(double), s));
-    CUDA_OK(cudaMemsetAsync(c->keys, 0, static_cast<size_t>(c->B) * 1024 * sizeof(unsigned long long), s));
-    if (ce) CUDA_OK(cudaMemsetAsync(ce, 0, sizeof(pcseg_ce_accum), s));
     const bool folded = c->folded && !rag;
     const bool fold6 = folded && c->fold6;
-    if (folded) CUDA_OK(cudaMemsetAsync(c->colsum[4], 0, 128 * sizeof(double), s));
-    if (fold6) CUDA_OK(cudaMemsetAsync(c->colsum[6], 0, static_cast<size_t>(c->B) * 64 * sizeof(double), s));
+    const bool xf = c->xf && !rag;
 
     auto fin_args = [&](int i) {
         BnFinalizeArgs f;
@@ -1287,8 +1325,19 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
                                            c->y[0], c->stats_f + c->stat_off[0], 0);
         LAUNCH_OK("k_ingest");
         TRY(stats_fix(0));
-        TRY(bn_relu(0, 0, 0, 1.f));
+        if (!xf) TRY(bn_relu(0, 0, 0, 1.f));
     }
+    // transform-stage GEMM of layer i: BatchNorm + ReLU (+ dropout, column sums) of layer i - 1 happen on its A tiles
+    auto xf_gemm = [&](int i, unsigned long long sd, unsigned int thr, float ks, double* colsum) -> int {
+        GemmOp op = O.fwx[i];
+        op.p.xf_fin = fin_args(i - 1);
+        op.p.xf_seed = sd;
+        op.p.seed_ptr = c->seed_ptr;
+        op.p.xf_thr16 = thr;
+        op.p.xf_keep_scale = ks;
+        op.p.xf_colsum = colsum;
+        return timed_gemm(c, op, i, s);
+    };
     for (int i = 1; i <= 5; ++i) {
         if (i == 5) {
             GemmOp op = O.fw[5];
@@ -1311,10 +1360,14 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
             }
             TRY(timed_gemm(c, O.fw[4], 4, s));
             continue;
+        } else if (xf && i <= 3) {
+            // conv2 / conv3 / conv4 apply bn1 / bn2 / bn3 themselves; conv3 also takes the per-cloud column sums of point_feat
+            TRY(xf_gemm(i, 0, 0, 1.f, (i == 2 && fold6) ? c->colsum[6] : nullptr));
         } else {
             TRY(timed_gemm(c, O.fw[i], i, s));
         }
         TRY(stats_fix(i));
+        if (xf && i <= 2) continue;            // the next layer's transform stage applies this BatchNorm
         if (i == 1 && fold6) TRY(bn_relu(1, 0, 0, 1.f, c->colsum[6], c->N));      // per-cloud column sums of point_feat
         else if (i < 5) TRY(bn_relu(i, 0, 0, 1.f, (i == 3 && folded) ? c->colsum[4] : nullptr));
     }
@@ -1356,8 +1409,12 @@ static int forward_train_rows(pcseg_ctx* c, const bool rag, const float* x, cons
     }
     TRY(timed_gemm(c, O.fw[7], 7, s));
     TRY(stats_fix(7));
-    TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
-    TRY(timed_gemm(c, O.fw[8], 8, s));
+    if (xf && c->xf_seg3) {
+        TRY(xf_gemm(8, seed + 2, c->thr16, c->keep_scale, nullptr));      // seg_conv3 applies bn_seg2 + ReLU + dropout itself
+    } else {
+        TRY(bn_relu(7, seed + 2, c->thr16, c->keep_scale));
+        TRY(timed_gemm(c, O.fw[8], 8, s));
+    }
     TRY(stats_fix(8));
     {
         int grid = static_cast<int>((P + 255) / 256);        // one thread per point
@@ -1459,11 +1516,25 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     }
 
     if (phase != 2) {
-        CUDA_OK(cudaMemsetAsync(grads, 0, static_cast<size_t>(L.total) * sizeof(float), s));
-        CUDA_OK(cudaMemsetAsync(c->stats_b, 0, c->stat_total * sizeof(double), s));
-        CUDA_OK(cudaMemsetAsync(c->dcb, 0, static_cast<size_t>(B) * 512 * sizeof(float), s));
-        if (c->folded && !rag && c->fold6)
-            CUDA_OK(cudaMemsetAsync(c->cloudsum6, 0, (static_cast<size_t>(B) * 512 + 512 * 64) * sizeof(float), s));
+        // every accumulator of the backward pass is cleared by ONE launch (one graph node instead of up to nine memset
+        // nodes on the critical path); the buffers of the later layers are not touched by anything in between
+        FillJobs fj;
+        int nf = 0;
+        auto zero = [&](void* ptr, size_t bytes, unsigned int value = 0u) { fj.fill[nf++] = FillJob{ptr, bytes, value}; };
+        zero(grads, static_cast<size_t>(L.total) * sizeof(float));
+        zero(c->stats_b, c->stat_total * sizeof(double));
+        zero(c->dcb, static_cast<size_t>(B) * 512 * sizeof(float));
+        if (c->folded && !rag) {
+            if (c->fold6) zero(c->cloudsum6, (static_cast<size_t>(B) * 512 + 512 * 64) * sizeof(float));
+            zero(c->cstf[5], 1024 * sizeof(float));       // (Q5 and the side rows are written, not accumulated)
+            zero(c->rowslot5, static_cast<size_t>(c->P) * sizeof(int), 0x7f7f7f7fu);
+            zero(c->gramf[5], 1024 * 1024 * sizeof(float));
+            zero(c->qraw[4], FOLD4_ZERO_FLOATS * sizeof(float));
+        }
+        fj.count = nf;
+        StampScope ts(c, 93, s);
+        pdl_launch(k_fill_multi, dim3(128, nf), 256, 0, s, fj);
+        LAUNCH_OK("k_fill_multi");
     }
 
     auto bwd_args = [&](int i) {
@@ -1609,12 +1680,6 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
         // folded BatchNorm backward (neither y5 nor dy5 exist): coefficients from {sum dzv, sum dzv*yhat}, S5 on the tensor
         // cores, the max-pool gradient rows through the side buffer, ONE data-gradient GEMM over a4; then the Gram matrix of
         // a4 and the weight gradient in the epilogue of the W5 Gc4 GEMM
-        {
-            StampScope ts(c, 93, s);
-            CUDA_OK(cudaMemsetAsync(c->cstf[5], 0, 1024 * sizeof(float), s));       // (Q5 and the side rows are written, not accumulated)
-            CUDA_OK(cudaMemsetAsync(c->rowslot5, 0x7f, static_cast<size_t>(c->P) * sizeof(int), s));
-            CUDA_OK(cudaMemsetAsync(c->gramf[5], 0, 1024 * 1024 * sizeof(float), s));
-        }
         Fold5Args f5;
         f5.stats_b = c->stats_b + c->stat_off[5];
         f5.bnp = c->bnp[5];
@@ -1681,7 +1746,6 @@ extern "C" int pcseg_backward(pcseg_ctx* c, const float* x, const float* params,
     if (c->folded && !rag) {
         // folded BatchNorm backward: neither y4 nor dy4 exist.  Q = dz4^T a3, per-channel coefficients, dW / S / const on
         // CUDA cores (K = 128), then ONE data-gradient GEMM over [dz4 | a3]
-        CUDA_OK(cudaMemsetAsync(c->qraw[4], 0, FOLD4_ZERO_FLOATS * sizeof(float), s));
         TRY(timed_gemm(c, O.wg_op[4], 32 + 4, s));
         FoldArgs f;
         f.Q = c->qraw[4];

@@ -3,6 +3,7 @@
 // All activation tensors are point-major [P][C] bf16 with C contiguous.
 #pragma once
 #include "ptx.cuh"
+#include "bn.cuh"
 
 namespace pcseg {
 
@@ -55,13 +56,40 @@ struct ConvertJob {
     int ld_src, ld_dst, rows, cols, transpose;
 };
 constexpr int MAX_CONVERT_JOBS = 20;
+// Buffers that a step needs zeroed (or filled with a 32-bit pattern) ride along as extra blockIdx.y slices: one graph node
+// instead of one memset node per buffer on the critical path.
+struct FillJob {
+    void* dst;
+    unsigned long long bytes;   // multiple of 4
+    unsigned int value;
+};
+constexpr int MAX_FILL_JOBS = 10;
 struct ConvertJobs {
     ConvertJob job[MAX_CONVERT_JOBS];
     int count;
+    FillJob fill[MAX_FILL_JOBS];
+    int fill_count;
 };
+__device__ __forceinline__ void fill_slice(const FillJob f) {
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, nth = static_cast<size_t>(gridDim.x) * blockDim.x;
+    unsigned int* w = static_cast<unsigned int*>(f.dst);
+    const size_t nw = f.bytes >> 2;
+    size_t head = ((16u - (reinterpret_cast<uintptr_t>(w) & 15u)) & 15u) >> 2;     // words up to 16-byte alignment
+    if (head > nw) head = nw;
+    const size_t n16 = (nw - head) >> 2;
+    uint4* v = reinterpret_cast<uint4*>(w + head);
+    const uint4 val = make_uint4(f.value, f.value, f.value, f.value);
+    for (size_t i = tid; i < n16; i += nth) v[i] = val;
+    for (size_t i = tid; i < head; i += nth) w[i] = f.value;
+    for (size_t i = head + (n16 << 2) + tid; i < nw; i += nth) w[i] = f.value;
+}
 __global__ void __launch_bounds__(256) k_convert_multi(const ConvertJobs jobs) {
     pdl_launch_dependents();
     pdl_wait();
+    if (static_cast<int>(blockIdx.y) >= jobs.count) {
+        fill_slice(jobs.fill[blockIdx.y - jobs.count]);
+        return;
+    }
     // blockIdx.y = job; 32x32 tiles through shared memory so that both the fp32 reads and the (possibly transposed)
     // bf16 writes are coalesced
     __shared__ float tile[32][33];
@@ -91,6 +119,16 @@ __global__ void __launch_bounds__(256) k_convert_multi(const ConvertJobs jobs) {
         }
         __syncthreads();
     }
+}
+// the fills alone (backward: gradient arena, BN-backward sums, per-cloud sums, side buffers)
+struct FillJobs {
+    FillJob fill[MAX_FILL_JOBS];
+    int count;
+};
+__global__ void __launch_bounds__(256) k_fill_multi(const FillJobs jobs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    fill_slice(jobs.fill[blockIdx.y]);
 }
 
 // Eval-mode BatchNorm folding: alpha[c] = gamma/sqrt(var+eps), delta[c] = (bias - mean)*alpha + beta.
@@ -164,54 +202,6 @@ __global__ void __launch_bounds__(256) k_ingest(const float4* __restrict__ x, in
             double s = 0.0;
             for (int i = 0; i < 32; ++i) s += static_cast<double>(red[q][i][c]);
             atomicAdd(stats + q * 64 + c, s);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Train-mode BatchNorm finalize, folded into the kernels that consume the normalisation (no launch of its own).
-//   stats = {sum y, sum y^2} over n rows (conv bias excluded) ->
-//   {scale = gamma*invstd, shift = beta - mean*scale, invstd, -mean*invstd}
-// Every consumer thread evaluates `bn_from_stats` for the channels it needs; block 0 of the consumer also stores the
-// result (later kernels and backward read it) and updates running_mean / running_var (momentum, unbiased variance,
-// conv bias re-added to the mean).
-// ---------------------------------------------------------------------------------------------
-struct BnFinalizeArgs {
-    const double* stats;      // [2][C]
-    const float* gamma;
-    const float* beta;
-    const float* conv_bias;
-    float* rmean;             // running statistics (updated by block 0), may be null
-    float* rvar;
-    float4* bnp;              // [C] output copy for later kernels
-    double n;
-    double inv_n;             // 1 / n, computed on the host: CUDA-core fp64 (a division above all) is slow on this part and every
-                              // consumer thread evaluates bn_from_stats
-    float eps, momentum;
-    int C;
-};
-__device__ __forceinline__ float4 bn_from_stats(const BnFinalizeArgs& f, int c) {
-    // only the cancellation-prone part (E[y^2] - mean^2) is done in fp64: this runs in every consumer thread
-    const double inv_n = f.inv_n;
-    const double mean = f.stats[c] * inv_n;
-    double var = fma(-mean, mean, f.stats[f.C + c] * inv_n);
-    if (var < 0.0) var = 0.0;
-    const float invstd = rsqrtf(static_cast<float>(var) + f.eps);
-    const float meanf = static_cast<float>(mean);
-    const float sc = f.gamma[c] * invstd;
-    return make_float4(sc, fmaf(-meanf, sc, f.beta[c]), invstd, -meanf * invstd);
-}
-__device__ __forceinline__ void bn_publish(const BnFinalizeArgs& f, bool first_block) {
-    if (!first_block) return;
-    for (int c = threadIdx.x; c < f.C; c += blockDim.x) {
-        f.bnp[c] = bn_from_stats(f, c);
-        if (f.rmean != nullptr) {
-            const double mean = f.stats[c] / f.n;
-            double var = f.stats[f.C + c] / f.n - mean * mean;
-            if (var < 0.0) var = 0.0;
-            const double unb = f.n > 1.0 ? var * f.n / (f.n - 1.0) : var;
-            f.rmean[c] = static_cast<float>((1.0 - f.momentum) * f.rmean[c] + f.momentum * (mean + f.conv_bias[c]));
-            f.rvar[c] = static_cast<float>((1.0 - f.momentum) * f.rvar[c] + f.momentum * unb);
         }
     }
 }

@@ -172,6 +172,45 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) 
     else tmem_ld_32x16(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait for a load that was issued EARLIER (software-pipelined epilogues): the destination registers are tied to
+// the wait as read-write operands, so no use of them can be scheduled ahead of it.
+template <int CW>
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[CW]) {
+    static_assert(CW == 16 || CW == 32, "unsupported TMEM load width");
+    if constexpr (CW == 16) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                       "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                     :: "memory");
+    } else {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                       "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                       "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                       "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                     :: "memory");
+    }
+}
+
+// ---------------------------------------------------------------- packed fp32 pairs (FADD2 / FFMA2 on sm_100)
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 // ---------------------------------------------------------------- explicit shared-space accesses
 // (the dynamic smem base is re-aligned through an integer cast, after which the compiler can only emit generic
@@ -183,6 +222,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 }
 __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t saddr, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(saddr), "l"(v) : "memory");
 }
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     float v;
