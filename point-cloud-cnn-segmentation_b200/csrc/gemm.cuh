@@ -129,8 +129,9 @@ struct GemmParams {
     double* xf_colsum;           // [clouds][64] per-cloud column sums of the stored activation (K == 64 only), or nullptr
 };
 
-template <int BN, int EPI, bool MN, bool XF = false>
+template <int BN, int EPI, bool MN, bool XF = false, bool C2 = false>
 struct GemmCfg {
+    static_assert(!C2 || (!MN && !XF && BN == 256), "CTA-pair kernels: K-major, BN = 256, no transform stage");
     static constexpr int EPI_WARPS = epi_warps_for(EPI);
     static constexpr int EPI_THREADS = EPI_WARPS * 32;
 #ifndef PCSEG_XF_WARPS
@@ -141,7 +142,7 @@ struct GemmCfg {
     static constexpr int THREADS = 128 + EPI_THREADS + XF_THREADS;
     static_assert(!XF || (EPI == EPI_STATS && !MN && BN <= 256), "transform stage: K-major EPI_STATS kernels only");
     static constexpr int STAGE_A = GEMM_BM * GEMM_BK * 2;
-    static constexpr int STAGE_B = BN * GEMM_BK * 2;
+    static constexpr int STAGE_B = (C2 ? BN / 2 : BN) * GEMM_BK * 2;      // CTA pair: each CTA holds half of the B tile
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr bool HAS_OUT = (EPI == EPI_BIAS_RELU || EPI == EPI_STATS || EPI == EPI_STATS_POOL || EPI == EPI_DGRAD ||
                                      EPI == EPI_BN_RELU || EPI == EPI_DGRAD_ACT || EPI == EPI_BIAS_RELU_X3 || EPI == EPI_BN_RELU_DROP);
@@ -277,12 +278,12 @@ __device__ __forceinline__ void dgrad_act_pass2_rows(uint32_t tile_s, uint32_t a
     }
 }
 
-template <int BN, int EPI, bool MN, bool XF = false>
-__global__ void __launch_bounds__(GemmCfg<BN, EPI, MN, XF>::THREADS, 1)
+template <int BN, int EPI, bool MN, bool XF = false, bool C2 = false>
+__global__ void __launch_bounds__(GemmCfg<BN, EPI, MN, XF, C2>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmY,
             const GemmParams p) {
-    using Cfg = GemmCfg<BN, EPI, MN, XF>;
+    using Cfg = GemmCfg<BN, EPI, MN, XF, C2>;
     constexpr int EPI_WARPS = Cfg::EPI_WARPS;
     constexpr int EPI_THREADS = Cfg::EPI_THREADS;
     constexpr int GEMM_THREADS = Cfg::THREADS;
@@ -310,7 +311,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int warp_idx = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
 
-    const int total_tiles = ((EPI == EPI_WGRAD && p.sym_tiles > 0) ? p.sym_tiles : p.num_m_tiles * p.num_n_tiles) * p.num_splits;
+    // CTA pairs (C2): a "tile" is 256 rows x BN columns, shared by the two CTAs of a cluster (rank r owns rows 128 r ..);
+    // tile_start / tile_step enumerate tiles per CTA (1-CTA kernels) or per cluster
+    const uint32_t pair_rank = C2 ? cluster_ctarank() : 0u;
+    const int tile_start = C2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = C2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int total_tiles = C2 ? (p.num_m_tiles >> 1) * p.num_n_tiles
+                               : ((EPI == EPI_WGRAD && p.sym_tiles > 0) ? p.sym_tiles : p.num_m_tiles * p.num_n_tiles) * p.num_splits;
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -327,14 +334,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], EPI_THREADS);
+            mbar_init(&tmem_empty[i], C2 ? 2 * EPI_THREADS : EPI_THREADS);     // pair: the leader's barrier counts both epilogues
             mbar_init(&y_full[i], 1);
         }
         fence_barrier_init();
     }
     if (warp_idx == 2) {
-        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (C2) {
+            tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     pdl_wait();          // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel
     if (EPI == EPI_LOGITS) {
@@ -342,7 +354,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int i = threadIdx.x; i < p.num_classes; i += GEMM_THREADS) w4s[MAX_CLASSES * 128 + i] = p.b4[i];
     }
     tc_fence_before();
-    __syncthreads();
+    if (C2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -362,6 +375,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         n_tile = t % p.num_n_tiles;
         m_tile = t / p.num_n_tiles;
+        if (C2) m_tile = 2 * m_tile + static_cast<int>(pair_rank);
     };
 
     auto kb_range = [&](int split, int& kb0, int& kb1) {
@@ -381,7 +395,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile_start; tile < total_tiles; tile += tile_step) {
                 int m_tile, n_tile, split;
                 tile_coords(tile, m_tile, n_tile, split);
                 int kb0, kb1;
@@ -390,6 +404,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = stage_base + stage * Cfg::STAGE;
                     uint8_t* sb = sa + Cfg::STAGE_A;
+                    if constexpr (C2) {
+                        // both producers load their share; all bytes are counted on the leader's barrier, where the MMA waits
+                        if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE);
+                        const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        tma_load_2d_pair(sa, &tmA, lbar, kb * GEMM_BK, m_tile * GEMM_BM);
+                        tma_load_2d_pair(sb, &tmB, lbar, kb * GEMM_BK, n_tile * BN + static_cast<int>(pair_rank) * (BN / 2));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
                     if (!MN) {
                         int ka = kb, kbb = kb;                  // k-block columns of A and B
@@ -417,7 +440,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else if (warp_idx == 1) {
         // ------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+        constexpr uint32_t idesc = make_idesc_bf16(C2 ? 2 * GEMM_BM : GEMM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
 #ifdef PCSEG_PROF_WAIT
         // diagnostic build: where does the MMA warp wait -- for operands (full_bar) or for a free accumulator (tmem_empty)?
         long long prof_wait_acc = 0, prof_wait_full = 0;
@@ -426,7 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = (C2 && pair_rank != 0) ? total_tiles : tile_start; tile < total_tiles; tile += tile_step, ++iter) {   // pair: leader only
             int m_tile, n_tile, split;
             tile_coords(tile, m_tile, n_tile, split);
             int kb0, kb1;
@@ -464,10 +487,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             da = make_smem_desc_sw128(sa + k * 2048, 8192, 1024);
                             db = make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
                         }
-                        umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (C2) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+                    if (C2) {
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -485,7 +514,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile_start; tile < total_tiles; tile += tile_step) {
                 int m_tile, n_tile, split;
                 tile_coords(tile, m_tile, n_tile, split);
                 int kb0, kb1;
@@ -548,7 +577,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         };
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile_start; tile < total_tiles; tile += tile_step) {
             int m_tile, n_tile, split;
             tile_coords(tile, m_tile, n_tile, split);
             int kb0, kb1;
@@ -632,11 +661,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t comb_s = smem_u32(comb);
         int iter = 0;
         uint32_t sub_it = 0;                          // global 64-column sub-tile counter (buffer parity)
+        // this thread has read everything it needs from accumulator buffer `a`: tell the MMA warp (pair: the leader's)
+        const uint32_t tmem_empty_leader = C2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+        auto release_acc = [&](int a) {
+            if (C2) mbar_arrive_cluster(tmem_empty_leader + 8u * a);
+            else mbar_arrive(&tmem_empty[a]);
+        };
 
         auto issue_y_load = [&](uint32_t it) {        // elected thread only
             const int t_ord = it / SUBS;
             const int sub = it % SUBS;
-            const long tile = static_cast<long>(blockIdx.x) + static_cast<long>(t_ord) * gridDim.x;
+            const long tile = static_cast<long>(tile_start) + static_cast<long>(t_ord) * tile_step;
             if (tile >= total_tiles) return;
             int m_tile, n_tile, split;
             tile_coords(static_cast<int>(tile), m_tile, n_tile, split);
@@ -665,7 +700,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if constexpr (EPI == EPI_STATS_POOL) {
                 // sign of the BN weight per column of this CTA (n_tile is fixed per CTA): the train-mode max-pool takes the
                 // max of gamma >= 0 columns and the min of the others, i.e. the max after flipping the sign bit
-                const int n0_fixed = (blockIdx.x % p.num_n_tiles) * BN;
+                const int n0_fixed = (tile_start % p.num_n_tiles) * BN;
                 for (int i = et; i < BN; i += EPI_THREADS)
                     reinterpret_cast<uint32_t*>(comb)[NH * 2 * BN + i] =
                         (n0_fixed + i < p.N && __ldg(p.gamma + n0_fixed + i) >= 0.f) ? 0u : 0x80000000u;
@@ -675,7 +710,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if constexpr (EPI == EPI_BN_RELU || EPI == EPI_BN_RELU_DROP) {
             // {scale, shift} of this CTA's BN columns (n_tile is fixed per CTA): comb[0..BN) = scale, comb[BN..2BN) = shift
-            const int n0_fixed = (blockIdx.x % p.num_n_tiles) * BN;
+            const int n0_fixed = (tile_start % p.num_n_tiles) * BN;
             for (int i = et; i < BN; i += EPI_THREADS) {
                 const float4 bp = __ldg(p.bnp + n0_fixed + i);
                 comb[i] = bp.x;
@@ -689,7 +724,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int cur_cl = -1;
         auto flush_cloud = [&](int cl) {
             named_bar_sync(1, EPI_THREADS);
-            const int n0f = (blockIdx.x % p.num_n_tiles) * BN;
+            const int n0f = (tile_start % p.num_n_tiles) * BN;
             for (int c = et; c < BN; c += EPI_THREADS) {
                 float a0 = 0.f;
 #pragma unroll
@@ -710,7 +745,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t pool_s = comb_s + 4u * (NH * 2 * BN + BN);
         auto flush_pool = [&](int cl) {
             named_bar_sync(1, EPI_THREADS);
-            const int n0f = (blockIdx.x % p.num_n_tiles) * BN;
+            const int n0f = (tile_start % p.num_n_tiles) * BN;
             for (int c = et; c < BN; c += EPI_THREADS) {
                 unsigned long long best = 0ull;
 #pragma unroll
@@ -726,7 +761,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         (void)pool_s;
         (void)flush_pool;
 
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = tile_start; tile < total_tiles; tile += tile_step, ++iter) {
             int m_tile, n_tile, split;
             tile_coords(tile, m_tile, n_tile, split);
             const int acc = iter & 1;
@@ -806,7 +841,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[acc]);
+                release_acc(acc);
             } else if constexpr (EPI == EPI_LOGITS) {
                 static_assert(EPI != EPI_LOGITS || BN == 128, "logits epilogue needs all 128 channels in one tile");
                 float lg[MAX_CLASSES];
@@ -827,7 +862,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&tmem_empty[acc]);
+                release_acc(acc);
                 // combine the NQ column groups through shared memory: comb[cq-1][row][class]
                 named_bar_sync(1, EPI_THREADS);       // previous tile's readers are done with comb
                 if (cq > 0) {
@@ -900,7 +935,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tmem_ld_wait_regs<CW>(v);
                     if (sub == SUBS - 1) {       // all TMEM reads of this accumulator (by this thread) are done
                         tc_fence_before();
-                        mbar_arrive(&tmem_empty[acc]);
+                        release_acc(acc);
                     }
                     if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_COLMAX || EPI == EPI_BIAS_RELU_X3) {
                         float o[CW];
@@ -1266,8 +1301,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if constexpr (COLACC) {
             named_bar_sync(1, EPI_THREADS);
-            const int n0_fixed = (blockIdx.x % p.num_n_tiles) * BN;
-            if (blockIdx.x < total_tiles) {
+            const int n0_fixed = (tile_start % p.num_n_tiles) * BN;
+            if (tile_start < total_tiles) {
                 for (int c = et; c < BN; c += EPI_THREADS) {
                     const int col = n0_fixed + c;
                     if (col >= p.N) continue;
@@ -1295,10 +1330,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // kernel's CTAs then sit resident on the SMs for the whole GEMM.
     pdl_launch_dependents();
     tc_fence_before();
-    __syncthreads();
+    if (C2) cluster_sync_all();      // neither CTA frees tensor memory (or exits) while its peer may still signal or read it
+    else __syncthreads();
     if (warp_idx == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (C2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

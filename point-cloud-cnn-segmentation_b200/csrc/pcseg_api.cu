@@ -98,6 +98,25 @@ static void pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through cudaGetLastError() in LAUNCH_OK
 }
+// the same for kernels that run as clusters of two CTAs (cta_group::2 GEMMs)
+template <typename... KArgs, typename... Args>
+static void pdl_launch_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // model layout (reference pcs.py:70-94)
@@ -203,8 +222,31 @@ struct GemmOp {
     int bn, epi;
     bool mn;
     bool xf = false;       // transform-stage variant (tmA = pre-BN input, tmA2 = its activation tensor, written by the kernel)
+    bool c2 = false;       // CTA-pair variant (cta_group::2): tmB boxes hold half a tile (bn / 2 rows)
     bool ready = false;
 };
+
+// CTA-pair GEMM: clusters of two CTAs, every cluster keeps one n_tile (the cluster count is a multiple of num_n_tiles)
+template <int EPI>
+int launch_gemm_pair_t(const GemmOp& op, cudaStream_t s) {
+    using Cfg = GemmCfg<256, EPI, false, false, true>;
+    static unsigned long long attr_set_mask = 0;
+    auto kern = gemm_kernel<256, EPI, false, false, true>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set_mask & (1ull << (dev & 63)))) {
+        CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set_mask |= 1ull << (dev & 63);
+    }
+    const int tiles = (op.p.num_m_tiles / 2) * op.p.num_n_tiles;
+    int clusters = num_sms() / 2;
+    if (clusters > tiles) clusters = tiles;
+    clusters = (clusters / op.p.num_n_tiles) * op.p.num_n_tiles;
+    if (clusters < 1) return fail("internal: CTA-pair GEMM with %d tiles", tiles);
+    pdl_launch_pair(kern, 2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, s, op.tmA, op.tmA2, op.tmB, op.tmOut, op.tmY, op.p);
+    LAUNCH_OK("gemm_kernel<pair>");
+    return 0;
+}
 
 template <int BN, int EPI, bool MN, bool XF = false>
 int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
@@ -227,6 +269,12 @@ int launch_gemm_t(const GemmOp& op, cudaStream_t s) {
 
 int launch_gemm(const GemmOp& op, cudaStream_t s) {
     if (!op.ready) return fail("internal: GEMM op not initialised");
+    if (op.c2) {
+        if (op.bn == 256 && op.epi == EPI_STATS_POOL && !op.mn) return launch_gemm_pair_t<EPI_STATS_POOL>(op, s);
+        if (op.bn == 256 && op.epi == EPI_DGRAD_ACT && !op.mn) return launch_gemm_pair_t<EPI_DGRAD_ACT>(op, s);
+        if (op.bn == 256 && op.epi == EPI_COLMAX && !op.mn) return launch_gemm_pair_t<EPI_COLMAX>(op, s);
+        return fail("internal: no CTA-pair GEMM instantiation for BN=%d EPI=%d", op.bn, op.epi);
+    }
     if (op.xf) {
         if (op.bn == 64 && op.epi == EPI_STATS && !op.mn) return launch_gemm_t<64, EPI_STATS, false, true>(op, s);
         if (op.bn == 128 && op.epi == EPI_STATS && !op.mn) return launch_gemm_t<128, EPI_STATS, false, true>(op, s);
@@ -275,6 +323,25 @@ int setup_gemm_kmajor(GemmOp* op, int epi, const void* A, int lda, const void* B
     op->p.keep_scale = 1.f;
     op->p.store_out = 1;
     op->ready = true;
+    return 0;
+}
+
+// CTA-pair form of a K-major BN = 256 op (cta_group::2): every CTA of a pair loads half of the B tile.  Needs whole pairs
+// of 128-row tiles.  PCSEG_PAIR=1 selects it for the three K = 1024 GEMMs (global_feat forward / data gradient / inference
+// max-pool).  OFF by default -- measured on cfg2 (tools/gpu_r2_prof.sh, MMA-warp wait accounting): the pair kernels are
+// bit-identical but not faster.  With 6 x 32 KB stages instead of 4 x 48 KB the MMA warp still waits 18 % of the time for
+// operands and issues one 128 x 256 x 16 MMA per SM every ~175 cycles either way (the rate cuBLAS reaches at this part's
+// clocks), while 72 clusters x 2 leave 4 SMs idle and round 27.7 tiles per CTA up to 29: 256 vs 242 us forward, 290 vs 259 us
+// data gradient (whose epilogue, not its operands, is what the MMA warp waits for in the pair form).
+int make_pair_op(GemmOp* op, const void* B, int ldb) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("PCSEG_PAIR");
+        enabled = (e && e[0] == '1');
+    }
+    if (!enabled || op->bn != 256 || op->mn || op->p.kb_switch != 0 || (op->p.num_m_tiles & 1) || (op->p.M % 256) != 0) return 0;
+    TRY(make_tmap(&op->tmB, B, op->p.K, op->p.N, ldb, 64, 128));
+    op->c2 = true;
     return 0;
 }
 
@@ -714,6 +781,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         O.ev[5].p.colmax = reinterpret_cast<unsigned int*>(c->gmax);
         O.ev[5].p.pts_per_cloud = N;
         O.ev[5].p.tile_cloud = tile_cloud;
+        if (!rag) TRY(make_pair_op(&O.ev[5], c->wk[5], 1024));
         // seg_conv1: point-feature part + per-cloud bias
         TRY(setup_gemm_kmajor(&O.ev[6], EPI_BIAS_RELU, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->act[6], 512, nullptr, 0));
         O.ev[6].p.bias = c->zeros1024;
@@ -763,6 +831,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
         O.fw[5].p.pts_per_cloud = N;
         O.fw[5].p.tile_cloud = tile_cloud;
         O.fw[5].p.cloud_off = cloud_off;
+        if (!rag) TRY(make_pair_op(&O.fw[5], c->wk[5], 1024));
         TRY(setup_gemm_kmajor(&O.fw[6], EPI_STATS, c->act[1], 64, c->wk[6], 64, P, 512, 64, c->y[6], 512, nullptr, 0));
         O.fw[6].p.stats = c->stats_f + c->stat_off[6];
         O.fw[6].p.cloud_bias = c->cb;
@@ -841,6 +910,7 @@ extern "C" int pcseg_bind(pcseg_ctx* c, int B, int N, void* ws, long long ws_byt
             O.dg[5].p.rowslot = c->rowslot5;
             O.dg[5].p.side = c->side5;
             O.dg[5].p.side_rows = B * 1024;
+            TRY(make_pair_op(&O.dg[5], c->s5b, 1024));
             // weight gradient: G4 = a4^T a4 (upper-triangle tiles only), then dW5 = A Q5 + Bc (W5 Gc4) + D s4^T in the
             // epilogue of the W5 Gc4 GEMM
             TRY(setup_gemm_wgrad(&c->gram_op[5], c->act[4], 1024, 1024, c->act[4], 1024, 1024, P, c->gramf[5], 1024));

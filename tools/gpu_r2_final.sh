@@ -2,7 +2,7 @@
 # round 2 final measurements on one B200: test-suite, smoke, bench lines, reference arm, ncu launch lists + full captures
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 2400 python -m pytest tests -q -m gpu 2>&1 | tail -8 | cut -c1-300
+timeout 2400 python -m pytest tests -q -m gpu 2>&1 | tail -8 | cut -c1-300 | tee $O/r02_gpu_tests_tail.txt
 echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
 timeout 900 python bench.py > $O/r02_bench_cfg2_train.json 2> $O/bench_cfg2.err; echo "cfg2 rc=$?"; tail -2 $O/bench_cfg2.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_cfg2_reference_arm.json 2> $O/bench_ref.err; echo "ref rc=$?"
@@ -36,5 +36,5 @@ timeout 900 ncu --set full --clock-control none -k regex:gemm_kernel -s 15 -c 5 
 python tools/ncu_summary.py /tmp/prof_gemm_eval.ncu-rep > $O/r02_ncu_full_gemm_cfg2_eval.txt 2>&1
 python tools/ncu_traffic_lines.py $O/r02_ncu_full_gemm_cfg2_train.txt $O/r02_ncu_full_gemm_cfg2_eval.txt >> $O/r02_ncu_full_gemm_cfg2_train.txt
 cat $O/r02_ncu_full_gemm_cfg2_train.txt; cat $O/r02_ncu_full_gemm_cfg2_eval.txt
-timeout 1200 ncu --set full --clock-control none -k regex:"k_bn_bwd_apply|k_bn_relu|k_head|k_ingest|k_convert|k_adam|k_cloud|k_maxpool|k_predict|k_fold|k_gram|k_pool" -s 90 -c 40 -f -o /tmp/prof_ew $CMD > $O/ncu_ew.log 2>&1
+timeout 1200 ncu --set full --clock-control none -k regex:"k_bn_bwd_apply|k_bn_relu|k_head|k_ingest|k_convert|k_fill|k_adam|k_cloud|k_maxpool|k_predict|k_fold|k_gram|k_pool" -s 90 -c 40 -f -o /tmp/prof_ew $CMD > $O/ncu_ew.log 2>&1
 python tools/ncu_summary.py /tmp/prof_ew.ncu-rep > $O/r02_ncu_full_pointwise_cfg2_train.txt 2>&1; cat $O/r02_ncu_full_pointwise_cfg2_train.txt
