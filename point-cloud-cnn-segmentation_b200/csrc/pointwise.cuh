@@ -628,19 +628,34 @@ __global__ void __launch_bounds__(256) k_head_bwd(const __nv_bfloat16* __restric
     __syncthreads();
     const long warp_g = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+    // The kernel runs one block per SM (NC x 16 + 96 accumulator registers per lane) and every iteration is a chain
+    // load -> softmax shuffles -> FMAs: the loads of the NEXT iteration are issued before the arithmetic of the current one,
+    // otherwise each of the ~28 iterations per warp pays a full memory latency.
+    uint4 y0n = make_uint4(0, 0, 0, 0), y1n = y0n;
+    float zinn = 0.f;
+    long long lab0n = -1;
+    auto fetch = [&](long p0) {
+        const long pnt = p0 + grp;
+        y0n = make_uint4(0, 0, 0, 0);
+        y1n = y0n;
+        zinn = 0.f;
+        lab0n = -1;
+        if (pnt < P) {
+            const uint4* src = reinterpret_cast<const uint4*>(ys3 + pnt * 128 + sub * 16);
+            y0n = src[0];
+            y1n = src[1];
+            if (sub < C) zinn = zsrc[pnt * C + sub];
+            if (fused && sub == 0) lab0n = labels[pnt];
+        }
+    };
+    if (warp_g * 4 < P) fetch(warp_g * 4);
     for (long p0 = warp_g * 4; p0 < P; p0 += nwarps * 4) {
         const long pnt = p0 + grp;
         const bool ok = pnt < P;
-        uint4 y0 = make_uint4(0, 0, 0, 0), y1 = y0;
-        float zin = 0.f;
-        long long lab0 = -1;
-        if (ok) {
-            const uint4* src = reinterpret_cast<const uint4*>(ys3 + pnt * 128 + sub * 16);
-            y0 = src[0];
-            y1 = src[1];
-            if (sub < C) zin = zsrc[pnt * C + sub];
-            if (fused && sub == 0) lab0 = labels[pnt];
-        }
+        const uint4 y0 = y0n, y1 = y1n;
+        const float zin = zinn;
+        const long long lab0 = lab0n;
+        if (p0 + nwarps * 4 < P) fetch(p0 + nwarps * 4);
         float dl_mine = zin;                               // lane with sub == k holds dlogit k of its point
         if (fused) {
             const long long lab = __shfl_sync(0xffffffffu, lab0, grp * 8);

@@ -37,3 +37,4 @@ def test_cta_pair_gemms_pass_the_parity_suites():
 
 def test_cta_pair_and_transform_stage_together():
     _rerun({"PCSEG_PAIR": "1", "PCSEG_XF": "1"}, ["test_layerwise_gpu.py"])
+
