@@ -250,13 +250,22 @@ __global__ void __launch_bounds__(256) k_bn_relu(const __nv_bfloat16* __restrict
         r_begin = blockIdx.x * rows_per_block;
         r_end = min(P, r_begin + rows_per_block);
     }
-    for (long r = r_begin + rslot; r < r_end; r += 4L * rpp) {
-        uint4 yw[4];
+    // software pipelined: the four loads of the NEXT pass are in flight while this pass does its arithmetic (the Philox
+    // rounds of the dropout variant are a long dependent chain that otherwise delays the next loads)
+    uint4 ynext[4];
+    auto fetch = [&](long r) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const long rr = r + static_cast<long>(u) * rpp;
-            if (rr < r_end) yw[u] = *reinterpret_cast<const uint4*>(y + rr * ld_y + c0);
+            if (rr < r_end) ynext[u] = *reinterpret_cast<const uint4*>(y + rr * ld_y + c0);
         }
+    };
+    if (r_begin + rslot < r_end) fetch(r_begin + rslot);
+    for (long r = r_begin + rslot; r < r_end; r += 4L * rpp) {
+        uint4 yw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) yw[u] = ynext[u];
+        if (r + 4L * rpp < r_end) fetch(r + 4L * rpp);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const long rr = r + static_cast<long>(u) * rpp;
