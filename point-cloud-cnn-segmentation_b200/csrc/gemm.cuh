@@ -439,46 +439,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp_idx == 1) {
-        // ------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------ MMA issuer (one lane)
+        // Measured (tools/gpu_r2_prof.sh): the operands of a k-block were ALWAYS in shared memory already when this thread asked,
+        // yet every mbarrier.try_wait cost ~90-100 cycles of latency during which the tensor pipe ran dry (tcgen05.mma issue
+        // blocks until the pipe accepts the instruction, so nothing is queued behind it): 15-25 % of the loop.  The barrier of
+        // the NEXT stage is therefore probed (non-blocking test_wait) between the MMAs of the current one, where its latency
+        // hides behind their execution; the blocking wait remains only for stages that really are not there yet.
         constexpr uint32_t idesc = make_idesc_bf16(C2 ? 2 * GEMM_BM : GEMM_BM, BN, MN ? 1 : 0, MN ? 1 : 0);
-#ifdef PCSEG_PROF_WAIT
-        // diagnostic build: where does the MMA warp wait -- for operands (full_bar) or for a free accumulator (tmem_empty)?
-        long long prof_wait_acc = 0, prof_wait_full = 0;
-        const long long prof_t0 = clock64();
+        constexpr int KSTEPS = GEMM_BK / 16;
+#ifndef PCSEG_MMA_PROBE_AHEAD
+#define PCSEG_MMA_PROBE_AHEAD 1
 #endif
-        int stage = 0;
-        uint32_t phase = 0;
-        int iter = 0;
-        for (int tile = (C2 && pair_rank != 0) ? total_tiles : tile_start; tile < total_tiles; tile += tile_step, ++iter) {   // pair: leader only
-            int m_tile, n_tile, split;
-            tile_coords(tile, m_tile, n_tile, split);
-            int kb0, kb1;
-            kb_range(split, kb0, kb1);
-            const int acc = iter & 1;
-            const uint32_t acc_phase = (iter >> 1) & 1;
+        if (lane == 0) {
 #ifdef PCSEG_PROF_WAIT
-            const long long w0 = clock64();
+            // diagnostic build: where does this thread wait -- for operands (full_bar) or for a free accumulator (tmem_empty)?
+            long long prof_wait_acc = 0, prof_wait_full = 0, prof_issue = 0;
+            int prof_ready = 0, prof_kb = 0;
+            const long long prof_t0 = clock64();
 #endif
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            uint64_t* const op_bar = XF ? xf_bar : full_bar;
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            bool ready = false;            // op_bar[stage] is already known to have completed `phase`
+            for (int tile = (C2 && pair_rank != 0) ? total_tiles : tile_start; tile < total_tiles; tile += tile_step, ++iter) {   // pair: leader only
+                int m_tile, n_tile, split;
+                tile_coords(tile, m_tile, n_tile, split);
+                int kb0, kb1;
+                kb_range(split, kb0, kb1);
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
 #ifdef PCSEG_PROF_WAIT
-            prof_wait_acc += clock64() - w0;
+                const long long w0 = clock64();
 #endif
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
 #ifdef PCSEG_PROF_WAIT
-                const long long w1 = clock64();
-#endif
-                mbar_wait(XF ? &xf_bar[stage] : &full_bar[stage], phase);
-#ifdef PCSEG_PROF_WAIT
-                prof_wait_full += clock64() - w1;
+                prof_wait_acc += clock64() - w0;
 #endif
                 tc_fence_after();
-                if (lane == 0) {
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+#ifdef PCSEG_PROF_WAIT
+                    const long long w1 = clock64();
+                    if (ready) ++prof_ready;
+#endif
+                    if (!ready) mbar_wait(&op_bar[stage], phase);
+#ifdef PCSEG_PROF_WAIT
+                    const long long w2 = clock64();
+                    prof_wait_full += w2 - w1;
+                    ++prof_kb;
+#endif
+                    tc_fence_after();
+                    ready = false;
+                    const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+                    const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1) : phase;
                     const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE);
                     const uint32_t sb = sa + Cfg::STAGE_A;
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    for (int k = 0; k < KSTEPS; ++k) {
                         uint64_t da, db;
                         if (!MN) {
                             da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
@@ -489,6 +507,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                         if (C2) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (PCSEG_MMA_PROBE_AHEAD && k == KSTEPS - 2) ready = mbar_test_wait(&op_bar[nstage], nphase);
                     }
                     if (C2) {
                         umma_commit_pair(&empty_bar[stage]);
@@ -497,18 +516,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         umma_commit(&empty_bar[stage]);
                         if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
                     }
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-            if (kb1 <= kb0 && lane == 0) umma_commit(&tmem_full[acc]);   // empty split: still release the epilogue
-            __syncwarp();
-        }
 #ifdef PCSEG_PROF_WAIT
-        if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && p.K >= 1024)
-            printf("PROF gemm<%d,%d,%d> cta %d tiles %d: total %lld cyc, wait accumulator %lld, wait operands %lld\n", BN, EPI, (int)MN,
-                   blockIdx.x, iter, clock64() - prof_t0, prof_wait_acc, prof_wait_full);
+                    prof_issue += clock64() - w2;
 #endif
+                    stage = nstage;
+                    phase = nphase;
+                }
+                if (kb1 <= kb0) umma_commit(&tmem_full[acc]);   // empty split: still release the epilogue
+            }
+#ifdef PCSEG_PROF_WAIT
+            if ((blockIdx.x == 0 || blockIdx.x == 77) && p.K >= 1024)
+                printf("PROF gemm<%d,%d,%d> cta %d tiles %d: total %lld cyc, wait accumulator %lld, wait operands %lld, issue %lld, k-blocks %d ready %d\n",
+                       BN, EPI, (int)MN, blockIdx.x, iter, clock64() - prof_t0, prof_wait_acc, prof_wait_full, prof_issue, prof_kb, prof_ready);
+#endif
+        }
+        __syncwarp();
     } else if (XF && warp_idx == 3) {
         // ------------------------------------------------------------ activation store (XF): transformed A tiles -> tmA2
         if (lane == 0) {
