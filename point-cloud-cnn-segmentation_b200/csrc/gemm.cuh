@@ -65,12 +65,23 @@ enum : int { EPI_BIAS_RELU = 0, EPI_COLMAX = 1, EPI_STATS = 2, EPI_DGRAD = 3, EP
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-// Epilogue warps per kernel variant: 8 everywhere except the train-mode global_feat forward (stats + fused max-pool), whose
-// epilogue is the longest and measurably profits from 16 (282 vs 296 us); 16 everywhere was slower overall.
+// Epilogue warps per kernel variant: 8 everywhere except the train-mode global_feat forward (stats + fused max-pool) and the
+// seg_conv1 forward with dropout; measured per variant (tools/gpu_r2_ab.sh): EPI_DGRAD 16 warps 61.8 -> 70.0 us (seg_conv3 data
+// gradient), EPI_DGRAD_ACT 16 warps 259 -> 272 us.  The global_feat forward's epilogue is the longest and measurably profits
+// from 16 (282 vs 296 us); 16 everywhere was slower overall.
 #ifndef PCSEG_DGRAD_ACT_WARPS
 #define PCSEG_DGRAD_ACT_WARPS 8
 #endif
-constexpr int epi_warps_for(int epi) { return epi == 6 /* EPI_STATS_POOL */ ? 16 : epi == 8 /* EPI_DGRAD_ACT */ ? PCSEG_DGRAD_ACT_WARPS : 8; }
+#ifndef PCSEG_BN_RELU_DROP_WARPS
+#define PCSEG_BN_RELU_DROP_WARPS 16     // seg_conv1 forward (K = 64: all epilogue, Philox dropout): 78.0 -> 74.8 us with 16
+#endif
+#ifndef PCSEG_DGRAD_WARPS
+#define PCSEG_DGRAD_WARPS 8
+#endif
+constexpr int epi_warps_for(int epi) {
+    return epi == 6 /* EPI_STATS_POOL */ ? 16 : epi == 8 /* EPI_DGRAD_ACT */ ? PCSEG_DGRAD_ACT_WARPS
+           : epi == 10 /* EPI_BN_RELU_DROP */ ? PCSEG_BN_RELU_DROP_WARPS : epi == 3 /* EPI_DGRAD */ ? PCSEG_DGRAD_WARPS : 8;
+}
 constexpr int MAX_CLASSES = 8;    // compile-time cap on num_classes for the fused head kernels
 
 struct GemmParams {
