@@ -1281,9 +1281,14 @@ extern "C" int pcseg_forward_eval_ragged(pcseg_ctx* c, const float* x, const int
 // training forward
 // ------------------------------------------------------------------------------------------------
 // grid for the row-strip elementwise kernels: enough blocks to fill the GPU, each with >= 4 passes of rows
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
 static int strip_grid(long long rows, int C) {
     const int rpp = 256 / (C / 8);
-    long long g = rows / (4LL * rpp * 4);
+    static const int passes = env_int("PCSEG_STRIP_PASSES", 4);       // loop iterations (of 4 x rpp rows) per block
+    long long g = rows / (4LL * rpp * (passes > 0 ? passes : 4));
     const long long cap = static_cast<long long>(num_sms()) * 16;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
@@ -1541,7 +1546,8 @@ extern "C" int pcseg_forward_train_ragged(pcseg_ctx* c, const float* x, const in
 static int apply_rows_per_strip(int N, int B, int C) {
     const int rpp = 256 / (C / 8);
     const int unit = rpp * 4;                                    // rows consumed per loop iteration of a block
-    long long target_blocks = 2LL * num_sms();      // == resident blocks (102 regs x 256 threads -> 2 per SM): one wave, half the atomics
+    static const int per_sm = env_int("PCSEG_APPLY_BLOCKS_PER_SM", 2);
+    long long target_blocks = static_cast<long long>(per_sm > 0 ? per_sm : 2) * num_sms();      // == resident blocks (102 regs x 256 threads -> 2 per SM): one wave, half the atomics
     long long strips_per_cloud = (target_blocks + B - 1) / B;
     if (strips_per_cloud < 1) strips_per_cloud = 1;
     int rps = static_cast<int>((N + strips_per_cloud - 1) / strips_per_cloud);
