@@ -319,7 +319,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(xf_bar + (XF ? STAGES : 0));
     static_assert((2 * STAGES + 6 + (XF ? STAGES : 0)) * 8 + 4 <= Cfg::BAR_BYTES, "barrier block too small");
 
-    const int warp_idx = threadIdx.x >> 5;
+    // (broadcast from lane 0: the compiler then knows the role branches and everything derived from them are warp-uniform
+    //  and keeps barrier addresses, shared-memory descriptors and TMEM addresses in uniform registers)
+    const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const uint32_t lane = lane_id();
 
     // CTA pairs (C2): a "tile" is 256 rows x BN columns, shared by the two CTAs of a cluster (rank r owns rows 128 r ..);
@@ -368,7 +370,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (C2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
     else __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
     auto tile_coords = [&](int tile, int& m_tile, int& n_tile, int& split) {
         split = tile % p.num_splits;
@@ -450,7 +452,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp_idx == 1) {
-        // ------------------------------------------------------------ MMA issuer (one lane)
+        // ------------------------------------------------------------ MMA issuer
         // Measured (tools/gpu_r2_prof.sh): the operands of a k-block were ALWAYS in shared memory already when this thread asked,
         // yet every mbarrier.try_wait cost ~90-100 cycles of latency during which the tensor pipe ran dry (tcgen05.mma issue
         // blocks until the pipe accepts the instruction, so nothing is queued behind it): 15-25 % of the loop.  The barrier of
@@ -461,9 +463,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #ifndef PCSEG_MMA_PROBE_AHEAD
 #define PCSEG_MMA_PROBE_AHEAD 1
 #endif
-        if (lane == 0) {
+        {
+            // the whole warp walks the loop (warp-uniform control flow); ONE elected lane issues the MMAs and commits
 #ifdef PCSEG_PROF_WAIT
-            // diagnostic build: where does this thread wait -- for operands (full_bar) or for a free accumulator (tmem_empty)?
+            // diagnostic build: where does this warp wait -- for operands (full_bar) or for a free accumulator (tmem_empty)?
             long long prof_wait_acc = 0, prof_wait_full = 0, prof_issue = 0;
             int prof_ready = 0, prof_kb = 0;
             const long long prof_t0 = clock64();
@@ -501,42 +504,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     ++prof_kb;
 #endif
                     tc_fence_after();
-                    ready = false;
                     const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
                     const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1) : phase;
                     const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE);
                     const uint32_t sb = sa + Cfg::STAGE_A;
+                    uint32_t probe = 0;
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < KSTEPS; ++k) {
-                        uint64_t da, db;
-                        if (!MN) {
-                            da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
-                            db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
-                        } else {
-                            da = make_smem_desc_sw128(sa + k * 2048, 8192, 1024);
-                            db = make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
+                        for (int k = 0; k < KSTEPS; ++k) {
+                            uint64_t da, db;
+                            if (!MN) {
+                                da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
+                                db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
+                            } else {
+                                da = make_smem_desc_sw128(sa + k * 2048, 8192, 1024);
+                                db = make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
+                            }
+                            if (C2) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            if (PCSEG_MMA_PROBE_AHEAD && k == KSTEPS - 2) probe = mbar_test_wait(&op_bar[nstage], nphase) ? 1u : 0u;
                         }
-                        if (C2) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        if (PCSEG_MMA_PROBE_AHEAD && k == KSTEPS - 2) ready = mbar_test_wait(&op_bar[nstage], nphase);
+                        if (C2) {
+                            umma_commit_pair(&empty_bar[stage]);
+                            if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
+                        } else {
+                            umma_commit(&empty_bar[stage]);
+                            if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+                        }
                     }
-                    if (C2) {
-                        umma_commit_pair(&empty_bar[stage]);
-                        if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
-                    } else {
-                        umma_commit(&empty_bar[stage]);
-                        if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
-                    }
+                    ready = __any_sync(0xffffffffu, probe != 0u);      // (the elected lane's probe, known to the whole warp)
 #ifdef PCSEG_PROF_WAIT
                     prof_issue += clock64() - w2;
 #endif
                     stage = nstage;
                     phase = nphase;
                 }
-                if (kb1 <= kb0) umma_commit(&tmem_full[acc]);   // empty split: still release the epilogue
+                if (kb1 <= kb0 && elect_one_sync()) umma_commit(&tmem_full[acc]);   // empty split: still release the epilogue
+                __syncwarp();
             }
 #ifdef PCSEG_PROF_WAIT
-            if ((blockIdx.x == 0 || blockIdx.x == 77) && p.K >= 1024)
+            if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && p.K >= 1024)
                 printf("PROF gemm<%d,%d,%d> cta %d tiles %d: total %lld cyc, wait accumulator %lld, wait operands %lld, issue %lld, k-blocks %d ready %d\n",
                        BN, EPI, (int)MN, blockIdx.x, iter, clock64() - prof_t0, prof_wait_acc, prof_wait_full, prof_issue, prof_kb, prof_ready);
 #endif

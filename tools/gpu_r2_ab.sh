@@ -16,7 +16,7 @@ try:
 except Exception as e:
     print("variant", v, "no json", e); raise SystemExit
 g = d['gemm_kernels']
-tags = ["5", "21", "89", "90", "91", "92"]
+tags = ["4", "5", "6", "7", "20", "21", "23", "24", "36", "53"]
 print(f"variant '{v}': ms/step {d['ms_per_step']:.4f}  Mpts/s {d['value']/1e6:.2f}  clk {d['clocks']['sm_mhz']} {d['clocks']['reasons']}  " +
       "  ".join(f"t{t}={g[t]['ms_per_launch']*1e3:.1f}x{g[t]['launches']//d['steps']}" for t in tags if t in g))
 PY
