@@ -3,7 +3,8 @@
 //   D[128 x BN] (fp32, TMEM, double buffered)  +=  A[128 x 64] * B[BN x 64]^T   per k-block
 //
 //   warp 0      : TMA producer (A and B tiles, 128B-swizzled, mbarrier complete_tx)
-//   warp 1      : MMA issuer   (one lane issues tcgen05.mma, tcgen05.commit frees smem stages)
+//   warp 1      : MMA issuer   (the warp walks the loop warp-uniformly, ONE elected lane issues tcgen05.mma / tcgen05.commit;
+//                 the next stage's mbarrier is probed between the MMAs of the current one)
 //   warp 2      : TMEM allocator
 //   warps 4..11 : epilogue     (tcgen05.ld -> fused math -> swizzled smem -> TMA store / reductions); 4..19 for the
 //                 stats + max-pool variant.  STATS / DGRAD epilogues work in two passes per 64-column sub-tile: pass 1 is
