@@ -33,3 +33,21 @@ def test_reference_arm_json_line():
 def test_reference_arm_other_ranks_stay_silent():
     """under torchrun only rank 0 runs and prints the reference arm"""
     assert _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], {"RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_capture():
+    """bench.py's roofline.traffic (dram read + write bytes per launch of the dominant kernels) is parsed from the `# traffic`
+    lines of the committed `ncu --set full` summary, not hard-coded: the file must be there and carry the four global_feat
+    kernels (forward, data gradient, Gram matrix, inference forward) with plausible sizes (>= the 268 MB of one 1024-channel
+    bf16 tensor at 8 x 16 384 points)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench_mod", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert os.path.exists(os.path.join(root, mod.NCU_TRAFFIC_SOURCE)), mod.NCU_TRAFFIC_SOURCE
+    t = mod.load_ncu_traffic()
+    for tag in (5, 21, 53, 69):
+        assert tag in t and 260.0 < t[tag] < 700.0, (tag, t)
+    assert t[21] > t[5]          # the data gradient also writes its 268 MB result
